@@ -1,0 +1,75 @@
+"""ctypes loader for libblis_b200.so (the C-ABI engine).
+
+There is deliberately no fallback: if the CUDA library is missing or does not
+load, importing the compute API raises.  `oracle/` is never imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libblis_b200.so"
+
+# BLIS enum values (frame/include/bli_type_defs.h:278-455), same as include/blis_b200.h
+BLIS_FLOAT, BLIS_SCOMPLEX, BLIS_DOUBLE, BLIS_DCOMPLEX = 0, 1, 2, 3
+BLIS_NO_TRANSPOSE, BLIS_TRANSPOSE, BLIS_CONJ_NO_TRANSPOSE, BLIS_CONJ_TRANSPOSE = 0x00, 0x08, 0x10, 0x18
+BLIS_UPPER, BLIS_LOWER = 0x60, 0xC0
+BLIS_LEFT, BLIS_RIGHT = 0, 1
+BLIS_NONUNIT_DIAG, BLIS_UNIT_DIAG = 0x000, 0x100
+BLIS_SUCCESS, BLIS_FAILURE = -1, -2
+
+# every symbol include/blis_b200.h declares
+EXPORTS = [
+    "b200_init", "b200_finalize", "b200_last_error", "b200_device_count", "b200_info",
+    "b200_set_stream", "b200_get_stream", "b200_sync",
+    "b200_gemm", "b200_sgemm", "b200_dgemm", "b200_cgemm", "b200_zgemm",
+    "b200_trsm", "b200_strsm", "b200_dtrsm", "b200_ctrsm", "b200_ztrsm",
+    "b200_blksz", "b200_measure_peak",
+]
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    """Raised when the engine returns BLIS_FAILURE (the BLIS glue aborts instead)."""
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m blis_b200.build` "
+            "(nvcc, sm_100a). blis_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    i64, vp, ci = C.c_int64, C.c_void_p, C.c_int
+    lib.b200_init.argtypes = [ci]; lib.b200_init.restype = ci
+    lib.b200_finalize.argtypes = []; lib.b200_finalize.restype = None
+    lib.b200_last_error.argtypes = []; lib.b200_last_error.restype = C.c_char_p
+    lib.b200_device_count.argtypes = []; lib.b200_device_count.restype = ci
+    lib.b200_info.argtypes = []; lib.b200_info.restype = C.c_char_p
+    lib.b200_set_stream.argtypes = [vp]; lib.b200_set_stream.restype = None
+    lib.b200_get_stream.argtypes = []; lib.b200_get_stream.restype = vp
+    lib.b200_sync.argtypes = []; lib.b200_sync.restype = ci
+    gemm_tail = [i64, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
+    lib.b200_gemm.argtypes = [ci, ci, ci] + gemm_tail; lib.b200_gemm.restype = ci
+    for ch in "sdcz":
+        f = getattr(lib, f"b200_{ch}gemm"); f.argtypes = [ci, ci] + gemm_tail; f.restype = ci
+    trsm_tail = [i64, i64, vp, vp, i64, i64, vp, i64, i64]
+    lib.b200_trsm.argtypes = [ci, ci, ci, ci, ci] + trsm_tail; lib.b200_trsm.restype = ci
+    for ch in "sdcz":
+        f = getattr(lib, f"b200_{ch}trsm"); f.argtypes = [ci, ci, ci, ci] + trsm_tail; f.restype = ci
+    lib.b200_blksz.argtypes = [ci, ci]; lib.b200_blksz.restype = i64
+    lib.b200_measure_peak.argtypes = [ci, ci]; lib.b200_measure_peak.restype = C.c_double
+    lib.b200_set_option.argtypes = [C.c_char_p, C.c_longlong]; lib.b200_set_option.restype = ci
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != BLIS_SUCCESS:
+        msg = load().b200_last_error().decode(errors="replace")
+        raise EngineError(f"{what} failed: {msg}")

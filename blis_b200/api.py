@@ -1,0 +1,233 @@
+"""Host-side mirror of the reference's level-3 API for the gemm/trsm hot path.
+
+Three layers, named as in BLIS so that tests read like the reference's own:
+
+* typed API   `bli_?gemm`, `bli_?trsm`            frame/3/bli_l3_tapi.c
+* object API  `bli_gemm`, `bli_trsm` on `Obj`     frame/3/bli_l3_oapi.c
+* BLAS compat `dgemm_`-style column-major calls   frame/compat/bla_gemm.c:127-259,
+                                                 frame/compat/bla_trsm.c:126-217
+
+All of them end in the C ABI of libblis_b200.so (include/blis_b200.h).  Operands
+are torch tensors used purely as memory handles (CUDA tensors are used in place,
+CPU tensors are staged by the engine) or raw integer addresses.  Error
+behaviour follows the reference: invalid arguments and engine failures raise
+(the C glue calls bli_abort()); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import (BLIS_CONJ_NO_TRANSPOSE, BLIS_CONJ_TRANSPOSE, BLIS_DCOMPLEX, BLIS_DOUBLE,
+                   BLIS_FLOAT, BLIS_LEFT, BLIS_LOWER, BLIS_NO_TRANSPOSE, BLIS_NONUNIT_DIAG,
+                   BLIS_RIGHT, BLIS_SCOMPLEX, BLIS_TRANSPOSE, BLIS_UNIT_DIAG, BLIS_UPPER,
+                   EngineError, check)
+
+_DT = {torch.float32: BLIS_FLOAT, torch.float64: BLIS_DOUBLE,
+       torch.complex64: BLIS_SCOMPLEX, torch.complex128: BLIS_DCOMPLEX}
+_CH = {"s": torch.float32, "d": torch.float64, "c": torch.complex64, "z": torch.complex128}
+
+
+def _scalar_buf(dtype: torch.dtype, v):
+    if dtype == torch.float32:
+        return (C.c_float * 1)(float(v))
+    if dtype == torch.float64:
+        return (C.c_double * 1)(float(v))
+    v = complex(v)
+    if dtype == torch.complex64:
+        return (C.c_float * 2)(v.real, v.imag)
+    return (C.c_double * 2)(v.real, v.imag)
+
+
+def _ptr(x) -> int:
+    return x.data_ptr() if isinstance(x, torch.Tensor) else int(x)
+
+
+def _bind_stream(*ts) -> None:
+    """Issue the engine's work on torch's current stream of the operands' device."""
+    lib = _lib.load()
+    for t in ts:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            h = torch.cuda.current_stream(t.device).cuda_stream
+            lib.b200_set_stream(C.c_void_p(h if h != 0 else 1))   # 1 == cudaStreamLegacy
+            return
+    lib.b200_set_stream(None)
+
+
+# ----------------------------------------------------------------------------- typed API
+def _typed_gemm(dtype):
+    def f(transa, transb, m, n, k, alpha, a, rs_a, cs_a, b, rs_b, cs_b, beta, c, rs_c, cs_c):
+        lib = _lib.load()
+        _bind_stream(a, b, c)
+        al, be = _scalar_buf(dtype, alpha), _scalar_buf(dtype, beta)
+        rc = lib.b200_gemm(_DT[dtype], int(transa), int(transb), m, n, k, C.addressof(al),
+                           _ptr(a), rs_a, cs_a, _ptr(b), rs_b, cs_b, C.addressof(be),
+                           _ptr(c), rs_c, cs_c)
+        check(rc, "bli_gemm")
+    return f
+
+
+def _typed_trsm(dtype):
+    def f(side, uploa, transa, diaga, m, n, alpha, a, rs_a, cs_a, b, rs_b, cs_b):
+        lib = _lib.load()
+        _bind_stream(a, b)
+        al = _scalar_buf(dtype, alpha)
+        rc = lib.b200_trsm(_DT[dtype], int(side), int(uploa), int(transa), int(diaga), m, n,
+                           C.addressof(al), _ptr(a), rs_a, cs_a, _ptr(b), rs_b, cs_b)
+        check(rc, "bli_trsm")
+    return f
+
+
+bli_sgemm, bli_dgemm = _typed_gemm(torch.float32), _typed_gemm(torch.float64)
+bli_cgemm, bli_zgemm = _typed_gemm(torch.complex64), _typed_gemm(torch.complex128)
+bli_strsm, bli_dtrsm = _typed_trsm(torch.float32), _typed_trsm(torch.float64)
+bli_ctrsm, bli_ztrsm = _typed_trsm(torch.complex64), _typed_trsm(torch.complex128)
+
+
+# ----------------------------------------------------------------------------- object API
+@dataclass
+class Obj:
+    """The part of obj_t (frame/include/bli_type_defs.h:1230-1275) this path reads:
+    buffer, dims, strides and the conjtrans / uplo / diag bits of `info`."""
+    buf: torch.Tensor
+    conjtrans: int = BLIS_NO_TRANSPOSE
+    uplo: int = 0xE0          # BLIS_DENSE
+    diag: int = BLIS_NONUNIT_DIAG
+
+    def __post_init__(self):
+        if self.buf.dim() != 2:
+            raise ValueError("Obj wraps a 2-D tensor")
+
+    @property
+    def dt(self): return self.buf.dtype
+    @property
+    def m(self): return self.buf.shape[0]
+    @property
+    def n(self): return self.buf.shape[1]
+    @property
+    def rs(self): return self.buf.stride(0)
+    @property
+    def cs(self): return self.buf.stride(1)
+
+    def dims_after_trans(self):
+        return (self.n, self.m) if self.conjtrans & BLIS_TRANSPOSE else (self.m, self.n)
+
+
+def bli_obj_create_with_attached_buffer(t: torch.Tensor) -> Obj:
+    return Obj(t)
+
+
+def bli_obj_set_conjtrans(trans: int, o: Obj) -> None: o.conjtrans = trans
+def bli_obj_set_uplo(uplo: int, o: Obj) -> None: o.uplo = uplo
+def bli_obj_set_diag(diag: int, o: Obj) -> None: o.diag = diag
+
+
+def bli_gemm(alpha, a: Obj, b: Obj, beta, c: Obj) -> None:
+    """C := beta*C + alpha*trans(A)*trans(B)  (bli_gemm, frame/3/bli_l3_oapi.c).
+
+    Checks follow bli_gemm_check (frame/3/bli_l3_check.c:37-63): conformal
+    dimensions and one datatype; mixed-datatype gemm is out of scope here."""
+    if not (a.dt == b.dt == c.dt):
+        raise EngineError("bli_gemm: mixed-datatype operands are out of scope for the b200 engine")
+    ma, ka = a.dims_after_trans()
+    kb, nb = b.dims_after_trans()
+    if (ma, nb) != (c.m, c.n) or ka != kb:
+        raise EngineError("bli_gemm: non-conformal dimensions")
+    _typed_gemm(c.dt)(a.conjtrans, b.conjtrans, c.m, c.n, ka, alpha,
+                      a.buf, a.rs, a.cs, b.buf, b.rs, b.cs, beta, c.buf, c.rs, c.cs)
+
+
+def bli_trsm(side: int, alpha, a: Obj, b: Obj) -> None:
+    """Solve trans(A) X = alpha B (left) or X trans(A) = alpha B (right), B := X
+    (bli_trsm, frame/3/bli_l3_oapi.c; checks as bli_trsm_check)."""
+    if a.dt != b.dt:
+        raise EngineError("bli_trsm: mixed-datatype operands are out of scope")
+    if a.m != a.n:
+        raise EngineError("bli_trsm: A must be square")
+    if a.uplo not in (BLIS_LOWER, BLIS_UPPER):
+        raise EngineError("bli_trsm: A must be triangular (uplo lower or upper)")
+    if (side == BLIS_LEFT and a.m != b.m) or (side == BLIS_RIGHT and a.m != b.n):
+        raise EngineError("bli_trsm: non-conformal dimensions")
+    _typed_trsm(b.dt)(side, a.uplo, a.conjtrans, a.diag, b.m, b.n, alpha,
+                      a.buf, a.rs, a.cs, b.buf, b.rs, b.cs)
+
+
+# ----------------------------------------------------------------------------- BLAS compat
+_TR = {"N": BLIS_NO_TRANSPOSE, "T": BLIS_TRANSPOSE, "C": BLIS_CONJ_TRANSPOSE}
+
+
+def _blas_gemm(ch):
+    dtype = _CH[ch]
+
+    def f(transa: str, transb: str, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc):
+        """?gemm_ (frame/compat/bla_gemm.c:127-259): column-major, rs=1, cs=ld.
+        Argument errors raise like xerbla (frame/compat/check/bla_gemm_check.h)."""
+        ta, tb = transa.upper(), transb.upper()
+        if ta not in _TR: raise ValueError(f"{ch}gemm_: parameter 1 (transa) invalid")
+        if tb not in _TR: raise ValueError(f"{ch}gemm_: parameter 2 (transb) invalid")
+        if m < 0: raise ValueError(f"{ch}gemm_: parameter 3 (m) invalid")
+        if n < 0: raise ValueError(f"{ch}gemm_: parameter 4 (n) invalid")
+        if k < 0: raise ValueError(f"{ch}gemm_: parameter 5 (k) invalid")
+        nrowa = m if ta == "N" else k
+        nrowb = k if tb == "N" else n
+        if lda < max(1, nrowa): raise ValueError(f"{ch}gemm_: parameter 8 (lda) invalid")
+        if ldb < max(1, nrowb): raise ValueError(f"{ch}gemm_: parameter 10 (ldb) invalid")
+        if ldc < max(1, m): raise ValueError(f"{ch}gemm_: parameter 13 (ldc) invalid")
+        _typed_gemm(dtype)(_TR[ta], _TR[tb], m, n, k, alpha, a, 1, lda, b, 1, ldb, beta, c, 1, ldc)
+    return f
+
+
+def _blas_trsm(ch):
+    dtype = _CH[ch]
+
+    def f(side: str, uplo: str, transa: str, diag: str, m, n, alpha, a, lda, b, ldb):
+        """?trsm_ (frame/compat/bla_trsm.c:126-217)."""
+        s, u, t, d = side.upper(), uplo.upper(), transa.upper(), diag.upper()
+        if s not in "LR": raise ValueError(f"{ch}trsm_: parameter 1 (side) invalid")
+        if u not in "LU": raise ValueError(f"{ch}trsm_: parameter 2 (uplo) invalid")
+        if t not in _TR: raise ValueError(f"{ch}trsm_: parameter 3 (transa) invalid")
+        if d not in "NU": raise ValueError(f"{ch}trsm_: parameter 4 (diag) invalid")
+        if m < 0: raise ValueError(f"{ch}trsm_: parameter 5 (m) invalid")
+        if n < 0: raise ValueError(f"{ch}trsm_: parameter 6 (n) invalid")
+        nrowa = m if s == "L" else n
+        if lda < max(1, nrowa): raise ValueError(f"{ch}trsm_: parameter 9 (lda) invalid")
+        if ldb < max(1, m): raise ValueError(f"{ch}trsm_: parameter 11 (ldb) invalid")
+        _typed_trsm(dtype)(BLIS_LEFT if s == "L" else BLIS_RIGHT,
+                           BLIS_LOWER if u == "L" else BLIS_UPPER, _TR[t],
+                           BLIS_UNIT_DIAG if d == "U" else BLIS_NONUNIT_DIAG,
+                           m, n, alpha, a, 1, lda, b, 1, ldb)
+    return f
+
+
+sgemm_, dgemm_, cgemm_, zgemm_ = (_blas_gemm(ch) for ch in "sdcz")
+strsm_, dtrsm_, ctrsm_, ztrsm_ = (_blas_trsm(ch) for ch in "sdcz")
+
+
+# ----------------------------------------------------------------------------- info / tuning
+def info() -> str:
+    return _lib.load().b200_info().decode()
+
+
+def blksz(dtype: torch.dtype, which: str) -> int:
+    idx = {"MR": 0, "NR": 1, "MC": 2, "KC": 3, "NC": 4}[which]
+    return int(_lib.load().b200_blksz(_DT[dtype], idx))
+
+
+def measure_peak(kind: str, millis: int = 200) -> float:
+    """TFLOP/s of the DFMA / DMMA / FFMA pipe microbenchmark."""
+    k = {"dfma": 0, "dmma": 1, "ffma": 2}[kind]
+    v = float(_lib.load().b200_measure_peak(k, millis))
+    if v < 0:
+        raise EngineError("peak microbenchmark failed (no GPU?)")
+    return v
+
+
+def set_option(key: str, value: int) -> None:
+    check(_lib.load().b200_set_option(key.encode(), int(value)), f"set_option({key})")
+
+
+def sync() -> None:
+    check(_lib.load().b200_sync(), "b200_sync")

@@ -1,0 +1,80 @@
+"""Build the C-ABI shared library (blis_b200/libblis_b200.so) with nvcc for sm_100a.
+
+nvcc cross-compiles without a GPU.  The library is built in-tree so that it
+travels with the repository snapshot to the GPU box.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libblis_b200.so"
+STAMP = PKG / ".libblis_b200.stamp"
+
+SOURCES = ["capi.cu", "context.cu", "peaks.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-std=c++17", "-lineinfo",
+    "--shared", "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-pthread",
+    "--expt-relaxed-constexpr",
+]
+
+
+def _nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found; cannot build libblis_b200.so")
+    return exe
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [ROOT / "include" / "blis_b200.h"]):
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile the library if sources changed.  Returns the path of the .so."""
+    dig = _digest()
+    if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == dig:
+        return LIB
+    objs = []
+    procs = []
+    nvcc = _nvcc()
+    objdir = PKG / "build"
+    objdir.mkdir(exist_ok=True)
+    for src in SOURCES:
+        obj = objdir / (src + ".o")
+        cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "--shared"], "-c", str(CSRC / src), "-o", str(obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(str(obj))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(out)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}")
+    link = [nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", str(LIB)]
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("link of libblis_b200.so failed")
+    STAMP.write_text(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,584 @@
+// capi.cu -- the extern "C" level-3 entry points and their host-side front ends.
+//
+// Host logic that mirrors the reference's object-API front ends:
+//   bli_gemm_ex   frame/3/bli_l3_oapi_ex.c:48-148   (trivial cases, storage
+//                 based operand swap as in bli_gemm_cntl.c:98-161)
+//   bli_trsm_ex   frame/3/bli_l3_oapi_ex.c:692-801  (right side solved as the
+//                 transposed left-side problem, :748-759)
+//   bli_l3_return_early_if_trivial   frame/3/bli_l3_util.c:40-65
+//   bli_trsm_blk_var1 (solve block, then rank-k update of the remaining rows)
+//                 frame/3/trsm/bli_trsm_blk_var1.c:40-188
+#include "context.cuh"
+#include "gemm_dmma.cuh"
+#include "gemm_ffma.cuh"
+#include "trsm.cuh"
+#include "../../include/blis_b200.h"
+#include <algorithm>
+#include <utility>
+
+namespace b200 {
+
+// ---- small helpers -------------------------------------------------------------
+template <typename T> struct Scalar;
+template <> struct Scalar<float>
+{
+	static float   make( double r, double ) { return (float)r; }
+	static bool    is_zero( float a ) { return a == 0.0f; }
+	static bool    is_one( float a )  { return a == 1.0f; }
+};
+template <> struct Scalar<double>
+{
+	static double  make( double r, double ) { return r; }
+	static bool    is_zero( double a ) { return a == 0.0; }
+	static bool    is_one( double a )  { return a == 1.0; }
+};
+template <> struct Scalar<float2>
+{
+	static float2  make( double r, double i ) { return make_float2( (float)r, (float)i ); }
+	static bool    is_zero( float2 a ) { return a.x == 0.0f && a.y == 0.0f; }
+	static bool    is_one( float2 a )  { return a.x == 1.0f && a.y == 0.0f; }
+};
+template <> struct Scalar<double2>
+{
+	static double2 make( double r, double i ) { return make_double2( r, i ); }
+	static bool    is_zero( double2 a ) { return a.x == 0.0 && a.y == 0.0; }
+	static bool    is_one( double2 a )  { return a.x == 1.0 && a.y == 0.0; }
+};
+
+// ---- strided copy / scale kernels (component-wise, so complex data only
+//      needs the alignment of its real type) -----------------------------------
+template <typename R, int NC>
+__global__ void copy2d_kernel( R* __restrict__ dst, int64_t rsd, int64_t csd,
+                               const R* __restrict__ src, int64_t rss, int64_t css,
+                               int64_t m, int64_t n, int inner_is_row )
+{
+	const int64_t total = m * n;
+	for ( int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x )
+	{
+		int64_t i, j;
+		if ( inner_is_row ) { i = e % m; j = e / m; } else { j = e % n; i = e / n; }
+		const R* s = src + ( i * rss + j * css ) * NC;
+		R*       d = dst + ( i * rsd + j * csd ) * NC;
+		#pragma unroll
+		for ( int c = 0; c < NC; ++c ) d[c] = s[c];
+	}
+}
+
+// C := beta * C  (beta == 0 stores zeros without reading C: bli_scalm / bli_setm)
+template <typename R, int NC>
+__global__ void scal2d_kernel( R* __restrict__ c, int64_t rs, int64_t cs, int64_t m, int64_t n,
+                               R br, R bi, int beta_is_zero, int inner_is_row )
+{
+	const int64_t total = m * n;
+	for ( int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x )
+	{
+		int64_t i, j;
+		if ( inner_is_row ) { i = e % m; j = e / m; } else { j = e % n; i = e / n; }
+		R* p = c + ( i * rs + j * cs ) * NC;
+		if ( beta_is_zero ) { for ( int q = 0; q < NC; ++q ) p[q] = (R)0; }
+		else if ( NC == 1 ) p[0] = br * p[0];
+		else { const R xr = p[0], xi = p[1]; p[0] = br * xr - bi * xi; p[1] = br * xi + bi * xr; }
+	}
+}
+
+static inline int64_t iabs64( int64_t x ) { return x < 0 ? -x : x; }
+
+template <typename T>
+static int copy2d( T* dst, int64_t rsd, int64_t csd, const T* src, int64_t rss, int64_t css,
+                   int64_t m, int64_t n, cudaStream_t st )
+{
+	if ( m <= 0 || n <= 0 ) return kSuccess;
+	using R = typename Elem<T>::real;
+	constexpr int NC = Elem<T>::cplx ? 2 : 1;
+	const int inner_is_row = ( iabs64( rss ) + iabs64( rsd ) <= iabs64( css ) + iabs64( csd ) );
+	const int64_t total = m * n;
+	const int blocks = (int)std::min<int64_t>( ( total + 255 ) / 256, (int64_t)ctx().num_sms * 16 );
+	copy2d_kernel<R, NC><<<blocks, 256, 0, st>>>( (R*)dst, rsd, csd, (const R*)src, rss, css, m, n, inner_is_row );
+	B200_CUDA( cudaGetLastError() );
+	return kSuccess;
+}
+
+template <typename T>
+static int scal2d( T* c, int64_t rs, int64_t cs, int64_t m, int64_t n, T beta, cudaStream_t st )
+{
+	if ( m <= 0 || n <= 0 || Scalar<T>::is_one( beta ) ) return kSuccess;
+	using R = typename Elem<T>::real;
+	constexpr int NC = Elem<T>::cplx ? 2 : 1;
+	R br, bi;
+	if constexpr ( Elem<T>::cplx ) { br = beta.x; bi = beta.y; } else { br = beta; bi = 0; }
+	const int inner_is_row = ( iabs64( rs ) <= iabs64( cs ) );
+	const int64_t total = m * n;
+	const int blocks = (int)std::min<int64_t>( ( total + 255 ) / 256, (int64_t)ctx().num_sms * 16 );
+	scal2d_kernel<R, NC><<<blocks, 256, 0, st>>>( (R*)c, rs, cs, m, n, br, bi, Scalar<T>::is_zero( beta ) ? 1 : 0, inner_is_row );
+	B200_CUDA( cudaGetLastError() );
+	return kSuccess;
+}
+
+// ---- kernel launchers -------------------------------------------------------------
+template <typename KernT>
+static int set_smem( KernT kern, int bytes )
+{
+	B200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes ) );
+	return kSuccess;
+}
+
+template <typename T, int BP, int BQ, int BK, int WP, int WQ, int ST>
+static int launch_dmma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
+{
+	auto go = [&]( auto XKc, auto YKc, auto ALc ) -> int
+	{
+		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
+		using Cfg = DmmaCfg<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
+		auto kern = gemm_dmma_kernel<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
+		static bool attr = false;
+		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>( g );
+		B200_CUDA( cudaGetLastError() );
+		return kSuccess;
+	};
+	using Tt = std::true_type; using Ff = std::false_type;
+	const int sel = ( xk ? 4 : 0 ) | ( yk ? 2 : 0 ) | ( al ? 1 : 0 );
+	switch ( sel )
+	{
+		case 0: return go( Ff{}, Ff{}, Ff{} );  case 1: return go( Ff{}, Ff{}, Tt{} );
+		case 2: return go( Ff{}, Tt{}, Ff{} );  case 3: return go( Ff{}, Tt{}, Tt{} );
+		case 4: return go( Tt{}, Ff{}, Ff{} );  case 5: return go( Tt{}, Ff{}, Tt{} );
+		case 6: return go( Tt{}, Tt{}, Ff{} );  default: return go( Tt{}, Tt{}, Tt{} );
+	}
+}
+
+template <typename T, int BP, int BQ, int BK, int TP, int TQ, int ST>
+static int launch_ffma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
+{
+	auto go = [&]( auto XKc, auto YKc, auto ALc ) -> int
+	{
+		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
+		using Cfg = FfmaCfg<T, BP, BQ, BK, TP, TQ, ST>;
+		auto kern = gemm_ffma_kernel<T, BP, BQ, BK, TP, TQ, ST, XK, YK, AL>;
+		static bool attr = false;
+		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>( g );
+		B200_CUDA( cudaGetLastError() );
+		return kSuccess;
+	};
+	using Tt = std::true_type; using Ff = std::false_type;
+	const int sel = ( xk ? 4 : 0 ) | ( yk ? 2 : 0 ) | ( al ? 1 : 0 );
+	switch ( sel )
+	{
+		case 0: return go( Ff{}, Ff{}, Ff{} );  case 1: return go( Ff{}, Ff{}, Tt{} );
+		case 2: return go( Ff{}, Tt{}, Ff{} );  case 3: return go( Ff{}, Tt{}, Tt{} );
+		case 4: return go( Tt{}, Ff{}, Ff{} );  case 5: return go( Tt{}, Ff{}, Tt{} );
+		case 6: return go( Tt{}, Tt{}, Ff{} );  default: return go( Tt{}, Tt{}, Tt{} );
+	}
+}
+
+// Tile shapes per datatype = the "blocksizes" this engine registers
+// (MR/NR become the warp tile, MC/NC the CTA tile, KC the staged k slab).
+template <typename T> struct Tiles;
+template <> struct Tiles<double>  { static constexpr int BP = 128, BQ = 128, BK = 16, MR = 64, NR = 32; };
+template <> struct Tiles<double2> { static constexpr int BP = 64,  BQ = 128, BK = 8,  MR = 32, NR = 32; };
+template <> struct Tiles<float>   { static constexpr int BP = 128, BQ = 128, BK = 16, MR = 8,  NR = 8;  };
+template <> struct Tiles<float2>  { static constexpr int BP = 64,  BQ = 128, BK = 16, MR = 4,  NR = 8;  };
+
+template <typename T>
+static int launch_gemm_kernel( GemmArgs<T>& g, bool xk, bool yk, bool al, cudaStream_t st );
+
+template <>
+int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, cudaStream_t st )
+{
+	Context& c = ctx();
+	auto tiles = [&]( int bp, int bq ) {
+		g.tiles_p = (int)( ( g.P + bp - 1 ) / bp ); g.tiles_q = (int)( ( g.Q + bq - 1 ) / bq );
+		return (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
+	};
+	switch ( c.dgemm_cfg )
+	{
+		default:
+		case 0: return launch_dmma<double, 128, 128, 16, 2, 4, 4>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 1: return launch_dmma<double, 128, 128, 16, 4, 2, 4>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 2: return launch_dmma<double, 128, 128, 8,  2, 4, 6>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 3: return launch_dmma<double, 128, 128, 32, 2, 4, 3>( g, xk, yk, al, tiles( 128, 128 ), st );
+	}
+}
+template <>
+int launch_gemm_kernel<double2>( GemmArgs<double2>& g, bool xk, bool yk, bool al, cudaStream_t st )
+{
+	Context& c = ctx();
+	g.tiles_p = (int)( ( g.P + 63 ) / 64 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
+	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
+	return launch_dmma<double2, 64, 128, 8, 2, 4, 4>( g, xk, yk, al, grid, st );
+}
+template <>
+int launch_gemm_kernel<float>( GemmArgs<float>& g, bool xk, bool yk, bool al, cudaStream_t st )
+{
+	Context& c = ctx();
+	g.tiles_p = (int)( ( g.P + 127 ) / 128 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
+	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
+	return launch_ffma<float, 128, 128, 16, 8, 8, 4>( g, xk, yk, al, grid, st );
+}
+template <>
+int launch_gemm_kernel<float2>( GemmArgs<float2>& g, bool xk, bool yk, bool al, cudaStream_t st )
+{
+	Context& c = ctx();
+	g.tiles_p = (int)( ( g.P + 63 ) / 64 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
+	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
+	return launch_ffma<float2, 64, 128, 16, 4, 8, 4>( g, xk, yk, al, grid, st );
+}
+
+// ---- gemm on device-resident strided views ------------------------------------
+// C(m x n) := beta*C + alpha * A(m x k) * B(k x n); A/B views already carry any
+// transposition in their strides; conja/conjb request conjugation.
+template <typename T>
+static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T alpha,
+                     const T* a, int64_t rs_a, int64_t cs_a,
+                     const T* b, int64_t rs_b, int64_t cs_b,
+                     T beta, T* c, int64_t rs_c, int64_t cs_c, cudaStream_t st )
+{
+	if ( m <= 0 || n <= 0 ) return kSuccess;
+	// bli_l3_return_early_if_trivial: alpha == 0 or k == 0  ->  C := beta*C
+	if ( k <= 0 || Scalar<T>::is_zero( alpha ) ) return scal2d( c, rs_c, cs_c, m, n, beta, st );
+
+	constexpr size_t ES = sizeof(T);
+	void *tmp_c = nullptr, *tmp_x = nullptr, *tmp_y = nullptr;
+	int rc = kSuccess;
+
+	// Complex element accesses in the kernels need natural alignment of T.
+	const bool c_misaligned = ( (uintptr_t)c % ( Elem<T>::cplx ? ES : sizeof( typename Elem<T>::real ) ) ) != 0;
+
+	// -- output: make it "q-contiguous" (D = C or D = C^T)
+	T* cd = c; int64_t rs_cd = rs_c, cs_cd = cs_c;
+	const bool c_general = !( ( rs_c == 1 && ( cs_c >= m || n == 1 ) ) || ( cs_c == 1 && ( rs_c >= n || m == 1 ) ) ) || c_misaligned;
+	if ( c_general )
+	{
+		if ( dev_alloc( &tmp_c, (size_t)m * n * ES, st ) != kSuccess ) return kFailure;
+		cd = (T*)tmp_c; rs_cd = 1; cs_cd = m;
+		if ( !Scalar<T>::is_zero( beta ) ) rc = copy2d( cd, rs_cd, cs_cd, c, rs_c, cs_c, m, n, st );
+	}
+
+	GemmArgs<T> g;
+	int64_t xs_p, xs_k, ys_k, ys_q;
+	if ( rs_cd == 1 && !( cs_cd == 1 && m > 1 ) )
+	{
+		// column-stored C: D = C^T,  X = B^T (P = n),  Y = A^T (Q = m)
+		g.P = n; g.Q = m; g.ldd = ( n == 1 ? m : cs_cd );
+		g.X = b; xs_p = cs_b; xs_k = rs_b; g.conjx = conjb;
+		g.Y = a; ys_k = cs_a; ys_q = rs_a; g.conjy = conja;
+	}
+	else
+	{
+		// row-stored C: D = C,  X = A (P = m),  Y = B (Q = n)
+		g.P = m; g.Q = n; g.ldd = ( m == 1 ? n : rs_cd );
+		g.X = a; xs_p = rs_a; xs_k = cs_a; g.conjx = conja;
+		g.Y = b; ys_k = rs_b; ys_q = cs_b; g.conjy = conjb;
+	}
+	g.D = cd; g.K = k; g.alpha = alpha; g.beta = beta;
+	g.beta_is_zero = Scalar<T>::is_zero( beta ) ? 1 : 0;
+
+	// -- X: k-contiguous, p-contiguous, or packed
+	bool xk = false, yk = false;
+	auto misaligned = [&]( const T* p ) { return Elem<T>::cplx && ( (uintptr_t)p % ES ) != 0 && ES == 8; };
+	if      ( !misaligned( g.X ) && ( xs_k == 1 || k == 1 ) && ( xs_p >= k || g.P == 1 ) && xs_k >= 0 ) { xk = true;  g.ldx = ( g.P == 1 ? k : xs_p ); }
+	else if ( !misaligned( g.X ) && ( xs_p == 1 || g.P == 1 ) && ( xs_k >= g.P || k == 1 ) )            { xk = false; g.ldx = ( k == 1 ? g.P : xs_k ); }
+	else if ( rc == kSuccess )
+	{
+		if ( dev_alloc( &tmp_x, (size_t)g.P * k * ES, st ) != kSuccess ) rc = kFailure;
+		else { rc = copy2d( (T*)tmp_x, k, (int64_t)1, g.X, xs_p, xs_k, g.P, k, st ); g.X = (const T*)tmp_x; xk = true; g.ldx = k; }
+	}
+	if      ( !misaligned( g.Y ) && ( ys_k == 1 || k == 1 ) && ( ys_q >= k || g.Q == 1 ) && ys_k >= 0 ) { yk = true;  g.ldy = ( g.Q == 1 ? k : ys_q ); }
+	else if ( !misaligned( g.Y ) && ( ys_q == 1 || g.Q == 1 ) && ( ys_k >= g.Q || k == 1 ) )            { yk = false; g.ldy = ( k == 1 ? g.Q : ys_k ); }
+	else if ( rc == kSuccess )
+	{
+		if ( dev_alloc( &tmp_y, (size_t)g.Q * k * ES, st ) != kSuccess ) rc = kFailure;
+		else { rc = copy2d( (T*)tmp_y, (int64_t)1, k, g.Y, ys_k, ys_q, k, g.Q, st ); g.Y = (const T*)tmp_y; yk = true; g.ldy = k; }
+	}
+
+	if ( rc == kSuccess )
+	{
+		const bool al = ( (uintptr_t)g.X % 16 == 0 ) && ( (uintptr_t)g.Y % 16 == 0 ) &&
+		                ( ( g.ldx * ES ) % 16 == 0 ) && ( ( g.ldy * ES ) % 16 == 0 );
+		g.d_vec_ok = ( (uintptr_t)g.D % 16 == 0 ) && ( ( g.ldd * ES ) % 16 == 0 );
+		rc = launch_gemm_kernel<T>( g, xk, yk, al, st );
+	}
+	if ( rc == kSuccess && c_general ) rc = copy2d( c, rs_c, cs_c, cd, rs_cd, cs_cd, m, n, st );
+	dev_free( tmp_x, st ); dev_free( tmp_y, st ); dev_free( tmp_c, st );
+	return rc;
+}
+
+// ---- gemm front end: transposition bits + host operand staging ---------------------
+template <typename T>
+static int gemm_front( int transa, int transb, int64_t m, int64_t n, int64_t k,
+                       const T* alpha, const T* a, int64_t rs_a, int64_t cs_a,
+                       const T* b, int64_t rs_b, int64_t cs_b,
+                       const T* beta, T* c, int64_t rs_c, int64_t cs_c )
+{
+	if ( ensure_init() != kSuccess ) return kFailure;
+	if ( m < 0 || n < 0 || k < 0 ) return fail( "b200_gemm: negative dimension" );
+	if ( !alpha || !beta ) return fail( "b200_gemm: alpha/beta must be non-NULL host pointers" );
+	if ( m == 0 || n == 0 ) return kSuccess;
+	cudaStream_t st = cur_stream();
+	constexpr size_t ES = sizeof(T);
+
+	if ( transa & B200_TRANSPOSE ) std::swap( rs_a, cs_a );
+	if ( transb & B200_TRANSPOSE ) std::swap( rs_b, cs_b );
+	const bool conja = Elem<T>::cplx && ( transa & B200_CONJ_NO_TRANSPOSE );
+	const bool conjb = Elem<T>::cplx && ( transb & B200_CONJ_NO_TRANSPOSE );
+	const T al = *alpha, be = *beta;
+	const bool need_ab = ( k > 0 && !Scalar<T>::is_zero( al ) );
+
+	void *da = nullptr, *db = nullptr, *dc = nullptr;
+	int rc = kSuccess;
+	const bool c_host = ( classify( c ) != MemKind::Device );
+	if ( need_ab && classify( a ) != MemKind::Device )
+	{
+		if ( dev_alloc( &da, (size_t)m * k * ES, st ) != kSuccess ) return kFailure;
+		rc = stage_to_device( da, a, m, k, rs_a, cs_a, ES, st );
+		a = (const T*)da; rs_a = 1; cs_a = m;
+	}
+	if ( rc == kSuccess && need_ab && classify( b ) != MemKind::Device )
+	{
+		if ( dev_alloc( &db, (size_t)k * n * ES, st ) != kSuccess ) rc = kFailure;
+		else rc = stage_to_device( db, b, k, n, rs_b, cs_b, ES, st );
+		b = (const T*)db; rs_b = 1; cs_b = k;
+	}
+	T* cdev = c; int64_t rs_cd = rs_c, cs_cd = cs_c;
+	if ( rc == kSuccess && c_host )
+	{
+		if ( dev_alloc( &dc, (size_t)m * n * ES, st ) != kSuccess ) rc = kFailure;
+		else if ( !Scalar<T>::is_zero( be ) ) rc = stage_to_device( dc, c, m, n, rs_c, cs_c, ES, st );
+		cdev = (T*)dc; rs_cd = 1; cs_cd = m;
+	}
+	if ( rc == kSuccess )
+		rc = gemm_dev<T>( conja, conjb, m, n, k, al, a, rs_a, cs_a, b, rs_b, cs_b, be, cdev, rs_cd, cs_cd, st );
+	if ( rc == kSuccess && c_host )
+	{
+		rc = stage_to_host( c, rs_c, cs_c, dc, m, n, ES, st );
+		if ( rc == kSuccess && cudaStreamSynchronize( st ) != cudaSuccess ) rc = fail( "b200_gemm: stream sync failed: %s", cudaGetErrorString( cudaGetLastError() ) );
+	}
+	dev_free( da, st ); dev_free( db, st ); dev_free( dc, st );
+	return rc;
+}
+
+// ---- trsm -----------------------------------------------------------------------------
+template <typename T> struct TrsmBlk;
+template <> struct TrsmBlk<float>   { static constexpr int NB = 64, CN = 64; };
+template <> struct TrsmBlk<double>  { static constexpr int NB = 64, CN = 64; };
+template <> struct TrsmBlk<float2>  { static constexpr int NB = 32, CN = 64; };
+template <> struct TrsmBlk<double2> { static constexpr int NB = 32, CN = 64; };
+
+template <typename T>
+struct TrsmPlan
+{
+	const T* A; int64_t rs_a, cs_a;      // effective triangular matrix (trans folded into strides)
+	T*       B; int64_t rs_b, cs_b;
+	int64_t  n;
+	bool     upper, unit, conj;
+	cudaStream_t st;
+};
+
+template <typename T>
+static int trsm_base( const TrsmPlan<T>& p, int64_t i0, int mb, T alpha )
+{
+	constexpr int NB = TrsmBlk<T>::NB, CN = TrsmBlk<T>::CN;
+	TrsmBaseArgs<T> a;
+	a.A = p.A + i0 * ( p.rs_a + p.cs_a ); a.rs_a = p.rs_a; a.cs_a = p.cs_a;
+	a.B = p.B + i0 * p.rs_b;              a.rs_b = p.rs_b; a.cs_b = p.cs_b;
+	a.n = p.n; a.mb = mb; a.upper = p.upper; a.unit = p.unit; a.conj = p.conj; a.alpha = alpha;
+	auto kern = trsm_base_kernel<T, NB, CN>;
+	constexpr int smem = trsm_base_smem<T, NB, CN>();
+	static bool attr = false;
+	if ( !attr ) { if ( set_smem( kern, smem ) != kSuccess ) return kFailure; attr = true; }
+	const int64_t grid = ( p.n + CN - 1 ) / CN;
+	kern<<<(unsigned)grid, CN, smem, p.st>>>( a );
+	B200_CUDA( cudaGetLastError() );
+	return kSuccess;
+}
+
+// Recursive blocked solve of rows [i0, i0+mb): solve one half, rank-k update of
+// the other half with the gemm kernel, solve the other half.  alpha is applied
+// exactly once to every row (either by the base kernel or as the update's beta,
+// as bli_trsm_ex passes alpha as beta: bli_l3_oapi_ex.c:778-789).
+template <typename T>
+static int trsm_rec( const TrsmPlan<T>& p, int64_t i0, int64_t mb, T alpha )
+{
+	constexpr int NB = TrsmBlk<T>::NB;
+	if ( mb <= NB ) return trsm_base( p, i0, (int)mb, alpha );
+	const int64_t nblk = ( mb + NB - 1 ) / NB;
+	const int64_t m1 = ( ( nblk + 1 ) / 2 ) * NB, m2 = mb - m1;
+	const T one = Scalar<T>::make( 1.0, 0.0 ), mone = Scalar<T>::make( -1.0, 0.0 );
+	if ( !p.upper )
+	{
+		if ( trsm_rec( p, i0, m1, alpha ) != kSuccess ) return kFailure;
+		// B2 := alpha*B2 - A21 * X1
+		if ( gemm_dev<T>( p.conj, false, m2, p.n, m1, mone,
+		                  p.A + ( i0 + m1 ) * p.rs_a + i0 * p.cs_a, p.rs_a, p.cs_a,
+		                  p.B + i0 * p.rs_b, p.rs_b, p.cs_b,
+		                  alpha, p.B + ( i0 + m1 ) * p.rs_b, p.rs_b, p.cs_b, p.st ) != kSuccess ) return kFailure;
+		return trsm_rec( p, i0 + m1, m2, one );
+	}
+	else
+	{
+		// upper: the trailing block is solved first; split so the LAST block is the ragged one's partner
+		if ( trsm_rec( p, i0 + m2, m1, alpha ) != kSuccess ) return kFailure;
+		// B1 := alpha*B1 - A12 * X2
+		if ( gemm_dev<T>( p.conj, false, m2, p.n, m1, mone,
+		                  p.A + i0 * p.rs_a + ( i0 + m2 ) * p.cs_a, p.rs_a, p.cs_a,
+		                  p.B + ( i0 + m2 ) * p.rs_b, p.rs_b, p.cs_b,
+		                  alpha, p.B + i0 * p.rs_b, p.rs_b, p.cs_b, p.st ) != kSuccess ) return kFailure;
+		return trsm_rec( p, i0, m2, one );
+	}
+}
+
+template <typename T>
+static int trsm_front( int side, int uplo, int transa, int diag, int64_t m, int64_t n,
+                       const T* alpha, const T* a, int64_t rs_a, int64_t cs_a,
+                       T* b, int64_t rs_b, int64_t cs_b )
+{
+	if ( ensure_init() != kSuccess ) return kFailure;
+	if ( m < 0 || n < 0 ) return fail( "b200_trsm: negative dimension" );
+	if ( !alpha ) return fail( "b200_trsm: alpha must be a non-NULL host pointer" );
+	if ( uplo != B200_LOWER && uplo != B200_UPPER ) return fail( "b200_trsm: uplo must be BLIS_LOWER or BLIS_UPPER" );
+	if ( m == 0 || n == 0 ) return kSuccess;
+	cudaStream_t st = cur_stream();
+	constexpr size_t ES = sizeof(T);
+	const T al = *alpha;
+
+	// right side: X * op(A) = alpha*B  <=>  op(A)^T * X^T = alpha * B^T   (bli_l3_oapi_ex.c:748-759)
+	if ( side == B200_RIGHT )
+	{
+		std::swap( m, n ); std::swap( rs_b, cs_b );
+		transa ^= B200_TRANSPOSE;
+	}
+	bool upper = ( uplo == B200_UPPER );
+	if ( transa & B200_TRANSPOSE ) { std::swap( rs_a, cs_a ); upper = !upper; }
+	const bool conj = Elem<T>::cplx && ( transa & B200_CONJ_NO_TRANSPOSE );
+	// now: A is m x m (effective uplo `upper`), B is m x n
+
+	void *da = nullptr, *db = nullptr;
+	int rc = kSuccess;
+	const bool b_host = ( classify( b ) != MemKind::Device );
+	const bool zero_alpha = Scalar<T>::is_zero( al );
+	T* bdev = b; int64_t rs_bd = rs_b, cs_bd = cs_b;
+	if ( b_host )
+	{
+		if ( dev_alloc( &db, (size_t)m * n * ES, st ) != kSuccess ) return kFailure;
+		if ( !zero_alpha ) rc = stage_to_device( db, b, m, n, rs_b, cs_b, ES, st );
+		bdev = (T*)db; rs_bd = 1; cs_bd = m;
+	}
+	if ( zero_alpha )
+	{
+		// bli_l3_return_early_if_trivial( alpha, a, b, &BLIS_ZERO, b ):  B := 0
+		if ( rc == kSuccess ) rc = scal2d( bdev, rs_bd, cs_bd, m, n, al, st );
+	}
+	else
+	{
+		if ( rc == kSuccess && classify( a ) != MemKind::Device )
+		{
+			if ( dev_alloc( &da, (size_t)m * m * ES, st ) != kSuccess ) rc = kFailure;
+			else rc = stage_to_device( da, a, m, m, rs_a, cs_a, ES, st );
+			a = (const T*)da; rs_a = 1; cs_a = m;
+		}
+		if ( rc == kSuccess )
+		{
+			TrsmPlan<T> p{ a, rs_a, cs_a, bdev, rs_bd, cs_bd, n, upper, diag == B200_UNIT_DIAG, conj, st };
+			rc = trsm_rec( p, 0, m, al );
+		}
+	}
+	if ( rc == kSuccess && b_host )
+	{
+		rc = stage_to_host( b, rs_b, cs_b, db, m, n, ES, st );
+		if ( rc == kSuccess && cudaStreamSynchronize( st ) != cudaSuccess ) rc = fail( "b200_trsm: stream sync failed" );
+	}
+	dev_free( da, st ); dev_free( db, st );
+	return rc;
+}
+
+} // namespace b200
+
+// ---- C ABI --------------------------------------------------------------------------
+using namespace b200;
+
+#define B200_DEF_GEMM( ch, ctype, T ) \
+extern "C" b200_err_t b200_##ch##gemm( int transa, int transb, b200_dim_t m, b200_dim_t n, b200_dim_t k, \
+	const ctype* alpha, const ctype* a, b200_inc_t rs_a, b200_inc_t cs_a, \
+	const ctype* b, b200_inc_t rs_b, b200_inc_t cs_b, const ctype* beta, \
+	ctype* c, b200_inc_t rs_c, b200_inc_t cs_c ) \
+{ \
+	return gemm_front<T>( transa, transb, m, n, k, (const T*)alpha, (const T*)a, rs_a, cs_a, \
+	                      (const T*)b, rs_b, cs_b, (const T*)beta, (T*)c, rs_c, cs_c ); \
+}
+B200_DEF_GEMM( s, float, float )
+B200_DEF_GEMM( d, double, double )
+B200_DEF_GEMM( c, b200_scomplex, float2 )
+B200_DEF_GEMM( z, b200_dcomplex, double2 )
+
+extern "C" b200_err_t b200_gemm( int dt, int transa, int transb, b200_dim_t m, b200_dim_t n, b200_dim_t k,
+	const void* alpha, const void* a, b200_inc_t rs_a, b200_inc_t cs_a,
+	const void* b, b200_inc_t rs_b, b200_inc_t cs_b, const void* beta,
+	void* c, b200_inc_t rs_c, b200_inc_t cs_c )
+{
+	switch ( dt )
+	{
+		case B200_FLOAT:    return gemm_front<float>  ( transa, transb, m, n, k, (const float*)alpha,   (const float*)a,   rs_a, cs_a, (const float*)b,   rs_b, cs_b, (const float*)beta,   (float*)c,   rs_c, cs_c );
+		case B200_DOUBLE:   return gemm_front<double> ( transa, transb, m, n, k, (const double*)alpha,  (const double*)a,  rs_a, cs_a, (const double*)b,  rs_b, cs_b, (const double*)beta,  (double*)c,  rs_c, cs_c );
+		case B200_SCOMPLEX: return gemm_front<float2> ( transa, transb, m, n, k, (const float2*)alpha,  (const float2*)a,  rs_a, cs_a, (const float2*)b,  rs_b, cs_b, (const float2*)beta,  (float2*)c,  rs_c, cs_c );
+		case B200_DCOMPLEX: return gemm_front<double2>( transa, transb, m, n, k, (const double2*)alpha, (const double2*)a, rs_a, cs_a, (const double2*)b, rs_b, cs_b, (const double2*)beta, (double2*)c, rs_c, cs_c );
+	}
+	return fail( "b200_gemm: unsupported datatype %d (mixed-datatype gemm is out of scope)", dt );
+}
+
+#define B200_DEF_TRSM( ch, ctype, T ) \
+extern "C" b200_err_t b200_##ch##trsm( int side, int uploa, int transa, int diaga, b200_dim_t m, b200_dim_t n, \
+	const ctype* alpha, const ctype* a, b200_inc_t rs_a, b200_inc_t cs_a, \
+	ctype* b, b200_inc_t rs_b, b200_inc_t cs_b ) \
+{ \
+	return trsm_front<T>( side, uploa, transa, diaga, m, n, (const T*)alpha, (const T*)a, rs_a, cs_a, (T*)b, rs_b, cs_b ); \
+}
+B200_DEF_TRSM( s, float, float )
+B200_DEF_TRSM( d, double, double )
+B200_DEF_TRSM( c, b200_scomplex, float2 )
+B200_DEF_TRSM( z, b200_dcomplex, double2 )
+
+extern "C" b200_err_t b200_trsm( int dt, int side, int uploa, int transa, int diaga, b200_dim_t m, b200_dim_t n,
+	const void* alpha, const void* a, b200_inc_t rs_a, b200_inc_t cs_a,
+	void* b, b200_inc_t rs_b, b200_inc_t cs_b )
+{
+	switch ( dt )
+	{
+		case B200_FLOAT:    return trsm_front<float>  ( side, uploa, transa, diaga, m, n, (const float*)alpha,   (const float*)a,   rs_a, cs_a, (float*)b,   rs_b, cs_b );
+		case B200_DOUBLE:   return trsm_front<double> ( side, uploa, transa, diaga, m, n, (const double*)alpha,  (const double*)a,  rs_a, cs_a, (double*)b,  rs_b, cs_b );
+		case B200_SCOMPLEX: return trsm_front<float2> ( side, uploa, transa, diaga, m, n, (const float2*)alpha,  (const float2*)a,  rs_a, cs_a, (float2*)b,  rs_b, cs_b );
+		case B200_DCOMPLEX: return trsm_front<double2>( side, uploa, transa, diaga, m, n, (const double2*)alpha, (const double2*)a, rs_a, cs_a, (double2*)b, rs_b, cs_b );
+	}
+	return fail( "b200_trsm: unsupported datatype %d", dt );
+}
+
+extern "C" b200_dim_t b200_blksz( int dt, int bs )
+{
+	auto pick = [&]( int mr, int nr, int mc, int kc, int nc ) -> b200_dim_t
+	{
+		switch ( bs ) { case B200_BS_MR: return mr; case B200_BS_NR: return nr; case B200_BS_MC: return mc;
+		                case B200_BS_KC: return kc; case B200_BS_NC: return nc; }
+		return -1;
+	};
+	switch ( dt )
+	{
+		case B200_FLOAT:    return pick( Tiles<float>::MR,   Tiles<float>::NR,   Tiles<float>::BQ,   Tiles<float>::BK,   Tiles<float>::BP );
+		case B200_DOUBLE:   return pick( Tiles<double>::MR,  Tiles<double>::NR,  Tiles<double>::BQ,  Tiles<double>::BK,  Tiles<double>::BP );
+		case B200_SCOMPLEX: return pick( Tiles<float2>::MR,  Tiles<float2>::NR,  Tiles<float2>::BQ,  Tiles<float2>::BK,  Tiles<float2>::BP );
+		case B200_DCOMPLEX: return pick( Tiles<double2>::MR, Tiles<double2>::NR, Tiles<double2>::BQ, Tiles<double2>::BK, Tiles<double2>::BP );
+	}
+	return -1;
+}
+
+// Tuning knobs for sweeps (not part of the reference surface).
+extern "C" b200_err_t b200_set_option( const char* key, long long value )
+{
+	Context& c = ctx();
+	if      ( !strcmp( key, "dgemm_cfg" ) ) c.dgemm_cfg = (int)value;
+	else if ( !strcmp( key, "zgemm_cfg" ) ) c.zgemm_cfg = (int)value;
+	else if ( !strcmp( key, "sgemm_cfg" ) ) c.sgemm_cfg = (int)value;
+	else if ( !strcmp( key, "cgemm_cfg" ) ) c.cgemm_cfg = (int)value;
+	else if ( !strcmp( key, "grid_mult" ) ) c.grid_mult = (int)std::max<long long>( 1, value );
+	else return fail( "b200_set_option: unknown key %s", key );
+	return kSuccess;
+}

@@ -1,0 +1,247 @@
+// context.cu -- engine runtime: init, streams, errors, pinned staging.
+#include "context.cuh"
+#include "../../include/blis_b200.h"
+#include <algorithm>
+#include <thread>
+#include <vector>
+
+namespace b200 {
+
+thread_local char g_err[512] = "";
+static thread_local cudaStream_t t_stream = nullptr;
+static thread_local bool t_stream_set = false;
+
+int fail( const char* fmt, ... )
+{
+	va_list ap; va_start( ap, fmt );
+	vsnprintf( g_err, sizeof( g_err ), fmt, ap );
+	va_end( ap );
+	return kFailure;
+}
+
+Context& ctx() { static Context c; return c; }
+static std::mutex g_init_mu;
+
+static int do_init( int device )
+{
+	Context& c = ctx();
+	std::lock_guard<std::mutex> lk( g_init_mu );
+	if ( c.ready ) return kSuccess;
+	int ndev = 0;
+	if ( cudaGetDeviceCount( &ndev ) != cudaSuccess || ndev == 0 )
+		return fail( "b200_init: no CUDA device visible; this engine has no CPU fallback" );
+	if ( device < 0 ) B200_CUDA( cudaGetDevice( &device ) );
+	B200_CUDA( cudaSetDevice( device ) );
+	cudaDeviceProp prop;
+	B200_CUDA( cudaGetDeviceProperties( &prop, device ) );
+	if ( prop.major != 10 )
+		return fail( "b200_init: device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor );
+	c.device  = device;
+	c.num_sms = prop.multiProcessorCount;
+	B200_CUDA( cudaStreamCreateWithFlags( &c.stream, cudaStreamNonBlocking ) );
+	B200_CUDA( cudaStreamCreateWithFlags( &c.copy_stream, cudaStreamNonBlocking ) );
+	// keep freed workspace cached in the pool instead of returning it to the OS
+	cudaMemPool_t pool;
+	if ( cudaDeviceGetDefaultMemPool( &pool, device ) == cudaSuccess )
+	{
+		uint64_t thresh = UINT64_MAX;
+		cudaMemPoolSetAttribute( pool, cudaMemPoolAttrReleaseThreshold, &thresh );
+	}
+	c.ready = true;
+	return kSuccess;
+}
+
+int ensure_init()
+{
+	if ( ctx().ready ) return kSuccess;
+	return do_init( -1 );
+}
+
+cudaStream_t cur_stream()
+{
+	return t_stream_set ? t_stream : ctx().stream;
+}
+
+MemKind classify( const void* p )
+{
+	cudaPointerAttributes at;
+	if ( cudaPointerGetAttributes( &at, p ) != cudaSuccess ) { cudaGetLastError(); return MemKind::HostPageable; }
+	if ( at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged ) return MemKind::Device;
+	if ( at.type == cudaMemoryTypeHost ) return MemKind::HostPinned;
+	return MemKind::HostPageable;
+}
+
+int dev_alloc( void** p, size_t bytes, cudaStream_t st )
+{
+	*p = nullptr;
+	if ( bytes == 0 ) bytes = 16;
+	B200_CUDA( cudaMallocAsync( p, bytes, st ) );
+	return kSuccess;
+}
+void dev_free( void* p, cudaStream_t st ) { if ( p ) cudaFreeAsync( p, st ); }
+
+// ---- pinned staging --------------------------------------------------------------
+static int ensure_stage_bufs()
+{
+	Context& c = ctx();
+	if ( c.stage[0] ) return kSuccess;
+	for ( int i = 0; i < Context::kStageBufs; ++i )
+	{
+		B200_CUDA( cudaMallocHost( &c.stage[i], Context::kStageBytes ) );
+		B200_CUDA( cudaEventCreateWithFlags( &c.stage_free[i], cudaEventDisableTiming ) );
+	}
+	return kSuccess;
+}
+
+// memcpy of `lines` lines of `len` bytes with different pitches, split over a
+// few host threads when the block is large.
+static void copy_lines( char* dst, size_t dpitch, const char* src, size_t spitch, size_t len, size_t lines )
+{
+	const size_t total = len * lines;
+	unsigned nthr = 1;
+	if ( total >= ( (size_t)8 << 20 ) )
+		nthr = std::min<unsigned>( 8, std::max<unsigned>( 1, std::thread::hardware_concurrency() ) );
+	auto work = [=]( size_t l0, size_t l1 )
+	{
+		if ( dpitch == len && spitch == len ) { memcpy( dst + l0 * len, src + l0 * len, ( l1 - l0 ) * len ); return; }
+		for ( size_t l = l0; l < l1; ++l ) memcpy( dst + l * dpitch, src + l * spitch, len );
+	};
+	if ( nthr <= 1 || lines < nthr ) { work( 0, lines ); return; }
+	std::vector<std::thread> th;
+	for ( unsigned t = 0; t < nthr; ++t )
+		th.emplace_back( work, lines * t / nthr, lines * ( t + 1 ) / nthr );
+	for ( auto& x : th ) x.join();
+}
+
+// Generic element gather for general-stride host matrices (rs != 1 && cs != 1).
+static void gather_elems( char* dst, const char* src, int64_t m, int64_t j0, int64_t j1, int64_t rs, int64_t cs, size_t es, bool to_host )
+{
+	// dense side: column-major m x (j1-j0) block starting at dst/src
+	for ( int64_t j = j0; j < j1; ++j )
+		for ( int64_t i = 0; i < m; ++i )
+		{
+			const int64_t so = ( i * rs + j * cs ) * (int64_t)es;
+			const int64_t d  = ( i + ( j - j0 ) * m ) * (int64_t)es;
+			if ( !to_host ) memcpy( dst + d, src + so, es );
+			else            memcpy( dst + so, src + d, es );
+		}
+}
+
+// dense column-major device (ld = m)  <->  host (rs, cs)
+static int stage_xfer( void* dev, void* host, int64_t m, int64_t n, int64_t rs, int64_t cs, size_t es,
+                       cudaStream_t st, bool to_host )
+{
+	if ( m <= 0 || n <= 0 ) return kSuccess;
+	Context& c = ctx();
+	const MemKind kind = classify( host );
+	// Dense device image is column-major m x n.  If the host matrix is
+	// row-stored (cs == 1) we view the transposed problem: lines are rows.
+	const bool col_lines = ( rs == 1 );
+	const bool row_lines = ( !col_lines && cs == 1 );
+	if ( kind == MemKind::HostPinned && col_lines )
+	{
+		if ( !to_host ) B200_CUDA( cudaMemcpy2DAsync( dev, m * es, host, cs * es, m * es, n, cudaMemcpyHostToDevice, st ) );
+		else            B200_CUDA( cudaMemcpy2DAsync( host, cs * es, dev, m * es, m * es, n, cudaMemcpyDeviceToHost, st ) );
+		return kSuccess;
+	}
+	(void)row_lines;
+	// pageable (or pinned but not column-stored): go through the pinned ring,
+	// packing to / unpacking from dense column-major blocks of columns.
+	std::lock_guard<std::mutex> lk( c.stage_mu );
+	if ( ensure_stage_bufs() != kSuccess ) return kFailure;
+	const size_t colb = (size_t)m * es;
+	if ( colb > Context::kStageBytes )
+		return fail( "stage: one column (%zu bytes) exceeds the staging buffer", colb );
+	const int64_t cols_per = std::max<int64_t>( 1, (int64_t)( Context::kStageBytes / colb ) );
+	int buf = 0;
+	for ( int64_t j0 = 0; j0 < n; j0 += cols_per, buf ^= 1 )
+	{
+		const int64_t j1 = std::min( n, j0 + cols_per );
+		char* pin = (char*)c.stage[buf];
+		char* d   = (char*)dev + (size_t)j0 * colb;
+		B200_CUDA( cudaEventSynchronize( c.stage_free[buf] ) );
+		if ( !to_host )
+		{
+			if ( col_lines ) copy_lines( pin, colb, (const char*)host + (size_t)j0 * cs * es, (size_t)cs * es, colb, (size_t)( j1 - j0 ) );
+			else             gather_elems( pin, (const char*)host, m, j0, j1, rs, cs, es, false );
+			B200_CUDA( cudaMemcpyAsync( d, pin, colb * ( j1 - j0 ), cudaMemcpyHostToDevice, st ) );
+			B200_CUDA( cudaEventRecord( c.stage_free[buf], st ) );
+		}
+		else
+		{
+			B200_CUDA( cudaMemcpyAsync( pin, d, colb * ( j1 - j0 ), cudaMemcpyDeviceToHost, st ) );
+			B200_CUDA( cudaStreamSynchronize( st ) );
+			if ( col_lines ) copy_lines( (char*)host + (size_t)j0 * cs * es, (size_t)cs * es, pin, colb, colb, (size_t)( j1 - j0 ) );
+			else             gather_elems( (char*)host, pin, m, j0, j1, rs, cs, es, true );
+		}
+	}
+	return kSuccess;
+}
+
+int stage_to_device( void* dst, const void* src, int64_t m, int64_t n, int64_t rs, int64_t cs, size_t es, cudaStream_t st )
+{
+	return stage_xfer( dst, const_cast<void*>( src ), m, n, rs, cs, es, st, false );
+}
+int stage_to_host( void* dst, int64_t rs, int64_t cs, const void* src, int64_t m, int64_t n, size_t es, cudaStream_t st )
+{
+	return stage_xfer( const_cast<void*>( src ), dst, m, n, rs, cs, es, st, true );
+}
+
+} // namespace b200
+
+// ---- C ABI: lifetime -----------------------------------------------------------
+using namespace b200;
+
+extern "C" b200_err_t b200_init( int device )
+{
+	if ( ctx().ready ) return kSuccess;
+	return do_init( device );
+}
+
+extern "C" void b200_finalize( void )
+{
+	Context& c = ctx();
+	std::lock_guard<std::mutex> lk( g_init_mu );
+	if ( !c.ready ) return;
+	cudaStreamSynchronize( c.stream );
+	for ( int i = 0; i < Context::kStageBufs; ++i )
+	{
+		if ( c.stage[i] ) { cudaFreeHost( c.stage[i] ); c.stage[i] = nullptr; }
+		if ( c.stage_free[i] ) { cudaEventDestroy( c.stage_free[i] ); c.stage_free[i] = nullptr; }
+	}
+	cudaStreamDestroy( c.stream ); cudaStreamDestroy( c.copy_stream );
+	c.stream = c.copy_stream = nullptr;
+	c.ready = false;
+}
+
+extern "C" const char* b200_last_error( void ) { return g_err; }
+
+extern "C" int b200_device_count( void )
+{
+	int n = 0;
+	if ( cudaGetDeviceCount( &n ) != cudaSuccess ) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+extern "C" const char* b200_info( void )
+{
+	return "blis_b200 0.1 (sm_100a; d/z: DMMA.8x8x4 tiles, s/c: FFMA register tiles; "
+	       "cp.async multi-stage staging; persistent tile scheduler)";
+}
+
+extern "C" void b200_set_stream( void* stream )
+{
+	t_stream = (cudaStream_t)stream;
+	t_stream_set = ( stream != nullptr );
+}
+extern "C" void* b200_get_stream( void )
+{
+	if ( ensure_init() != kSuccess ) return nullptr;
+	return (void*)cur_stream();
+}
+extern "C" b200_err_t b200_sync( void )
+{
+	if ( ensure_init() != kSuccess ) return kFailure;
+	B200_CUDA( cudaStreamSynchronize( cur_stream() ) );
+	return kSuccess;
+}

@@ -1,0 +1,72 @@
+// context.cuh -- host-side runtime of the engine: device context, per-thread
+// stream, error reporting, pointer classification and pinned staging.
+//
+// Reference counterparts (what this stands in for on the device side):
+//   bli_init_once / bli_finalize          frame/base/bli_init.c:87-99
+//   pack-buffer allocator (pba) + pools   frame/base/bli_pba.c:93-188
+//   bli_check_error_code -> abort         frame/base/bli_error.c:126-139
+// BLIS is re-entrant and may be called from many application threads at once
+// (SURVEY.md 8b "Threading"), so global state is guarded and the stream
+// selection is thread-local.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <mutex>
+#include "common.cuh"
+
+namespace b200 {
+
+// ---- errors -------------------------------------------------------------------
+extern thread_local char g_err[512];
+int fail( const char* fmt, ... );
+
+#define B200_CUDA( call ) \
+	do { cudaError_t e__ = ( call ); if ( e__ != cudaSuccess ) \
+	     return ::b200::fail( "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString( e__ ) ); } while ( 0 )
+
+// ---- context --------------------------------------------------------------------
+struct Context
+{
+	bool         ready   = false;
+	int          device  = -1;
+	int          num_sms = kNumSMs;
+	cudaStream_t stream  = nullptr;       // engine-owned default stream
+	cudaStream_t copy_stream = nullptr;   // host staging
+	// pinned staging ring for pageable host operands
+	static constexpr int    kStageBufs  = 2;
+	static constexpr size_t kStageBytes = (size_t)64 << 20;
+	void*        stage[kStageBufs]      = { nullptr, nullptr };
+	cudaEvent_t  stage_free[kStageBufs] = { nullptr, nullptr };
+	std::mutex   stage_mu;
+	// tuning knobs (b200_set_option)
+	int          dgemm_cfg = 0;
+	int          zgemm_cfg = 0;
+	int          sgemm_cfg = 0;
+	int          cgemm_cfg = 0;
+	int          trsm_nb   = 0;           // 0 = default
+	int          grid_mult = 1;           // persistent CTAs per SM
+};
+
+Context& ctx();
+int ensure_init();                         // lazy init; returns kSuccess/kFailure
+cudaStream_t cur_stream();                 // thread's selected stream or the engine's
+
+// ---- pointer classification ------------------------------------------------------
+enum class MemKind { Device, HostPinned, HostPageable };
+MemKind classify( const void* p );
+
+// Temporary device memory, stream ordered (cudaMallocAsync pool).
+int dev_alloc( void** p, size_t bytes, cudaStream_t st );
+void dev_free( void* p, cudaStream_t st );
+
+// Copy an m x n matrix of `es`-byte elements between host (rs,cs strides, any
+// kind of host memory) and a dense column-major device buffer (ld = m).
+int stage_to_device( void* dst, const void* src, int64_t m, int64_t n, int64_t rs, int64_t cs,
+                     size_t es, cudaStream_t st );
+int stage_to_host( void* dst, int64_t rs, int64_t cs, const void* src, int64_t m, int64_t n,
+                   size_t es, cudaStream_t st );
+
+} // namespace b200

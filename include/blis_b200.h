@@ -1,0 +1,165 @@
+/*
+ * blis_b200.h -- C ABI of the B200-native level-3 engine for BLIS.
+ *
+ * This is the drop-in boundary: plain pointers and
+ * 64-bit sizes, no C++/torch types.  Every entry point states the reference
+ * interface it stands in for (paths relative to the BLIS tree).
+ *
+ * Conventions shared with the reference
+ *   - dimensions and strides are 64-bit signed (BLIS dim_t/inc_t = gint_t,
+ *     frame/include/bli_type_defs.h:78-116);
+ *   - trans/conj/uplo/diag/side/datatype arguments use the numeric values of
+ *     BLIS's own enums (frame/include/bli_type_defs.h:278-455), so the BLIS
+ *     side binding passes its trans_t/uplo_t/... straight through;
+ *   - matrices are described by (pointer, row stride, column stride) exactly
+ *     like the typed API (frame/3/bli_l3_tapi.c:43-70); any of rs==1, cs==1
+ *     or general stride is accepted;
+ *   - return value is a BLIS err_t: B200_SUCCESS (-1) or B200_FAILURE (-2)
+ *     (frame/include/bli_type_defs.h:1502-1607).  On failure
+ *     b200_last_error() holds the message; the BLIS glue turns it into
+ *     bli_abort() because this engine has no CPU fallback.
+ *
+ * Operand pointers may be device pointers (used in place), pinned host
+ * pointers or pageable host pointers (staged through the engine's pinned
+ * buffers); each pointer is classified per call.
+ */
+#ifndef BLIS_B200_H
+#define BLIS_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int64_t b200_dim_t;   /* BLIS dim_t  */
+typedef int64_t b200_inc_t;   /* BLIS inc_t  */
+typedef int     b200_err_t;   /* BLIS err_t  */
+
+#define B200_SUCCESS (-1)     /* BLIS_SUCCESS */
+#define B200_FAILURE (-2)     /* BLIS_FAILURE */
+
+/* num_t  (bli_type_defs.h:448-451) */
+#define B200_FLOAT     0
+#define B200_SCOMPLEX  1
+#define B200_DOUBLE    2
+#define B200_DCOMPLEX  3
+/* trans_t (bli_type_defs.h:397-400) */
+#define B200_NO_TRANSPOSE       0x00
+#define B200_TRANSPOSE          0x08
+#define B200_CONJ_NO_TRANSPOSE  0x10
+#define B200_CONJ_TRANSPOSE     0x18
+/* uplo_t (bli_type_defs.h:412-414) */
+#define B200_UPPER  0x60
+#define B200_LOWER  0xC0
+/* side_t (bli_type_defs.h:419-420) */
+#define B200_LEFT   0
+#define B200_RIGHT  1
+/* diag_t (bli_type_defs.h:425-426) */
+#define B200_NONUNIT_DIAG 0x000
+#define B200_UNIT_DIAG    0x100
+
+typedef struct { float  real, imag; } b200_scomplex;  /* BLIS scomplex */
+typedef struct { double real, imag; } b200_dcomplex;  /* BLIS dcomplex */
+
+/* ---- lifetime ------------------------------------------------------------
+ * Replaces bli_init()/bli_finalize() for the device side
+ * (frame/base/bli_init.c:87-99).  b200_init is idempotent and thread safe;
+ * device < 0 means "current CUDA device".  The engine also initialises
+ * itself lazily on first use. */
+b200_err_t  b200_init( int device );
+void        b200_finalize( void );
+const char* b200_last_error( void );
+int         b200_device_count( void );
+/* Version / build info string, like bli_info_get_version_str()
+ * (frame/base/bli_info.c). */
+const char* b200_info( void );
+
+/* All work of the calling thread is issued on this CUDA stream
+ * (cudaStream_t passed as void*); NULL selects the engine's own stream.
+ * The torch harness passes torch's current stream so CUDA events see it. */
+void        b200_set_stream( void* stream );
+void*       b200_get_stream( void );
+/* Block until everything the engine queued on its stream has finished. */
+b200_err_t  b200_sync( void );
+
+/* ---- gemm ------------------------------------------------------------------
+ * C := beta*C + alpha*transa(A)*transb(B),  C is m x n, k is the inner dim.
+ *
+ * b200_gemm is what the whole-operation gemm hook registered with
+ *   bli_cntx_set_l3_sup_handler( BLIS_GEMM, ... )       frame/base/bli_cntx.h:335-343
+ * (signature gemmsup_oft, frame/3/bli_l3_sup_oft.h:46-59) calls after
+ * unpacking its obj_t arguments; the typed variants have the parameter list
+ * of bli_?gemm (frame/3/bli_l3_tapi.c:43-70).
+ * alpha/beta point to one element of type dt in HOST memory. */
+b200_err_t b200_gemm( int dt, int transa, int transb,
+                      b200_dim_t m, b200_dim_t n, b200_dim_t k,
+                      const void* alpha,
+                      const void* a, b200_inc_t rs_a, b200_inc_t cs_a,
+                      const void* b, b200_inc_t rs_b, b200_inc_t cs_b,
+                      const void* beta,
+                      void*       c, b200_inc_t rs_c, b200_inc_t cs_c );
+
+#define B200_DECL_GEMM( ch, ctype ) \
+b200_err_t b200_##ch##gemm( int transa, int transb, \
+                      b200_dim_t m, b200_dim_t n, b200_dim_t k, \
+                      const ctype* alpha, \
+                      const ctype* a, b200_inc_t rs_a, b200_inc_t cs_a, \
+                      const ctype* b, b200_inc_t rs_b, b200_inc_t cs_b, \
+                      const ctype* beta, \
+                      ctype*       c, b200_inc_t rs_c, b200_inc_t cs_c );
+B200_DECL_GEMM( s, float )
+B200_DECL_GEMM( d, double )
+B200_DECL_GEMM( c, b200_scomplex )
+B200_DECL_GEMM( z, b200_dcomplex )
+
+/* ---- trsm ------------------------------------------------------------------
+ * Solve  transa(A) * X = alpha * B  (side = left)  or
+ *        X * transa(A) = alpha * B  (side = right), overwriting B with X.
+ * A is triangular (uplo), unit or non-unit diagonal; B is m x n.
+ *
+ * Stands in for bli_trsm_ex (frame/3/bli_l3_oapi_ex.c:692-801); the typed
+ * variants have the parameter list of bli_?trsm (frame/3/bli_l3_tapi.c,
+ * GENTFUNC trsm). */
+b200_err_t b200_trsm( int dt, int side, int uploa, int transa, int diaga,
+                      b200_dim_t m, b200_dim_t n,
+                      const void* alpha,
+                      const void* a, b200_inc_t rs_a, b200_inc_t cs_a,
+                      void*       b, b200_inc_t rs_b, b200_inc_t cs_b );
+
+#define B200_DECL_TRSM( ch, ctype ) \
+b200_err_t b200_##ch##trsm( int side, int uploa, int transa, int diaga, \
+                      b200_dim_t m, b200_dim_t n, \
+                      const ctype* alpha, \
+                      const ctype* a, b200_inc_t rs_a, b200_inc_t cs_a, \
+                      ctype*       b, b200_inc_t rs_b, b200_inc_t cs_b );
+B200_DECL_TRSM( s, float )
+B200_DECL_TRSM( d, double )
+B200_DECL_TRSM( c, b200_scomplex )
+B200_DECL_TRSM( z, b200_dcomplex )
+
+/* ---- blocksizes ------------------------------------------------------------
+ * What bli_cntx_init_b200 registers through bli_cntx_set_blkszs()
+ * (config/zen3/bli_cntx_init_zen3.c:37-258 is the pattern): the CTA tile
+ * shape the engine uses for datatype dt.  bs is one of the bszid_t names
+ * below (frame/include/bli_type_defs.h, bszid_t). Returns -1 if unknown. */
+#define B200_BS_MR 0
+#define B200_BS_NR 1
+#define B200_BS_MC 2
+#define B200_BS_KC 3
+#define B200_BS_NC 4
+b200_dim_t b200_blksz( int dt, int bs );
+
+/* ---- measurement helpers ---------------------------------------------------
+ * Device-side peak microbenchmarks (no reference analogue; they provide the
+ * FP64/FP32 roofline denominators SURVEY.md section 8d asks for).
+ * kind: 0 = DFMA (fp64 FMA pipe), 1 = DMMA (mma.sync m8n8k4 f64),
+ *       2 = FFMA (fp32 FMA pipe).
+ * Runs for about `millis` ms and returns achieved TFLOP/s (< 0 on error). */
+double b200_measure_peak( int kind, int millis );
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLIS_B200_H */
