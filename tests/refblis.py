@@ -1,0 +1,159 @@
+"""ctypes access to the checkers (TEST INFRASTRUCTURE ONLY):
+
+* `Oracle`  -- oracle/liboracle.so, the C restatement of the reference algorithm
+* `RefBlis` -- oracle/_ref/libblis_ref.so, the real reference BLIS built from
+               /root/reference by oracle/build_ref.py (present in the build
+               container and shipped to the GPU box with the snapshot)
+
+Nothing under blis_b200/ imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_SO = ROOT / "oracle" / "liboracle.so"
+REF_SO = ROOT / "oracle" / "_ref" / "libblis_ref.so"
+
+NO_TRANSPOSE, TRANSPOSE, CONJ_NO_TRANSPOSE, CONJ_TRANSPOSE = 0x00, 0x08, 0x10, 0x18
+UPPER, LOWER, DENSE = 0x60, 0xC0, 0xE0
+LEFT, RIGHT = 0, 1
+NONUNIT_DIAG, UNIT_DIAG = 0x000, 0x100
+CH = {np.dtype(np.float32): "s", np.dtype(np.float64): "d", np.dtype(np.complex64): "c", np.dtype(np.complex128): "z"}
+DT = {"s": 0, "c": 1, "d": 2, "z": 3}
+i64, vp, ci = C.c_int64, C.c_void_p, C.c_int
+
+
+def _p(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+def _estr(a: np.ndarray):
+    """(rs, cs) in elements of a 2-D numpy array."""
+    return a.strides[0] // a.itemsize, a.strides[1] // a.itemsize
+
+
+def _scalar(dtype, v):
+    return np.array([v], dtype=dtype)
+
+
+def build_oracle() -> Path:
+    src = ROOT / "oracle" / "blis_oracle.c"
+    inc = ROOT / "oracle" / "blis_oracle_t.inc"
+    if not ORACLE_SO.exists() or ORACLE_SO.stat().st_mtime < max(src.stat().st_mtime, inc.stat().st_mtime):
+        subprocess.run(["make", "-C", str(ROOT / "oracle"), "liboracle.so"], check=True, stdout=subprocess.DEVNULL)
+    return ORACLE_SO
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = C.CDLL(str(build_oracle()))
+        L = self.lib
+        L.orc_determine_blocksize.argtypes = [ci, i64, i64, i64, i64]; L.orc_determine_blocksize.restype = i64
+        L.orc_thread_range_sub.argtypes = [i64, i64, i64, i64, ci, C.POINTER(i64), C.POINTER(i64)]
+        L.orc_thread_partition_2x2.argtypes = [i64, i64, i64, C.POINTER(i64), C.POINTER(i64)]
+        L.orc_align_dim_to_mult.argtypes = [i64, i64]; L.orc_align_dim_to_mult.restype = i64
+        L.orc_packm_panel_stride.argtypes = [i64, i64]; L.orc_packm_panel_stride.restype = i64
+        L.orc_set_blksz.argtypes = [ci, i64, i64, i64, i64, i64, ci]
+        for ch in "sdcz":
+            getattr(L, f"orc_{ch}gemm").argtypes = [ci, ci, i64, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
+            getattr(L, f"orc_{ch}trsm").argtypes = [ci, ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64]
+            getattr(L, f"orc_{ch}packm_cxk").argtypes = [ci, i64, i64, i64, i64, vp, vp, i64, i64, vp, i64]
+            getattr(L, f"orc_{ch}packm_struc_cxk").argtypes = [ci, ci, ci, ci, ci, i64, i64, i64, i64, i64, i64, vp, vp, i64, i64, vp, i64]
+            getattr(L, f"orc_{ch}gemm_ukr").argtypes = [i64, i64, i64, vp, vp, vp, vp, vp, i64, i64, i64, i64]
+            getattr(L, f"orc_{ch}gemmtrsm_ukr").argtypes = [ci, i64, i64, i64, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64]
+
+    def set_blksz(self, ch, mr, nr, mc, kc, nc, row_pref=0):
+        self.lib.orc_set_blksz(DT[ch], mr, nr, mc, kc, nc, int(row_pref))
+
+    def determine_blocksize(self, backward, i, dim, b_alg, b_max):
+        return int(self.lib.orc_determine_blocksize(int(backward), i, dim, b_alg, b_max))
+
+    def thread_range_sub(self, work_id, n_way, n, bf, edge_low):
+        s, e = i64(), i64()
+        self.lib.orc_thread_range_sub(work_id, n_way, n, bf, int(edge_low), C.byref(s), C.byref(e))
+        return s.value, e.value
+
+    def thread_partition_2x2(self, nt, w1, w2):
+        a, b = i64(), i64()
+        self.lib.orc_thread_partition_2x2(nt, w1, w2, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def gemm(self, transa, transb, alpha, a, b, beta, c):
+        """c := beta*c + alpha*op(a)*op(b), in place on numpy arrays with any strides."""
+        ch = CH[c.dtype]
+        m, n = c.shape
+        k = a.shape[0] if (transa & TRANSPOSE) else a.shape[1]
+        al, be = _scalar(c.dtype, alpha), _scalar(c.dtype, beta)
+        getattr(self.lib, f"orc_{ch}gemm")(transa, transb, m, n, k, _p(al), _p(a), *_estr(a), _p(b), *_estr(b), _p(be), _p(c), *_estr(c))
+
+    def trsm(self, side, uplo, transa, diag, alpha, a, b):
+        ch = CH[b.dtype]
+        m, n = b.shape
+        al = _scalar(b.dtype, alpha)
+        getattr(self.lib, f"orc_{ch}trsm")(side, uplo, transa, diag, m, n, _p(al), _p(a), *_estr(a), _p(b), *_estr(b))
+
+
+class RefBlis:
+    """The real reference: typed API bli_?gemm / bli_?trsm (frame/3/bli_l3_tapi.c)
+    plus the helper functions the oracle restates."""
+
+    def __init__(self, threads: int | None = None):
+        if not REF_SO.exists():
+            raise FileNotFoundError(f"{REF_SO} missing (run oracle/build_ref.py where /root/reference exists)")
+        self.lib = C.CDLL(str(REF_SO))
+        L = self.lib
+        L.bli_init()
+        for ch in "sdcz":
+            getattr(L, f"bli_{ch}gemm").argtypes = [ci, ci, i64, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
+            getattr(L, f"bli_{ch}trsm").argtypes = [ci, ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64]
+        L.bli_determine_blocksize.argtypes = [ci, i64, i64, i64, i64]; L.bli_determine_blocksize.restype = i64
+        L.bli_thread_range_sub.argtypes = [i64, i64, i64, i64, C.c_bool, C.POINTER(i64), C.POINTER(i64)]
+        L.bli_thread_partition_2x2.argtypes = [i64, i64, i64, C.POINTER(i64), C.POINTER(i64)]
+        L.bli_thread_set_num_threads.argtypes = [i64]
+        L.bli_arch_query_id.restype = ci
+        L.bli_arch_string.restype = C.c_char_p; L.bli_arch_string.argtypes = [ci]
+        L.bli_gks_query_cntx.restype = vp
+        if threads is not None:
+            L.bli_thread_set_num_threads(threads)
+
+    def arch(self) -> str:
+        return self.lib.bli_arch_string(self.lib.bli_arch_query_id()).decode()
+
+    def set_num_threads(self, n: int):
+        self.lib.bli_thread_set_num_threads(n)
+
+    def determine_blocksize(self, backward, i, dim, b_alg, b_max):
+        return int(self.lib.bli_determine_blocksize(1 if backward else 0, i, dim, b_alg, b_max))   # dir_t: BLIS_FWD=0, BLIS_BWD=1
+
+    def thread_range_sub(self, work_id, n_way, n, bf, edge_low):
+        s, e = i64(), i64()
+        self.lib.bli_thread_range_sub(work_id, n_way, n, bf, bool(edge_low), C.byref(s), C.byref(e))
+        return s.value, e.value
+
+    def thread_partition_2x2(self, nt, w1, w2):
+        a, b = i64(), i64()
+        self.lib.bli_thread_partition_2x2(nt, w1, w2, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def gemm(self, transa, transb, alpha, a, b, beta, c):
+        ch = CH[c.dtype]
+        m, n = c.shape
+        k = a.shape[0] if (transa & TRANSPOSE) else a.shape[1]
+        al, be = _scalar(c.dtype, alpha), _scalar(c.dtype, beta)
+        getattr(self.lib, f"bli_{ch}gemm")(transa, transb, m, n, k, _p(al), _p(a), *_estr(a), _p(b), *_estr(b), _p(be), _p(c), *_estr(c))
+
+    def trsm(self, side, uplo, transa, diag, alpha, a, b):
+        ch = CH[b.dtype]
+        m, n = b.shape
+        al = _scalar(b.dtype, alpha)
+        getattr(self.lib, f"bli_{ch}trsm")(side, uplo, transa, diag, m, n, _p(al), _p(a), *_estr(a), _p(b), *_estr(b))
+
+
+def have_ref() -> bool:
+    return REF_SO.exists()
