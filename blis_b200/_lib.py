@@ -25,7 +25,7 @@ EXPORTS = [
     "b200_set_stream", "b200_get_stream", "b200_sync",
     "b200_gemm", "b200_sgemm", "b200_dgemm", "b200_cgemm", "b200_zgemm",
     "b200_trsm", "b200_strsm", "b200_dtrsm", "b200_ctrsm", "b200_ztrsm",
-    "b200_blksz", "b200_measure_peak",
+    "b200_blksz", "b200_measure_peak", "b200_launch_count", "b200_set_option",
 ]
 
 _lib = None
@@ -64,6 +64,7 @@ def load() -> C.CDLL:
         f = getattr(lib, f"b200_{ch}trsm"); f.argtypes = [ci, ci, ci, ci] + trsm_tail; f.restype = ci
     lib.b200_blksz.argtypes = [ci, ci]; lib.b200_blksz.restype = i64
     lib.b200_measure_peak.argtypes = [ci, ci]; lib.b200_measure_peak.restype = C.c_double
+    lib.b200_launch_count.argtypes = []; lib.b200_launch_count.restype = C.c_ulonglong
     lib.b200_set_option.argtypes = [C.c_char_p, C.c_longlong]; lib.b200_set_option.restype = ci
     _lib = lib
     return lib

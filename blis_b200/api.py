@@ -229,5 +229,10 @@ def set_option(key: str, value: int) -> None:
     check(_lib.load().b200_set_option(key.encode(), int(value)), f"set_option({key})")
 
 
+def launch_count() -> int:
+    """Kernels launched by the engine so far (for bench.py's gpu_launches)."""
+    return int(_lib.load().b200_launch_count())
+
+
 def sync() -> None:
     check(_lib.load().b200_sync(), "b200_sync")

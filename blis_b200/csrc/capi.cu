@@ -95,6 +95,7 @@ static int copy2d( T* dst, int64_t rsd, int64_t csd, const T* src, int64_t rss, 
 	const int blocks = (int)std::min<int64_t>( ( total + 255 ) / 256, (int64_t)ctx().num_sms * 16 );
 	copy2d_kernel<R, NC><<<blocks, 256, 0, st>>>( (R*)dst, rsd, csd, (const R*)src, rss, css, m, n, inner_is_row );
 	B200_CUDA( cudaGetLastError() );
+	ctx().launches++;
 	return kSuccess;
 }
 
@@ -111,6 +112,7 @@ static int scal2d( T* c, int64_t rs, int64_t cs, int64_t m, int64_t n, T beta, c
 	const int blocks = (int)std::min<int64_t>( ( total + 255 ) / 256, (int64_t)ctx().num_sms * 16 );
 	scal2d_kernel<R, NC><<<blocks, 256, 0, st>>>( (R*)c, rs, cs, m, n, br, bi, Scalar<T>::is_zero( beta ) ? 1 : 0, inner_is_row );
 	B200_CUDA( cudaGetLastError() );
+	ctx().launches++;
 	return kSuccess;
 }
 
@@ -134,6 +136,7 @@ static int launch_dmma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int gri
 		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>( g );
 		B200_CUDA( cudaGetLastError() );
+		ctx().launches++;
 		return kSuccess;
 	};
 	using Tt = std::true_type; using Ff = std::false_type;
@@ -159,6 +162,7 @@ static int launch_ffma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int gri
 		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>( g );
 		B200_CUDA( cudaGetLastError() );
+		ctx().launches++;
 		return kSuccess;
 	};
 	using Tt = std::true_type; using Ff = std::false_type;
@@ -390,6 +394,7 @@ static int trsm_base( const TrsmPlan<T>& p, int64_t i0, int mb, T alpha )
 	const int64_t grid = ( p.n + CN - 1 ) / CN;
 	kern<<<(unsigned)grid, CN, smem, p.st>>>( a );
 	B200_CUDA( cudaGetLastError() );
+	ctx().launches++;
 	return kSuccess;
 }
 
@@ -569,6 +574,8 @@ extern "C" b200_dim_t b200_blksz( int dt, int bs )
 	}
 	return -1;
 }
+
+extern "C" unsigned long long b200_launch_count( void ) { return ctx().launches.load(); }
 
 // Tuning knobs for sweeps (not part of the reference surface).
 extern "C" b200_err_t b200_set_option( const char* key, long long value )

@@ -15,6 +15,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <mutex>
+#include <atomic>
 #include "common.cuh"
 
 namespace b200 {
@@ -48,6 +49,7 @@ struct Context
 	int          cgemm_cfg = 0;
 	int          trsm_nb   = 0;           // 0 = default
 	int          grid_mult = 1;           // persistent CTAs per SM
+	std::atomic<unsigned long long> launches{0};   // kernels launched by this engine (b200_launch_count)
 };
 
 Context& ctx();

@@ -1,0 +1,174 @@
+"""Multi-GPU gemm/trsm: one process per GPU, torch.distributed (NCCL) plumbing.
+
+The reference has no distributed layer ("Distributed
+communication backend: none"); what it has is the jc x ic thread partitioning of
+C (frame/base/bli_rntm.c:424-489 -> bli_thread_partition_2x2) and contiguous
+per-thread ranges (bli_thread_range_sub).  This module applies exactly that
+arithmetic (blis_b200.partition) across GPUs:
+
+gemm  -- C is split into a Pr x Pc grid of blocks (Pr, Pc from
+         thread_partition_2x2(world, M, N)); rank (i, j) owns C_ij.  k is never
+         split across GPUs (as the reference never splits k across threads), so
+         there is no reduction and a block's bits do not depend on the GPU count
+         beyond the k-panel order.  A's row panel i is distributed over the Pc
+         ranks of grid row i and B's column panel j over the Pr ranks of grid
+         column j, both block-cyclically along k with panel width kb.  Each step
+         all-gathers the next L = lcm(Pr, Pc) k-panels inside the row group (A)
+         and the column group (B) -- NCCL all-gather over NVLink -- double
+         buffered, so the gather of step s+1 runs under the DMMA kernels of step s.
+trsm  -- B (and X) split into column blocks by thread_range_sub, A replicated:
+         no collective on the data path, exactly the reference's jc/jr
+         parallelism (frame/3/trsm/bli_trsm_cntl.c:446-451).
+
+The index logic (`SummaPlan`) and the exchange (`PanelExchange`) are backend
+agnostic so that they are tested on CPU with gloo (tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+from . import partition
+
+
+@dataclass
+class SummaPlan:
+    """Pure index arithmetic of the 2D decomposition."""
+    world: int
+    rank: int
+    M: int
+    N: int
+    K: int
+    kb: int
+
+    def __post_init__(self):
+        self.pr, self.pc = partition.thread_partition_2x2(self.world, self.M, self.N)
+        assert self.pr * self.pc == self.world
+        self.i, self.j = divmod(self.rank, self.pc)
+        self.L = math.lcm(self.pr, self.pc)
+        self.T = -(-self.K // self.kb)                       # number of k panels
+        if self.K % self.kb or self.T % self.L:
+            raise ValueError(f"K={self.K} must be a multiple of kb*lcm(Pr,Pc)={self.kb * self.L}")
+        self.steps = self.T // self.L
+        # my block of C (ragged edge on the last rank, as bli_thread_range_sub does)
+        self.m0, self.m1 = partition.thread_range_sub(self.i, self.pr, self.M, 1)
+        self.n0, self.n1 = partition.thread_range_sub(self.j, self.pc, self.N, 1)
+
+    @property
+    def m_loc(self): return self.m1 - self.m0
+    @property
+    def n_loc(self): return self.n1 - self.n0
+
+    def row_group(self):  return [self.i * self.pc + jj for jj in range(self.pc)]
+    def col_group(self):  return [ii * self.pc + self.j for ii in range(self.pr)]
+    def a_panels(self):   return [t for t in range(self.T) if t % self.pc == self.j]      # k panels of A I own
+    def b_panels(self):   return [t for t in range(self.T) if t % self.pr == self.i]      # k panels of B I own
+
+    def step_panels(self, s):
+        """For step s: list of (t, a_src_rank_in_row, a_slot, b_src_rank_in_col, b_slot)."""
+        out = []
+        for t in range(s * self.L, (s + 1) * self.L):
+            out.append((t, t % self.pc, (t - s * self.L) // self.pc, t % self.pr, (t - s * self.L) // self.pr))
+        return out
+
+
+class PanelExchange:
+    """All-gather of the step's A panels in the row group and B panels in the column group."""
+
+    def __init__(self, plan: SummaPlan, a_loc: torch.Tensor, b_loc: torch.Tensor):
+        # a_loc: [n_a_panels, kb, m_loc]  (panel, k, m)  -> each panel is column-major m_loc x kb
+        # b_loc: [n_b_panels, n_loc, kb]  (panel, n, k)  -> each panel is column-major kb x n_loc
+        self.p, self.a_loc, self.b_loc = plan, a_loc, b_loc
+        self.row_pg = self.col_pg = None
+        # every rank must create every group, in the same order
+        for i in range(plan.pr):
+            g = dist.new_group([i * plan.pc + jj for jj in range(plan.pc)])
+            if i == plan.i:
+                self.row_pg = g
+        for j in range(plan.pc):
+            g = dist.new_group([ii * plan.pc + j for ii in range(plan.pr)])
+            if j == plan.j:
+                self.col_pg = g
+        self.qa, self.qb = plan.L // plan.pc, plan.L // plan.pr       # panels I contribute per step
+        kw = dict(dtype=a_loc.dtype, device=a_loc.device)
+        self.abuf = [torch.empty(plan.pc, self.qa, plan.kb, plan.m_loc, **kw) for _ in range(2)]
+        self.bbuf = [torch.empty(plan.pr, self.qb, plan.n_loc, plan.kb, **kw) for _ in range(2)]
+
+    def start(self, s: int):
+        """Launch the (asynchronous) gathers of step s into buffer s%2; returns work handles."""
+        p = self.p
+        a_src = self.a_loc[s * self.qa:(s + 1) * self.qa]
+        b_src = self.b_loc[s * self.qb:(s + 1) * self.qb]
+        # flat views: rank r's contribution lands in slot [r] of the (contiguous) buffer
+        wa = dist.all_gather_into_tensor(self.abuf[s % 2].view(-1), a_src.reshape(-1), group=self.row_pg, async_op=True)
+        wb = dist.all_gather_into_tensor(self.bbuf[s % 2].view(-1), b_src.reshape(-1), group=self.col_pg, async_op=True)
+        return wa, wb
+
+    def panels(self, s: int):
+        """After the step's gathers completed: yields (t, A_t [kb, m_loc], B_t [n_loc, kb])."""
+        ab, bb = self.abuf[s % 2], self.bbuf[s % 2]
+        for t, ja, qa, ib, qb in self.p.step_panels(s):
+            yield t, ab[ja, qa], bb[ib, qb]
+
+
+def summa(plan: SummaPlan, ex: PanelExchange, gemm_panel, n_steps=None):
+    """Drive the pipeline: gemm_panel(first, A_t, B_t) accumulates one k panel into C_ij."""
+    steps = plan.steps if n_steps is None else n_steps
+    works = {0: ex.start(0)}
+    if steps > 1:
+        works[1] = ex.start(1)
+    first = True
+    for s in range(steps):
+        for w in works.pop(s):
+            w.wait()
+        for _, a_t, b_t in ex.panels(s):
+            gemm_panel(first, a_t, b_t)
+            first = False
+        if s + 2 < steps:
+            works[s + 2] = ex.start(s + 2)       # ordered after this step's kernels: its buffer is free again
+
+
+class WeakScalingGemm:
+    """bench.py's N>1 workload: every rank owns an n x n block of C of the
+    (Pr*n) x (Pc*n) x n product; per-GPU flops equal the single-GPU workload."""
+
+    def __init__(self, n: int, world: int, rank: int, device, alpha=2.0, beta=1.2, kb: int = 1024):
+        from . import api
+        self.api = api
+        pr, pc = partition.thread_partition_2x2(world, n, n)     # grid for equal work per dimension
+        self.plan = SummaPlan(world, rank, pr * n, pc * n, n, kb)
+        p = self.plan
+        assert (p.pr, p.pc) == (pr, pc)
+        self.alpha, self.beta, self.n = alpha, beta, n
+        g = torch.Generator(device=device); g.manual_seed(0xB200 + rank)
+        scale = 1.0 / n
+        na, nb = len(p.a_panels()), len(p.b_panels())
+        self.a_loc = (torch.rand(na, kb, p.m_loc, dtype=torch.float64, device=device, generator=g) * 2 - 1) * scale
+        self.b_loc = (torch.rand(nb, p.n_loc, kb, dtype=torch.float64, device=device, generator=g) * 2 - 1) * scale
+        self.c = (torch.rand(p.n_loc, p.m_loc, dtype=torch.float64, device=device, generator=g) * 2 - 1).t()
+        self.ex = PanelExchange(p, self.a_loc, self.b_loc)
+        self.total_flops = 2.0 * p.M * p.N * p.K
+        self.launches_per_step = p.T
+
+    def describe(self) -> str:
+        p = self.plan
+        return (f"2D block decomposition of C on a {p.pr}x{p.pc} grid (bli_thread_partition_2x2), C_ij {p.m_loc}x{p.n_loc} per GPU, "
+                f"global {p.M}x{p.N}x{p.K}; A/B k-panels (kb={p.kb}) all-gathered in row/column groups with NCCL, "
+                f"double buffered under the DMMA kernels; no reduction (k not split across GPUs)")
+
+    def _panel(self, first, a_t, b_t):
+        p = self.plan
+        # a_t: [kb, m_loc] contiguous == column-major m_loc x kb (rs=1, cs=m_loc); b_t: [n_loc, kb] == column-major kb x n_loc
+        self.api.bli_dgemm(0, 0, p.m_loc, p.n_loc, p.kb, self.alpha, a_t, 1, p.m_loc, b_t, 1, p.kb,
+                           self.beta if first else 1.0, self.c, 1, p.m_loc)
+
+    def step(self):
+        summa(self.plan, self.ex, self._panel)
+
+
+def trsm_column_block(rank: int, world: int, n: int, nr: int = 128):
+    """Columns [start, end) of B that `rank` solves (multi-GPU trsm: B split by column blocks)."""
+    return partition.thread_range_sub(rank, world, n, nr)

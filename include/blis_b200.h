@@ -159,6 +159,14 @@ b200_dim_t b200_blksz( int dt, int bs );
  * Runs for about `millis` ms and returns achieved TFLOP/s (< 0 on error). */
 double b200_measure_peak( int kind, int millis );
 
+/* Number of CUDA kernels this engine has launched so far in this process
+ * (gemm tile kernels, trsm block solves, strided copy/scale helpers); bench.py
+ * reports the difference over its timed region as "gpu_launches". */
+unsigned long long b200_launch_count( void );
+
+/* Tuning knob for sweeps, e.g. ("dgemm_cfg", 1); not part of the reference surface. */
+b200_err_t b200_set_option( const char* key, long long value );
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,209 @@
+"""Parity of the CUDA gemm (through the C ABI) with the reference.
+
+Checkers: the committed golden fixtures (real reference outputs), the oracle
+restatement, and the real reference library when it travelled (oracle/_ref).
+Bars: bit-exact on power-of-two inputs (any summation order must agree);
+elementwise TOL otherwise (util.TOL: 1e-12 for d/z, 5e-5 for s/c, relative to
+max(1,|ref|max)); at BASELINE sizes the testsuite's own residual
+(testsuite/src/test_gemm.c:393-401) with its pass thresholds (:44-47).
+"""
+import numpy as np
+import pytest
+import torch
+
+import gen
+import make_golden as G
+from refblis import CONJ_NO_TRANSPOSE, CONJ_TRANSPOSE, NO_TRANSPOSE, TRANSPOSE
+from util import NP2T, TOL, estr, rel_err, to_numpy, to_torch
+
+pytestmark = pytest.mark.gpu
+GOLD = G.HERE
+GEMM = {"s": "bli_sgemm", "d": "bli_dgemm", "c": "bli_cgemm", "z": "bli_zgemm"}
+
+
+def run_gemm(engine, ch, ta, tb, alpha, a, b, beta, c, device="cuda"):
+    """a, b, c: numpy arrays (any strides).  Returns C as numpy."""
+    ta_, tb_, tc_ = to_torch(a, device), to_torch(b, device), to_torch(c, device)
+    m, n = c.shape
+    k = a.shape[0] if (ta & TRANSPOSE) else a.shape[1]
+    getattr(engine, GEMM[ch])(ta, tb, m, n, k, alpha, ta_, *estr(a), tb_, *estr(b), beta, tc_, *estr(c))
+    if device == "cuda":
+        torch.cuda.synchronize()
+    return to_numpy(tc_)
+
+
+def test_gemm_golden_fixtures(engine):
+    gold = np.load(GOLD / "gemm.npz")
+    for idx, cs in enumerate(G.gemm_cases()):
+        ch, kind = cs[0], cs[1]
+        a, b, c = G.gemm_inputs(cs, idx)
+        got = run_gemm(engine, ch, cs[5], cs[6], cs[10], a, b, cs[11], c)
+        want = gold[f"c{idx}"]
+        if kind == "pow2":
+            assert np.array_equal(got, want), f"gemm golden case {idx} {cs}: not bit-exact"
+        else:
+            assert rel_err(got, want) <= TOL[ch], f"gemm golden case {idx} {cs}: {rel_err(got, want)}"
+
+
+SHAPES = [(1, 1, 1), (2, 3, 4), (8, 8, 4), (127, 129, 65), (128, 128, 16), (129, 127, 17), (256, 384, 100),
+          (300, 77, 513), (1, 700, 33), (515, 1, 64), (64, 1000, 1), (33, 65, 1025)]
+
+
+@pytest.mark.parametrize("ch", list("sdcz"))
+def test_gemm_vs_oracle_all_params(engine, oracle, ch):
+    """Every trans/conj combination x storage combination x edge shapes."""
+    cx = ch in "cz"
+    trs = (NO_TRANSPOSE, TRANSPOSE, CONJ_NO_TRANSPOSE, CONJ_TRANSPOSE) if cx else (NO_TRANSPOSE, TRANSPOSE)
+    al, be = ((2.0 + 0.2j, 1.2 + 0.5j) if cx else (2.0, 1.2))
+    seed = 100
+    for (m, n, k) in SHAPES:
+        for ta in trs:
+            for tb in trs:
+                for (oa, ob, oc) in (("c", "c", "c"), ("r", "r", "r"), ("c", "r", "g"), ("g", "c", "r")):
+                    if m * n * k > 2_000_000 and (oa, ob, oc) != ("c", "c", "c"):
+                        continue
+                    seed += 1
+                    am, ak = (k, m) if ta & TRANSPOSE else (m, k)
+                    bk, bn = (n, k) if tb & TRANSPOSE else (k, n)
+                    a = gen.matrix(ch, am, ak, seed, "frac", oa, pad=1)
+                    b = gen.matrix(ch, bk, bn, seed + 5000, "frac", ob, pad=2)
+                    c = gen.matrix(ch, m, n, seed + 9000, "frac", oc, pad=3)
+                    want = c.copy(order="K")
+                    oracle.gemm(ta, tb, al, a, b, be, want)
+                    got = run_gemm(engine, ch, ta, tb, al, a, b, be, c)
+                    assert rel_err(got, want) <= TOL[ch], (ch, m, n, k, ta, tb, oa, ob, oc, rel_err(got, want))
+
+
+@pytest.mark.parametrize("ch", list("sdcz"))
+def test_gemm_pow2_bit_exact_vs_oracle(engine, oracle, ch):
+    """Power-of-two inputs: products and sums are exact, so the tile order of the
+    GPU kernel and the KC-blocked order of the reference must give identical bits."""
+    for idx, (m, n, k, ta, tb, oc) in enumerate(((257, 131, 64, 0, 0, "c"), (130, 260, 48, 8, 0, "r"),
+                                                 (64, 64, 64, 0, 8, "c"), (513, 9, 33, 8, 8, "c"))):
+        am, ak = (k, m) if ta & TRANSPOSE else (m, k)
+        bk, bn = (n, k) if tb & TRANSPOSE else (k, n)
+        a = gen.matrix(ch, am, ak, 700 + idx, "pow2"); b = gen.matrix(ch, bk, bn, 800 + idx, "pow2")
+        c = gen.matrix(ch, m, n, 900 + idx, "pow2", oc)
+        want = c.copy(order="K")
+        oracle.gemm(ta, tb, 2.0, a, b, 0.5, want)
+        got = run_gemm(engine, ch, ta, tb, 2.0, a, b, 0.5, c)
+        assert np.array_equal(got, want), (ch, m, n, k, ta, tb)
+
+
+@pytest.mark.parametrize("ch", list("sdcz"))
+def test_gemm_vs_real_reference(engine, ref, ch):
+    """Against the real reference BLIS (optimized CPU kernels) on the same inputs."""
+    al, be = ((2.0 + 0.2j, 1.2 + 0.5j) if ch in "cz" else (2.0, 1.2))
+    for idx, (m, n, k) in enumerate(((1000, 1000, 1000), (511, 769, 300))):      # config #1 size: dgemm 1000^3
+        a = gen.matrix(ch, m, k, 40 + idx, "frac"); b = gen.matrix(ch, k, n, 50 + idx, "frac")
+        c = gen.matrix(ch, m, n, 60 + idx, "frac")
+        want = c.copy(order="K")
+        ref.gemm(0, 0, al, a, b, be, want)
+        got = run_gemm(engine, ch, 0, 0, al, a, b, be, c)
+        assert rel_err(got, want) <= TOL[ch] * 4, (ch, m, n, k, rel_err(got, want))
+
+
+def test_gemm_trivial_and_special_cases(engine):
+    """Empty dims, k == 0, alpha == 0 (C := beta*C), beta == 0 must not read C
+    (docs/KernelsHowTo.md:342; frame/3/bli_l3_util.c:40-65)."""
+    dev = "cuda"
+    a = torch.ones(5, 4, dtype=torch.float64, device=dev); b = torch.ones(4, 3, dtype=torch.float64, device=dev)
+    c = torch.full((5, 3), 3.0, dtype=torch.float64, device=dev)
+    engine.bli_dgemm(0, 0, 0, 3, 4, 1.0, a, 4, 1, b, 3, 1, 1.0, c, 3, 1)         # m == 0: no-op
+    engine.bli_dgemm(0, 0, 5, 0, 4, 1.0, a, 4, 1, b, 3, 1, 1.0, c, 3, 1)         # n == 0: no-op
+    torch.cuda.synchronize(); assert bool((c == 3.0).all())
+    engine.bli_dgemm(0, 0, 5, 3, 0, 1.0, a, 4, 1, b, 3, 1, 0.5, c, 3, 1)         # k == 0: C := beta*C
+    torch.cuda.synchronize(); assert bool((c == 1.5).all())
+    engine.bli_dgemm(0, 0, 5, 3, 4, 0.0, a, 4, 1, b, 3, 1, 2.0, c, 3, 1)         # alpha == 0
+    torch.cuda.synchronize(); assert bool((c == 3.0).all())
+    for dt, fn in ((torch.float32, engine.bli_sgemm), (torch.float64, engine.bli_dgemm),
+                   (torch.complex64, engine.bli_cgemm), (torch.complex128, engine.bli_zgemm)):
+        a = torch.ones(70, 50, dtype=dt, device=dev); b = torch.ones(50, 90, dtype=dt, device=dev)
+        c = torch.full((70, 90), float("nan"), dtype=dt, device=dev)
+        fn(0, 0, 70, 90, 50, 1.0, a, 50, 1, b, 90, 1, 0.0, c, 90, 1)
+        torch.cuda.synchronize()
+        assert bool((c == 50).all()), dt
+        c.fill_(float("nan"))
+        fn(0, 0, 70, 90, 50, 0.0, a, 50, 1, b, 90, 1, 0.0, c, 90, 1)               # alpha == beta == 0: C := 0
+        torch.cuda.synchronize()
+        assert bool((c == 0).all()), dt
+
+
+@pytest.mark.parametrize("ch", list("sdcz"))
+def test_gemm_host_operands_pinned_staging(engine, oracle, ch):
+    """Host pointers (pageable and pinned, column/row/general storage) go through
+    the engine's pinned staging and come back in the caller's buffer."""
+    al, be = ((2.0 + 0.2j, 1.2 + 0.5j) if ch in "cz" else (2.0, 1.2))
+    for idx, (oa, ob, oc, pin) in enumerate((("c", "c", "c", False), ("r", "c", "r", False), ("g", "r", "g", False), ("c", "c", "c", True))):
+        m, n, k = 211, 97, 150
+        a = gen.matrix(ch, m, k, 300 + idx, "frac", oa, pad=2); b = gen.matrix(ch, k, n, 310 + idx, "frac", ob)
+        c = gen.matrix(ch, m, n, 320 + idx, "frac", oc, pad=1)
+        want = c.copy(order="K"); oracle.gemm(0, 0, al, a, b, be, want)
+        ta_, tb_, tc_ = (to_torch(x, "cpu", pin=pin) for x in (a, b, c))
+        assert tc_.is_pinned() == pin
+        getattr(engine, GEMM[ch])(0, 0, m, n, k, al, ta_, *estr(a), tb_, *estr(b), be, tc_, *estr(c))
+        assert rel_err(to_numpy(tc_), want) <= TOL[ch], (ch, oa, ob, oc, pin)
+
+
+def test_gemm_object_and_blas_layers(engine, oracle):
+    """The object API (bli_gemm on Obj) and the BLAS layer (dgemm_) reach the same kernel."""
+    from blis_b200 import api
+    m, n, k = 150, 130, 70
+    a = gen.matrix("d", k, m, 1, "frac"); b = gen.matrix("d", k, n, 2, "frac"); c = gen.matrix("d", m, n, 3, "frac")
+    want = c.copy(order="K"); oracle.gemm(TRANSPOSE, 0, 2.0, a, b, 1.2, want)
+    ta_, tb_, tc_ = to_torch(a), to_torch(b), to_torch(c)
+    ao = api.Obj(ta_); api.bli_obj_set_conjtrans(TRANSPOSE, ao)
+    api.bli_gemm(2.0, ao, api.Obj(tb_), 1.2, api.Obj(tc_))
+    torch.cuda.synchronize()
+    assert rel_err(to_numpy(tc_), want) <= TOL["d"]
+    tc2 = to_torch(c)
+    api.dgemm_("T", "N", m, n, k, 2.0, ta_, k, tb_, k, 1.2, tc2, m)
+    torch.cuda.synchronize()
+    assert np.array_equal(to_numpy(tc2), to_numpy(tc_))
+
+
+def _testsuite_resid(alpha, a, b, beta, c0, c):
+    """resid = || C t - ( beta C0 t + alpha A (B t) ) ||_F, t random  (testsuite/src/test_gemm.c:393-401)."""
+    n = c.shape[1]
+    g = torch.Generator(device=c.device); g.manual_seed(7)
+    t = torch.rand(n, dtype=torch.float64, device=c.device, generator=g) * 2 - 1
+    t = (t / n).to(c.dtype)
+    z = beta * (c0 @ t) + alpha * (a @ (b @ t))
+    return float(torch.linalg.vector_norm(c @ t - z))
+
+
+@pytest.mark.parametrize("ch,n", [("d", 16384), ("z", 8192), ("s", 16384), ("c", 8192)])
+def test_gemm_full_size_testsuite_residual(engine, ch, n):
+    """BASELINE config #2/#3 sizes, column-major, device-resident: the reference
+    testsuite's own randomized residual and pass thresholds, plus a linearity
+    property: gemm(alpha) + gemm(alpha) into the same C == gemm(2*alpha)."""
+    dt = NP2T[np.dtype(gen.NP_DT[ch])]
+    dev = "cuda"
+    g = torch.Generator(device=dev); g.manual_seed(int(0xB200))
+    rdt = torch.float32 if ch in "sc" else torch.float64
+
+    def rnd(m, k):
+        x = torch.rand(k, m, dtype=rdt, device=dev, generator=g) * 2 - 1
+        if ch in "cz":
+            x = torch.complex(x, torch.rand(k, m, dtype=rdt, device=dev, generator=g) * 2 - 1)
+        # libblis_test_mobj_randomize: normalise by the 1-norm rounded up to a power of two (test_libblis.c:2529-2565)
+        nrm = float(x.abs().sum(dim=1).max())
+        return (x / float(2 ** np.ceil(np.log2(nrm)))).t()
+
+    a, b, c = rnd(n, n), rnd(n, n), rnd(n, n)
+    c0 = c.clone()
+    al, be = ((2.0 + 0.2j, 1.2 + 0.5j) if ch in "cz" else (2.0, 1.2))
+    getattr(engine, GEMM[ch])(0, 0, n, n, n, al, a, 1, n, b, 1, n, be, c, 1, n)
+    torch.cuda.synchronize()
+    resid = _testsuite_resid(al, a, b, be, c0, c)
+    thresh = 1e-5 if ch in "sc" else 1e-14                     # testsuite/src/test_gemm.c:44-47 "pass"
+    assert resid <= thresh, (ch, n, resid)
+    # linearity (size independent): C1 = 0 + al*A*B twice accumulated == 2*al*A*B
+    m2 = 4096
+    c1 = torch.zeros(m2, m2, dtype=dt, device=dev).t(); c2 = torch.zeros(m2, m2, dtype=dt, device=dev).t()
+    f = getattr(engine, GEMM[ch])
+    f(0, 0, m2, m2, n, 1.0, a, 1, n, b, 1, n, 0.0, c1, 1, m2)
+    f(0, 0, m2, m2, n, 1.0, a, 1, n, b, 1, n, 1.0, c1, 1, m2)
+    f(0, 0, m2, m2, n, 2.0, a, 1, n, b, 1, n, 0.0, c2, 1, m2)
+    torch.cuda.synchronize()
+    assert bool(torch.equal(c1, c2)), "x + x != 2x: gemm is not deterministic/linear"

@@ -19,11 +19,13 @@ def _span(a: np.ndarray):
     return (a.shape[0] - 1) * rs + (a.shape[1] - 1) * cs + 1 if a.size else 1
 
 
-def to_torch(a: np.ndarray, device="cuda") -> torch.Tensor:
-    """Tensor on `device` with the same shape AND the same element strides as a."""
+def to_torch(a: np.ndarray, device="cuda", pin: bool = False) -> torch.Tensor:
+    """Tensor on `device` with the same shape AND the same element strides as a
+    (pin=True: page-locked host memory)."""
     rs, cs = estr(a)
     flat = np.lib.stride_tricks.as_strided(a, shape=(_span(a),), strides=(a.itemsize,))
-    t = torch.from_numpy(np.array(flat, copy=True)).to(device)
+    t = torch.from_numpy(np.array(flat, copy=True))
+    t = t.pin_memory() if pin else t.to(device)
     return t.as_strided(a.shape, (rs, cs))
 
 
