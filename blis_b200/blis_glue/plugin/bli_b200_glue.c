@@ -1,0 +1,191 @@
+/*
+   bli_b200_glue.c -- BLIS-side binding of the B200 engine (C99, includes blis.h).
+
+   This is the reference-facing half of the drop-in: everything here speaks
+   BLIS types (obj_t, cntx_t, rntm_t, err_t) and forwards to the C ABI in
+   include/blis_b200.h.  It is shared by the two integration routes described
+   in INTEGRATION.md:
+
+     (1) plugin route  -- bli_plugin_register_b200() installs the whole-operation
+         gemm hook on the active context of ANY stock libblis at run time
+         (the mechanism of build/plugin/bli_plugin_register.c:37-81 and
+         docs/PluginHowTo.md), no rebuild of BLIS needed;
+     (2) config route  -- config/b200/bli_cntx_init_b200.c calls
+         bli_b200_install( cntx ) while the gks registers the sub-configuration
+         (frame/base/bli_gks.c:58-93).
+
+   gemm: the hook has the gemmsup_oft signature (frame/3/bli_l3_sup_oft.h:46-59)
+   and is reached from bli_gemm_ex before any host packing
+   (frame/3/bli_l3_oapi_ex.c:76-77 -> frame/3/bli_l3_sup.c:37-135) for every
+   homogeneous-datatype problem because the MT/NT/KT thresholds are set huge.
+   trsm: BLIS has no whole-operation slot for trsm (bli_l3_oapi_ex.c:692-801
+   goes straight to the control tree), so this file provides bli_trsm_ex_b200
+   with bli_trsm_ex's exact signature; INTEGRATION.md shows the two-line guard
+   that lets the b200 configuration resolve bli_trsm_ex to it (the sandbox
+   trick of bli_l3_oapi_ex.c:45-49).
+
+   Error convention: the engine has no CPU fallback, so a failure inside it is
+   fatal exactly like every other BLIS error: message + bli_abort()
+   (frame/base/bli_error.c:126-139).
+*/
+#include <stdio.h>
+#include "blis.h"
+#include "blis_b200.h"
+
+static void bli_b200_die( const char* op )
+{
+	fprintf( stderr, "libblis (b200): %s failed: %s\n", op, b200_last_error() );
+	fflush( stderr );
+	bli_abort();
+}
+
+/* -- gemm: whole-operation handler (gemmsup_oft) ------------------------------ */
+
+err_t bli_gemmsup_b200
+     (
+       const obj_t*  alpha,
+       const obj_t*  a,
+       const obj_t*  b,
+       const obj_t*  beta,
+       const obj_t*  c,
+       const cntx_t* cntx,
+             rntm_t* rntm
+     )
+{
+	( void )cntx; ( void )rntm;
+
+	/* Guaranteed by the caller (bli_gemmsup): one datatype, comp precision ==
+	   storage precision, alpha/beta already cast to dt, non-trivial dims. */
+	const num_t dt = bli_obj_dt( c );
+
+	/* Scalars attached to A/B by earlier API layers must be the identity at
+	   this point of the call stack (they are only set inside the control
+	   tree, bli_gemm_cntl.c:168-207). */
+
+	const err_t r = b200_gemm
+	(
+	  ( int )dt,
+	  ( int )bli_obj_conjtrans_status( a ),
+	  ( int )bli_obj_conjtrans_status( b ),
+	  bli_obj_length( c ),
+	  bli_obj_width( c ),
+	  bli_obj_width_after_trans( a ),
+	  bli_obj_buffer_for_1x1( dt, alpha ),
+	  bli_obj_buffer_at_off( a ), bli_obj_row_stride( a ), bli_obj_col_stride( a ),
+	  bli_obj_buffer_at_off( b ), bli_obj_row_stride( b ), bli_obj_col_stride( b ),
+	  bli_obj_buffer_for_1x1( dt, beta ),
+	  bli_obj_buffer_at_off( c ), bli_obj_row_stride( c ), bli_obj_col_stride( c )
+	);
+	if ( r != BLIS_SUCCESS ) bli_b200_die( "gemm" );
+
+	/* BLIS_SUCCESS ends bli_gemm_ex; returning BLIS_FAILURE would send the
+	   problem to the CPU control tree, which the b200 configuration forbids. */
+	return BLIS_SUCCESS;
+}
+
+/* -- trsm: same parameter list as bli_trsm_ex --------------------------------- */
+
+void bli_trsm_ex_b200
+     (
+             side_t  side,
+       const obj_t*  alpha,
+       const obj_t*  a,
+       const obj_t*  b,
+       const cntx_t* cntx,
+       const rntm_t* rntm
+     )
+{
+	( void )rntm;
+	bli_init_once();
+
+	if ( bli_error_checking_is_enabled() )
+		bli_trsm_check( side, alpha, a, b, cntx );
+
+	const num_t dt = bli_obj_dt( b );
+	if ( bli_obj_dt( a ) != dt )
+	{
+		fprintf( stderr, "libblis (b200): mixed-datatype trsm is not supported by the b200 engine.\n" );
+		bli_abort();
+	}
+	if ( bli_obj_has_zero_dim( b ) ) return;
+
+	obj_t alpha_cast;
+	bli_obj_scalar_init_detached_copy_of( dt, BLIS_NO_CONJUGATE, alpha, &alpha_cast );
+
+	/* alpha == 0 (B := 0) is handled by the engine so that it also works for
+	   device-resident B; the reference's bli_l3_return_early_if_trivial would
+	   run bli_scalm on the host pointer (frame/3/bli_l3_util.c:57-60). */
+	const err_t r = b200_trsm
+	(
+	  ( int )dt,
+	  ( int )side,
+	  ( int )bli_obj_uplo( a ),
+	  ( int )bli_obj_conjtrans_status( a ),
+	  ( int )bli_obj_diag( a ),
+	  bli_obj_length( b ),
+	  bli_obj_width( b ),
+	  bli_obj_buffer_for_1x1( dt, &alpha_cast ),
+	  bli_obj_buffer_at_off( a ), bli_obj_row_stride( a ), bli_obj_col_stride( a ),
+	  bli_obj_buffer_at_off( b ), bli_obj_row_stride( b ), bli_obj_col_stride( b )
+	);
+	if ( r != BLIS_SUCCESS ) bli_b200_die( "trsm" );
+}
+
+#ifdef BLIS_B200_OVERRIDE_TRSM_EX
+/* Build-time switch of the config route / LD_PRELOAD demo: bli_trsm_ex itself
+   resolves to the engine ("trsm"). */
+void bli_trsm_ex( side_t side, const obj_t* alpha, const obj_t* a, const obj_t* b,
+                  const cntx_t* cntx, const rntm_t* rntm )
+{
+	bli_trsm_ex_b200( side, alpha, a, b, cntx, rntm );
+}
+#endif
+
+/* -- registration ----------------------------------------------------------- */
+
+/* Install the engine into one context: tile shapes as blocksizes, thresholds
+   that route every gemm to the handler, and the handler itself. */
+void bli_b200_install( cntx_t* cntx )
+{
+	/* "every size": m < MT || n < NT || k < KT is the dispatch test
+	   (frame/base/bli_cntx.h:186-192). */
+	const dim_t all = ( dim_t )1 << 62;
+	blksz_t mt, nt, kt;
+	bli_blksz_init_easy( &mt, all, all, all, all );
+	bli_blksz_init_easy( &nt, all, all, all, all );
+	bli_blksz_init_easy( &kt, all, all, all, all );
+	bli_cntx_set_blkszs
+	(
+	  cntx,
+	  BLIS_MT, &mt, BLIS_MT,
+	  BLIS_NT, &nt, BLIS_NT,
+	  BLIS_KT, &kt, BLIS_KT,
+	  BLIS_VA_END
+	);
+	bli_cntx_set_l3_sup_handlers
+	(
+	  cntx,
+	  BLIS_GEMM, bli_gemmsup_b200,
+	  BLIS_VA_END
+	);
+}
+
+/* Plugin entry point: call once after bli_init() and before any computation
+   ("registration must happen before any computations are performed with the
+   plugin", docs/PluginHowTo.md:178). */
+err_t bli_plugin_register_b200( void )
+{
+	bli_init();
+	if ( b200_init( -1 ) != BLIS_SUCCESS ) bli_b200_die( "b200_init" );
+
+	/* the context the library dispatches on (frame/base/bli_gks.c:276) */
+	cntx_t* cntx = ( cntx_t* )bli_gks_lookup_id( bli_arch_query_id() );
+	if ( cntx == NULL ) return BLIS_FAILURE;
+	bli_b200_install( cntx );
+	return BLIS_SUCCESS;
+}
+
+#ifdef BLIS_B200_AUTO_REGISTER
+/* LD_PRELOAD / link-time demo: register as soon as the library is loaded. */
+__attribute__((constructor)) static void bli_b200_ctor( void ) { bli_plugin_register_b200(); }
+#endif

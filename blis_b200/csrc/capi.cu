@@ -10,6 +10,7 @@
 //                 frame/3/trsm/bli_trsm_blk_var1.c:40-188
 #include "context.cuh"
 #include "gemm_dmma.cuh"
+#include "gemm_dmma_ws.cuh"
 #include "gemm_ffma.cuh"
 #include "trsm.cuh"
 #include "../../include/blis_b200.h"
@@ -150,6 +151,32 @@ static int launch_dmma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int gri
 	}
 }
 
+template <typename T, int BP, int BQ, int BK, int WP, int WQ, int ST>
+static int launch_dmma_ws( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
+{
+	auto go = [&]( auto XKc, auto YKc, auto ALc ) -> int
+	{
+		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
+		using Cfg = DmmaWsCfg<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
+		auto kern = gemm_dmma_ws_kernel<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
+		static bool attr = false;
+		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<grid, Cfg::NT_ALL, Cfg::SMEM_BYTES, st>>>( g );
+		B200_CUDA( cudaGetLastError() );
+		ctx().launches++;
+		return kSuccess;
+	};
+	using Tt = std::true_type; using Ff = std::false_type;
+	const int sel = ( xk ? 4 : 0 ) | ( yk ? 2 : 0 ) | ( al ? 1 : 0 );
+	switch ( sel )
+	{
+		case 0: return go( Ff{}, Ff{}, Ff{} );  case 1: return go( Ff{}, Ff{}, Tt{} );
+		case 2: return go( Ff{}, Tt{}, Ff{} );  case 3: return go( Ff{}, Tt{}, Tt{} );
+		case 4: return go( Tt{}, Ff{}, Ff{} );  case 5: return go( Tt{}, Ff{}, Tt{} );
+		case 6: return go( Tt{}, Tt{}, Ff{} );  default: return go( Tt{}, Tt{}, Tt{} );
+	}
+}
+
 template <typename T, int BP, int BQ, int BK, int TP, int TQ, int ST>
 static int launch_ffma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
 {
@@ -179,7 +206,7 @@ static int launch_ffma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int gri
 // Tile shapes per datatype = the "blocksizes" this engine registers
 // (MR/NR become the warp tile, MC/NC the CTA tile, KC the staged k slab).
 template <typename T> struct Tiles;
-template <> struct Tiles<double>  { static constexpr int BP = 128, BQ = 128, BK = 16, MR = 64, NR = 32; };
+template <> struct Tiles<double>  { static constexpr int BP = 128, BQ = 128, BK = 16, MR = 32, NR = 64; };
 template <> struct Tiles<double2> { static constexpr int BP = 64,  BQ = 128, BK = 8,  MR = 32, NR = 32; };
 template <> struct Tiles<float>   { static constexpr int BP = 128, BQ = 128, BK = 16, MR = 8,  NR = 8;  };
 template <> struct Tiles<float2>  { static constexpr int BP = 64,  BQ = 128, BK = 16, MR = 4,  NR = 8;  };
@@ -202,6 +229,9 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 		case 1: return launch_dmma<double, 128, 128, 16, 4, 2, 4>( g, xk, yk, al, tiles( 128, 128 ), st );
 		case 2: return launch_dmma<double, 128, 128, 8,  2, 4, 6>( g, xk, yk, al, tiles( 128, 128 ), st );
 		case 3: return launch_dmma<double, 128, 128, 32, 2, 4, 3>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 4: return launch_dmma_ws<double, 128, 128, 16, 2, 4, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 5: return launch_dmma_ws<double, 128, 128, 32, 2, 4, 3>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 6: return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
 	}
 }
 template <>
@@ -210,6 +240,7 @@ int launch_gemm_kernel<double2>( GemmArgs<double2>& g, bool xk, bool yk, bool al
 	Context& c = ctx();
 	g.tiles_p = (int)( ( g.P + 63 ) / 64 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
 	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
+	if ( c.zgemm_cfg == 1 ) return launch_dmma_ws<double2, 64, 128, 8, 2, 4, 5>( g, xk, yk, al, grid, st );
 	return launch_dmma<double2, 64, 128, 8, 2, 4, 4>( g, xk, yk, al, grid, st );
 }
 template <>

@@ -216,6 +216,17 @@ extern "C" void b200_finalize( void )
 
 extern "C" const char* b200_last_error( void ) { return g_err; }
 
+// BLIS_MALLOC_USER / BLIS_FREE_USER hooks of config/b200 (bli_family_b200.h):
+// page-locked host memory for matrices created by bli_obj_create().
+extern "C" void* b200_malloc_pinned( size_t size )
+{
+	void* p = nullptr;
+	if ( ensure_init() != kSuccess ) return nullptr;
+	if ( cudaMallocHost( &p, size ? size : 1 ) != cudaSuccess ) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+extern "C" void b200_free_pinned( void* p ) { if ( p ) cudaFreeHost( p ); }
+
 extern "C" int b200_device_count( void )
 {
 	int n = 0;

@@ -43,8 +43,8 @@ struct Context
 	cudaEvent_t  stage_free[kStageBufs] = { nullptr, nullptr };
 	std::mutex   stage_mu;
 	// tuning knobs (b200_set_option)
-	int          dgemm_cfg = 0;
-	int          zgemm_cfg = 0;
+	int          dgemm_cfg = 6;          // warp-specialised 128x128x16, 5 stages, warp tile 32x64
+	int          zgemm_cfg = 1;          // warp-specialised 64x128x8, 5 stages
 	int          sgemm_cfg = 0;
 	int          cgemm_cfg = 0;
 	int          trsm_nb   = 0;           // 0 = default

@@ -70,7 +70,8 @@ __device__ __forceinline__ void load_tile( uint32_t sbase, const T* __restrict__
 	constexpr int TOTAL = LS * CPR;
 	constexpr int ITERS = ( TOTAL + NT - 1 ) / NT;
 	const int lim_bytes = c_lim * (int)sizeof(T);
-	#pragma unroll
+	constexpr int UNROLL = ITERS <= 8 ? ITERS : 4;     // long (unaligned / producer-warp) copies: bound register use
+	#pragma unroll UNROLL
 	for ( int i = 0; i < ITERS; ++i )
 	{
 		const int id = tid + i * NT;

@@ -84,6 +84,11 @@ void*       b200_get_stream( void );
 /* Block until everything the engine queued on its stream has finished. */
 b200_err_t  b200_sync( void );
 
+/* Page-locked host allocation: the BLIS_MALLOC_USER / BLIS_FREE_USER hooks of
+ * config/b200 (docs/ConfigurationHowTo.md:195-207), signature void* f(size_t). */
+void*       b200_malloc_pinned( size_t size );
+void        b200_free_pinned( void* p );
+
 /* ---- gemm ------------------------------------------------------------------
  * C := beta*C + alpha*transa(A)*transb(B),  C is m x n, k is the inner dim.
  *

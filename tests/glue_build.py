@@ -1,0 +1,49 @@
+"""Build the BLIS-side glue (blis_b200/blis_glue/plugin/bli_b200_glue.c) against the
+reference's headers.  Only possible where /root/reference is mounted; the result
+(oracle/_ref/libblis_b200_glue.so) travels with the snapshot to the GPU box.
+
+TEST INFRASTRUCTURE: in a real installation the same file is compiled by the
+plugin / config/b200 build against the installed blis.h."""
+from __future__ import annotations
+
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+GLUE_SRC = ROOT / "blis_b200" / "blis_glue" / "plugin" / "bli_b200_glue.c"
+CFG_SRC = ROOT / "blis_b200" / "blis_glue" / "config" / "b200" / "bli_cntx_init_b200.c"
+GLUE_SO = ROOT / "oracle" / "_ref" / "libblis_b200_glue.so"
+
+
+def build(force: bool = False) -> Path:
+    if not Path("/root/reference").exists():
+        if GLUE_SO.exists():
+            return GLUE_SO
+        raise FileNotFoundError("no /root/reference and no prebuilt glue library")
+    if GLUE_SO.exists() and not force and GLUE_SO.stat().st_mtime >= GLUE_SRC.stat().st_mtime:
+        return GLUE_SO
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import build_ref
+    build_ref.build()
+    incs = [f"-I{d}" for d in build_ref._inc_dirs()] + [f"-I{ROOT / 'include'}"]
+    cmd = ["gcc", "-std=c99", "-O2", "-fPIC", "-shared", "-D_POSIX_C_SOURCE=200112L", "-Wall", "-Wno-unused-function",
+           "-DBLIS_B200_OVERRIDE_TRSM_EX", *incs, str(GLUE_SRC), "-o", str(GLUE_SO),
+           f"-L{ROOT / 'blis_b200'}", "-lblis_b200", "-Wl,-rpath,$ORIGIN/../../blis_b200"]
+    subprocess.run(cmd, check=True)
+    return GLUE_SO
+
+
+def syntax_check_config() -> None:
+    """config/b200/bli_cntx_init_b200.c must compile against the reference headers (with the
+    b200 names a maintainer adds to bli_arch_config.h declared here)."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import build_ref
+    incs = [f"-I{d}" for d in build_ref._inc_dirs()] + [f"-I{ROOT / 'include'}"]
+    cmd = ["gcc", "-std=c99", "-fsyntax-only", "-D_POSIX_C_SOURCE=200112L", "-Wall", "-Wno-unused-function",
+           "-include", str(ROOT / "tests" / "b200_arch_decls.h"), *incs, str(CFG_SRC)]
+    subprocess.run(cmd, check=True)
+
+
+if __name__ == "__main__":
+    print(build(force=True))
