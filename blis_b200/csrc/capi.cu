@@ -12,6 +12,7 @@
 #include "gemm_dmma.cuh"
 #include "gemm_dmma_ws.cuh"
 #include "gemm_ffma.cuh"
+#include "gemm_ffma_ws.cuh"
 #include "trsm.cuh"
 #include "../../include/blis_b200.h"
 #include <algorithm>
@@ -203,6 +204,32 @@ static int launch_ffma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int gri
 	}
 }
 
+template <typename T, int BP, int BQ, int BK, int TP, int TQ, int ST>
+static int launch_ffma_ws( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
+{
+	auto go = [&]( auto XKc, auto YKc, auto ALc ) -> int
+	{
+		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
+		using Cfg = FfmaWsCfg<T, BP, BQ, BK, TP, TQ, ST>;
+		auto kern = gemm_ffma_ws_kernel<T, BP, BQ, BK, TP, TQ, ST, XK, YK, AL>;
+		static bool attr = false;
+		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<grid, Cfg::NT_ALL, Cfg::SMEM_BYTES, st>>>( g );
+		B200_CUDA( cudaGetLastError() );
+		ctx().launches++;
+		return kSuccess;
+	};
+	using Tt = std::true_type; using Ff = std::false_type;
+	const int sel = ( xk ? 4 : 0 ) | ( yk ? 2 : 0 ) | ( al ? 1 : 0 );
+	switch ( sel )
+	{
+		case 0: return go( Ff{}, Ff{}, Ff{} );  case 1: return go( Ff{}, Ff{}, Tt{} );
+		case 2: return go( Ff{}, Tt{}, Ff{} );  case 3: return go( Ff{}, Tt{}, Tt{} );
+		case 4: return go( Tt{}, Ff{}, Ff{} );  case 5: return go( Tt{}, Ff{}, Tt{} );
+		case 6: return go( Tt{}, Tt{}, Ff{} );  default: return go( Tt{}, Tt{}, Tt{} );
+	}
+}
+
 // Tile shapes per datatype = the "blocksizes" this engine registers
 // (MR/NR become the warp tile, MC/NC the CTA tile, KC the staged k slab).
 template <typename T> struct Tiles;
@@ -222,7 +249,14 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 		g.tiles_p = (int)( ( g.P + bp - 1 ) / bp ); g.tiles_q = (int)( ( g.Q + bq - 1 ) / bq );
 		return (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
 	};
-	switch ( c.dgemm_cfg )
+	int cfg = c.dgemm_cfg;
+	if ( cfg < 0 )
+	{
+		// auto: the cooperative 128x128 tile unless it cannot fill the SMs once; then 128x64 tiles, two CTAs per SM
+		const int64_t t128 = ( ( g.P + 127 ) / 128 ) * ( ( g.Q + 127 ) / 128 );
+		cfg = ( t128 < c.num_sms ) ? 7 : 6;
+	}
+	switch ( cfg )
 	{
 		default:
 		case 0: return launch_dmma<double, 128, 128, 16, 2, 4, 4>( g, xk, yk, al, tiles( 128, 128 ), st );
@@ -232,6 +266,10 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 		case 4: return launch_dmma_ws<double, 128, 128, 16, 2, 4, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
 		case 5: return launch_dmma_ws<double, 128, 128, 32, 2, 4, 3>( g, xk, yk, al, tiles( 128, 128 ), st );
 		case 6: return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 7: { const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 128, 64 ); c.grid_mult = gm;
+		          return launch_dmma_ws<double, 128, 64, 16, 4, 1, 3>( g, xk, yk, al, grid, st ); }
+		case 8: { const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 64, 128 ); c.grid_mult = gm;
+		          return launch_dmma_ws<double, 64, 128, 16, 1, 4, 3>( g, xk, yk, al, grid, st ); }
 	}
 }
 template <>
@@ -249,6 +287,8 @@ int launch_gemm_kernel<float>( GemmArgs<float>& g, bool xk, bool yk, bool al, cu
 	Context& c = ctx();
 	g.tiles_p = (int)( ( g.P + 127 ) / 128 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
 	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
+	if ( c.sgemm_cfg == 1 ) return launch_ffma_ws<float, 128, 128, 16, 8, 8, 5>( g, xk, yk, al, grid, st );
+	if ( c.sgemm_cfg == 2 ) return launch_ffma_ws<float, 128, 128, 32, 8, 8, 4>( g, xk, yk, al, grid, st );
 	return launch_ffma<float, 128, 128, 16, 8, 8, 4>( g, xk, yk, al, grid, st );
 }
 template <>
@@ -257,6 +297,7 @@ int launch_gemm_kernel<float2>( GemmArgs<float2>& g, bool xk, bool yk, bool al, 
 	Context& c = ctx();
 	g.tiles_p = (int)( ( g.P + 63 ) / 64 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
 	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
+	if ( c.cgemm_cfg == 1 ) return launch_ffma_ws<float2, 64, 128, 16, 4, 8, 5>( g, xk, yk, al, grid, st );
 	return launch_ffma<float2, 64, 128, 16, 4, 8, 4>( g, xk, yk, al, grid, st );
 }
 

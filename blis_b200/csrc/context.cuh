@@ -43,10 +43,10 @@ struct Context
 	cudaEvent_t  stage_free[kStageBufs] = { nullptr, nullptr };
 	std::mutex   stage_mu;
 	// tuning knobs (b200_set_option)
-	int          dgemm_cfg = 6;          // warp-specialised 128x128x16, 5 stages, warp tile 32x64
+	int          dgemm_cfg = -1;         // auto: ws 128x128x16 (cfg 6) or ws 128x64x16 with 2 CTAs/SM (cfg 7)
 	int          zgemm_cfg = 1;          // warp-specialised 64x128x8, 5 stages
 	int          sgemm_cfg = 0;
-	int          cgemm_cfg = 0;
+	int          cgemm_cfg = 1;          // warp-specialised 64x128x16
 	int          trsm_nb   = 0;           // 0 = default
 	int          grid_mult = 1;           // persistent CTAs per SM
 	std::atomic<unsigned long long> launches{0};   // kernels launched by this engine (b200_launch_count)

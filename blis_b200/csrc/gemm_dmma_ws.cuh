@@ -64,11 +64,15 @@ struct DmmaWsCfg : DmmaCfg<T, BP, BQ, BK, WP, WQ, STAGES, XK, YK, AL>
 	static constexpr int NT_ALL = NCONS + NPROD;
 	static constexpr int BAR_BYTES  = 2 * STAGES * 8;
 	static constexpr int SMEM_BYTES = Base::STAGE_BYTES * STAGES + BAR_BYTES;
-	static_assert( NCONS == 256, "two consumer warpgroups" );
+	static_assert( NCONS == 256 || NCONS == 128, "one or two consumer warpgroups" );
+	// one consumer warpgroup: two CTAs share an SM (one CTA's epilogue overlaps the other's MMAs)
+	static constexpr int CTAS_PER_SM = ( NCONS == 128 ) ? 2 : 1;
+	static constexpr int REG_PROD = ( NCONS == 128 ) ? 40 : 56;
+	static constexpr int REG_CONS = ( NCONS == 128 ) ? 216 : 224;
 };
 
 template <typename T, int BP, int BQ, int BK, int WP, int WQ, int STAGES, bool XK, bool YK, bool AL>
-__global__ void __launch_bounds__( 384, 1 )
+__global__ void __launch_bounds__( WP * WQ * 32 + 128, ( WP * WQ == 4 ) ? 2 : 1 )
 gemm_dmma_ws_kernel( const GemmArgs<T> g )
 {
 	using Cfg = DmmaWsCfg<T, BP, BQ, BK, WP, WQ, STAGES, XK, YK, AL>;
@@ -101,7 +105,7 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 	if ( tid >= Cfg::NCONS )
 	{
 		// =========================== PRODUCER warpgroup ===========================
-		setmaxnreg_dec<56>();
+		setmaxnreg_dec<Cfg::REG_PROD>();
 		const int ptid = tid - Cfg::NCONS;
 		int stage = 0; uint32_t phase = 0;
 		for ( int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x )
@@ -113,6 +117,20 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 			const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );
 			const T* gx = XK ? g.X + p0 * g.ldx : g.X + p0;
 			const T* gy = YK ? g.Y + q0 * g.ldy : g.Y + q0;
+			if ( !g.beta_is_zero )
+			{
+				// pull this tile of D towards L2 while the k loop runs; the epilogue reads it
+				constexpr int LINES_PER_ROW = ( BQ * (int)sizeof(T) + 127 ) / 128;
+				for ( int e = ptid; e < BP * LINES_PER_ROW; e += Cfg::NPROD )
+				{
+					const int r = e / LINES_PER_ROW, l = e % LINES_PER_ROW;
+					if ( r < p_lim && l * ( 128 / (int)sizeof(T) ) < q_lim )
+					{
+						const T* pd = g.D + ( p0 + r ) * g.ldd + q0 + l * ( 128 / (int)sizeof(T) );
+						asm volatile( "prefetch.global.L2 [%0];\n" :: "l"(pd) );
+					}
+				}
+			}
 			for ( int64_t kt = 0; kt < KT; ++kt )
 			{
 				mbar_wait( empty_bar( stage ), phase ^ 1u );
@@ -132,7 +150,7 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 	}
 
 	// =============================== CONSUMER warps ===============================
-	setmaxnreg_inc<224>();
+	setmaxnreg_inc<Cfg::REG_CONS>();
 	const int lane = tid & 31, warp = tid >> 5;
 	const int gq   = lane >> 2, t4 = lane & 3;
 	const int wp0  = ( warp / WQ ) * Cfg::WTP;
@@ -240,6 +258,37 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 		}
 
 		// ---- epilogue: D = alpha*acc + beta*D   (beta == 0: D is not read)
+		if ( !CPLX && g.d_vec_ok && q_lim == BQ )
+		{
+			// Interior tile, real type: all loads of a tile row are issued before the first
+			// store, so a lane has NTL 16-byte loads in flight instead of one (small-k
+			// problems are bound by exactly this read-modify-write of C).
+			if constexpr ( !CPLX )
+			{
+				#pragma unroll
+				for ( int i = 0; i < MT; ++i )
+				{
+					const int pl = wp0 + i * 8 + gq;
+					if ( pl >= p_lim ) continue;
+					double2* __restrict__ dp = reinterpret_cast<double2*>( g.D + ( p0 + pl ) * g.ldd + q0 + wq0 + 2 * t4 );
+					double2 o[NTL];
+					if ( !g.beta_is_zero )
+					{
+						#pragma unroll
+						for ( int j = 0; j < NTL; ++j ) o[j] = __ldcs( dp + j * 4 );
+					}
+					#pragma unroll
+					for ( int j = 0; j < NTL; ++j )
+					{
+						double r0 = g.alpha * acc[0][i][j][0];
+						double r1 = g.alpha * acc[0][i][j][1];
+						if ( !g.beta_is_zero ) { r0 = fma( g.beta, o[j].x, r0 ); r1 = fma( g.beta, o[j].y, r1 ); }
+						__stcs( dp + j * 4, make_double2( r0, r1 ) );
+					}
+				}
+			}
+			continue;
+		}
 		#pragma unroll
 		for ( int i = 0; i < MT; ++i )
 		{

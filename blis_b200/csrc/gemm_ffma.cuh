@@ -22,7 +22,8 @@ __device__ __forceinline__ void load_tile_t( uint32_t sbase, const T* __restrict
 	constexpr int PER   = (int)sizeof(T) / CPB;          // 1 (float, float2) or 2 (double2)
 	constexpr int TOTAL = LS * LC;
 	constexpr int ITERS = ( TOTAL + NT - 1 ) / NT;
-	#pragma unroll
+	constexpr int UNROLL = ITERS <= 8 ? ITERS : 4;
+	#pragma unroll UNROLL
 	for ( int i = 0; i < ITERS; ++i )
 	{
 		const int id = tid + i * NT;

@@ -1,10 +1,19 @@
-"""Sweep of dgemm/zgemm kernel configurations: quick correctness + perf (dev tool)."""
-import json, os, sys, time
+"""Sweep of gemm kernel configurations: quick correctness + perf (dev tool).
+
+usage: python -m tools.gpu_probe2 <s|d|c|z> cfg[,cfg...] shape[,shape...]   shape = n or nxk (m=n)
+"""
+import json
+import os
+import sys
+
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 from blis_b200 import api
+
 dev = torch.device("cuda:0")
-OUT = {}
+DT = {"s": torch.float32, "d": torch.float64, "c": torch.complex64, "z": torch.complex128}
+FN = {"s": api.bli_sgemm, "d": api.bli_dgemm, "c": api.bli_cgemm, "z": api.bli_zgemm}
+
 
 def timeit(fn, reps=3):
     fn(); torch.cuda.synchronize(); best = 1e30
@@ -13,11 +22,13 @@ def timeit(fn, reps=3):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1) * 1e-3)
     return best
 
+
 def rnd(m, n, dt):
     if dt.is_complex:
         r = torch.float64 if dt == torch.complex128 else torch.float32
         return torch.view_as_complex(torch.empty(n, m, 2, dtype=r, device=dev).uniform_(-1, 1)).t()
     return torch.empty(n, m, dtype=dt, device=dev).uniform_(-1, 1).t()
+
 
 def check(dt, fn):
     worst = 0.0
@@ -31,27 +42,30 @@ def check(dt, fn):
                 worst = max(worst, float((c - ref).abs().max()))
     return worst
 
+
 def perf(dt, fn, n, k=None):
     k = k or n
     a, b, c = rnd(n, k, dt), rnd(k, n, dt), rnd(n, n, dt)
     t = timeit(lambda: fn(0, 0, n, n, k, 2.0, a, 1, n, b, 1, k, 1.2, c, 1, n))
     return (4 if dt.is_complex else 1) * 2.0 * n * n * k / t / 1e12
 
-for cfg in (0, 3, 4, 5, 6):
-    api.set_option("dgemm_cfg", cfg)
-    r = {"max_abs_err": check(torch.float64, api.bli_dgemm)}
-    for n in (2048, 4096, 8192, 16384):
-        r[f"n{n}"] = perf(torch.float64, api.bli_dgemm, n)
-    r["k64_16384"] = perf(torch.float64, api.bli_dgemm, 16384, 64)
-    r["k512_8192"] = perf(torch.float64, api.bli_dgemm, 8192, 512)
-    OUT[f"dgemm_cfg{cfg}"] = r
-    print(cfg, json.dumps(r), flush=True)
-for cfg in (0, 1):
-    api.set_option("zgemm_cfg", cfg)
-    r = {"max_abs_err": check(torch.complex128, api.bli_zgemm)}
-    for n in (4096, 8192):
-        r[f"n{n}"] = perf(torch.complex128, api.bli_zgemm, n)
-    OUT[f"zgemm_cfg{cfg}"] = r
-    print("z", cfg, json.dumps(r), flush=True)
-os.makedirs("gpurun_out", exist_ok=True)
-json.dump(OUT, open("gpurun_out/probe2.json", "w"), indent=1)
+
+def main():
+    ch = sys.argv[1]
+    cfgs = [int(x) for x in sys.argv[2].split(",")]
+    shapes = [tuple(int(v) for v in s.split("x")) for s in sys.argv[3].split(",")]
+    out = {}
+    for cfg in cfgs:
+        api.set_option(ch + "gemm_cfg", cfg)
+        r = {"max_abs_err": check(DT[ch], FN[ch])}
+        for sh in shapes:
+            n, k = (sh[0], sh[0]) if len(sh) == 1 else sh
+            r[f"{n}x{k}"] = round(perf(DT[ch], FN[ch], n, k), 2)
+        out[f"{ch}gemm_cfg{cfg}"] = r
+        print(ch, cfg, json.dumps(r), flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open(f"gpurun_out/probe2_{ch}.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
