@@ -185,7 +185,22 @@ err_t bli_plugin_register_b200( void )
 	return BLIS_SUCCESS;
 }
 
-#ifdef BLIS_B200_AUTO_REGISTER
-/* LD_PRELOAD / link-time demo: register as soon as the library is loaded. */
-__attribute__((constructor)) static void bli_b200_ctor( void ) { bli_plugin_register_b200(); }
-#endif
+/* LD_PRELOAD route: with BLIS_B200_PLUGIN=1 in the environment the plugin
+   registers itself as soon as the library is loaded, so an UNMODIFIED binary
+   linked against libblis (e.g. the reference's own test_libblis.x) runs its
+   gemm/trsm on the B200.  BLIS_B200_VERBOSE=1 reports the number of CUDA
+   kernels the engine launched when the process exits. */
+#include <stdlib.h>
+unsigned long long b200_launch_count( void );
+static void bli_b200_report( void )
+{
+	fprintf( stderr, "libblis (b200): %llu CUDA kernels launched by the engine\n", b200_launch_count() );
+}
+__attribute__((constructor)) static void bli_b200_ctor( void )
+{
+	const char* e = getenv( "BLIS_B200_PLUGIN" );
+	if ( e == NULL || e[0] != '1' ) return;
+	bli_plugin_register_b200();
+	const char* v = getenv( "BLIS_B200_VERBOSE" );
+	if ( v != NULL && v[0] == '1' ) atexit( bli_b200_report );
+}

@@ -1,0 +1,73 @@
+"""Runs in a FRESH process: loads the BLIS-side glue (which pulls in the real reference
+libblis and the engine), registers the plugin, then calls the REFERENCE's own API entry points
+(dgemm_, cblas_dgemm, bli_?gemm, dtrsm_, bli_?trsm) on host arrays and reports errors vs numpy
+plus the number of engine kernels launched.  Printed as one JSON line."""
+import ctypes as C
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "tests"))
+import gen  # noqa: E402
+
+glue = C.CDLL(str(ROOT / "oracle" / "_ref" / "libblis_b200_glue.so"), mode=C.RTLD_GLOBAL)   # first: interposes bli_trsm_ex
+from refblis import RefBlis, LEFT, RIGHT, LOWER, UPPER, TRANSPOSE, CONJ_TRANSPOSE, NONUNIT_DIAG, UNIT_DIAG  # noqa: E402
+ref = RefBlis(threads=4)
+glue.bli_plugin_register_b200.restype = C.c_int
+assert glue.bli_plugin_register_b200() == -1
+eng = C.CDLL(str(ROOT / "blis_b200" / "libblis_b200.so"))
+eng.b200_launch_count.restype = C.c_ulonglong
+L = ref.lib
+out = {"arch": ref.arch()}
+n0 = eng.b200_launch_count()
+
+# --- Fortran BLAS: dgemm_ (column-major, 32-bit ints)
+m, n, k = 300, 200, 150
+a = gen.matrix("d", k, m, 1, "frac"); b = gen.matrix("d", k, n, 2, "frac"); c = gen.matrix("d", m, n, 3, "frac", pad=5)
+want = 1.2 * c + 2.0 * (a.T @ b)
+i32 = lambda v: C.byref(C.c_int(v))  # noqa: E731
+f64 = lambda v: C.byref(C.c_double(v))  # noqa: E731
+L.dgemm_(C.c_char_p(b"T"), C.c_char_p(b"N"), i32(m), i32(n), i32(k), f64(2.0), a.ctypes.data_as(C.c_void_p), i32(a.strides[1] // 8),
+         b.ctypes.data_as(C.c_void_p), i32(b.strides[1] // 8), f64(1.2), c.ctypes.data_as(C.c_void_p), i32(c.strides[1] // 8))
+out["dgemm_"] = float(np.abs(c - want).max())
+out["launches_after_dgemm_"] = int(eng.b200_launch_count() - n0)
+
+# --- CBLAS row-major: cblas_dgemm(order=101 RowMajor, NoTrans=111, Trans=112, ...)
+a = gen.matrix("d", m, k, 4, "frac", "r"); b = gen.matrix("d", n, k, 5, "frac", "r"); c = gen.matrix("d", m, n, 6, "frac", "r")
+want = 0.5 * c - 1.0 * (a @ b.T)
+L.cblas_dgemm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                          C.c_double, C.c_void_p, C.c_int]
+L.cblas_dgemm(101, 111, 112, m, n, k, -1.0, a.ctypes.data, a.strides[0] // 8, b.ctypes.data, b.strides[0] // 8, 0.5, c.ctypes.data, c.strides[0] // 8)
+out["cblas_dgemm"] = float(np.abs(c - want).max())
+
+# --- typed BLIS API, all four datatypes (bli_?gemm)
+for ch in "sdcz":
+    a = gen.matrix(ch, m, k, 7, "frac"); b = gen.matrix(ch, k, n, 8, "frac", "r"); c = gen.matrix(ch, m, n, 9, "frac", "g")
+    al, be = ((2.0 + 0.2j, 1.2 + 0.5j) if ch in "cz" else (2.0, 1.2))
+    hi = np.complex128 if ch in "cz" else np.float64
+    want = be * c.astype(hi) + al * (a.astype(hi) @ b.astype(hi))
+    ref.gemm(0, 0, al, a, b, be, c)
+    out[f"bli_{ch}gemm"] = float(np.abs(c - want).max())
+
+# --- trsm through dtrsm_ and bli_?trsm (bli_trsm_ex interposed by the glue)
+before = eng.b200_launch_count()
+ma, nb = 257, 130
+a = gen.triangular("d", ma, 10, "frac"); gen.poison_unstored(a, True); b = gen.matrix("d", ma, nb, 11, "frac")
+b0 = b.copy(order="K")
+L.dtrsm_(C.c_char_p(b"L"), C.c_char_p(b"L"), C.c_char_p(b"N"), C.c_char_p(b"N"), i32(ma), i32(nb), f64(2.0),
+         a.ctypes.data_as(C.c_void_p), i32(a.strides[1] // 8), b.ctypes.data_as(C.c_void_p), i32(b.strides[1] // 8))
+out["dtrsm_"] = float(np.abs(np.tril(np.nan_to_num(a)) @ b - 2.0 * b0).max())
+for ch in "sdcz":
+    a = gen.triangular(ch, nb, 12, "frac", "r"); b = gen.matrix(ch, ma, nb, 13, "frac")
+    b0 = b.copy(order="K")
+    al = (2.0 + 0.3j) if ch in "cz" else 2.0
+    ref.trsm(RIGHT, UPPER, CONJ_TRANSPOSE if ch in "cz" else TRANSPOSE, NONUNIT_DIAG, al, a, b)
+    hi = np.complex128 if ch in "cz" else np.float64
+    t = np.triu(a).astype(hi).conj().T
+    out[f"bli_{ch}trsm"] = float(np.abs(b.astype(hi) @ t - al * b0.astype(hi)).max())
+out["launches_trsm"] = int(eng.b200_launch_count() - before)
+out["launches_total"] = int(eng.b200_launch_count() - n0)
+print(json.dumps(out))
