@@ -17,6 +17,7 @@
 #include "../../include/blis_b200.h"
 #include <algorithm>
 #include <utility>
+#include <vector>
 
 namespace b200 {
 
@@ -410,25 +411,76 @@ static int gemm_front( int transa, int transb, int64_t m, int64_t n, int64_t k,
 		rc = stage_to_device( da, a, m, k, rs_a, cs_a, ES, st );
 		a = (const T*)da; rs_a = 1; cs_a = m;
 	}
+	// Host C of a large problem: pipeline over column blocks of C (and of B when it is a host
+	// operand) so that H2D of block j+1 and D2H of block j-1 run under the kernels of block j.
+	const bool pipelined = c_host && need_ab && n >= 1024 && (double)m * (double)n * (double)k >= 2e9;
+	const T* b_host = nullptr; int64_t rs_bh = 0, cs_bh = 0;      // set when B moves block-wise
 	if ( rc == kSuccess && need_ab && classify( b ) != MemKind::Device )
 	{
 		if ( dev_alloc( &db, (size_t)k * n * ES, st ) != kSuccess ) rc = kFailure;
+		else if ( pipelined ) { b_host = b; rs_bh = rs_b; cs_bh = cs_b; }
 		else rc = stage_to_device( db, b, k, n, rs_b, cs_b, ES, st );
 		b = (const T*)db; rs_b = 1; cs_b = k;
 	}
 	T* cdev = c; int64_t rs_cd = rs_c, cs_cd = cs_c;
-	if ( rc == kSuccess && c_host )
+	if ( rc == kSuccess && c_host && !pipelined )
 	{
 		if ( dev_alloc( &dc, (size_t)m * n * ES, st ) != kSuccess ) rc = kFailure;
 		else if ( !Scalar<T>::is_zero( be ) ) rc = stage_to_device( dc, c, m, n, rs_c, cs_c, ES, st );
 		cdev = (T*)dc; rs_cd = 1; cs_cd = m;
 	}
-	if ( rc == kSuccess )
+	if ( rc == kSuccess && !pipelined )
 		rc = gemm_dev<T>( conja, conjb, m, n, k, al, a, rs_a, cs_a, b, rs_b, cs_b, be, cdev, rs_cd, cs_cd, st );
-	if ( rc == kSuccess && c_host )
+	if ( rc == kSuccess && c_host && !pipelined )
 	{
 		rc = stage_to_host( c, rs_c, cs_c, dc, m, n, ES, st );
 		if ( rc == kSuccess && cudaStreamSynchronize( st ) != cudaSuccess ) rc = fail( "b200_gemm: stream sync failed: %s", cudaGetErrorString( cudaGetLastError() ) );
+	}
+	if ( rc == kSuccess && pipelined )
+	{
+		// A is needed in full by every block and was staged above; B and C move block-wise.
+		Context& cx = ctx();
+		cudaStream_t s_in = cx.copy_stream, s_out = cx.d2h_stream;
+		const int64_t nb = std::max<int64_t>( 512, ( ( n + 7 ) / 8 + 127 ) / 128 * 128 );
+		const int nblk = (int)( ( n + nb - 1 ) / nb );
+		std::vector<cudaEvent_t> ev_in( nblk ), ev_done( nblk );
+		for ( int j = 0; j < nblk; ++j )
+		{
+			cudaEventCreateWithFlags( &ev_in[j], cudaEventDisableTiming );
+			cudaEventCreateWithFlags( &ev_done[j], cudaEventDisableTiming );
+		}
+		cudaEvent_t ev_alloc; cudaEventCreateWithFlags( &ev_alloc, cudaEventDisableTiming );
+		if ( dev_alloc( &dc, (size_t)m * n * ES, st ) != kSuccess ) rc = kFailure;
+		cudaEventRecord( ev_alloc, st );                 // dc usable on the other streams after this
+		cudaStreamWaitEvent( s_in, ev_alloc, 0 );
+		cudaStreamWaitEvent( s_out, ev_alloc, 0 );
+		const bool load_c = !Scalar<T>::is_zero( be );
+		auto h2d_block = [&]( int j ) -> int
+		{
+			const int64_t j0 = (int64_t)j * nb, w = std::min( nb, n - j0 );
+			int r = kSuccess;
+			if ( b_host ) r = stage_to_device( (T*)db + j0 * k, b_host + j0 * cs_bh, k, w, rs_bh, cs_bh, ES, s_in );
+			if ( r == kSuccess && load_c ) r = stage_to_device( (T*)dc + j0 * m, c + j0 * cs_c, m, w, rs_c, cs_c, ES, s_in );
+			cudaEventRecord( ev_in[j], s_in );
+			return r;
+		};
+		if ( rc == kSuccess ) rc = h2d_block( 0 );
+		for ( int j = 0; j < nblk && rc == kSuccess; ++j )
+		{
+			const int64_t j0 = (int64_t)j * nb, w = std::min( nb, n - j0 );
+			cudaStreamWaitEvent( st, ev_in[j], 0 );
+			rc = gemm_dev<T>( conja, conjb, m, w, k, al, a, rs_a, cs_a, b + j0 * cs_b, rs_b, cs_b, be,
+			                  (T*)dc + j0 * m, 1, m, st );
+			cudaEventRecord( ev_done[j], st );
+			if ( rc == kSuccess && j + 1 < nblk ) rc = h2d_block( j + 1 );
+			cudaStreamWaitEvent( s_out, ev_done[j], 0 );
+			if ( rc == kSuccess ) rc = stage_to_host( c + j0 * cs_c, rs_c, cs_c, (T*)dc + j0 * m, m, w, ES, s_out );
+		}
+		if ( cudaStreamSynchronize( s_out ) != cudaSuccess || cudaStreamSynchronize( s_in ) != cudaSuccess ||
+		     cudaStreamSynchronize( st ) != cudaSuccess )
+			rc = fail( "b200_gemm: stream sync failed: %s", cudaGetErrorString( cudaGetLastError() ) );
+		for ( int j = 0; j < nblk; ++j ) { cudaEventDestroy( ev_in[j] ); cudaEventDestroy( ev_done[j] ); }
+		cudaEventDestroy( ev_alloc );
 	}
 	dev_free( da, st ); dev_free( db, st ); dev_free( dc, st );
 	return rc;

@@ -40,6 +40,7 @@ static int do_init( int device )
 	c.num_sms = prop.multiProcessorCount;
 	B200_CUDA( cudaStreamCreateWithFlags( &c.stream, cudaStreamNonBlocking ) );
 	B200_CUDA( cudaStreamCreateWithFlags( &c.copy_stream, cudaStreamNonBlocking ) );
+	B200_CUDA( cudaStreamCreateWithFlags( &c.d2h_stream, cudaStreamNonBlocking ) );
 	// keep freed workspace cached in the pool instead of returning it to the OS
 	cudaMemPool_t pool;
 	if ( cudaDeviceGetDefaultMemPool( &pool, device ) == cudaSuccess )
@@ -209,8 +210,8 @@ extern "C" void b200_finalize( void )
 		if ( c.stage[i] ) { cudaFreeHost( c.stage[i] ); c.stage[i] = nullptr; }
 		if ( c.stage_free[i] ) { cudaEventDestroy( c.stage_free[i] ); c.stage_free[i] = nullptr; }
 	}
-	cudaStreamDestroy( c.stream ); cudaStreamDestroy( c.copy_stream );
-	c.stream = c.copy_stream = nullptr;
+	cudaStreamDestroy( c.stream ); cudaStreamDestroy( c.copy_stream ); cudaStreamDestroy( c.d2h_stream );
+	c.stream = c.copy_stream = c.d2h_stream = nullptr;
 	c.ready = false;
 }
 

@@ -35,7 +35,8 @@ struct Context
 	int          device  = -1;
 	int          num_sms = kNumSMs;
 	cudaStream_t stream  = nullptr;       // engine-owned default stream
-	cudaStream_t copy_stream = nullptr;   // host staging
+	cudaStream_t copy_stream = nullptr;   // host->device staging of pipelined calls
+	cudaStream_t d2h_stream  = nullptr;   // device->host of pipelined calls
 	// pinned staging ring for pageable host operands
 	static constexpr int    kStageBufs  = 2;
 	static constexpr size_t kStageBytes = (size_t)64 << 20;

@@ -207,3 +207,19 @@ def test_gemm_full_size_testsuite_residual(engine, ch, n):
     f(0, 0, m2, m2, n, 2.0, a, 1, n, b, 1, n, 0.0, c2, 1, m2)
     torch.cuda.synchronize()
     assert bool(torch.equal(c1, c2)), "x + x != 2x: gemm is not deterministic/linear"
+
+
+@pytest.mark.parametrize("pin", [False, True])
+def test_gemm_host_operands_pipelined_blocks(engine, pin):
+    """Large host problem: the engine pipelines column blocks of B/C (H2D, kernels, D2H on three
+    streams).  Ragged last block, beta != 0 and beta == 0, pageable and pinned memory."""
+    m, n, k = 1000, 1100 + 37, 2000
+    a = gen.matrix("d", m, k, 71, "frac"); b = gen.matrix("d", k, n, 72, "frac", pad=3)
+    for beta in (1.2, 0.0):
+        c = gen.matrix("d", m, n, 73, "frac", pad=1)
+        want = beta * c + 2.0 * (a @ b)
+        ta_, tb_, tc_ = (to_torch(x, "cpu", pin=pin) for x in (a, b, c))
+        if beta == 0.0:
+            tc_.fill_(float("nan"))
+        engine.bli_dgemm(0, 0, m, n, k, 2.0, ta_, *estr(a), tb_, *estr(b), beta, tc_, *estr(c))
+        assert rel_err(to_numpy(tc_), want) <= TOL["d"], (pin, beta)
