@@ -23,7 +23,7 @@ BLIS_SUCCESS, BLIS_FAILURE = -1, -2
 EXPORTS = [
     "b200_init", "b200_finalize", "b200_last_error", "b200_device_count", "b200_info",
     "b200_set_stream", "b200_get_stream", "b200_sync", "b200_malloc_pinned", "b200_free_pinned",
-    "b200_gemm", "b200_sgemm", "b200_dgemm", "b200_cgemm", "b200_zgemm",
+    "b200_gemm", "b200_gemm_kpanels", "b200_sgemm", "b200_dgemm", "b200_cgemm", "b200_zgemm",
     "b200_trsm", "b200_strsm", "b200_dtrsm", "b200_ctrsm", "b200_ztrsm",
     "b200_blksz", "b200_measure_peak", "b200_launch_count", "b200_set_option",
 ]
@@ -58,6 +58,8 @@ def load() -> C.CDLL:
     lib.b200_gemm.argtypes = [ci, ci, ci] + gemm_tail; lib.b200_gemm.restype = ci
     for ch in "sdcz":
         f = getattr(lib, f"b200_{ch}gemm"); f.argtypes = [ci, ci] + gemm_tail; f.restype = ci
+    lib.b200_gemm_kpanels.argtypes = [ci, ci, ci, i64, i64, i64, ci, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
+    lib.b200_gemm_kpanels.restype = ci
     trsm_tail = [i64, i64, vp, vp, i64, i64, vp, i64, i64]
     lib.b200_trsm.argtypes = [ci, ci, ci, ci, ci] + trsm_tail; lib.b200_trsm.restype = ci
     for ch in "sdcz":

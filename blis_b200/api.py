@@ -70,6 +70,21 @@ def _typed_gemm(dtype):
     return f
 
 
+def bli_gemm_kpanels(dtype, transa, transb, m, n, k, alpha, a_panels, rs_a, cs_a, b_panels, rs_b, cs_b, beta, c, rs_c, cs_c):
+    """C := beta*C + alpha * sum_s op(A_s) op(B_s) in one launch (the pc loop of
+    frame/3/gemm/bli_gemm_blk_var3.c folded into the kernel); d and z, device operands."""
+    lib = _lib.load()
+    _bind_stream(c)
+    np_ = len(a_panels)
+    assert np_ == len(b_panels)
+    al, be = _scalar_buf(dtype, alpha), _scalar_buf(dtype, beta)
+    pa = (C.c_void_p * np_)(*[_ptr(x) for x in a_panels])
+    pb = (C.c_void_p * np_)(*[_ptr(x) for x in b_panels])
+    rc = lib.b200_gemm_kpanels(_DT[dtype], int(transa), int(transb), m, n, k, np_, C.addressof(al), pa, rs_a, cs_a,
+                               pb, rs_b, cs_b, C.addressof(be), _ptr(c), rs_c, cs_c)
+    check(rc, "bli_gemm_kpanels")
+
+
 def _typed_trsm(dtype):
     def f(side, uploa, transa, diaga, m, n, alpha, a, rs_a, cs_a, b, rs_b, cs_b):
         lib = _lib.load()

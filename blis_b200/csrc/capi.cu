@@ -251,6 +251,7 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 		return (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
 	};
 	int cfg = c.dgemm_cfg;
+	if ( g.nseg > 1 && ( cfg < 4 ) ) cfg = -1;          // k-panel accumulation needs a warp-specialised kernel
 	if ( cfg < 0 )
 	{
 		// auto: the cooperative 128x128 tile unless it cannot fill the SMs once; then 128x64 tiles, two CTAs per SM
@@ -279,13 +280,14 @@ int launch_gemm_kernel<double2>( GemmArgs<double2>& g, bool xk, bool yk, bool al
 	Context& c = ctx();
 	g.tiles_p = (int)( ( g.P + 63 ) / 64 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
 	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
-	if ( c.zgemm_cfg == 1 ) return launch_dmma_ws<double2, 64, 128, 8, 2, 4, 5>( g, xk, yk, al, grid, st );
+	if ( c.zgemm_cfg == 1 || g.nseg > 1 ) return launch_dmma_ws<double2, 64, 128, 8, 2, 4, 5>( g, xk, yk, al, grid, st );
 	return launch_dmma<double2, 64, 128, 8, 2, 4, 4>( g, xk, yk, al, grid, st );
 }
 template <>
 int launch_gemm_kernel<float>( GemmArgs<float>& g, bool xk, bool yk, bool al, cudaStream_t st )
 {
 	Context& c = ctx();
+	if ( g.nseg > 1 ) return fail( "b200_gemm_kpanels: only d and z are supported" );
 	g.tiles_p = (int)( ( g.P + 127 ) / 128 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
 	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
 	if ( c.sgemm_cfg == 1 ) return launch_ffma_ws<float, 128, 128, 16, 8, 8, 5>( g, xk, yk, al, grid, st );
@@ -296,6 +298,7 @@ template <>
 int launch_gemm_kernel<float2>( GemmArgs<float2>& g, bool xk, bool yk, bool al, cudaStream_t st )
 {
 	Context& c = ctx();
+	if ( g.nseg > 1 ) return fail( "b200_gemm_kpanels: only d and z are supported" );
 	g.tiles_p = (int)( ( g.P + 63 ) / 64 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
 	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
 	if ( c.cgemm_cfg == 1 ) return launch_ffma_ws<float2, 64, 128, 16, 4, 8, 5>( g, xk, yk, al, grid, st );
@@ -309,7 +312,8 @@ template <typename T>
 static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T alpha,
                      const T* a, int64_t rs_a, int64_t cs_a,
                      const T* b, int64_t rs_b, int64_t cs_b,
-                     T beta, T* c, int64_t rs_c, int64_t cs_c, cudaStream_t st )
+                     T beta, T* c, int64_t rs_c, int64_t cs_c, cudaStream_t st,
+                     int nseg = 1, const T* const* a_more = nullptr, const T* const* b_more = nullptr )
 {
 	if ( m <= 0 || n <= 0 ) return kSuccess;
 	// bli_l3_return_early_if_trivial: alpha == 0 or k == 0  ->  C := beta*C
@@ -334,8 +338,10 @@ static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T 
 
 	GemmArgs<T> g;
 	int64_t xs_p, xs_k, ys_k, ys_q;
+	bool swapped = false;                              // column-stored C: X panels come from B, Y panels from A
 	if ( rs_cd == 1 && !( cs_cd == 1 && m > 1 ) )
 	{
+		swapped = true;
 		// column-stored C: D = C^T,  X = B^T (P = n),  Y = A^T (Q = m)
 		g.P = n; g.Q = m; g.ldd = ( n == 1 ? m : cs_cd );
 		g.X = b; xs_p = cs_b; xs_k = rs_b; g.conjx = conjb;
@@ -350,12 +356,19 @@ static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T 
 	}
 	g.D = cd; g.K = k; g.alpha = alpha; g.beta = beta;
 	g.beta_is_zero = Scalar<T>::is_zero( beta ) ? 1 : 0;
+	g.nseg = nseg;
+	for ( int sgm = 1; sgm < nseg; ++sgm )
+	{
+		g.Xseg[sgm - 1] = swapped ? b_more[sgm - 1] : a_more[sgm - 1];
+		g.Yseg[sgm - 1] = swapped ? a_more[sgm - 1] : b_more[sgm - 1];
+	}
 
 	// -- X: k-contiguous, p-contiguous, or packed
 	bool xk = false, yk = false;
 	auto misaligned = [&]( const T* p ) { return Elem<T>::cplx && ( (uintptr_t)p % ES ) != 0 && ES == 8; };
 	if      ( !misaligned( g.X ) && ( xs_k == 1 || k == 1 ) && ( xs_p >= k || g.P == 1 ) && xs_k >= 0 ) { xk = true;  g.ldx = ( g.P == 1 ? k : xs_p ); }
 	else if ( !misaligned( g.X ) && ( xs_p == 1 || g.P == 1 ) && ( xs_k >= g.P || k == 1 ) )            { xk = false; g.ldx = ( k == 1 ? g.P : xs_k ); }
+	else if ( nseg > 1 ) rc = fail( "b200_gemm_kpanels: panels must be row- or column-stored" );
 	else if ( rc == kSuccess )
 	{
 		if ( dev_alloc( &tmp_x, (size_t)g.P * k * ES, st ) != kSuccess ) rc = kFailure;
@@ -363,6 +376,7 @@ static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T 
 	}
 	if      ( !misaligned( g.Y ) && ( ys_k == 1 || k == 1 ) && ( ys_q >= k || g.Q == 1 ) && ys_k >= 0 ) { yk = true;  g.ldy = ( g.Q == 1 ? k : ys_q ); }
 	else if ( !misaligned( g.Y ) && ( ys_q == 1 || g.Q == 1 ) && ( ys_k >= g.Q || k == 1 ) )            { yk = false; g.ldy = ( k == 1 ? g.Q : ys_k ); }
+	else if ( nseg > 1 ) rc = fail( "b200_gemm_kpanels: panels must be row- or column-stored" );
 	else if ( rc == kSuccess )
 	{
 		if ( dev_alloc( &tmp_y, (size_t)g.Q * k * ES, st ) != kSuccess ) rc = kFailure;
@@ -371,8 +385,10 @@ static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T 
 
 	if ( rc == kSuccess )
 	{
-		const bool al = ( (uintptr_t)g.X % 16 == 0 ) && ( (uintptr_t)g.Y % 16 == 0 ) &&
-		                ( ( g.ldx * ES ) % 16 == 0 ) && ( ( g.ldy * ES ) % 16 == 0 );
+		bool al = ( (uintptr_t)g.X % 16 == 0 ) && ( (uintptr_t)g.Y % 16 == 0 ) &&
+		          ( ( g.ldx * ES ) % 16 == 0 ) && ( ( g.ldy * ES ) % 16 == 0 );
+		for ( int sgm = 1; sgm < nseg; ++sgm )
+			al = al && ( (uintptr_t)g.Xseg[sgm - 1] % 16 == 0 ) && ( (uintptr_t)g.Yseg[sgm - 1] % 16 == 0 );
 		g.d_vec_ok = ( (uintptr_t)g.D % 16 == 0 ) && ( ( g.ldd * ES ) % 16 == 0 );
 		rc = launch_gemm_kernel<T>( g, xk, yk, al, st );
 	}
@@ -679,6 +695,42 @@ extern "C" b200_err_t b200_trsm( int dt, int side, int uploa, int transa, int di
 		case B200_DCOMPLEX: return trsm_front<double2>( side, uploa, transa, diaga, m, n, (const double2*)alpha, (const double2*)a, rs_a, cs_a, (double2*)b, rs_b, cs_b );
 	}
 	return fail( "b200_trsm: unsupported datatype %d", dt );
+}
+
+// k-panel accumulation: C := beta*C + alpha * sum_{s<npanels} op(A_s) * op(B_s), every panel k wide, all
+// A panels (resp. B panels) with the same strides.  Device-resident operands, d and z only.
+template <typename T>
+static int kpanels_front( int transa, int transb, int64_t m, int64_t n, int64_t k, int npanels, const T* alpha,
+                          const T* const* a, int64_t rs_a, int64_t cs_a, const T* const* b, int64_t rs_b, int64_t cs_b,
+                          const T* beta, T* c, int64_t rs_c, int64_t cs_c )
+{
+	if ( ensure_init() != kSuccess ) return kFailure;
+	if ( npanels < 1 || npanels > 8 ) return fail( "b200_gemm_kpanels: 1..8 panels per call" );
+	if ( m < 0 || n < 0 || k < 0 ) return fail( "b200_gemm_kpanels: negative dimension" );
+	if ( m == 0 || n == 0 ) return kSuccess;
+	if ( transa & B200_TRANSPOSE ) std::swap( rs_a, cs_a );
+	if ( transb & B200_TRANSPOSE ) std::swap( rs_b, cs_b );
+	const bool conja = Elem<T>::cplx && ( transa & B200_CONJ_NO_TRANSPOSE );
+	const bool conjb = Elem<T>::cplx && ( transb & B200_CONJ_NO_TRANSPOSE );
+	for ( int sgm = 0; sgm < npanels; ++sgm )
+		if ( classify( a[sgm] ) != MemKind::Device || classify( b[sgm] ) != MemKind::Device )
+			return fail( "b200_gemm_kpanels: panels must be device resident" );
+	if ( classify( c ) != MemKind::Device ) return fail( "b200_gemm_kpanels: C must be device resident" );
+	return gemm_dev<T>( conja, conjb, m, n, k, *alpha, a[0], rs_a, cs_a, b[0], rs_b, cs_b, *beta, c, rs_c, cs_c,
+	                    cur_stream(), npanels, a + 1, b + 1 );
+}
+
+extern "C" b200_err_t b200_gemm_kpanels( int dt, int transa, int transb, b200_dim_t m, b200_dim_t n, b200_dim_t k, int npanels,
+	const void* alpha, const void* const* a, b200_inc_t rs_a, b200_inc_t cs_a,
+	const void* const* b, b200_inc_t rs_b, b200_inc_t cs_b, const void* beta, void* c, b200_inc_t rs_c, b200_inc_t cs_c )
+{
+	if ( dt == B200_DOUBLE )
+		return kpanels_front<double>( transa, transb, m, n, k, npanels, (const double*)alpha, (const double* const*)a, rs_a, cs_a,
+		                              (const double* const*)b, rs_b, cs_b, (const double*)beta, (double*)c, rs_c, cs_c );
+	if ( dt == B200_DCOMPLEX )
+		return kpanels_front<double2>( transa, transb, m, n, k, npanels, (const double2*)alpha, (const double2* const*)a, rs_a, cs_a,
+		                               (const double2* const*)b, rs_b, cs_b, (const double2*)beta, (double2*)c, rs_c, cs_c );
+	return fail( "b200_gemm_kpanels: only d and z are supported" );
 }
 
 extern "C" b200_dim_t b200_blksz( int dt, int bs )

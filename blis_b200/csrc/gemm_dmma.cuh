@@ -40,6 +40,12 @@ struct GemmArgs
 	int      tiles_p, tiles_q;
 	int      beta_is_zero;
 	int      d_vec_ok;          // D rows 16B aligned -> vector epilogue
+	// k-panel accumulation (the pc loop of bli_gemm_blk_var3 inside one launch):
+	// D = beta*D + alpha * sum_s X_s * Y_s, every panel K wide with the same strides.
+	// Panel 0 is (X, Y); panels 1..nseg-1 are (Xseg[s-1], Yseg[s-1]).  Warp-specialised kernels only.
+	int      nseg;
+	const T* Xseg[7];
+	const T* Yseg[7];
 };
 
 // Tile -> (tp,tq) with a grouped raster so that the ~148 concurrently running

@@ -99,7 +99,8 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 	}
 	__syncthreads();
 
-	const int64_t KT = ( g.K + BK - 1 ) / BK;
+	const int64_t KT_SEG = ( g.K + BK - 1 ) / BK;          // k tiles per panel
+	const int64_t KT = KT_SEG * g.nseg;                     // the consumers see one long k loop
 	const int num_tiles = g.tiles_p * g.tiles_q;
 
 	if ( tid >= Cfg::NCONS )
@@ -115,8 +116,7 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 			const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
 			const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
 			const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );
-			const T* gx = XK ? g.X + p0 * g.ldx : g.X + p0;
-			const T* gy = YK ? g.Y + q0 * g.ldy : g.Y + q0;
+			const int64_t xo = XK ? p0 * g.ldx : p0, yo = YK ? q0 * g.ldy : q0;
 			if ( !g.beta_is_zero )
 			{
 				// pull this tile of D towards L2 while the k loop runs; the epilogue reads it
@@ -131,7 +131,11 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 					}
 				}
 			}
-			for ( int64_t kt = 0; kt < KT; ++kt )
+			for ( int seg = 0; seg < g.nseg; ++seg )
+			{
+			const T* gx = ( seg == 0 ? g.X : g.Xseg[seg - 1] ) + xo;
+			const T* gy = ( seg == 0 ? g.Y : g.Yseg[seg - 1] ) + yo;
+			for ( int64_t kt = 0; kt < KT_SEG; ++kt )
 			{
 				mbar_wait( empty_bar( stage ), phase ^ 1u );
 				const int k_lim = (int)min( (int64_t)BK, g.K - kt * BK );
@@ -143,6 +147,7 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 				else                load_tile<T, BK, BQ, Cfg::PADC, Cfg::NPROD, AL>( smem_u32( ys ), gy + kt * BK * g.ldy, g.ldy, k_lim, q_lim, ptid );
 				cp_async_arrive_noinc( full_bar( stage ) );
 				if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
+			}
 			}
 		}
 		cp_async_wait<0>();

@@ -114,8 +114,9 @@ class PanelExchange:
             yield t, ab[ja, qa], bb[ib, qb]
 
 
-def summa(plan: SummaPlan, ex: PanelExchange, gemm_panel, n_steps=None):
-    """Drive the pipeline: gemm_panel(first, A_t, B_t) accumulates one k panel into C_ij."""
+def summa(plan: SummaPlan, ex: PanelExchange, gemm_panel, n_steps=None, gemm_step=None):
+    """Drive the pipeline: gemm_panel(first, A_t, B_t) accumulates one k panel into C_ij, or, when
+    gemm_step is given, gemm_step(first, [A_t...], [B_t...]) accumulates all panels of a step at once."""
     steps = plan.steps if n_steps is None else n_steps
     works = {0: ex.start(0)}
     if steps > 1:
@@ -124,9 +125,14 @@ def summa(plan: SummaPlan, ex: PanelExchange, gemm_panel, n_steps=None):
     for s in range(steps):
         for w in works.pop(s):
             w.wait()
-        for _, a_t, b_t in ex.panels(s):
-            gemm_panel(first, a_t, b_t)
+        if gemm_step is not None:
+            ps = list(ex.panels(s))
+            gemm_step(first, [p[1] for p in ps], [p[2] for p in ps])
             first = False
+        else:
+            for _, a_t, b_t in ex.panels(s):
+                gemm_panel(first, a_t, b_t)
+                first = False
         if s + 2 < steps:
             works[s + 2] = ex.start(s + 2)       # ordered after this step's kernels: its buffer is free again
 
@@ -151,7 +157,7 @@ class WeakScalingGemm:
         self.c = (torch.rand(p.n_loc, p.m_loc, dtype=torch.float64, device=device, generator=g) * 2 - 1).t()
         self.ex = PanelExchange(p, self.a_loc, self.b_loc)
         self.total_flops = 2.0 * p.M * p.N * p.K
-        self.launches_per_step = p.T
+        self.launches_per_step = p.steps
 
     def describe(self) -> str:
         p = self.plan
@@ -165,8 +171,15 @@ class WeakScalingGemm:
         self.api.bli_dgemm(0, 0, p.m_loc, p.n_loc, p.kb, self.alpha, a_t, 1, p.m_loc, b_t, 1, p.kb,
                            self.beta if first else 1.0, self.c, 1, p.m_loc)
 
+    def _step_panels(self, first, a_ts, b_ts):
+        """All L panels of a step in ONE launch (b200_gemm_kpanels): the k loop runs over L*kb."""
+        p = self.plan
+        for lo in range(0, len(a_ts), 8):
+            self.api.bli_gemm_kpanels(torch.float64, 0, 0, p.m_loc, p.n_loc, p.kb, self.alpha, a_ts[lo:lo + 8], 1, p.m_loc,
+                                      b_ts[lo:lo + 8], 1, p.kb, self.beta if (first and lo == 0) else 1.0, self.c, 1, p.m_loc)
+
     def step(self):
-        summa(self.plan, self.ex, self._panel)
+        summa(self.plan, self.ex, self._panel, gemm_step=self._step_panels)
 
 
 def trsm_column_block(rank: int, world: int, n: int, nr: int = 128):

@@ -119,6 +119,20 @@ B200_DECL_GEMM( d, double )
 B200_DECL_GEMM( c, b200_scomplex )
 B200_DECL_GEMM( z, b200_dcomplex )
 
+/* k-panel accumulation in ONE launch:
+ *   C := beta*C + alpha * sum_{s < npanels} transa(A_s) * transb(B_s)
+ * i.e. the pc loop of bli_gemm_blk_var3 (frame/3/gemm/bli_gemm_blk_var3.c:37-114: one rank-KC update
+ * per k block, beta reset to one after the first) folded into the kernel's k loop.  Every A_s has the same
+ * shape/strides (m x k after transa) and every B_s likewise (k x n); 1 <= npanels <= 8; device-resident
+ * operands; dt = d or z.  Used by the multi-GPU gemm to accumulate all-gathered k-panels (blis_b200/dist.py). */
+b200_err_t b200_gemm_kpanels( int dt, int transa, int transb,
+                      b200_dim_t m, b200_dim_t n, b200_dim_t k, int npanels,
+                      const void* alpha,
+                      const void* const* a, b200_inc_t rs_a, b200_inc_t cs_a,
+                      const void* const* b, b200_inc_t rs_b, b200_inc_t cs_b,
+                      const void* beta,
+                      void*       c, b200_inc_t rs_c, b200_inc_t cs_c );
+
 /* ---- trsm ------------------------------------------------------------------
  * Solve  transa(A) * X = alpha * B  (side = left)  or
  *        X * transa(A) = alpha * B  (side = right), overwriting B with X.

@@ -223,3 +223,23 @@ def test_gemm_host_operands_pipelined_blocks(engine, pin):
             tc_.fill_(float("nan"))
         engine.bli_dgemm(0, 0, m, n, k, 2.0, ta_, *estr(a), tb_, *estr(b), beta, tc_, *estr(c))
         assert rel_err(to_numpy(tc_), want) <= TOL["d"], (pin, beta)
+
+
+@pytest.mark.parametrize("ch", ["d", "z"])
+def test_gemm_kpanels_accumulates_like_blk_var3(engine, oracle, ch):
+    """b200_gemm_kpanels == the reference's pc loop: one rank-k update per panel with beta reset
+    to one after the first (frame/3/gemm/bli_gemm_blk_var3.c:110-112), folded into one launch."""
+    from blis_b200 import api
+    m, n, k, npan = 210, 150, 96, 5
+    al, be = ((2.0 + 0.2j, 1.2 + 0.5j) if ch == "z" else (2.0, 1.2))
+    for (oa, ob, oc) in (("c", "c", "c"), ("r", "c", "r")):
+        a_p = [gen.matrix(ch, m, k, 400 + s, "frac", oa) for s in range(npan)]
+        b_p = [gen.matrix(ch, k, n, 500 + s, "frac", ob) for s in range(npan)]
+        c = gen.matrix(ch, m, n, 600, "frac", oc)
+        want = c.copy(order="K")
+        for s in range(npan):
+            oracle.gemm(0, 0, al, a_p[s], b_p[s], be if s == 0 else 1.0, want)
+        ta = [to_torch(x) for x in a_p]; tb = [to_torch(x) for x in b_p]; tc = to_torch(c)
+        api.bli_gemm_kpanels(NP2T[np.dtype(gen.NP_DT[ch])], 0, 0, m, n, k, al, ta, *estr(a_p[0]), tb, *estr(b_p[0]), be, tc, *estr(c))
+        torch.cuda.synchronize()
+        assert rel_err(to_numpy(tc), want) <= TOL[ch], (ch, oa, ob, oc)
