@@ -186,7 +186,13 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # the panel all-gathers move ~10 GB/s per GPU: a few NCCL channels are plenty, and every channel is
+        # an SM taken from the DMMA kernel; the gemm grid leaves exactly those SMs free (reserve_sms)
+        nch = int(os.environ.get("B200_NCCL_CHANNELS", "2"))
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", str(nch))
+        os.environ.setdefault("NCCL_MIN_NCHANNELS", str(nch))
         dist.init_process_group("nccl", device_id=dev)
+        api.set_option("reserve_sms", int(os.environ.get("B200_RESERVE_SMS", str(2 * nch))))
 
     def barrier():
         if dist is not None:

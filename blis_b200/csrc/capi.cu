@@ -357,6 +357,7 @@ static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T 
 	g.D = cd; g.K = k; g.alpha = alpha; g.beta = beta;
 	g.beta_is_zero = Scalar<T>::is_zero( beta ) ? 1 : 0;
 	g.nseg = nseg;
+	g.tile_counter = ctx().dynamic_tiles ? ctx().sched_counters + 2 * ( ctx().sched_next++ % 64 ) : nullptr;
 	for ( int sgm = 1; sgm < nseg; ++sgm )
 	{
 		g.Xseg[sgm - 1] = swapped ? b_more[sgm - 1] : a_more[sgm - 1];
@@ -762,6 +763,13 @@ extern "C" b200_err_t b200_set_option( const char* key, long long value )
 	else if ( !strcmp( key, "sgemm_cfg" ) ) c.sgemm_cfg = (int)value;
 	else if ( !strcmp( key, "cgemm_cfg" ) ) c.cgemm_cfg = (int)value;
 	else if ( !strcmp( key, "grid_mult" ) ) c.grid_mult = (int)std::max<long long>( 1, value );
+	else if ( !strcmp( key, "dynamic_tiles" ) ) c.dynamic_tiles = (int)value;
+	else if ( !strcmp( key, "reserve_sms" ) )
+	{
+		// leave SMs free for concurrently running communication kernels (multi-GPU overlap)
+		cudaDeviceProp prop; int dev = 0; cudaGetDevice( &dev ); cudaGetDeviceProperties( &prop, dev );
+		c.num_sms = std::max( 1, prop.multiProcessorCount - (int)std::max<long long>( 0, value ) );
+	}
 	else return fail( "b200_set_option: unknown key %s", key );
 	return kSuccess;
 }

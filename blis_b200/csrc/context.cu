@@ -48,6 +48,8 @@ static int do_init( int device )
 		uint64_t thresh = UINT64_MAX;
 		cudaMemPoolSetAttribute( pool, cudaMemPoolAttrReleaseThreshold, &thresh );
 	}
+	B200_CUDA( cudaMalloc( (void**)&c.sched_counters, 128 * sizeof(int) ) );
+	B200_CUDA( cudaMemset( c.sched_counters, 0, 128 * sizeof(int) ) );
 	c.ready = true;
 	return kSuccess;
 }

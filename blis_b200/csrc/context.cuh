@@ -50,6 +50,9 @@ struct Context
 	int          cgemm_cfg = 1;          // warp-specialised 64x128x16
 	int          trsm_nb   = 0;           // 0 = default
 	int          grid_mult = 1;           // persistent CTAs per SM
+	int*         sched_counters = nullptr;   // 64 self-resetting {tile, done} pairs for dynamic tile scheduling
+	std::atomic<unsigned> sched_next{0};
+	int          dynamic_tiles = 1;
 	std::atomic<unsigned long long> launches{0};   // kernels launched by this engine (b200_launch_count)
 };
 

@@ -43,6 +43,7 @@ struct GemmArgs
 	// k-panel accumulation (the pc loop of bli_gemm_blk_var3 inside one launch):
 	// D = beta*D + alpha * sum_s X_s * Y_s, every panel K wide with the same strides.
 	// Panel 0 is (X, Y); panels 1..nseg-1 are (Xseg[s-1], Yseg[s-1]).  Warp-specialised kernels only.
+	int*     tile_counter;      // {next tile, finished CTAs}: dynamic tile scheduling (nullptr = static stride)
 	int      nseg;
 	const T* Xseg[7];
 	const T* Yseg[7];

@@ -62,7 +62,7 @@ struct DmmaWsCfg : DmmaCfg<T, BP, BQ, BK, WP, WQ, STAGES, XK, YK, AL>
 	static constexpr int NCONS  = WP * WQ * 32;        // consumer threads (8 warps)
 	static constexpr int NPROD  = 128;                 // one producer warpgroup
 	static constexpr int NT_ALL = NCONS + NPROD;
-	static constexpr int BAR_BYTES  = 2 * STAGES * 8;
+	static constexpr int BAR_BYTES  = 2 * STAGES * 8 + 4 * 8 + 16;   // stage ring + tile-scheduler ring (2 slots)
 	static constexpr int SMEM_BYTES = Base::STAGE_BYTES * STAGES + BAR_BYTES;
 	static_assert( NCONS == 256 || NCONS == 128, "one or two consumer warpgroups" );
 	// one consumer warpgroup: two CTAs share an SM (one CTA's epilogue overlaps the other's MMAs)
@@ -86,6 +86,12 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 	const uint32_t bar_base = smem_u32( smem_raw + (size_t)Cfg::STAGE_BYTES * STAGES );
 	auto full_bar  = [&]( int s ) { return bar_base + (uint32_t)s * 8u; };
 	auto empty_bar = [&]( int s ) { return bar_base + (uint32_t)( STAGES + s ) * 8u; };
+	// Tile scheduler: producer thread 0 draws the next output tile (dynamically from a global counter
+	// when g.tile_counter is set: CTAs that start late or share their SM simply draw fewer tiles) and
+	// publishes it to the consumers through a 2-slot ring guarded by mbarriers.
+	auto sched_full  = [&]( int s ) { return bar_base + (uint32_t)( 2 * STAGES + s ) * 8u; };
+	auto sched_empty = [&]( int s ) { return bar_base + (uint32_t)( 2 * STAGES + 2 + s ) * 8u; };
+	volatile int* const sched_tile = reinterpret_cast<volatile int*>( smem_raw + (size_t)Cfg::STAGE_BYTES * STAGES + ( 2 * STAGES + 4 ) * 8 );
 
 	const int tid = threadIdx.x;
 	if ( tid == 0 )
@@ -95,6 +101,12 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 		{
 			mbar_init( full_bar( s ),  Cfg::NPROD );      // one cp.async-completion arrival per producer thread
 			mbar_init( empty_bar( s ), WP * WQ );         // one arrival per consumer warp
+		}
+		#pragma unroll
+		for ( int s = 0; s < 2; ++s )
+		{
+			mbar_init( sched_full( s ),  1 );             // the scheduling thread
+			mbar_init( sched_empty( s ), WP * WQ );       // one arrival per consumer warp
 		}
 	}
 	__syncthreads();
@@ -109,8 +121,19 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 		setmaxnreg_dec<Cfg::REG_PROD>();
 		const int ptid = tid - Cfg::NCONS;
 		int stage = 0; uint32_t phase = 0;
-		for ( int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x )
+		for ( int it = 0; ; ++it )
 		{
+			const int slot = it & 1;
+			if ( ptid == 0 )
+			{
+				mbar_wait( sched_empty( slot ), ( ( it >> 1 ) & 1 ) ^ 1u );
+				const int t = g.tile_counter ? atomicAdd( g.tile_counter, 1 ) : (int)( blockIdx.x + (unsigned)it * gridDim.x );
+				sched_tile[slot] = t;
+				mbar_arrive( sched_full( slot ) );
+			}
+			asm volatile( "bar.sync 1, 128;\n" ::: "memory" );      // producer warpgroup only
+			const int tile = sched_tile[slot];
+			if ( tile >= num_tiles ) break;
 			int tp, tq;
 			tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
 			const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
@@ -151,6 +174,11 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 			}
 		}
 		cp_async_wait<0>();
+		if ( ptid == 0 && g.tile_counter )
+		{
+			// the last CTA to finish re-arms the counter pair for the next launch
+			if ( atomicAdd( g.tile_counter + 1, 1 ) == (int)gridDim.x - 1 ) { g.tile_counter[0] = 0; g.tile_counter[1] = 0; __threadfence(); }
+		}
 		return;
 	}
 
@@ -182,8 +210,14 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 		for ( int j = 0; j < NTL; ++j ) yf[j] = ys[j * YJ];
 	};
 
-	for ( int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x )
+	for ( int it = 0; ; ++it )
 	{
+		const int slot = it & 1;
+		mbar_wait( sched_full( slot ), ( it >> 1 ) & 1 );
+		const int tile = sched_tile[slot];
+		__syncwarp();
+		if ( lane == 0 ) mbar_arrive( sched_empty( slot ) );
+		if ( tile >= num_tiles ) break;
 		int tp, tq;
 		tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
 		const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;

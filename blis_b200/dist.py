@@ -26,6 +26,7 @@ agnostic so that they are tested on CPU with gloo (tests/test_dist_cpu.py).
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -122,9 +123,15 @@ def summa(plan: SummaPlan, ex: PanelExchange, gemm_panel, n_steps=None, gemm_ste
     if steps > 1:
         works[1] = ex.start(1)
     first = True
+    trace = [] if os.environ.get("B200_DIST_TRACE") == "1" else None
     for s in range(steps):
+        if trace is not None:
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            trace.append(e); e[0].record()
         for w in works.pop(s):
             w.wait()
+        if trace is not None:
+            trace[-1][1].record()
         if gemm_step is not None:
             ps = list(ex.panels(s))
             gemm_step(first, [p[1] for p in ps], [p[2] for p in ps])
@@ -133,8 +140,14 @@ def summa(plan: SummaPlan, ex: PanelExchange, gemm_panel, n_steps=None, gemm_ste
             for _, a_t, b_t in ex.panels(s):
                 gemm_panel(first, a_t, b_t)
                 first = False
+        if trace is not None:
+            trace[-1][2].record()
         if s + 2 < steps:
             works[s + 2] = ex.start(s + 2)       # ordered after this step's kernels: its buffer is free again
+    if trace is not None:
+        torch.cuda.synchronize()
+        print(f"[rank {plan.rank}] step (wait_ms, gemm_ms): " +
+              " ".join(f"({e[0].elapsed_time(e[1]):.1f},{e[1].elapsed_time(e[2]):.1f})" for e in trace), flush=True)
 
 
 class WeakScalingGemm:
