@@ -149,6 +149,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-peak", action="store_true", help="skip the FP64 peak microbenchmark (profiling runs)")
+    ap.add_argument("--workload", default="headline", choices=["headline", "g3"],
+                    help="g3 = BASELINE configs[4]: dgemm m=n=k=65536 2D-sharded over all ranks")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     rank = int(os.environ.get("RANK", "0"))
@@ -186,13 +188,13 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # the panel all-gathers move ~10 GB/s per GPU: a few NCCL channels are plenty, and every channel is
-        # an SM taken from the DMMA kernel; the gemm grid leaves exactly those SMs free (reserve_sms)
-        nch = int(os.environ.get("B200_NCCL_CHANNELS", "2"))
+        # the panel all-gathers move ~10 GB/s per GPU: a few NCCL channels are plenty; every channel is an SM
+        # taken from the DMMA kernel for a moment, which its dynamic tile scheduler absorbs (no SMs reserved)
+        nch = int(os.environ.get("B200_NCCL_CHANNELS", "8"))
         os.environ.setdefault("NCCL_MAX_NCHANNELS", str(nch))
         os.environ.setdefault("NCCL_MIN_NCHANNELS", str(nch))
         dist.init_process_group("nccl", device_id=dev)
-        api.set_option("reserve_sms", int(os.environ.get("B200_RESERVE_SMS", str(2 * nch))))
+        api.set_option("reserve_sms", int(os.environ.get("B200_RESERVE_SMS", "0")))
 
     def barrier():
         if dist is not None:
@@ -223,9 +225,33 @@ def main():
                 flops_per_step = 1.0 * m_t * m_t * n_t
             total_flops = flops_per_step
             parallelism = "single GPU"
+        elif args.op == "dtrsm":
+            # multi-GPU trsm: B (and X) split into column blocks by bli_thread_range_sub, A replicated,
+            # no data-path collective (the reference's jc/jr parallelism, frame/3/trsm/bli_trsm_cntl.c:446-451)
+            from blis_b200 import dist as bdist
+            m_t, n_t = 2 * n, n // 2
+            j0, j1 = bdist.trsm_column_block(rank, world, n_t)
+            g = torch.Generator(device=dev); g.manual_seed(0xB200)
+            at = torch.rand(m_t, m_t, dtype=torch.float64, device=dev, generator=g) * 2 - 1
+            at = at / float(at.abs().sum(dim=1).max()); at.diagonal().add_(2.0)
+            at = at.t()
+            bt0 = (torch.rand(j1 - j0, m_t, dtype=torch.float64, device=dev, generator=g) * 2 - 1).t()
+            bt = bt0.clone(memory_format=torch.preserve_format)
+
+            def step():
+                bt.copy_(bt0)
+                api.bli_dtrsm(0, 0xC0, 0, 0, m_t, j1 - j0, ALPHA, at, 1, m_t, bt, 1, m_t)
+            flops_per_step = 1.0 * m_t * m_t * (j1 - j0)
+            total_flops = 1.0 * m_t * m_t * n_t
+            parallelism = f"B split into {world} column blocks (bli_thread_range_sub, bf=128), A replicated; strong scaling, no collective"
         else:
             from blis_b200 import dist as bdist
-            job = bdist.WeakScalingGemm(n, world, rank, dev, alpha=ALPHA, beta=BETA)
+            kb = int(os.environ.get("B200_DIST_KB", "2048"))
+            if args.workload == "g3":
+                job = bdist.DistGemm(65536, 65536, 65536, world, rank, dev, alpha=ALPHA, beta=BETA, kb=kb)
+                workload = "dgemm m=n=k=65536 column-major fp64, 2D-sharded, alpha=2.0 beta=1.2 (BASELINE configs[4])"
+            else:
+                job = bdist.WeakScalingGemm(n, world, rank, dev, alpha=ALPHA, beta=BETA, kb=kb)
 
             def step():
                 job.step()
@@ -307,7 +333,8 @@ def main():
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "GFLOPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if (args.op == "dtrsm" or args.workload == "g3") and world > 1 else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "parallelism": parallelism,
                        "l2": "inputs (3 x 2 GiB per GPU) far exceed the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the launching stream, max over ranks"},

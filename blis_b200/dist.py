@@ -150,20 +150,18 @@ def summa(plan: SummaPlan, ex: PanelExchange, gemm_panel, n_steps=None, gemm_ste
               " ".join(f"({e[0].elapsed_time(e[1]):.1f},{e[1].elapsed_time(e[2]):.1f})" for e in trace), flush=True)
 
 
-class WeakScalingGemm:
-    """bench.py's N>1 workload: every rank owns an n x n block of C of the
-    (Pr*n) x (Pc*n) x n product; per-GPU flops equal the single-GPU workload."""
+class DistGemm:
+    """C := beta*C + alpha*A*B on a Pr x Pc grid of GPUs; every rank holds its block of C and its
+    block-cyclic k-panels of A's row panel / B's column panel (synthetic data generated in place)."""
 
-    def __init__(self, n: int, world: int, rank: int, device, alpha=2.0, beta=1.2, kb: int = 1024):
+    def __init__(self, M: int, N: int, K: int, world: int, rank: int, device, alpha=2.0, beta=1.2, kb: int = 2048):
         from . import api
         self.api = api
-        pr, pc = partition.thread_partition_2x2(world, n, n)     # grid for equal work per dimension
-        self.plan = SummaPlan(world, rank, pr * n, pc * n, n, kb)
+        self.plan = SummaPlan(world, rank, M, N, K, kb)
         p = self.plan
-        assert (p.pr, p.pc) == (pr, pc)
-        self.alpha, self.beta, self.n = alpha, beta, n
+        self.alpha, self.beta = alpha, beta
         g = torch.Generator(device=device); g.manual_seed(0xB200 + rank)
-        scale = 1.0 / n
+        scale = 1.0 / K
         na, nb = len(p.a_panels()), len(p.b_panels())
         self.a_loc = (torch.rand(na, kb, p.m_loc, dtype=torch.float64, device=device, generator=g) * 2 - 1) * scale
         self.b_loc = (torch.rand(nb, p.n_loc, kb, dtype=torch.float64, device=device, generator=g) * 2 - 1) * scale
@@ -193,6 +191,16 @@ class WeakScalingGemm:
 
     def step(self):
         summa(self.plan, self.ex, self._panel, gemm_step=self._step_panels)
+
+
+class WeakScalingGemm(DistGemm):
+    """bench.py's N>1 workload: every rank owns an n x n block of C of the
+    (Pr*n) x (Pc*n) x n product; per-GPU flops equal the single-GPU workload."""
+
+    def __init__(self, n: int, world: int, rank: int, device, alpha=2.0, beta=1.2, kb: int = 2048):
+        pr, pc = partition.thread_partition_2x2(world, n, n)     # grid for equal work per dimension
+        super().__init__(pr * n, pc * n, n, world, rank, device, alpha, beta, kb)
+        assert (self.plan.pr, self.plan.pc) == (pr, pc)
 
 
 def trsm_column_block(rank: int, world: int, n: int, nr: int = 128):
