@@ -528,12 +528,13 @@ static int trsm_base( const TrsmPlan<T>& p, int64_t i0, int mb, T alpha )
 	a.A = p.A + i0 * ( p.rs_a + p.cs_a ); a.rs_a = p.rs_a; a.cs_a = p.cs_a;
 	a.B = p.B + i0 * p.rs_b;              a.rs_b = p.rs_b; a.cs_b = p.cs_b;
 	a.n = p.n; a.mb = mb; a.upper = p.upper; a.unit = p.unit; a.conj = p.conj; a.alpha = alpha;
-	auto kern = trsm_base_kernel<T, NB, CN>;
+	constexpr int NT = 256;
+	auto kern = trsm_base_kernel<T, NB, CN, NT>;
 	constexpr int smem = trsm_base_smem<T, NB, CN>();
 	static bool attr = false;
 	if ( !attr ) { if ( set_smem( kern, smem ) != kSuccess ) return kFailure; attr = true; }
 	const int64_t grid = ( p.n + CN - 1 ) / CN;
-	kern<<<(unsigned)grid, CN, smem, p.st>>>( a );
+	kern<<<(unsigned)grid, NT, smem, p.st>>>( a );
 	B200_CUDA( cudaGetLastError() );
 	ctx().launches++;
 	return kSuccess;

@@ -88,73 +88,117 @@ __device__ __forceinline__ float2  conj_if( float2 a, bool c )  { if ( c ) a.y =
 __device__ __forceinline__ double2 conj_if( double2 a, bool c ) { if ( c ) a.y = -a.y; return a; }
 
 template <typename T, int NB, int CN>
-constexpr int trsm_base_smem() { return (int)sizeof(T) * ( NB * ( NB + 1 ) + NB * ( CN + 1 ) ); }
+constexpr int trsm_base_smem() { return (int)sizeof(T) * ( NB * ( NB + 2 ) + NB * ( CN + 1 ) ); }
 
-template <typename T, int NB, int CN>
-__global__ void __launch_bounds__( CN )
+// NT threads stage and write back; the first CN threads each solve one column.
+// The solve is RIGHT-LOOKING: as soon as x_l is known every remaining row gets its update
+// b_i -= a_il * x_l.  Per element this is the reference's sequence (alpha*b_i - a_i0 x_0 - a_i1 x_1 ...,
+// increasing l, then * inv(a_ii)), so the bits are those of the row-by-row form, but the NB-l-1 updates
+// of a step are independent of each other: the kernel runs at FMA throughput, not at FMA latency.
+template <typename T, int NB, int CN, int NT>
+__global__ void __launch_bounds__( NT )
 trsm_base_kernel( const TrsmBaseArgs<T> a )
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	T (*As)[NB + 1] = reinterpret_cast<T (*)[NB + 1]>( smem_raw );
-	T (*Bs)[CN + 1] = reinterpret_cast<T (*)[CN + 1]>( smem_raw + sizeof(T) * NB * ( NB + 1 ) );
+	// At[l][i] = A(i,l): column l of the block is contiguous, rows padded to NB+2 (16-byte aligned pairs)
+	T (*At)[NB + 2] = reinterpret_cast<T (*)[NB + 2]>( smem_raw );
+	T (*Bs)[CN + 1] = reinterpret_cast<T (*)[CN + 1]>( smem_raw + sizeof(T) * NB * ( NB + 2 ) );
 
 	const int tid = threadIdx.x;
 	const int mb  = a.mb;
 	const int64_t j0 = (int64_t)blockIdx.x * CN;
 	const int nc = (int)min( (int64_t)CN, a.n - j0 );
+	const bool a_row_fast = ( a.rs_a <= a.cs_a );
+	const bool b_row_fast = ( a.rs_b <= a.cs_b );
 
-	// ---- stage the triangular block: lower form, conj applied, diagonal inverted.
-	// Index reversal turns an upper block into a lower one.
-	for ( int e = tid; e < NB * NB; e += CN )
+	// ---- stage the triangular block: lower form, conj applied, diagonal inverted, identity
+	// extension of a ragged block.  Index reversal turns an upper block into a lower one.
+	// Loads are issued in batches of 4 so that several global requests are in flight per thread.
+	constexpr int A_ITERS = ( NB * NB + NT - 1 ) / NT;
+	#pragma unroll 1
+	for ( int it = 0; it < A_ITERS; it += 4 )
 	{
-		// walk the stored matrix with its faster stride innermost
-		int i, l;
-		if ( a.rs_a <= a.cs_a ) { i = e % NB; l = e / NB; } else { l = e % NB; i = e / NB; }
-		T v = zero_of( T{} );
-		if ( i < mb && l < mb )
+		T v[4]; int ii[4], ll[4];
+		#pragma unroll
+		for ( int u = 0; u < 4; ++u )
 		{
-			const int si = a.upper ? mb - 1 - i : i;
-			const int sl = a.upper ? mb - 1 - l : l;
-			if ( l < i ) v = conj_if( a.A[si * a.rs_a + sl * a.cs_a], a.conj );
-			else if ( l == i ) v = a.unit ? one_of( T{} ) : recip( conj_if( a.A[si * a.rs_a + sl * a.cs_a], a.conj ) );
+			const int e = tid + ( it + u ) * NT;
+			int i, l;
+			if ( a_row_fast ) { i = e % NB; l = e / NB; } else { l = e % NB; i = e / NB; }
+			ii[u] = i; ll[u] = ( e < NB * NB ) ? l : -1;
+			v[u] = zero_of( T{} );
+			if ( e < NB * NB && i < mb && l <= i && !( l == i && a.unit ) )
+			{
+				const int si = a.upper ? mb - 1 - i : i;
+				const int sl = a.upper ? mb - 1 - l : l;
+				v[u] = a.A[si * a.rs_a + sl * a.cs_a];
+			}
 		}
-		else if ( i == l ) v = one_of( T{} );   // identity extension of a ragged block
-		As[i][l] = v;
+		#pragma unroll
+		for ( int u = 0; u < 4; ++u )
+		{
+			if ( ll[u] < 0 ) continue;
+			const int i = ii[u], l = ll[u];
+			T w = zero_of( T{} );
+			if ( i < mb )
+			{
+				if ( l < i ) w = conj_if( v[u], a.conj );
+				else if ( l == i ) w = a.unit ? one_of( T{} ) : recip( conj_if( v[u], a.conj ) );
+			}
+			else if ( i == l ) w = one_of( T{} );
+			At[l][i] = w;
+		}
 	}
 	// ---- stage the right-hand sides
-	for ( int e = tid; e < NB * CN; e += CN )
+	constexpr int B_ITERS = ( NB * CN + NT - 1 ) / NT;
+	#pragma unroll 1
+	for ( int it = 0; it < B_ITERS; it += 4 )
 	{
-		int i, j;
-		if ( a.rs_b <= a.cs_b ) { i = e % NB; j = e / NB; } else { j = e % CN; i = e / CN; }
-		T v = zero_of( T{} );
-		if ( i < mb && j < nc )
+		T v[4]; int ii[4], jj[4];
+		#pragma unroll
+		for ( int u = 0; u < 4; ++u )
 		{
-			const int si = a.upper ? mb - 1 - i : i;
-			v = a.B[si * a.rs_b + ( j0 + j ) * a.cs_b];
+			const int e = tid + ( it + u ) * NT;
+			int i, j;
+			if ( b_row_fast ) { i = e % NB; j = e / NB; } else { j = e % CN; i = e / CN; }
+			ii[u] = i; jj[u] = ( e < NB * CN ) ? j : -1;
+			v[u] = zero_of( T{} );
+			if ( e < NB * CN && i < mb && j < nc )
+			{
+				const int si = a.upper ? mb - 1 - i : i;
+				v[u] = a.B[si * a.rs_b + ( j0 + j ) * a.cs_b];
+			}
 		}
-		Bs[i][j] = v;
+		#pragma unroll
+		for ( int u = 0; u < 4; ++u ) if ( jj[u] >= 0 ) Bs[ii[u]][jj[u]] = v[u];
 	}
 	__syncthreads();
 
-	// ---- forward substitution, one column per thread, solution in registers
-	T x[NB];
-	#pragma unroll
-	for ( int i = 0; i < NB; ++i )
+	// ---- right-looking substitution, one column per thread, the column lives in registers
+	if ( tid < CN )
 	{
-		T acc = cmul( a.alpha, Bs[i][tid] );
+		T bc[NB];
 		#pragma unroll
-		for ( int l = 0; l < i; ++l ) acc = msub( acc, As[i][l], x[l] );
-		x[i] = cmul( acc, As[i][i] );
+		for ( int i = 0; i < NB; ++i ) bc[i] = cmul( a.alpha, Bs[i][tid] );
+		#pragma unroll
+		for ( int l = 0; l < NB; ++l )
+		{
+			const T x = cmul( bc[l], At[l][l] );
+			bc[l] = x;
+			#pragma unroll
+			for ( int i = l + 1; i < NB; ++i ) bc[i] = msub( bc[i], At[l][i], x );
+		}
+		#pragma unroll
+		for ( int i = 0; i < NB; ++i ) Bs[i][tid] = bc[i];
 	}
-	#pragma unroll
-	for ( int i = 0; i < NB; ++i ) Bs[i][tid] = x[i];
 	__syncthreads();
 
 	// ---- write back
-	for ( int e = tid; e < NB * CN; e += CN )
+	#pragma unroll 4
+	for ( int e = tid; e < NB * CN; e += NT )
 	{
 		int i, j;
-		if ( a.rs_b <= a.cs_b ) { i = e % NB; j = e / NB; } else { j = e % CN; i = e / CN; }
+		if ( b_row_fast ) { i = e % NB; j = e / NB; } else { j = e % CN; i = e / CN; }
 		if ( i < mb && j < nc )
 		{
 			const int si = a.upper ? mb - 1 - i : i;
