@@ -297,18 +297,18 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 		}
 
 		// ---- epilogue: D = alpha*acc + beta*D   (beta == 0: D is not read)
-		if ( !CPLX && g.d_vec_ok && q_lim == BQ )
+		if ( g.d_vec_ok && q_lim == BQ )
 		{
-			// Interior tile, real type: all loads of a tile row are issued before the first
-			// store, so a lane has NTL 16-byte loads in flight instead of one (small-k
-			// problems are bound by exactly this read-modify-write of C).
-			if constexpr ( !CPLX )
+			// Interior tile: all loads of a tile row are issued before the first store, so a lane has
+			// NTL (2*NTL for complex) 16-byte loads in flight instead of one (small-k problems are bound
+			// by exactly this read-modify-write of C).
+			#pragma unroll
+			for ( int i = 0; i < MT; ++i )
 			{
-				#pragma unroll
-				for ( int i = 0; i < MT; ++i )
+				const int pl = wp0 + i * 8 + gq;
+				if ( pl >= p_lim ) continue;
+				if constexpr ( !CPLX )
 				{
-					const int pl = wp0 + i * 8 + gq;
-					if ( pl >= p_lim ) continue;
 					double2* __restrict__ dp = reinterpret_cast<double2*>( g.D + ( p0 + pl ) * g.ldd + q0 + wq0 + 2 * t4 );
 					double2 o[NTL];
 					if ( !g.beta_is_zero )
@@ -324,6 +324,31 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 						if ( !g.beta_is_zero ) { r0 = fma( g.beta, o[j].x, r0 ); r1 = fma( g.beta, o[j].y, r1 ); }
 						__stcs( dp + j * 4, make_double2( r0, r1 ) );
 					}
+				}
+				else
+				{
+					double2* __restrict__ dp = reinterpret_cast<double2*>( g.D + ( p0 + pl ) * g.ldd + q0 + wq0 + 2 * t4 );
+					double2 o[NTL][2];
+					if ( !g.beta_is_zero )
+					{
+						#pragma unroll
+						for ( int j = 0; j < NTL; ++j ) { o[j][0] = __ldcs( dp + j * 8 ); o[j][1] = __ldcs( dp + j * 8 + 1 ); }
+					}
+					#pragma unroll
+					for ( int j = 0; j < NTL; ++j )
+						#pragma unroll
+						for ( int e = 0; e < 2; ++e )
+						{
+							const double ar = acc[0][i][j][e], ai = acc[1][i][j][e];
+							double rr = g.alpha.x * ar - g.alpha.y * ai;
+							double ri = g.alpha.x * ai + g.alpha.y * ar;
+							if ( !g.beta_is_zero )
+							{
+								rr += g.beta.x * o[j][e].x - g.beta.y * o[j][e].y;
+								ri += g.beta.x * o[j][e].y + g.beta.y * o[j][e].x;
+							}
+							__stcs( dp + j * 8 + e, make_double2( rr, ri ) );
+						}
 				}
 			}
 			continue;
