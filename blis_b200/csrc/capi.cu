@@ -11,6 +11,7 @@
 #include "context.cuh"
 #include "gemm_dmma.cuh"
 #include "gemm_dmma_ws.cuh"
+#include "gemm_dmma_tma.cuh"
 #include "gemm_ffma.cuh"
 #include "gemm_ffma_ws.cuh"
 #include "trsm.cuh"
@@ -179,6 +180,64 @@ static int launch_dmma_ws( const GemmArgs<T>& g, bool xk, bool yk, bool al, int 
 	}
 }
 
+// ---- TMA path (dgemm, 16-byte aligned operands) ---------------------------------------------
+typedef CUresult ( *EncodeTiledFn )( CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
+static EncodeTiledFn encode_tiled_fn()
+{
+	static EncodeTiledFn fn = nullptr;
+	if ( !fn )
+	{
+		void* p = nullptr; cudaDriverEntryPointQueryResult q;
+		if ( cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q ) == cudaSuccess && q == cudaDriverEntryPointSuccess )
+			fn = (EncodeTiledFn)p;
+	}
+	return fn;
+}
+// Tensor map of an operand with `rows` rows: k-contiguous (element (r,k) at base[r*ld + k]) -> dims {K, rows}, box {16, 128};
+// row-contiguous (element (r,k) at base[k*ld + r]) -> dims {rows, K}, box {16, 16}.  128-byte swizzle, zero fill out of bounds.
+static int make_tmap( CUtensorMap* tm, const double* base, bool kmajor, int64_t rows, int64_t K, int64_t ld )
+{
+	EncodeTiledFn enc = encode_tiled_fn();
+	if ( !enc ) return fail( "cuTensorMapEncodeTiled not available" );
+	cuuint64_t dims[2]    = { (cuuint64_t)( kmajor ? K : rows ), (cuuint64_t)( kmajor ? rows : K ) };
+	cuuint64_t strides[1] = { (cuuint64_t)ld * 8 };
+	cuuint32_t box[2]     = { 16, (cuuint32_t)( kmajor ? 128 : 16 ) };
+	cuuint32_t estr[2]    = { 1, 1 };
+	const CUresult r = enc( tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr,
+	                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+	                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+	if ( r != CUDA_SUCCESS ) return fail( "cuTensorMapEncodeTiled failed (%d)", (int)r );
+	return kSuccess;
+}
+static bool tma_eligible( const GemmArgs<double>& g, bool xk, bool yk, bool al )
+{
+	// TMA needs 16-byte aligned bases and strides (== al), a leading dimension that covers the row, 32-bit box coordinates
+	return al && g.nseg == 1 && g.P < ( 1ll << 31 ) && g.Q < ( 1ll << 31 ) && g.K < ( 1ll << 31 ) &&
+	       g.ldx >= ( xk ? g.K : g.P ) && g.ldy >= ( yk ? g.K : g.Q ) && g.ldx * 8 < ( 1ll << 40 ) && g.ldy * 8 < ( 1ll << 40 );
+}
+static int launch_dmma_tma( const GemmArgs<double>& g, bool xk, bool yk, int grid, cudaStream_t st )
+{
+	CUtensorMap tmx, tmy;
+	if ( make_tmap( &tmx, g.X, xk, g.P, g.K, g.ldx ) != kSuccess ) return kFailure;
+	if ( make_tmap( &tmy, g.Y, yk, g.Q, g.K, g.ldy ) != kSuccess ) return kFailure;
+	auto go = [&]( auto XKc, auto YKc ) -> int
+	{
+		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
+		auto kern = gemm_dmma_tma_kernel<XK, YK>;
+		static bool attr = false;
+		if ( !attr ) { if ( set_smem( kern, DmmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<grid, DmmaTmaCfg::NT_ALL, DmmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
+		B200_CUDA( cudaGetLastError() );
+		ctx().launches++;
+		return kSuccess;
+	};
+	using Tt = std::true_type; using Ff = std::false_type;
+	if ( xk ) return yk ? go( Tt{}, Tt{} ) : go( Tt{}, Ff{} );
+	return yk ? go( Ff{}, Tt{} ) : go( Ff{}, Ff{} );
+}
+
 template <typename T, int BP, int BQ, int BK, int TP, int TQ, int ST>
 static int launch_ffma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
 {
@@ -268,6 +327,8 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 		case 4: return launch_dmma_ws<double, 128, 128, 16, 2, 4, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
 		case 5: return launch_dmma_ws<double, 128, 128, 32, 2, 4, 3>( g, xk, yk, al, tiles( 128, 128 ), st );
 		case 6: return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 9: if ( tma_eligible( g, xk, yk, al ) ) return launch_dmma_tma( g, xk, yk, tiles( 128, 128 ), st );
+		        return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
 		case 7: { const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 128, 64 ); c.grid_mult = gm;
 		          return launch_dmma_ws<double, 128, 64, 16, 4, 1, 3>( g, xk, yk, al, grid, st ); }
 		case 8: { const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 64, 128 ); c.grid_mult = gm;

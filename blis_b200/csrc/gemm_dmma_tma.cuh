@@ -1,0 +1,282 @@
+// gemm_dmma_tma.cuh -- dgemm with TMA tensor-map staging (aligned operands).
+//
+// Same contract, same consumer math and same tile scheduler as gemm_dmma_ws.cuh;
+// what changes is the PRODUCER: instead of 128 threads issuing cp.async, ONE
+// thread issues cp.async.bulk.tensor (TMA, UTMALDG in SASS) per operand and
+// k-slab, straight from the caller's matrix described by a CUtensorMap, into
+// 128-byte-swizzled shared memory; completion is tracked by the stage's mbarrier
+// transaction count.  This is the north-star form of "packm replaced by TMA
+// tensor-map staging": the reference's packm (frame/1m/packm/bli_packm_blk_var1.c)
+// copies an MC x KC block into MR-row micropanels with zero padding at the edges;
+// here the tensor map describes the unpacked matrix and the TMA unit does the
+// copy, the bounds check and the zero fill (out-of-bounds box elements read as 0).
+//
+// Shared-memory layout (per stage, 2 x 16 KiB, no padding):
+//   k-contiguous operand  : ONE box {16 k, 128 rows}: row r = 128 bytes = 16 doubles of k
+//   p/q-contiguous operand: EIGHT boxes {16 rows, 16 k}: box b holds rows 16b..16b+15,
+//                           inside a box row k = 128 bytes = 16 consecutive p (or q)
+// both with CU_TENSOR_MAP_SWIZZLE_128B: 16-byte chunk c of line L is stored at chunk c ^ (L % 8).
+// An 8-byte fragment load of DMMA.8x8x4 touches, per half-warp, 4 lines x 4 k values.  To make
+// that bank-conflict free under the 128B swizzle the k index a lane uses in k4-step s is PERMUTED:
+//       k(s, t) = (t & 1) | ((t >> 1) << 3) | (((t + s) & 3) << 1)        t = lane % 4
+// (A and B fragments use the same k, so the product is unchanged; over s = 0..3 every k in 0..15
+// is used once).  For the k-contiguous layout the 16 lanes of a half-warp then hit 16 distinct
+// 8-byte bank pairs because (k>>1)^g covers both 4-chunk cosets x both halves; for the other layout
+// because the lines k(s,t) % 8 have pairwise distinct (k % 8) >> 1.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "gemm_dmma.cuh"
+#include "gemm_dmma_ws.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ void mbar_arrive_expect_tx( uint32_t bar, uint32_t bytes )
+{
+	asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"(bytes) : "memory" );
+}
+__device__ __forceinline__ void tma_load_2d( uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar )
+{
+	asm volatile( "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n"
+	              :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory" );
+}
+
+struct DmmaTmaCfg
+{
+	static constexpr int BP = 128, BQ = 128, BK = 16, WP = 4, WQ = 2, STAGES = 6;
+	static constexpr int WTP = BP / WP, WTQ = BQ / WQ, MT = WTP / 8, NTL = WTQ / 8;
+	static constexpr int OPER_BYTES  = 128 * 128;                 // 16 KiB per operand per stage
+	static constexpr int STAGE_BYTES = 2 * OPER_BYTES;
+	static constexpr int NCONS = WP * WQ * 32, NPROD = 128, NT_ALL = NCONS + NPROD;
+	static constexpr int BAR_BYTES  = 2 * STAGES * 8 + 4 * 8 + 16;
+	static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES + BAR_BYTES + 1024;   // + slack for 1 KiB alignment
+};
+
+template <bool XK, bool YK>
+__global__ void __launch_bounds__( 384, 1 )
+gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy )
+{
+	using Cfg = DmmaTmaCfg;
+	constexpr int BP = Cfg::BP, BQ = Cfg::BQ, BK = Cfg::BK, WQ = Cfg::WQ, STAGES = Cfg::STAGES;
+	constexpr int MT = Cfg::MT, NTL = Cfg::NTL, KS = BK / 4;
+
+	extern __shared__ unsigned char smem_unaligned[];
+	const uint32_t raw = smem_u32( smem_unaligned );
+	const uint32_t sbase = ( raw + 1023u ) & ~1023u;                         // swizzle atoms need 1 KiB alignment
+	unsigned char* const smem = smem_unaligned + ( sbase - raw );
+	const uint32_t bar_base = sbase + (uint32_t)Cfg::STAGE_BYTES * STAGES;
+	auto full_bar    = [&]( int s ) { return bar_base + (uint32_t)s * 8u; };
+	auto empty_bar   = [&]( int s ) { return bar_base + (uint32_t)( STAGES + s ) * 8u; };
+	auto sched_full  = [&]( int s ) { return bar_base + (uint32_t)( 2 * STAGES + s ) * 8u; };
+	auto sched_empty = [&]( int s ) { return bar_base + (uint32_t)( 2 * STAGES + 2 + s ) * 8u; };
+	volatile int* const sched_tile = reinterpret_cast<volatile int*>( smem + (size_t)Cfg::STAGE_BYTES * STAGES + ( 2 * STAGES + 4 ) * 8 );
+
+	const int tid = threadIdx.x;
+	if ( tid == 0 )
+	{
+		#pragma unroll
+		for ( int s = 0; s < STAGES; ++s )
+		{
+			mbar_init( full_bar( s ),  1 );                    // the producer's expect_tx arrival; bytes complete it
+			mbar_init( empty_bar( s ), Cfg::NCONS / 32 );
+		}
+		#pragma unroll
+		for ( int s = 0; s < 2; ++s )
+		{
+			mbar_init( sched_full( s ),  1 );
+			mbar_init( sched_empty( s ), Cfg::NCONS / 32 );
+		}
+		asm volatile( "fence.mbarrier_init.release.cluster;\n" ::: "memory" );   // visible to the async proxy
+	}
+	__syncthreads();
+
+	const int64_t KT = ( g.K + BK - 1 ) / BK;
+	const int num_tiles = g.tiles_p * g.tiles_q;
+
+	if ( tid >= Cfg::NCONS )
+	{
+		// ============ PRODUCER warpgroup: one thread drives the TMA unit ============
+		setmaxnreg_dec<40>();
+		if ( tid != Cfg::NCONS ) return;
+		asm volatile( "prefetch.tensormap [%0];\n" :: "l"(&tmx) : "memory" );
+		asm volatile( "prefetch.tensormap [%0];\n" :: "l"(&tmy) : "memory" );
+		int stage = 0; uint32_t phase = 0;
+		for ( int it = 0; ; ++it )
+		{
+			const int slot = it & 1;
+			mbar_wait( sched_empty( slot ), ( ( it >> 1 ) & 1 ) ^ 1u );
+			const int tile = g.tile_counter ? atomicAdd( g.tile_counter, 1 ) : (int)( blockIdx.x + (unsigned)it * gridDim.x );
+			sched_tile[slot] = tile;
+			mbar_arrive( sched_full( slot ) );
+			if ( tile >= num_tiles ) break;
+			int tp, tq;
+			tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
+			const int p0 = tp * BP, q0 = tq * BQ;
+			for ( int64_t kt = 0; kt < KT; ++kt )
+			{
+				mbar_wait( empty_bar( stage ), phase ^ 1u );
+				const uint32_t xs = sbase + (uint32_t)stage * Cfg::STAGE_BYTES, ys = xs + Cfg::OPER_BYTES;
+				const uint32_t fb = full_bar( stage );
+				const int k0 = (int)( kt * BK );
+				mbar_arrive_expect_tx( fb, 2u * Cfg::OPER_BYTES );
+				if constexpr ( XK ) tma_load_2d( xs, &tmx, k0, p0, fb );
+				else
+				{
+					#pragma unroll
+					for ( int b = 0; b < BP / 16; ++b ) tma_load_2d( xs + b * 2048, &tmx, p0 + b * 16, k0, fb );
+				}
+				if constexpr ( YK ) tma_load_2d( ys, &tmy, k0, q0, fb );
+				else
+				{
+					#pragma unroll
+					for ( int b = 0; b < BQ / 16; ++b ) tma_load_2d( ys + b * 2048, &tmy, q0 + b * 16, k0, fb );
+				}
+				if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
+			}
+		}
+		if ( g.tile_counter )
+		{
+			if ( atomicAdd( g.tile_counter + 1, 1 ) == (int)gridDim.x - 1 ) { g.tile_counter[0] = 0; g.tile_counter[1] = 0; __threadfence(); }
+		}
+		return;
+	}
+
+	// =============================== CONSUMER warps ===============================
+	setmaxnreg_inc<224>();
+	const int lane = tid & 31, warp = tid >> 5;
+	const int gq = lane >> 2, t4 = lane & 3;
+	const int wp0 = ( warp / WQ ) * Cfg::WTP;
+	const int wq0 = ( warp % WQ ) * Cfg::WTQ;
+
+	// byte offset of the fragment element of 8x8 tile `i` (rows w0 + 8i + g) in k4-step s
+	auto frag_off = [&]( bool kmajor, int w0, int i, int s ) -> int
+	{
+		const int ts = ( t4 + s ) & 3;
+		if ( kmajor )
+		{
+			const int chunk = ( ( t4 >> 1 ) << 2 ) | ts;                       // (k >> 1)
+			return ( w0 + i * 8 + gq ) * 128 + ( ( chunk ^ gq ) << 4 ) + ( t4 & 1 ) * 8;
+		}
+		const int k  = ( t4 & 1 ) | ( ( t4 >> 1 ) << 3 ) | ( ts << 1 );
+		const int k7 = ( t4 & 1 ) | ( ts << 1 );
+		const int chunk = ( ( i & 1 ) << 2 ) | ( gq >> 1 );                    // ((row % 16) >> 1)
+		return ( ( w0 >> 4 ) + ( i >> 1 ) ) * 2048 + k * 128 + ( ( chunk ^ k7 ) << 4 ) + ( gq & 1 ) * 8;
+	};
+
+	int stage = 0; uint32_t phase = 0;
+	auto load_frags = [&]( double ( &xf )[MT], double ( &yf )[NTL], int st, int s )
+	{
+		const unsigned char* xs = smem + (size_t)st * Cfg::STAGE_BYTES;
+		const unsigned char* ys = xs + Cfg::OPER_BYTES;
+		#pragma unroll
+		for ( int i = 0; i < MT; ++i ) xf[i] = *reinterpret_cast<const double*>( xs + frag_off( XK, wp0, i, s ) );
+		#pragma unroll
+		for ( int j = 0; j < NTL; ++j ) yf[j] = *reinterpret_cast<const double*>( ys + frag_off( YK, wq0, j, s ) );
+	};
+
+	for ( int it = 0; ; ++it )
+	{
+		const int slot = it & 1;
+		mbar_wait( sched_full( slot ), ( it >> 1 ) & 1 );
+		const int tile = sched_tile[slot];
+		__syncwarp();
+		if ( lane == 0 ) mbar_arrive( sched_empty( slot ) );
+		if ( tile >= num_tiles ) break;
+		int tp, tq;
+		tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
+		const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
+		const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
+		const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );
+
+		double acc[MT][NTL][2];
+		#pragma unroll
+		for ( int i = 0; i < MT; ++i )
+			#pragma unroll
+			for ( int j = 0; j < NTL; ++j ) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+		double xa[MT], ya[NTL], xb[MT], yb[NTL];
+		mbar_wait( full_bar( stage ), phase );
+		load_frags( xa, ya, stage, 0 );
+
+		auto mma_step = [&]( double ( &xf )[MT], double ( &yf )[NTL] )
+		{
+			#pragma unroll
+			for ( int i = 0; i < MT; ++i )
+				#pragma unroll
+				for ( int j = 0; j < NTL; ++j )
+					dmma884( acc[i][j][0], acc[i][j][1], xf[i], yf[j] );
+		};
+
+		for ( int64_t kt = 0; kt < KT; ++kt )
+		{
+			#pragma unroll
+			for ( int kk = 0; kk < KS; kk += 2 )
+			{
+				load_frags( xb, yb, stage, kk + 1 );
+				mma_step( xa, ya );
+				if ( kk + 2 < KS )
+				{
+					load_frags( xa, ya, stage, kk + 2 );
+					mma_step( xb, yb );
+				}
+				else
+				{
+					int ns = stage + 1; uint32_t nph = phase;
+					if ( ns == STAGES ) { ns = 0; nph ^= 1u; }
+					if ( kt + 1 < KT )
+					{
+						mbar_wait( full_bar( ns ), nph );
+						load_frags( xa, ya, ns, 0 );
+					}
+					mma_step( xb, yb );
+					__syncwarp();
+					if ( lane == 0 ) mbar_arrive( empty_bar( stage ) );
+					stage = ns; phase = nph;
+				}
+			}
+		}
+
+		// ---- epilogue: D = alpha*acc + beta*D   (beta == 0: D is not read)
+		#pragma unroll
+		for ( int i = 0; i < MT; ++i )
+		{
+			const int pl = wp0 + i * 8 + gq;
+			if ( pl >= p_lim ) continue;
+			double* drow = g.D + ( p0 + pl ) * g.ldd + q0;
+			if ( g.d_vec_ok && q_lim == BQ )
+			{
+				double2* __restrict__ dp = reinterpret_cast<double2*>( drow + wq0 + 2 * t4 );
+				double2 o[NTL];
+				if ( !g.beta_is_zero )
+				{
+					#pragma unroll
+					for ( int j = 0; j < NTL; ++j ) o[j] = __ldcs( dp + j * 4 );
+				}
+				#pragma unroll
+				for ( int j = 0; j < NTL; ++j )
+				{
+					double r0 = g.alpha * acc[i][j][0], r1 = g.alpha * acc[i][j][1];
+					if ( !g.beta_is_zero ) { r0 = fma( g.beta, o[j].x, r0 ); r1 = fma( g.beta, o[j].y, r1 ); }
+					__stcs( dp + j * 4, make_double2( r0, r1 ) );
+				}
+				continue;
+			}
+			#pragma unroll
+			for ( int j = 0; j < NTL; ++j )
+			{
+				const int ql = wq0 + j * 8 + 2 * t4;
+				if ( ql >= q_lim ) continue;
+				double r0 = g.alpha * acc[i][j][0], r1 = g.alpha * acc[i][j][1];
+				if ( !g.beta_is_zero ) r0 = fma( g.beta, drow[ql], r0 );
+				drow[ql] = r0;
+				if ( ql + 1 < q_lim )
+				{
+					if ( !g.beta_is_zero ) r1 = fma( g.beta, drow[ql + 1], r1 );
+					drow[ql + 1] = r1;
+				}
+			}
+		}
+	}
+}
+
+} // namespace b200
