@@ -304,7 +304,7 @@ def main():
                     "traffic": traffic,
                     "peak_source": "FP64 DMMA (mma.sync m8n8k4) microbenchmark measured in this run by b200_measure_peak; "
                                    "MEASURED_PEAKS.json holds only HBM GB/s and bf16 TFLOP/s",
-                    "kernel": "gemm_dmma_ws_kernel<double,128,128,16,4,2,5>", "algorithmic_flop_per_launch": flops_per_step if world == 1 else total_flops / world}
+                    "kernel": "gemm_dmma_tma_kernel<XK=1,YK=0> (128x128x16, 6 stages, TMA)", "algorithmic_flop_per_launch": flops_per_step if world == 1 else total_flops / world}
 
         # ---- e2e: same call through the public API with HOST (pinned) operands
         e2e = None

@@ -315,7 +315,7 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 	{
 		// auto: the cooperative 128x128 tile unless it cannot fill the SMs once; then 128x64 tiles, two CTAs per SM
 		const int64_t t128 = ( ( g.P + 127 ) / 128 ) * ( ( g.Q + 127 ) / 128 );
-		cfg = ( t128 < c.num_sms ) ? 7 : 6;
+		cfg = ( t128 < c.num_sms ) ? 7 : ( tma_eligible( g, xk, yk, al ) ? 9 : 6 );
 	}
 	switch ( cfg )
 	{

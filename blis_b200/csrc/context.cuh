@@ -44,7 +44,7 @@ struct Context
 	cudaEvent_t  stage_free[kStageBufs] = { nullptr, nullptr };
 	std::mutex   stage_mu;
 	// tuning knobs (b200_set_option)
-	int          dgemm_cfg = -1;         // auto: ws 128x128x16 (cfg 6) or ws 128x64x16 with 2 CTAs/SM (cfg 7)
+	int          dgemm_cfg = -1;         // auto: TMA 128x128x16 (cfg 9) when aligned, cp.async ws (cfg 6) otherwise, 128x64 2 CTAs/SM (cfg 7) for small problems
 	int          zgemm_cfg = 1;          // warp-specialised 64x128x8, 5 stages
 	int          sgemm_cfg = 0;
 	int          cgemm_cfg = 1;          // warp-specialised 64x128x16
