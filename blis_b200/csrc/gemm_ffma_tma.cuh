@@ -1,0 +1,285 @@
+// gemm_ffma_tma.cuh -- sgemm on the FP32 FMA pipe with TMA tensor-map staging (aligned operands).
+//
+// Same contract as the other gemm kernels (D = alpha*X*Y + beta*D, q contiguous; see gemm_dmma.cuh for the
+// reference files replaced) and the same skeleton as gemm_dmma_tma.cuh: one producer thread drives the TMA unit,
+// 8 consumer warps, full/empty mbarrier ring, dynamic tile scheduler, setmaxnreg.  No TF32: every product is an
+// IEEE fp32 FFMA.
+//
+// The FP32 pipe is ISSUE bound (one FFMA per scheduler per clock), so the design goal is the fewest non-FFMA
+// instructions per FFMA (ncu on gemm_ffma*.cuh: 16 % of the issue slots went to the element-wise transposing
+// loader, address arithmetic and multi-wavefront LDS.128):
+//   * no transposition at all: a k-contiguous operand stays k-contiguous in shared memory and is read with 16-byte
+//     loads ALONG k (one LDS.128 = one row, four k steps); a p/q-contiguous operand is read with 16-byte loads
+//     along p/q (one LDS.128 = four rows, one k step).  Either way: 16 LDS.128 per 256 FFMA;
+//   * the row/column ownership of a lane depends on the operand's orientation so that every LDS.128 of a warp
+//     touches distinct 16-byte chunks of distinct banks under the 128-byte TMA swizzle:
+//         k-contiguous X: rows  ty + 4*i          p-contiguous X: rows  16*(i/4) + 4*ty + i%4
+//         k-contiguous Y: cols  tx + 8*j          q-contiguous Y: cols  32*(j/4) + 4*tx + j%4
+//     (lane = 8*ty + tx, 4 x 8 lanes per warp, warp tile 32 x 64, CTA tile 128 x 128, BK = 32);
+//   * swizzled offsets are precomputed once per lane ((chunk ^ line%8) << 4 for the 8 possible line%8), so the k
+//     loop adds one register to the stage base per group of loads and uses immediate offsets for the rest.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "gemm_dmma.cuh"
+#include "gemm_dmma_ws.cuh"
+#include "gemm_dmma_tma.cuh"
+
+namespace b200 {
+
+struct FfmaTmaCfg
+{
+	static constexpr int BP = 128, BQ = 128, BK = 32, STAGES = 6;
+	static constexpr int OPER_BYTES  = 128 * 128;                 // 128 rows x 32 floats, or 4 boxes of 32 k x 32 rows
+	static constexpr int STAGE_BYTES = 2 * OPER_BYTES;
+	static constexpr int NCONS = 256, NPROD = 128, NT_ALL = NCONS + NPROD;
+	static constexpr int BAR_BYTES  = 2 * STAGES * 8 + 4 * 8 + 16;
+	static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES + BAR_BYTES + 1024;
+};
+
+template <bool XK, bool YK>
+__global__ void __launch_bounds__( 384, 1 )
+gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy )
+{
+	using Cfg = FfmaTmaCfg;
+	constexpr int BP = Cfg::BP, BQ = Cfg::BQ, BK = Cfg::BK, STAGES = Cfg::STAGES;
+
+	extern __shared__ unsigned char smem_unaligned[];
+	const uint32_t raw = smem_u32( smem_unaligned );
+	const uint32_t sbase = ( raw + 1023u ) & ~1023u;
+	unsigned char* const smem = smem_unaligned + ( sbase - raw );
+	const uint32_t bar_base = sbase + (uint32_t)Cfg::STAGE_BYTES * STAGES;
+	auto full_bar    = [&]( int s ) { return bar_base + (uint32_t)s * 8u; };
+	auto empty_bar   = [&]( int s ) { return bar_base + (uint32_t)( STAGES + s ) * 8u; };
+	auto sched_full  = [&]( int s ) { return bar_base + (uint32_t)( 2 * STAGES + s ) * 8u; };
+	auto sched_empty = [&]( int s ) { return bar_base + (uint32_t)( 2 * STAGES + 2 + s ) * 8u; };
+	volatile int* const sched_tile = reinterpret_cast<volatile int*>( smem + (size_t)Cfg::STAGE_BYTES * STAGES + ( 2 * STAGES + 4 ) * 8 );
+
+	const int tid = threadIdx.x;
+	if ( tid == 0 )
+	{
+		#pragma unroll
+		for ( int s = 0; s < STAGES; ++s ) { mbar_init( full_bar( s ), 1 ); mbar_init( empty_bar( s ), Cfg::NCONS / 32 ); }
+		#pragma unroll
+		for ( int s = 0; s < 2; ++s ) { mbar_init( sched_full( s ), 1 ); mbar_init( sched_empty( s ), Cfg::NCONS / 32 ); }
+		asm volatile( "fence.mbarrier_init.release.cluster;\n" ::: "memory" );
+	}
+	__syncthreads();
+
+	const int64_t KT = ( g.K + BK - 1 ) / BK;
+	const int num_tiles = g.tiles_p * g.tiles_q;
+
+	if ( tid >= Cfg::NCONS )
+	{
+		// ============ PRODUCER warpgroup: one thread drives the TMA unit ============
+		setmaxnreg_dec<40>();
+		if ( tid != Cfg::NCONS ) return;
+		asm volatile( "prefetch.tensormap [%0];\n" :: "l"(&tmx) : "memory" );
+		asm volatile( "prefetch.tensormap [%0];\n" :: "l"(&tmy) : "memory" );
+		int stage = 0; uint32_t phase = 0;
+		for ( int it = 0; ; ++it )
+		{
+			const int slot = it & 1;
+			mbar_wait( sched_empty( slot ), ( ( it >> 1 ) & 1 ) ^ 1u );
+			const int tile = g.tile_counter ? atomicAdd( g.tile_counter, 1 ) : (int)( blockIdx.x + (unsigned)it * gridDim.x );
+			sched_tile[slot] = tile;
+			mbar_arrive( sched_full( slot ) );
+			if ( tile >= num_tiles ) break;
+			int tp, tq;
+			tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
+			const int p0 = tp * BP, q0 = tq * BQ;
+			for ( int64_t kt = 0; kt < KT; ++kt )
+			{
+				mbar_wait( empty_bar( stage ), phase ^ 1u );
+				const uint32_t xs = sbase + (uint32_t)stage * Cfg::STAGE_BYTES, ys = xs + Cfg::OPER_BYTES;
+				const uint32_t fb = full_bar( stage );
+				const int k0 = (int)( kt * BK );
+				mbar_arrive_expect_tx( fb, 2u * Cfg::OPER_BYTES );
+				if constexpr ( XK ) tma_load_2d( xs, &tmx, k0, p0, fb );               // box {32 k, 128 rows}
+				else
+				{
+					#pragma unroll
+					for ( int b = 0; b < BP / 32; ++b ) tma_load_2d( xs + b * 4096, &tmx, p0 + b * 32, k0, fb );   // boxes {32 rows, 32 k}
+				}
+				if constexpr ( YK ) tma_load_2d( ys, &tmy, k0, q0, fb );
+				else
+				{
+					#pragma unroll
+					for ( int b = 0; b < BQ / 32; ++b ) tma_load_2d( ys + b * 4096, &tmy, q0 + b * 32, k0, fb );
+				}
+				if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
+			}
+		}
+		if ( g.tile_counter )
+		{
+			if ( atomicAdd( g.tile_counter + 1, 1 ) == (int)gridDim.x - 1 ) { g.tile_counter[0] = 0; g.tile_counter[1] = 0; __threadfence(); }
+		}
+		return;
+	}
+
+	// =============================== CONSUMER warps ===============================
+	setmaxnreg_inc<224>();
+	const int lane = tid & 31, warp = tid >> 5;
+	const int ty = lane >> 3, tx = lane & 7;
+	const int wr0 = ( warp >> 1 ) * 32;          // 4 x 2 warps: warp tile 32 rows x 64 cols
+	const int wc0 = ( warp & 1 ) * 64;
+
+	// ownership maps
+	auto row_of = [&]( int i ) { return XK ? wr0 + ty + 4 * i : wr0 + 16 * ( i >> 2 ) + 4 * ty + ( i & 3 ); };
+	auto col_of = [&]( int j ) { return YK ? wc0 + tx + 8 * j : wc0 + 32 * ( j >> 2 ) + 4 * tx + ( j & 3 ); };
+
+	// precomputed swizzle terms: ((chunk ^ c) << 4) for c = 0..7
+	//   k-contiguous X: chunk = k group (compile time), line = row -> row%8 = ty + 4*(i&1): term[c] uses c = k group
+	//   p-contiguous X: chunk = (row%32)>>2 = 4*(i>>2) + ty,  line = k  -> c = k%8
+	int xsw[2][8], ysw[2][8];
+	#pragma unroll
+	for ( int c = 0; c < 8; ++c )
+	{
+		if constexpr ( XK ) { xsw[0][c] = ( c ^ ty ) << 4;        xsw[1][c] = ( c ^ ( ty + 4 ) ) << 4; }
+		else                { xsw[0][c] = ( ty ^ c ) << 4;        xsw[1][c] = ( ( ty + 4 ) ^ c ) << 4; }
+		if constexpr ( YK ) { ysw[0][c] = ( c ^ tx ) << 4;        ysw[1][c] = 0; }
+		else                { ysw[0][c] = ( tx ^ c ) << 4;        ysw[1][c] = 0; }
+	}
+	// fixed byte offsets inside an operand buffer
+	const int xfix = XK ? ( wr0 + ty ) * 128 : ( wr0 >> 5 ) * 4096;      // + i*512 (XK) | + k*128 (PK)
+	const int yfix = YK ? ( wc0 + tx ) * 128 : ( wc0 >> 5 ) * 4096;      // + j*1024 (YK) | + (j>>2)*4096 + k*128 (QK)
+
+	int stage = 0; uint32_t phase = 0;
+
+	for ( int it = 0; ; ++it )
+	{
+		const int slot = it & 1;
+		mbar_wait( sched_full( slot ), ( it >> 1 ) & 1 );
+		const int tile = sched_tile[slot];
+		__syncwarp();
+		if ( lane == 0 ) mbar_arrive( sched_empty( slot ) );
+		if ( tile >= num_tiles ) break;
+		int tp, tq;
+		tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
+		const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
+		const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
+		const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );
+
+		float acc[8][8];
+		#pragma unroll
+		for ( int i = 0; i < 8; ++i )
+			#pragma unroll
+			for ( int j = 0; j < 8; ++j ) acc[i][j] = 0.f;
+
+		for ( int64_t kt = 0; kt < KT; ++kt )
+		{
+			mbar_wait( full_bar( stage ), phase );
+			const unsigned char* xs = smem + (size_t)stage * Cfg::STAGE_BYTES + xfix;
+			const unsigned char* ys = smem + (size_t)stage * Cfg::STAGE_BYTES + Cfg::OPER_BYTES + yfix;
+
+			#pragma unroll
+			for ( int kg = 0; kg < BK / 4; ++kg )          // groups of 4 k steps
+			{
+				float xv[8][4], yv[8][4];                  // [element][k step]
+				if constexpr ( XK )
+				{
+					// one LDS.128 per owned row: rows ty+4i, k chunk kg
+					#pragma unroll
+					for ( int i = 0; i < 8; ++i )
+					{
+						const float4 v = *reinterpret_cast<const float4*>( xs + i * 512 + xsw[i & 1][kg] );
+						xv[i][0] = v.x; xv[i][1] = v.y; xv[i][2] = v.z; xv[i][3] = v.w;
+					}
+				}
+				else
+				{
+					#pragma unroll
+					for ( int kk = 0; kk < 4; ++kk )
+					{
+						const int k = kg * 4 + kk;
+						#pragma unroll
+						for ( int h = 0; h < 2; ++h )
+						{
+							const float4 v = *reinterpret_cast<const float4*>( xs + k * 128 + xsw[h][k & 7] );
+							xv[h * 4 + 0][kk] = v.x; xv[h * 4 + 1][kk] = v.y; xv[h * 4 + 2][kk] = v.z; xv[h * 4 + 3][kk] = v.w;
+						}
+					}
+				}
+				if constexpr ( YK )
+				{
+					#pragma unroll
+					for ( int j = 0; j < 8; ++j )
+					{
+						const float4 v = *reinterpret_cast<const float4*>( ys + j * 1024 + ysw[0][kg] );
+						yv[j][0] = v.x; yv[j][1] = v.y; yv[j][2] = v.z; yv[j][3] = v.w;
+					}
+				}
+				else
+				{
+					#pragma unroll
+					for ( int kk = 0; kk < 4; ++kk )
+					{
+						const int k = kg * 4 + kk;
+						#pragma unroll
+						for ( int h = 0; h < 2; ++h )
+						{
+							const float4 v = *reinterpret_cast<const float4*>( ys + h * 4096 + k * 128 + ysw[0][k & 7] );
+							yv[h * 4 + 0][kk] = v.x; yv[h * 4 + 1][kk] = v.y; yv[h * 4 + 2][kk] = v.z; yv[h * 4 + 3][kk] = v.w;
+						}
+					}
+				}
+				#pragma unroll
+				for ( int kk = 0; kk < 4; ++kk )
+					#pragma unroll
+					for ( int i = 0; i < 8; ++i )
+						#pragma unroll
+						for ( int j = 0; j < 8; ++j )
+							acc[i][j] = fmaf( xv[i][kk], yv[j][kk], acc[i][j] );
+			}
+			__syncwarp();
+			if ( lane == 0 ) mbar_arrive( empty_bar( stage ) );
+			if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
+		}
+
+		// ---- epilogue: D = alpha*acc + beta*D (beta == 0: D is not read)
+		#pragma unroll
+		for ( int i = 0; i < 8; ++i )
+		{
+			const int pl = row_of( i );
+			if ( pl >= p_lim ) continue;
+			float* drow = g.D + ( p0 + pl ) * g.ldd + q0;
+			if ( !YK && g.d_vec_ok && q_lim == BQ )
+			{
+				float4* __restrict__ dp0 = reinterpret_cast<float4*>( drow + col_of( 0 ) );
+				float4* __restrict__ dp1 = reinterpret_cast<float4*>( drow + col_of( 4 ) );
+				float4 o0 = make_float4( 0.f, 0.f, 0.f, 0.f ), o1 = o0;
+				if ( !g.beta_is_zero ) { o0 = __ldcs( dp0 ); o1 = __ldcs( dp1 ); }
+				float4 r0, r1;
+				r0.x = fmaf( g.beta, o0.x, g.alpha * acc[i][0] ); r0.y = fmaf( g.beta, o0.y, g.alpha * acc[i][1] );
+				r0.z = fmaf( g.beta, o0.z, g.alpha * acc[i][2] ); r0.w = fmaf( g.beta, o0.w, g.alpha * acc[i][3] );
+				r1.x = fmaf( g.beta, o1.x, g.alpha * acc[i][4] ); r1.y = fmaf( g.beta, o1.y, g.alpha * acc[i][5] );
+				r1.z = fmaf( g.beta, o1.z, g.alpha * acc[i][6] ); r1.w = fmaf( g.beta, o1.w, g.alpha * acc[i][7] );
+				if ( g.beta_is_zero )
+				{
+					r0 = make_float4( g.alpha * acc[i][0], g.alpha * acc[i][1], g.alpha * acc[i][2], g.alpha * acc[i][3] );
+					r1 = make_float4( g.alpha * acc[i][4], g.alpha * acc[i][5], g.alpha * acc[i][6], g.alpha * acc[i][7] );
+				}
+				__stcs( dp0, r0 ); __stcs( dp1, r1 );
+				continue;
+			}
+			float o[8];
+			#pragma unroll
+			for ( int j = 0; j < 8; ++j )
+			{
+				const int ql = col_of( j );
+				o[j] = ( !g.beta_is_zero && ql < q_lim ) ? drow[ql] : 0.f;
+			}
+			#pragma unroll
+			for ( int j = 0; j < 8; ++j )
+			{
+				const int ql = col_of( j );
+				if ( ql >= q_lim ) continue;
+				float r = g.alpha * acc[i][j];
+				if ( !g.beta_is_zero ) r = fmaf( g.beta, o[j], r );
+				drow[ql] = r;
+			}
+		}
+	}
+}
+
+} // namespace b200
