@@ -233,7 +233,7 @@ def blksz(dtype: torch.dtype, which: str) -> int:
 
 def measure_peak(kind: str, millis: int = 200) -> float:
     """TFLOP/s of the DFMA / DMMA / FFMA pipe microbenchmark."""
-    k = {"dfma": 0, "dmma": 1, "ffma": 2}[kind]
+    k = {"dfma": 0, "dmma": 1, "ffma": 2, "ffma2": 3}[kind]
     v = float(_lib.load().b200_measure_peak(k, millis))
     if v < 0:
         raise EngineError("peak microbenchmark failed (no GPU?)")

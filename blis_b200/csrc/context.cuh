@@ -46,7 +46,7 @@ struct Context
 	// tuning knobs (b200_set_option)
 	int          dgemm_cfg = -1;         // auto: TMA 128x128x16 (cfg 9) when aligned, cp.async ws (cfg 6) otherwise, 128x64 2 CTAs/SM (cfg 7) for small problems
 	int          zgemm_cfg = 1;          // warp-specialised 64x128x8, 5 stages
-	int          sgemm_cfg = 0;
+	int          sgemm_cfg = -1;         // auto: TMA + FFMA2 kernel when aligned, cp.async kernel otherwise
 	int          cgemm_cfg = 1;          // warp-specialised 64x128x16
 	int          trsm_nb   = 0;           // 0 = default
 	int          grid_mult = 1;           // persistent CTAs per SM

@@ -43,6 +43,25 @@ __global__ void __launch_bounds__(256) peak_ffma( float* out, float a, float b )
 	out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+__global__ void __launch_bounds__(256) peak_ffma2( float* out, float a, float b )
+{
+	unsigned long long acc[16];
+	#pragma unroll
+	for ( int i = 0; i < 16; ++i ) acc[i] = (unsigned long long)( threadIdx.x + i );
+	unsigned long long a2, b2;
+	asm( "mov.b64 %0, {%1, %1};" : "=l"(a2) : "f"(a) );
+	asm( "mov.b64 %0, {%1, %1};" : "=l"(b2) : "f"(b) );
+	for ( int it = 0; it < kPeakIters; ++it )
+	{
+		#pragma unroll
+		for ( int i = 0; i < 16; ++i ) asm( "fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(a2), "l"(b2) );
+	}
+	unsigned long long s = 0;
+	#pragma unroll
+	for ( int i = 0; i < 16; ++i ) s ^= acc[i];
+	out[blockIdx.x * blockDim.x + threadIdx.x] = (float)( s & 0xffff );
+}
+
 __global__ void __launch_bounds__(256) peak_dmma( double* out, double a, double b )
 {
 	double acc[16][2];
@@ -65,7 +84,7 @@ __global__ void __launch_bounds__(256) peak_dmma( double* out, double a, double 
 extern "C" double b200_measure_peak( int kind, int millis )
 {
 	using namespace b200;
-	if ( kind < 0 || kind > 2 ) return -1.0;
+	if ( kind < 0 || kind > 3 ) return -1.0;
 	const int threads = 256;
 	const int blocks  = kNumSMs * 4;            // 32 warps per SM
 	void* out = nullptr;
@@ -76,11 +95,13 @@ extern "C" double b200_measure_peak( int kind, int millis )
 	{
 		if      ( kind == 0 ) peak_dfma<<<blocks, threads>>>( (double*)out, 1.0000001, 1e-9 );
 		else if ( kind == 1 ) peak_dmma<<<blocks, threads>>>( (double*)out, 1.0000001, 1e-9 );
-		else                  peak_ffma<<<blocks, threads>>>( (float*)out, 1.0000001f, 1e-9f );
+		else if ( kind == 2 ) peak_ffma<<<blocks, threads>>>( (float*)out, 1.0000001f, 1e-9f );
+		else                  peak_ffma2<<<blocks, threads>>>( (float*)out, 1.0000001f, 1e-9f );
 	};
 	// flop per launch
 	double flop;
 	if ( kind == 1 ) flop = (double)blocks * ( threads / 32 ) * kPeakIters * 16.0 * ( 2.0 * 8 * 8 * 4 );
+	else if ( kind == 3 ) flop = (double)blocks * threads * kPeakIters * 16.0 * 4.0;
 	else             flop = (double)blocks * threads * kPeakIters * 16.0 * 2.0;
 	launch(); launch();
 	cudaDeviceSynchronize();

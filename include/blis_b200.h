@@ -174,7 +174,7 @@ b200_dim_t b200_blksz( int dt, int bs );
  * Device-side peak microbenchmarks (no reference analogue; they provide the
  * FP64/FP32 roofline denominators SURVEY.md section 8d asks for).
  * kind: 0 = DFMA (fp64 FMA pipe), 1 = DMMA (mma.sync m8n8k4 f64),
- *       2 = FFMA (fp32 FMA pipe).
+ *       2 = FFMA (fp32 FMA pipe), 3 = FFMA2 (packed fma.rn.f32x2).
  * Runs for about `millis` ms and returns achieved TFLOP/s (< 0 on error). */
 double b200_measure_peak( int kind, int millis );
 
