@@ -13,6 +13,7 @@
 #include "gemm_dmma_ws.cuh"
 #include "gemm_dmma_tma.cuh"
 #include "gemm_ffma_tma.cuh"
+#include "gemm_cfma_tma.cuh"
 #include "gemm_ffma.cuh"
 #include "gemm_ffma_ws.cuh"
 #include "trsm.cuh"
@@ -199,14 +200,14 @@ static EncodeTiledFn encode_tiled_fn()
 // Tensor map of an operand with `rows` rows: k-contiguous (element (r,k) at base[r*ld + k]) -> dims {K, rows}, box {16, 128};
 // row-contiguous (element (r,k) at base[k*ld + r]) -> dims {rows, K}, box {16, 16}.  128-byte swizzle, zero fill out of bounds.
 // (float: the same with 32-element = 128-byte box rows: box {32, 128} resp. {32, 32}.)
-static int make_tmap( CUtensorMap* tm, const void* base, size_t es, bool kmajor, int64_t rows, int64_t K, int64_t ld )
+static int make_tmap( CUtensorMap* tm, const void* base, size_t es, bool kmajor, int64_t rows, int64_t K, int64_t ld, int box_rows = 128 )
 {
 	EncodeTiledFn enc = encode_tiled_fn();
 	if ( !enc ) return fail( "cuTensorMapEncodeTiled not available" );
 	const cuuint32_t inner = (cuuint32_t)( 128 / es );
 	cuuint64_t dims[2]    = { (cuuint64_t)( kmajor ? K : rows ), (cuuint64_t)( kmajor ? rows : K ) };
 	cuuint64_t strides[1] = { (cuuint64_t)ld * es };
-	cuuint32_t box[2]     = { inner, (cuuint32_t)( kmajor ? 128 : inner ) };
+	cuuint32_t box[2]     = { inner, (cuuint32_t)( kmajor ? box_rows : inner ) };
 	cuuint32_t estr[2]    = { 1, 1 };
 	const CUresult r = enc( tm, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
 	                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -254,6 +255,28 @@ static int launch_ffma_tma( const GemmArgs<float>& g, bool xk, bool yk, int grid
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, FfmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, FfmaTmaCfg::NT_ALL, FfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
+		B200_CUDA( cudaGetLastError() );
+		ctx().launches++;
+		return kSuccess;
+	};
+	using Tt = std::true_type; using Ff = std::false_type;
+	if ( xk ) return yk ? go( Tt{}, Tt{} ) : go( Tt{}, Ff{} );
+	return yk ? go( Ff{}, Tt{} ) : go( Ff{}, Ff{} );
+}
+
+static int launch_cfma_tma( const GemmArgs<float2>& g, bool xk, bool yk, int grid, cudaStream_t st )
+{
+	// float2 elements are moved as opaque 8-byte elements (FLOAT64-typed map; zero fill out of bounds)
+	CUtensorMap tmx, tmy;
+	if ( make_tmap( &tmx, g.X, 8, xk, g.P, g.K, g.ldx, CfmaTmaCfg::BP ) != kSuccess ) return kFailure;
+	if ( make_tmap( &tmy, g.Y, 8, yk, g.Q, g.K, g.ldy, CfmaTmaCfg::BQ ) != kSuccess ) return kFailure;
+	auto go = [&]( auto XKc, auto YKc ) -> int
+	{
+		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
+		auto kern = gemm_cfma_tma_kernel<XK, YK>;
+		static bool attr = false;
+		if ( !attr ) { if ( set_smem( kern, CfmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<grid, CfmaTmaCfg::NT_ALL, CfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
 		B200_CUDA( cudaGetLastError() );
 		ctx().launches++;
 		return kSuccess;
@@ -389,7 +412,8 @@ int launch_gemm_kernel<float2>( GemmArgs<float2>& g, bool xk, bool yk, bool al, 
 	if ( g.nseg > 1 ) return fail( "b200_gemm_kpanels: only d and z are supported" );
 	g.tiles_p = (int)( ( g.P + 63 ) / 64 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
 	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
-	if ( c.cgemm_cfg == 1 ) return launch_ffma_ws<float2, 64, 128, 16, 4, 8, 5>( g, xk, yk, al, grid, st );
+	if ( ( c.cgemm_cfg < 0 || c.cgemm_cfg == 3 ) && tma_eligible( g, xk, yk, al ) ) return launch_cfma_tma( g, xk, yk, grid, st );
+	if ( c.cgemm_cfg != 0 ) return launch_ffma_ws<float2, 64, 128, 16, 4, 8, 5>( g, xk, yk, al, grid, st );
 	return launch_ffma<float2, 64, 128, 16, 4, 8, 4>( g, xk, yk, al, grid, st );
 }
 

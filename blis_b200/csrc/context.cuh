@@ -47,7 +47,7 @@ struct Context
 	int          dgemm_cfg = -1;         // auto: TMA 128x128x16 (cfg 9) when aligned, cp.async ws (cfg 6) otherwise, 128x64 2 CTAs/SM (cfg 7) for small problems
 	int          zgemm_cfg = 1;          // warp-specialised 64x128x8, 5 stages
 	int          sgemm_cfg = -1;         // auto: TMA + FFMA2 kernel when aligned, cp.async kernel otherwise
-	int          cgemm_cfg = 1;          // warp-specialised 64x128x16
+	int          cgemm_cfg = -1;         // auto: TMA + FFMA2 kernel when aligned, cp.async ws kernel otherwise
 	int          trsm_nb   = 0;           // 0 = default
 	int          grid_mult = 1;           // persistent CTAs per SM
 	int*         sched_counters = nullptr;   // 64 self-resetting {tile, done} pairs for dynamic tile scheduling
