@@ -243,3 +243,56 @@ def test_gemm_kpanels_accumulates_like_blk_var3(engine, oracle, ch):
         api.bli_gemm_kpanels(NP2T[np.dtype(gen.NP_DT[ch])], 0, 0, m, n, k, al, ta, *estr(a_p[0]), tb, *estr(b_p[0]), be, tc, *estr(c))
         torch.cuda.synchronize()
         assert rel_err(to_numpy(tc), want) <= TOL[ch], (ch, oa, ob, oc)
+
+
+@pytest.mark.parametrize("ch", list("sdcz"))
+def test_gemm_aligned_operands_tma_paths(engine, oracle, ch):
+    """16-byte aligned operands (no padding, dimensions multiples of 4) take the TMA tensor-map kernels for
+    s/d/c: every trans combination = every (k-contiguous | p/q-contiguous) staging orientation, with ragged
+    tiles in m, n and k (TMA zero-fills out-of-bounds box elements)."""
+    cx = ch in "cz"
+    trs = (NO_TRANSPOSE, TRANSPOSE, CONJ_NO_TRANSPOSE, CONJ_TRANSPOSE) if cx else (NO_TRANSPOSE, TRANSPOSE)
+    al, be = ((2.0 + 0.2j, 1.2 + 0.5j) if cx else (2.0, 1.2))
+    seed = 3000
+    for (m, n, k) in ((260, 132, 68), (128, 128, 32), (4, 8, 4), (516, 260, 100)):
+        for ta in trs:
+            for tb in trs:
+                for oc in "cr":
+                    seed += 1
+                    am, ak = (k, m) if ta & TRANSPOSE else (m, k)
+                    bk, bn = (n, k) if tb & TRANSPOSE else (k, n)
+                    a = gen.matrix(ch, am, ak, seed, "frac", "c"); b = gen.matrix(ch, bk, bn, seed + 5000, "frac", "c")
+                    c = gen.matrix(ch, m, n, seed + 9000, "frac", oc)
+                    want = c.copy(order="K")
+                    oracle.gemm(ta, tb, al, a, b, be, want)
+                    got = run_gemm(engine, ch, ta, tb, al, a, b, be, c)
+                    assert rel_err(got, want) <= TOL[ch], (ch, m, n, k, ta, tb, oc, rel_err(got, want))
+
+
+def test_gemm_concurrent_host_threads(engine):
+    """BLIS is re-entrant (SURVEY 8b 'Threading'): several application threads call gemm at the same time,
+    each on its own CUDA stream; the engine's shared state (tile-scheduler counters, workspace pool, staging
+    ring) must not interfere."""
+    import threading
+    results = {}
+
+    def work(tid):
+        torch.cuda.set_device(0)
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            g = torch.Generator(device="cuda"); g.manual_seed(100 + tid)
+            n = 768 + 64 * tid
+            a = torch.rand(n, n, dtype=torch.float64, device="cuda", generator=g).t()
+            b = torch.rand(n, n, dtype=torch.float64, device="cuda", generator=g).t()
+            ok = True
+            for _ in range(20):
+                c = torch.zeros(n, n, dtype=torch.float64, device="cuda").t()
+                engine.bli_dgemm(0, 0, n, n, n, 1.0, a, 1, n, b, 1, n, 0.0, c, 1, n)
+                s.synchronize()
+                ok = ok and bool(torch.allclose(c, a @ b, rtol=1e-12, atol=1e-9))
+            results[tid] = ok
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in ts: t.start()
+    for t in ts: t.join()
+    assert results == {0: True, 1: True, 2: True, 3: True}, results
