@@ -25,6 +25,7 @@ EXPORTS = [
     "b200_set_stream", "b200_get_stream", "b200_sync", "b200_malloc_pinned", "b200_free_pinned",
     "b200_gemm", "b200_gemm_kpanels", "b200_sgemm", "b200_dgemm", "b200_cgemm", "b200_zgemm",
     "b200_trsm", "b200_strsm", "b200_dtrsm", "b200_ctrsm", "b200_ztrsm",
+    "b200_gemmt", "b200_syrk", "b200_herk", "b200_syr2k", "b200_her2k",
     "b200_blksz", "b200_measure_peak", "b200_launch_count", "b200_set_option",
 ]
 
@@ -64,6 +65,12 @@ def load() -> C.CDLL:
     lib.b200_trsm.argtypes = [ci, ci, ci, ci, ci] + trsm_tail; lib.b200_trsm.restype = ci
     for ch in "sdcz":
         f = getattr(lib, f"b200_{ch}trsm"); f.argtypes = [ci, ci, ci, ci] + trsm_tail; f.restype = ci
+    two_op = [ci, ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]     # dt uplo transa transb m k ...
+    one_op = [ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, vp, i64, i64]                        # dt uplo transa m k ...
+    for name in ("gemmt", "syr2k", "her2k"):
+        f = getattr(lib, f"b200_{name}"); f.argtypes = two_op; f.restype = ci
+    for name in ("syrk", "herk"):
+        f = getattr(lib, f"b200_{name}"); f.argtypes = one_op; f.restype = ci
     lib.b200_blksz.argtypes = [ci, ci]; lib.b200_blksz.restype = i64
     lib.b200_measure_peak.argtypes = [ci, ci]; lib.b200_measure_peak.restype = C.c_double
     lib.b200_launch_count.argtypes = []; lib.b200_launch_count.restype = C.c_ulonglong

@@ -2,7 +2,8 @@
 
 Three layers, named as in BLIS so that tests read like the reference's own:
 
-* typed API   `bli_?gemm`, `bli_?trsm`            frame/3/bli_l3_tapi.c
+* typed API   `bli_?gemm`, `bli_?trsm`, `bli_?gemmt`, `bli_?syrk`, `bli_?herk`, `bli_?syr2k`, `bli_?her2k`
+                                                 frame/3/bli_l3_tapi.c
 * object API  `bli_gemm`, `bli_trsm` on `Obj`     frame/3/bli_l3_oapi.c
 * BLAS compat `dgemm_`-style column-major calls   frame/compat/bla_gemm.c:127-259,
                                                  frame/compat/bla_trsm.c:126-217
@@ -95,6 +96,43 @@ def _typed_trsm(dtype):
         check(rc, "bli_trsm")
     return f
 
+
+_REAL = {torch.float32: torch.float32, torch.float64: torch.float64,
+         torch.complex64: torch.float32, torch.complex128: torch.float64}
+
+
+def _typed_two_operand(dtype, name):
+    """bli_?gemmt / bli_?syr2k / bli_?her2k (frame/3/bli_l3_tapi.c:77-112,189-220,254-296): one triangle of the
+    m x m matrix C is updated; her2k's beta is real."""
+    def f(uploc, transa, transb, m, k, alpha, a, rs_a, cs_a, b, rs_b, cs_b, beta, c, rs_c, cs_c):
+        lib = _lib.load()
+        _bind_stream(a, b, c)
+        al = _scalar_buf(dtype, alpha)
+        be = _scalar_buf(_REAL[dtype] if name == "her2k" else dtype, beta)
+        rc = getattr(lib, "b200_" + name)(_DT[dtype], int(uploc), int(transa), int(transb), m, k, C.addressof(al),
+                                          _ptr(a), rs_a, cs_a, _ptr(b), rs_b, cs_b, C.addressof(be), _ptr(c), rs_c, cs_c)
+        check(rc, "bli_" + name)
+    return f
+
+
+def _typed_one_operand(dtype, name):
+    """bli_?syrk / bli_?herk (frame/3/bli_l3_tapi.c:157-187,222-252); herk's alpha and beta are real."""
+    def f(uploc, transa, m, k, alpha, a, rs_a, cs_a, beta, c, rs_c, cs_c):
+        lib = _lib.load()
+        _bind_stream(a, c)
+        sdt = _REAL[dtype] if name == "herk" else dtype
+        al, be = _scalar_buf(sdt, alpha), _scalar_buf(sdt, beta)
+        rc = getattr(lib, "b200_" + name)(_DT[dtype], int(uploc), int(transa), m, k, C.addressof(al),
+                                          _ptr(a), rs_a, cs_a, C.addressof(be), _ptr(c), rs_c, cs_c)
+        check(rc, "bli_" + name)
+    return f
+
+
+for _ch, _dt in _CH.items():
+    for _name in ("gemmt", "syr2k", "her2k"):
+        globals()[f"bli_{_ch}{_name}"] = _typed_two_operand(_dt, _name)
+    for _name in ("syrk", "herk"):
+        globals()[f"bli_{_ch}{_name}"] = _typed_one_operand(_dt, _name)
 
 bli_sgemm, bli_dgemm = _typed_gemm(torch.float32), _typed_gemm(torch.float64)
 bli_cgemm, bli_zgemm = _typed_gemm(torch.complex64), _typed_gemm(torch.complex128)

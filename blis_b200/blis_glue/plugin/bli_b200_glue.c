@@ -141,6 +141,145 @@ void bli_trsm_ex( side_t side, const obj_t* alpha, const obj_t* a, const obj_t* 
 }
 #endif
 
+/* -- gemmt family: same parameter lists as bli_gemmt_ex / bli_syrk_ex / bli_herk_ex /
+      bli_syr2k_ex / bli_her2k_ex (frame/3/bli_l3_oapi_ex.c:151-346) ------------------
+
+   bli_gemmt_ex never consults the BLIS_GEMMT handler slot in this snapshot (the slot exists,
+   ref_kernels/bli_cntx_ref.c:563, but bli_l3_oapi_ex.c:151-228 goes straight to the control
+   tree), so these operations are bound like trsm: functions with the expert-API signatures
+   that the b200 configuration resolves the public names to ("gemmt family").
+   The rank-k/2k operations are bound individually rather than through gemmt because the
+   reference calls gemmt from inside the same translation unit. */
+
+static void bli_b200_scalar( num_t dt, const obj_t* s, obj_t* out )
+{
+	bli_obj_scalar_init_detached_copy_of( dt, BLIS_NO_CONJUGATE, s, out );
+}
+
+static bool bli_b200_same_dt( const obj_t* a, const obj_t* b, const obj_t* c, const char* op )
+{
+	const num_t dt = bli_obj_dt( c );
+	if ( bli_obj_dt( a ) == dt && ( b == NULL || bli_obj_dt( b ) == dt ) ) return TRUE;
+	fprintf( stderr, "libblis (b200): mixed-datatype %s is not supported by the b200 engine.\n", op );
+	bli_abort();
+	return FALSE;
+}
+
+void bli_gemmt_ex_b200( const obj_t* alpha, const obj_t* a, const obj_t* b, const obj_t* beta, const obj_t* c,
+                        const cntx_t* cntx, const rntm_t* rntm )
+{
+	( void )rntm;
+	bli_init_once();
+	if ( bli_error_checking_is_enabled() ) bli_gemmt_check( alpha, a, b, beta, c, cntx );
+	bli_b200_same_dt( a, b, c, "gemmt" );
+	if ( bli_obj_has_zero_dim( c ) ) return;
+	const num_t dt = bli_obj_dt( c );
+	obj_t al, be; bli_b200_scalar( dt, alpha, &al ); bli_b200_scalar( dt, beta, &be );
+	const err_t r = b200_gemmt( ( int )dt, ( int )bli_obj_uplo( c ),
+	  ( int )bli_obj_conjtrans_status( a ), ( int )bli_obj_conjtrans_status( b ),
+	  bli_obj_length( c ), bli_obj_width_after_trans( a ),
+	  bli_obj_buffer_for_1x1( dt, &al ),
+	  bli_obj_buffer_at_off( a ), bli_obj_row_stride( a ), bli_obj_col_stride( a ),
+	  bli_obj_buffer_at_off( b ), bli_obj_row_stride( b ), bli_obj_col_stride( b ),
+	  bli_obj_buffer_for_1x1( dt, &be ),
+	  bli_obj_buffer_at_off( c ), bli_obj_row_stride( c ), bli_obj_col_stride( c ) );
+	if ( r != BLIS_SUCCESS ) bli_b200_die( "gemmt" );
+}
+
+void bli_syrk_ex_b200( const obj_t* alpha, const obj_t* a, const obj_t* beta, const obj_t* c,
+                       const cntx_t* cntx, const rntm_t* rntm )
+{
+	( void )rntm;
+	bli_init_once();
+	if ( bli_error_checking_is_enabled() ) bli_syrk_check( alpha, a, beta, c, cntx );
+	bli_b200_same_dt( a, NULL, c, "syrk" );
+	if ( bli_obj_has_zero_dim( c ) ) return;
+	const num_t dt = bli_obj_dt( c );
+	obj_t al, be; bli_b200_scalar( dt, alpha, &al ); bli_b200_scalar( dt, beta, &be );
+	const err_t r = b200_syrk( ( int )dt, ( int )bli_obj_uplo( c ), ( int )bli_obj_conjtrans_status( a ),
+	  bli_obj_length( c ), bli_obj_width_after_trans( a ),
+	  bli_obj_buffer_for_1x1( dt, &al ),
+	  bli_obj_buffer_at_off( a ), bli_obj_row_stride( a ), bli_obj_col_stride( a ),
+	  bli_obj_buffer_for_1x1( dt, &be ),
+	  bli_obj_buffer_at_off( c ), bli_obj_row_stride( c ), bli_obj_col_stride( c ) );
+	if ( r != BLIS_SUCCESS ) bli_b200_die( "syrk" );
+}
+
+void bli_herk_ex_b200( const obj_t* alpha, const obj_t* a, const obj_t* beta, const obj_t* c,
+                       const cntx_t* cntx, const rntm_t* rntm )
+{
+	( void )rntm;
+	bli_init_once();
+	if ( bli_error_checking_is_enabled() ) bli_herk_check( alpha, a, beta, c, cntx );
+	bli_b200_same_dt( a, NULL, c, "herk" );
+	if ( bli_obj_has_zero_dim( c ) ) return;
+	const num_t dt = bli_obj_dt( c ), dt_r = bli_dt_proj_to_real( dt );
+	obj_t al, be; bli_b200_scalar( dt_r, alpha, &al ); bli_b200_scalar( dt_r, beta, &be );   /* real scalars */
+	const err_t r = b200_herk( ( int )dt, ( int )bli_obj_uplo( c ), ( int )bli_obj_conjtrans_status( a ),
+	  bli_obj_length( c ), bli_obj_width_after_trans( a ),
+	  bli_obj_buffer_for_1x1( dt_r, &al ),
+	  bli_obj_buffer_at_off( a ), bli_obj_row_stride( a ), bli_obj_col_stride( a ),
+	  bli_obj_buffer_for_1x1( dt_r, &be ),
+	  bli_obj_buffer_at_off( c ), bli_obj_row_stride( c ), bli_obj_col_stride( c ) );
+	if ( r != BLIS_SUCCESS ) bli_b200_die( "herk" );
+}
+
+void bli_syr2k_ex_b200( const obj_t* alpha, const obj_t* a, const obj_t* b, const obj_t* beta, const obj_t* c,
+                        const cntx_t* cntx, const rntm_t* rntm )
+{
+	( void )rntm;
+	bli_init_once();
+	if ( bli_error_checking_is_enabled() ) bli_syr2k_check( alpha, a, b, beta, c, cntx );
+	bli_b200_same_dt( a, b, c, "syr2k" );
+	if ( bli_obj_has_zero_dim( c ) ) return;
+	const num_t dt = bli_obj_dt( c );
+	obj_t al, be; bli_b200_scalar( dt, alpha, &al ); bli_b200_scalar( dt, beta, &be );
+	const err_t r = b200_syr2k( ( int )dt, ( int )bli_obj_uplo( c ),
+	  ( int )bli_obj_conjtrans_status( a ), ( int )bli_obj_conjtrans_status( b ),
+	  bli_obj_length( c ), bli_obj_width_after_trans( a ),
+	  bli_obj_buffer_for_1x1( dt, &al ),
+	  bli_obj_buffer_at_off( a ), bli_obj_row_stride( a ), bli_obj_col_stride( a ),
+	  bli_obj_buffer_at_off( b ), bli_obj_row_stride( b ), bli_obj_col_stride( b ),
+	  bli_obj_buffer_for_1x1( dt, &be ),
+	  bli_obj_buffer_at_off( c ), bli_obj_row_stride( c ), bli_obj_col_stride( c ) );
+	if ( r != BLIS_SUCCESS ) bli_b200_die( "syr2k" );
+}
+
+void bli_her2k_ex_b200( const obj_t* alpha, const obj_t* a, const obj_t* b, const obj_t* beta, const obj_t* c,
+                        const cntx_t* cntx, const rntm_t* rntm )
+{
+	( void )rntm;
+	bli_init_once();
+	if ( bli_error_checking_is_enabled() ) bli_her2k_check( alpha, a, b, beta, c, cntx );
+	bli_b200_same_dt( a, b, c, "her2k" );
+	if ( bli_obj_has_zero_dim( c ) ) return;
+	const num_t dt = bli_obj_dt( c ), dt_r = bli_dt_proj_to_real( dt );
+	obj_t al, be; bli_b200_scalar( dt, alpha, &al ); bli_b200_scalar( dt_r, beta, &be );     /* beta is real */
+	const err_t r = b200_her2k( ( int )dt, ( int )bli_obj_uplo( c ),
+	  ( int )bli_obj_conjtrans_status( a ), ( int )bli_obj_conjtrans_status( b ),
+	  bli_obj_length( c ), bli_obj_width_after_trans( a ),
+	  bli_obj_buffer_for_1x1( dt, &al ),
+	  bli_obj_buffer_at_off( a ), bli_obj_row_stride( a ), bli_obj_col_stride( a ),
+	  bli_obj_buffer_at_off( b ), bli_obj_row_stride( b ), bli_obj_col_stride( b ),
+	  bli_obj_buffer_for_1x1( dt_r, &be ),
+	  bli_obj_buffer_at_off( c ), bli_obj_row_stride( c ), bli_obj_col_stride( c ) );
+	if ( r != BLIS_SUCCESS ) bli_b200_die( "her2k" );
+}
+
+#ifdef BLIS_B200_OVERRIDE_GEMMT_EX
+/* Build-time switch of the config route / LD_PRELOAD demo, as for trsm. */
+void bli_gemmt_ex( const obj_t* alpha, const obj_t* a, const obj_t* b, const obj_t* beta, const obj_t* c, const cntx_t* cntx, const rntm_t* rntm )
+{ bli_gemmt_ex_b200( alpha, a, b, beta, c, cntx, rntm ); }
+void bli_syrk_ex( const obj_t* alpha, const obj_t* a, const obj_t* beta, const obj_t* c, const cntx_t* cntx, const rntm_t* rntm )
+{ bli_syrk_ex_b200( alpha, a, beta, c, cntx, rntm ); }
+void bli_herk_ex( const obj_t* alpha, const obj_t* a, const obj_t* beta, const obj_t* c, const cntx_t* cntx, const rntm_t* rntm )
+{ bli_herk_ex_b200( alpha, a, beta, c, cntx, rntm ); }
+void bli_syr2k_ex( const obj_t* alpha, const obj_t* a, const obj_t* b, const obj_t* beta, const obj_t* c, const cntx_t* cntx, const rntm_t* rntm )
+{ bli_syr2k_ex_b200( alpha, a, b, beta, c, cntx, rntm ); }
+void bli_her2k_ex( const obj_t* alpha, const obj_t* a, const obj_t* b, const obj_t* beta, const obj_t* c, const cntx_t* cntx, const rntm_t* rntm )
+{ bli_her2k_ex_b200( alpha, a, b, beta, c, cntx, rntm ); }
+#endif
+
 /* -- registration ----------------------------------------------------------- */
 
 /* Install the engine into one context: tile shapes as blocksizes, thresholds

@@ -56,13 +56,14 @@ template <> struct Scalar<double2>
 template <typename R, int NC>
 __global__ void copy2d_kernel( R* __restrict__ dst, int64_t rsd, int64_t csd,
                                const R* __restrict__ src, int64_t rss, int64_t css,
-                               int64_t m, int64_t n, int inner_is_row )
+                               int64_t m, int64_t n, int inner_is_row, int tri )
 {
 	const int64_t total = m * n;
 	for ( int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x )
 	{
 		int64_t i, j;
 		if ( inner_is_row ) { i = e % m; j = e / m; } else { j = e % n; i = e / n; }
+		if ( ( tri == 1 && i < j ) || ( tri == 2 && i > j ) ) continue;      // only the stored triangle (1: lower, 2: upper)
 		const R* s = src + ( i * rss + j * css ) * NC;
 		R*       d = dst + ( i * rsd + j * csd ) * NC;
 		#pragma unroll
@@ -73,13 +74,14 @@ __global__ void copy2d_kernel( R* __restrict__ dst, int64_t rsd, int64_t csd,
 // C := beta * C  (beta == 0 stores zeros without reading C: bli_scalm / bli_setm)
 template <typename R, int NC>
 __global__ void scal2d_kernel( R* __restrict__ c, int64_t rs, int64_t cs, int64_t m, int64_t n,
-                               R br, R bi, int beta_is_zero, int inner_is_row )
+                               R br, R bi, int beta_is_zero, int inner_is_row, int tri )
 {
 	const int64_t total = m * n;
 	for ( int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x )
 	{
 		int64_t i, j;
 		if ( inner_is_row ) { i = e % m; j = e / m; } else { j = e % n; i = e / n; }
+		if ( ( tri == 1 && i < j ) || ( tri == 2 && i > j ) ) continue;      // only the stored triangle (1: lower, 2: upper)
 		R* p = c + ( i * rs + j * cs ) * NC;
 		if ( beta_is_zero ) { for ( int q = 0; q < NC; ++q ) p[q] = (R)0; }
 		else if ( NC == 1 ) p[0] = br * p[0];
@@ -91,24 +93,26 @@ static inline int64_t iabs64( int64_t x ) { return x < 0 ? -x : x; }
 
 template <typename T>
 static int copy2d( T* dst, int64_t rsd, int64_t csd, const T* src, int64_t rss, int64_t css,
-                   int64_t m, int64_t n, cudaStream_t st )
+                   int64_t m, int64_t n, cudaStream_t st, int uplo = 0 )
 {
 	if ( m <= 0 || n <= 0 ) return kSuccess;
+	const int tri = ( uplo == B200_LOWER ) ? 1 : ( uplo == B200_UPPER ) ? 2 : 0;
 	using R = typename Elem<T>::real;
 	constexpr int NC = Elem<T>::cplx ? 2 : 1;
 	const int inner_is_row = ( iabs64( rss ) + iabs64( rsd ) <= iabs64( css ) + iabs64( csd ) );
 	const int64_t total = m * n;
 	const int blocks = (int)std::min<int64_t>( ( total + 255 ) / 256, (int64_t)ctx().num_sms * 16 );
-	copy2d_kernel<R, NC><<<blocks, 256, 0, st>>>( (R*)dst, rsd, csd, (const R*)src, rss, css, m, n, inner_is_row );
+	copy2d_kernel<R, NC><<<blocks, 256, 0, st>>>( (R*)dst, rsd, csd, (const R*)src, rss, css, m, n, inner_is_row, tri );
 	B200_CUDA( cudaGetLastError() );
 	ctx().launches++;
 	return kSuccess;
 }
 
 template <typename T>
-static int scal2d( T* c, int64_t rs, int64_t cs, int64_t m, int64_t n, T beta, cudaStream_t st )
+static int scal2d( T* c, int64_t rs, int64_t cs, int64_t m, int64_t n, T beta, cudaStream_t st, int uplo = 0 )
 {
 	if ( m <= 0 || n <= 0 || Scalar<T>::is_one( beta ) ) return kSuccess;
+	const int tri = ( uplo == B200_LOWER ) ? 1 : ( uplo == B200_UPPER ) ? 2 : 0;
 	using R = typename Elem<T>::real;
 	constexpr int NC = Elem<T>::cplx ? 2 : 1;
 	R br, bi;
@@ -116,7 +120,7 @@ static int scal2d( T* c, int64_t rs, int64_t cs, int64_t m, int64_t n, T beta, c
 	const int inner_is_row = ( iabs64( rs ) <= iabs64( cs ) );
 	const int64_t total = m * n;
 	const int blocks = (int)std::min<int64_t>( ( total + 255 ) / 256, (int64_t)ctx().num_sms * 16 );
-	scal2d_kernel<R, NC><<<blocks, 256, 0, st>>>( (R*)c, rs, cs, m, n, br, bi, Scalar<T>::is_zero( beta ) ? 1 : 0, inner_is_row );
+	scal2d_kernel<R, NC><<<blocks, 256, 0, st>>>( (R*)c, rs, cs, m, n, br, bi, Scalar<T>::is_zero( beta ) ? 1 : 0, inner_is_row, tri );
 	B200_CUDA( cudaGetLastError() );
 	ctx().launches++;
 	return kSuccess;
@@ -156,14 +160,14 @@ static int launch_dmma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int gri
 	}
 }
 
-template <typename T, int BP, int BQ, int BK, int WP, int WQ, int ST>
+template <typename T, int BP, int BQ, int BK, int WP, int WQ, int ST, bool TRI = false>
 static int launch_dmma_ws( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
 {
 	auto go = [&]( auto XKc, auto YKc, auto ALc ) -> int
 	{
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
 		using Cfg = DmmaWsCfg<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
-		auto kern = gemm_dmma_ws_kernel<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
+		auto kern = gemm_dmma_ws_kernel<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL, TRI>;
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, Cfg::NT_ALL, Cfg::SMEM_BYTES, st>>>( g );
@@ -222,6 +226,7 @@ static bool tma_eligible( const GemmArgs<T>& g, bool xk, bool yk, bool al )
 	return al && g.nseg == 1 && g.P < ( 1ll << 31 ) && g.Q < ( 1ll << 31 ) && g.K < ( 1ll << 31 ) &&
 	       g.ldx >= ( xk ? g.K : g.P ) && g.ldy >= ( yk ? g.K : g.Q ) && g.ldx * 8 < ( 1ll << 40 ) && g.ldy * 8 < ( 1ll << 40 );
 }
+template <bool TRI = false>
 static int launch_dmma_tma( const GemmArgs<double>& g, bool xk, bool yk, int grid, cudaStream_t st )
 {
 	CUtensorMap tmx, tmy;
@@ -230,7 +235,7 @@ static int launch_dmma_tma( const GemmArgs<double>& g, bool xk, bool yk, int gri
 	auto go = [&]( auto XKc, auto YKc ) -> int
 	{
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
-		auto kern = gemm_dmma_tma_kernel<XK, YK>;
+		auto kern = gemm_dmma_tma_kernel<XK, YK, TRI>;
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, DmmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, DmmaTmaCfg::NT_ALL, DmmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
@@ -243,6 +248,7 @@ static int launch_dmma_tma( const GemmArgs<double>& g, bool xk, bool yk, int gri
 	return yk ? go( Ff{}, Tt{} ) : go( Ff{}, Ff{} );
 }
 
+template <bool TRI = false>
 static int launch_ffma_tma( const GemmArgs<float>& g, bool xk, bool yk, int grid, cudaStream_t st )
 {
 	CUtensorMap tmx, tmy;
@@ -251,7 +257,7 @@ static int launch_ffma_tma( const GemmArgs<float>& g, bool xk, bool yk, int grid
 	auto go = [&]( auto XKc, auto YKc ) -> int
 	{
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
-		auto kern = gemm_ffma_tma_kernel<XK, YK>;
+		auto kern = gemm_ffma_tma_kernel<XK, YK, TRI>;
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, FfmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, FfmaTmaCfg::NT_ALL, FfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
@@ -264,6 +270,7 @@ static int launch_ffma_tma( const GemmArgs<float>& g, bool xk, bool yk, int grid
 	return yk ? go( Ff{}, Tt{} ) : go( Ff{}, Ff{} );
 }
 
+template <bool TRI = false>
 static int launch_cfma_tma( const GemmArgs<float2>& g, bool xk, bool yk, int grid, cudaStream_t st )
 {
 	// float2 elements are moved as opaque 8-byte elements (FLOAT64-typed map; zero fill out of bounds)
@@ -273,7 +280,7 @@ static int launch_cfma_tma( const GemmArgs<float2>& g, bool xk, bool yk, int gri
 	auto go = [&]( auto XKc, auto YKc ) -> int
 	{
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
-		auto kern = gemm_cfma_tma_kernel<XK, YK>;
+		auto kern = gemm_cfma_tma_kernel<XK, YK, TRI>;
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, CfmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, CfmaTmaCfg::NT_ALL, CfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
@@ -359,6 +366,18 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 	};
 	int cfg = c.dgemm_cfg;
 	if ( g.nseg > 1 && ( cfg < 4 ) ) cfg = -1;          // k-panel accumulation needs a warp-specialised kernel
+	if ( g.tri )
+	{
+		// triangular D (gemmt family): the TRI instantiations of the default kernels
+		const int64_t t128 = ( ( g.P + 127 ) / 128 ) * ( ( g.Q + 127 ) / 128 );
+		if ( t128 < 2 * c.num_sms )
+		{
+			const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 128, 64 ); c.grid_mult = gm;
+			return launch_dmma_ws<double, 128, 64, 16, 4, 1, 3, true>( g, xk, yk, al, grid, st );
+		}
+		if ( tma_eligible( g, xk, yk, al ) ) return launch_dmma_tma<true>( g, xk, yk, tiles( 128, 128 ), st );
+		return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5, true>( g, xk, yk, al, tiles( 128, 128 ), st );
+	}
 	if ( cfg < 0 )
 	{
 		// auto: the cooperative 128x128 tile unless it cannot fill the SMs once; then 128x64 tiles, two CTAs per SM
@@ -389,6 +408,7 @@ int launch_gemm_kernel<double2>( GemmArgs<double2>& g, bool xk, bool yk, bool al
 	Context& c = ctx();
 	g.tiles_p = (int)( ( g.P + 63 ) / 64 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
 	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
+	if ( g.tri ) return launch_dmma_ws<double2, 64, 128, 8, 2, 4, 5, true>( g, xk, yk, al, grid, st );
 	if ( c.zgemm_cfg == 1 || g.nseg > 1 ) return launch_dmma_ws<double2, 64, 128, 8, 2, 4, 5>( g, xk, yk, al, grid, st );
 	return launch_dmma<double2, 64, 128, 8, 2, 4, 4>( g, xk, yk, al, grid, st );
 }
@@ -400,6 +420,11 @@ int launch_gemm_kernel<float>( GemmArgs<float>& g, bool xk, bool yk, bool al, cu
 	g.tiles_p = (int)( ( g.P + 127 ) / 128 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
 	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
 	// default (sgemm_cfg < 0 or 3): TMA + packed-FFMA2 kernel when the operands are 16-byte aligned
+	if ( g.tri )
+	{
+		if ( tma_eligible( g, xk, yk, al ) ) return launch_ffma_tma<true>( g, xk, yk, grid, st );
+		return launch_ffma<float, 128, 128, 16, 8, 8, 4>( g, xk, yk, al, grid, st );       // run-time tri support
+	}
 	if ( ( c.sgemm_cfg < 0 || c.sgemm_cfg == 3 ) && tma_eligible( g, xk, yk, al ) ) return launch_ffma_tma( g, xk, yk, grid, st );
 	if ( c.sgemm_cfg == 1 ) return launch_ffma_ws<float, 128, 128, 16, 8, 8, 5>( g, xk, yk, al, grid, st );
 	if ( c.sgemm_cfg == 2 ) return launch_ffma_ws<float, 128, 128, 32, 8, 8, 4>( g, xk, yk, al, grid, st );
@@ -412,6 +437,11 @@ int launch_gemm_kernel<float2>( GemmArgs<float2>& g, bool xk, bool yk, bool al, 
 	if ( g.nseg > 1 ) return fail( "b200_gemm_kpanels: only d and z are supported" );
 	g.tiles_p = (int)( ( g.P + 63 ) / 64 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
 	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
+	if ( g.tri )
+	{
+		if ( tma_eligible( g, xk, yk, al ) ) return launch_cfma_tma<true>( g, xk, yk, grid, st );
+		return launch_ffma_ws<float2, 64, 128, 16, 4, 8, 5>( g, xk, yk, al, grid, st );     // run-time tri support
+	}
 	if ( ( c.cgemm_cfg < 0 || c.cgemm_cfg == 3 ) && tma_eligible( g, xk, yk, al ) ) return launch_cfma_tma( g, xk, yk, grid, st );
 	if ( c.cgemm_cfg != 0 ) return launch_ffma_ws<float2, 64, 128, 16, 4, 8, 5>( g, xk, yk, al, grid, st );
 	return launch_ffma<float2, 64, 128, 16, 4, 8, 4>( g, xk, yk, al, grid, st );
@@ -425,11 +455,12 @@ static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T 
                      const T* a, int64_t rs_a, int64_t cs_a,
                      const T* b, int64_t rs_b, int64_t cs_b,
                      T beta, T* c, int64_t rs_c, int64_t cs_c, cudaStream_t st,
-                     int nseg = 1, const T* const* a_more = nullptr, const T* const* b_more = nullptr )
+                     int nseg = 1, const T* const* a_more = nullptr, const T* const* b_more = nullptr,
+                     int uplo_c = 0 )     // 0: all of C; B200_LOWER / B200_UPPER: only that triangle of C is computed and stored
 {
 	if ( m <= 0 || n <= 0 ) return kSuccess;
 	// bli_l3_return_early_if_trivial: alpha == 0 or k == 0  ->  C := beta*C
-	if ( k <= 0 || Scalar<T>::is_zero( alpha ) ) return scal2d( c, rs_c, cs_c, m, n, beta, st );
+	if ( k <= 0 || Scalar<T>::is_zero( alpha ) ) return scal2d( c, rs_c, cs_c, m, n, beta, st, uplo_c );
 
 	constexpr size_t ES = sizeof(T);
 	void *tmp_c = nullptr, *tmp_x = nullptr, *tmp_y = nullptr;
@@ -445,7 +476,7 @@ static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T 
 	{
 		if ( dev_alloc( &tmp_c, (size_t)m * n * ES, st ) != kSuccess ) return kFailure;
 		cd = (T*)tmp_c; rs_cd = 1; cs_cd = m;
-		if ( !Scalar<T>::is_zero( beta ) ) rc = copy2d( cd, rs_cd, cs_cd, c, rs_c, cs_c, m, n, st );
+		if ( !Scalar<T>::is_zero( beta ) ) rc = copy2d( cd, rs_cd, cs_cd, c, rs_c, cs_c, m, n, st, uplo_c );
 	}
 
 	GemmArgs<T> g;
@@ -469,6 +500,11 @@ static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T 
 	g.D = cd; g.K = k; g.alpha = alpha; g.beta = beta;
 	g.beta_is_zero = Scalar<T>::is_zero( beta ) ? 1 : 0;
 	g.nseg = nseg;
+	// stored triangle in D coordinates: C lower = {i >= j}.  D = C: p = i, q = j -> q - p <= 0 (tri 1);
+	// D = C^T: p = j, q = i -> q - p >= 0 (tri 2); upper is the mirror image.
+	g.tri = 0; g.tri_off = 0;
+	if ( uplo_c == B200_LOWER ) g.tri = swapped ? 2 : 1;
+	if ( uplo_c == B200_UPPER ) g.tri = swapped ? 1 : 2;
 	g.tile_counter = ctx().dynamic_tiles ? ctx().sched_counters + 2 * ( ctx().sched_next++ % 64 ) : nullptr;
 	for ( int sgm = 1; sgm < nseg; ++sgm )
 	{
@@ -505,7 +541,7 @@ static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T 
 		g.d_vec_ok = ( (uintptr_t)g.D % 16 == 0 ) && ( ( g.ldd * ES ) % 16 == 0 );
 		rc = launch_gemm_kernel<T>( g, xk, yk, al, st );
 	}
-	if ( rc == kSuccess && c_general ) rc = copy2d( c, rs_c, cs_c, cd, rs_cd, cs_cd, m, n, st );
+	if ( rc == kSuccess && c_general ) rc = copy2d( c, rs_c, cs_c, cd, rs_cd, cs_cd, m, n, st, uplo_c );
 	dev_free( tmp_x, st ); dev_free( tmp_y, st ); dev_free( tmp_c, st );
 	return rc;
 }
@@ -751,6 +787,132 @@ static int trsm_front( int side, int uplo, int transa, int diag, int64_t m, int6
 	return rc;
 }
 
+// ---- gemmt family: gemmt, syrk, herk, syr2k, her2k ---------------------------------------
+// bli_gemmt_ex / bli_syrk_ex / bli_herk_ex / bli_syr2k_ex / bli_her2k_ex (frame/3/bli_l3_oapi_ex.c:151-346):
+// every one of them is one or two gemmt's, C := beta*C + alpha*A*B restricted to the stored triangle of the
+// m x m matrix C (macrokernels frame/3/gemmt/bli_gemmt_{l,u}_ker_var2.c); herk/her2k then zero the imaginary
+// part of the diagonal (bli_setid).  Here a gemmt is the gemm kernel with a triangular tile schedule.
+enum { kOpGemmt = 0, kOpSyrk = 1, kOpHerk = 2, kOpSyr2k = 3, kOpHer2k = 4 };
+
+template <typename R>
+__global__ void zero_diag_imag_kernel( R* c, int64_t inc, int64_t m )
+{
+	for ( int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x )
+		c[2 * i * inc + 1] = (R)0;
+}
+
+// Device view of a host or device operand: host data is staged into a dense column-major temporary.
+template <typename T>
+static int operand_to_device( const T*& p, int64_t& rs, int64_t& cs, int64_t m, int64_t n, void** tmp, cudaStream_t st )
+{
+	*tmp = nullptr;
+	if ( m <= 0 || n <= 0 || classify( p ) == MemKind::Device ) return kSuccess;
+	if ( dev_alloc( tmp, (size_t)m * n * sizeof(T), st ) != kSuccess ) return kFailure;
+	if ( stage_to_device( *tmp, p, m, n, rs, cs, sizeof(T), st ) != kSuccess ) return kFailure;
+	p = (const T*)*tmp; rs = 1; cs = m;
+	return kSuccess;
+}
+
+template <typename T>
+static int gemmt_family_front( int op, int uploc, int transa, int transb, int64_t m, int64_t k,
+                               const T* alpha, const T* a, int64_t rs_a, int64_t cs_a,
+                               const T* b, int64_t rs_b, int64_t cs_b,
+                               const T* beta, T* c, int64_t rs_c, int64_t cs_c, const char* name )
+{
+	if ( ensure_init() != kSuccess ) return kFailure;
+	if ( m < 0 || k < 0 ) return fail( "%s: negative dimension", name );
+	if ( !alpha || !beta ) return fail( "%s: alpha/beta must be non-NULL host pointers", name );
+	if ( uploc != B200_LOWER && uploc != B200_UPPER ) return fail( "%s: uplo must be BLIS_LOWER or BLIS_UPPER", name );
+	if ( m == 0 ) return kSuccess;
+	cudaStream_t st = cur_stream();
+	constexpr bool CPLX = Elem<T>::cplx;
+	const bool two_operands = ( op == kOpGemmt || op == kOpSyr2k || op == kOpHer2k );
+	const bool hermitian    = ( op == kOpHerk || op == kOpHer2k ); (void)hermitian;
+	if ( !two_operands ) { b = a; rs_b = rs_a; cs_b = cs_a; transb = transa; }
+
+	// op(A): m x k.  op(B): k x m for gemmt, m x k for the rank-2k operations (bli_l3_tapi_ex.c:251-252).
+	if ( transa & B200_TRANSPOSE ) std::swap( rs_a, cs_a );
+	if ( transb & B200_TRANSPOSE ) std::swap( rs_b, cs_b );
+	const bool ca = CPLX && ( transa & B200_CONJ_NO_TRANSPOSE );
+	const bool cb = CPLX && ( transb & B200_CONJ_NO_TRANSPOSE );
+	const T al = *alpha, be = *beta;
+	const bool need_ab = ( k > 0 && !Scalar<T>::is_zero( al ) );
+
+	void *da = nullptr, *db = nullptr, *dc = nullptr;
+	int rc = kSuccess;
+	const bool shared_ab = ( op != kOpGemmt && a == b && rs_a == rs_b && cs_a == cs_b );
+	if ( need_ab )
+	{
+		const T* a0 = a;
+		rc = operand_to_device( a, rs_a, cs_a, m, k, &da, st );
+		if ( rc == kSuccess )
+		{
+			if ( !two_operands || ( shared_ab && a0 != a ) ) { b = a; rs_b = rs_a; cs_b = cs_a; }
+			else if ( op == kOpGemmt ) rc = operand_to_device( b, rs_b, cs_b, k, m, &db, st );
+			else                       rc = operand_to_device( b, rs_b, cs_b, m, k, &db, st );
+		}
+	}
+	const bool c_host = ( classify( c ) != MemKind::Device );
+	T* cdev = c; int64_t rs_cd = rs_c, cs_cd = cs_c;
+	if ( rc == kSuccess && c_host )
+	{
+		// the whole array travels both ways, so the triangle that is not stored returns unchanged
+		const T* cc = c;
+		rc = operand_to_device( cc, rs_cd, cs_cd, m, m, &dc, st );
+		cdev = (T*)dc;
+	}
+
+	const T one = Scalar<T>::make( 1.0, 0.0 );
+	if ( rc == kSuccess )
+	{
+		switch ( op )
+		{
+			case kOpGemmt:          // C := beta*C + alpha * op(A) * op(B)
+				rc = gemm_dev<T>( ca, cb, m, m, k, al, a, rs_a, cs_a, b, rs_b, cs_b, be, cdev, rs_cd, cs_cd, st, 1, nullptr, nullptr, uploc );
+				break;
+			case kOpSyrk:           // C := beta*C + alpha * op(A) * op(A)^T
+				rc = gemm_dev<T>( ca, ca, m, m, k, al, a, rs_a, cs_a, a, cs_a, rs_a, be, cdev, rs_cd, cs_cd, st, 1, nullptr, nullptr, uploc );
+				break;
+			case kOpHerk:           // C := beta*C + alpha * op(A) * op(A)^H   (alpha, beta real)
+				rc = gemm_dev<T>( ca, !ca && CPLX, m, m, k, al, a, rs_a, cs_a, a, cs_a, rs_a, be, cdev, rs_cd, cs_cd, st, 1, nullptr, nullptr, uploc );
+				break;
+			case kOpSyr2k:          // C := beta*C + alpha * op(A) * op(B)^T + alpha * op(B) * op(A)^T
+				rc = gemm_dev<T>( ca, cb, m, m, k, al, a, rs_a, cs_a, b, cs_b, rs_b, be, cdev, rs_cd, cs_cd, st, 1, nullptr, nullptr, uploc );
+				if ( rc == kSuccess )
+				rc = gemm_dev<T>( cb, ca, m, m, k, al, b, rs_b, cs_b, a, cs_a, rs_a, one, cdev, rs_cd, cs_cd, st, 1, nullptr, nullptr, uploc );
+				break;
+			case kOpHer2k:          // C := beta*C + alpha * op(A) * op(B)^H + conj(alpha) * op(B) * op(A)^H   (beta real)
+			{
+				T alh = al;
+				if constexpr ( CPLX ) alh.y = -alh.y;
+				rc = gemm_dev<T>( ca, !cb && CPLX, m, m, k, al, a, rs_a, cs_a, b, cs_b, rs_b, be, cdev, rs_cd, cs_cd, st, 1, nullptr, nullptr, uploc );
+				if ( rc == kSuccess )
+				rc = gemm_dev<T>( cb, !ca && CPLX, m, m, k, alh, b, rs_b, cs_b, a, cs_a, rs_a, one, cdev, rs_cd, cs_cd, st, 1, nullptr, nullptr, uploc );
+				break;
+			}
+			default: rc = fail( "%s: unknown operation", name );
+		}
+	}
+	if constexpr ( CPLX )
+	{
+		if ( rc == kSuccess && hermitian )
+		{
+			using R = typename Elem<T>::real;
+			const int blocks = (int)std::min<int64_t>( ( m + 255 ) / 256, (int64_t)ctx().num_sms * 4 );
+			zero_diag_imag_kernel<R><<<blocks, 256, 0, st>>>( (R*)cdev, rs_cd + cs_cd, m );
+			if ( cudaGetLastError() != cudaSuccess ) rc = fail( "%s: launch failed", name );
+			ctx().launches++;
+		}
+	}
+	if ( rc == kSuccess && c_host )
+	{
+		rc = stage_to_host( c, rs_c, cs_c, dc, m, m, sizeof(T), st );
+		if ( rc == kSuccess && cudaStreamSynchronize( st ) != cudaSuccess ) rc = fail( "%s: stream sync failed", name );
+	}
+	dev_free( da, st ); dev_free( db, st ); dev_free( dc, st );
+	return rc;
+}
+
 } // namespace b200
 
 // ---- C ABI --------------------------------------------------------------------------
@@ -813,6 +975,64 @@ extern "C" b200_err_t b200_trsm( int dt, int side, int uploa, int transa, int di
 
 // k-panel accumulation: C := beta*C + alpha * sum_{s<npanels} op(A_s) * op(B_s), every panel k wide, all
 // A panels (resp. B panels) with the same strides.  Device-resident operands, d and z only.
+// ---- gemmt family C ABI ------------------------------------------------------------------
+// Real-typed scalars of herk (alpha, beta) and her2k (beta) are widened to the matrix datatype (imaginary part 0),
+// as bli_obj_init_finish_1x1( dt_r, ... ) + typecast does in bli_l3_tapi_ex.c:184-185,259-260.
+template <typename T> static T widen_real( const void* p )
+{
+	using R = typename Elem<T>::real;
+	return Scalar<T>::make( (double)*(const R*)p, 0.0 );
+}
+
+template <typename T>
+static int gemmt_family_any( int op, int uploc, int transa, int transb, int64_t m, int64_t k, const void* alpha,
+                             const void* a, int64_t rs_a, int64_t cs_a, const void* b, int64_t rs_b, int64_t cs_b,
+                             const void* beta, void* c, int64_t rs_c, int64_t cs_c, const char* name )
+{
+	if ( !alpha || !beta ) return fail( "%s: alpha/beta must be non-NULL host pointers", name );
+	const T al = ( op == kOpHerk )                    ? widen_real<T>( alpha ) : *(const T*)alpha;
+	const T be = ( op == kOpHerk || op == kOpHer2k ) ? widen_real<T>( beta )  : *(const T*)beta;
+	return gemmt_family_front<T>( op, uploc, transa, transb, m, k, &al, (const T*)a, rs_a, cs_a, (const T*)b, rs_b, cs_b,
+	                              &be, (T*)c, rs_c, cs_c, name );
+}
+
+static int gemmt_family_dt( int dt, int op, int uploc, int transa, int transb, int64_t m, int64_t k, const void* alpha,
+                            const void* a, int64_t rs_a, int64_t cs_a, const void* b, int64_t rs_b, int64_t cs_b,
+                            const void* beta, void* c, int64_t rs_c, int64_t cs_c, const char* name )
+{
+	switch ( dt )
+	{
+		case B200_FLOAT:    return gemmt_family_any<float>  ( op, uploc, transa, transb, m, k, alpha, a, rs_a, cs_a, b, rs_b, cs_b, beta, c, rs_c, cs_c, name );
+		case B200_DOUBLE:   return gemmt_family_any<double> ( op, uploc, transa, transb, m, k, alpha, a, rs_a, cs_a, b, rs_b, cs_b, beta, c, rs_c, cs_c, name );
+		case B200_SCOMPLEX: return gemmt_family_any<float2> ( op, uploc, transa, transb, m, k, alpha, a, rs_a, cs_a, b, rs_b, cs_b, beta, c, rs_c, cs_c, name );
+		case B200_DCOMPLEX: return gemmt_family_any<double2>( op, uploc, transa, transb, m, k, alpha, a, rs_a, cs_a, b, rs_b, cs_b, beta, c, rs_c, cs_c, name );
+	}
+	return fail( "%s: unsupported datatype %d", name, dt );
+}
+
+extern "C" b200_err_t b200_gemmt( int dt, int uploc, int transa, int transb, b200_dim_t m, b200_dim_t k,
+	const void* alpha, const void* a, b200_inc_t rs_a, b200_inc_t cs_a, const void* b, b200_inc_t rs_b, b200_inc_t cs_b,
+	const void* beta, void* c, b200_inc_t rs_c, b200_inc_t cs_c )
+{ return gemmt_family_dt( dt, kOpGemmt, uploc, transa, transb, m, k, alpha, a, rs_a, cs_a, b, rs_b, cs_b, beta, c, rs_c, cs_c, "b200_gemmt" ); }
+
+extern "C" b200_err_t b200_syr2k( int dt, int uploc, int transa, int transb, b200_dim_t m, b200_dim_t k,
+	const void* alpha, const void* a, b200_inc_t rs_a, b200_inc_t cs_a, const void* b, b200_inc_t rs_b, b200_inc_t cs_b,
+	const void* beta, void* c, b200_inc_t rs_c, b200_inc_t cs_c )
+{ return gemmt_family_dt( dt, kOpSyr2k, uploc, transa, transb, m, k, alpha, a, rs_a, cs_a, b, rs_b, cs_b, beta, c, rs_c, cs_c, "b200_syr2k" ); }
+
+extern "C" b200_err_t b200_her2k( int dt, int uploc, int transa, int transb, b200_dim_t m, b200_dim_t k,
+	const void* alpha, const void* a, b200_inc_t rs_a, b200_inc_t cs_a, const void* b, b200_inc_t rs_b, b200_inc_t cs_b,
+	const void* beta_real, void* c, b200_inc_t rs_c, b200_inc_t cs_c )
+{ return gemmt_family_dt( dt, kOpHer2k, uploc, transa, transb, m, k, alpha, a, rs_a, cs_a, b, rs_b, cs_b, beta_real, c, rs_c, cs_c, "b200_her2k" ); }
+
+extern "C" b200_err_t b200_syrk( int dt, int uploc, int transa, b200_dim_t m, b200_dim_t k,
+	const void* alpha, const void* a, b200_inc_t rs_a, b200_inc_t cs_a, const void* beta, void* c, b200_inc_t rs_c, b200_inc_t cs_c )
+{ return gemmt_family_dt( dt, kOpSyrk, uploc, transa, transa, m, k, alpha, a, rs_a, cs_a, a, rs_a, cs_a, beta, c, rs_c, cs_c, "b200_syrk" ); }
+
+extern "C" b200_err_t b200_herk( int dt, int uploc, int transa, b200_dim_t m, b200_dim_t k,
+	const void* alpha_real, const void* a, b200_inc_t rs_a, b200_inc_t cs_a, const void* beta_real, void* c, b200_inc_t rs_c, b200_inc_t cs_c )
+{ return gemmt_family_dt( dt, kOpHerk, uploc, transa, transa, m, k, alpha_real, a, rs_a, cs_a, a, rs_a, cs_a, beta_real, c, rs_c, cs_c, "b200_herk" ); }
+
 template <typename T>
 static int kpanels_front( int transa, int transb, int64_t m, int64_t n, int64_t k, int npanels, const T* alpha,
                           const T* const* a, int64_t rs_a, int64_t cs_a, const T* const* b, int64_t rs_b, int64_t cs_b,

@@ -34,7 +34,7 @@ struct CfmaTmaCfg
 	static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES + BAR_BYTES + 1024;
 };
 
-template <bool XK, bool YK>
+template <bool XK, bool YK, bool TRI = false>
 __global__ void __launch_bounds__( 384, 1 )
 gemm_cfma_tma_kernel( const GemmArgs<float2> g, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy )
 {
@@ -85,6 +85,7 @@ gemm_cfma_tma_kernel( const GemmArgs<float2> g, const __grid_constant__ CUtensor
 			int tp, tq;
 			tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
 			const int p0 = tp * BP, q0 = tq * BQ;
+			if ( TRI && tri_skip_tile( g, p0, q0, (int)min( (int64_t)BP, g.P - p0 ), (int)min( (int64_t)BQ, g.Q - q0 ) ) ) continue;
 			for ( int64_t kt = 0; kt < KT; ++kt )
 			{
 				mbar_wait( empty_bar( stage ), phase ^ 1u );
@@ -152,6 +153,7 @@ gemm_cfma_tma_kernel( const GemmArgs<float2> g, const __grid_constant__ CUtensor
 		const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
 		const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
 		const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );
+		if ( TRI && tri_skip_tile( g, p0, q0, p_lim, q_lim ) ) continue;
 
 		unsigned long long accP[4][8], accQ[4][8];  // P = sum xr*(yr,yi), Q = sum xi*(yr,yi)
 		#pragma unroll
@@ -249,6 +251,9 @@ gemm_cfma_tma_kernel( const GemmArgs<float2> g, const __grid_constant__ CUtensor
 		}
 
 		// ---- epilogue: D = alpha*acc + beta*D (beta == 0: D is not read); complex scalars as bli_tscals / bli_txpbys
+		int dlo = 0, dhi = 0;
+		if constexpr ( TRI ) tri_band( g, p0, q0, dlo, dhi );
+		auto keep = [&]( int d ) { if constexpr ( TRI ) return in_band( d, dlo, dhi ); else return true; };
 		#pragma unroll
 		for ( int i = 0; i < 4; ++i )
 		{
@@ -260,13 +265,13 @@ gemm_cfma_tma_kernel( const GemmArgs<float2> g, const __grid_constant__ CUtensor
 			for ( int j = 0; j < 8; ++j )
 			{
 				const int ql = col_of( j );
-				o[j] = ( !g.beta_is_zero && ql < q_lim ) ? drow[ql] : make_float2( 0.f, 0.f );
+				o[j] = ( !g.beta_is_zero && ql < q_lim && keep( ql - pl ) ) ? drow[ql] : make_float2( 0.f, 0.f );
 			}
 			#pragma unroll
 			for ( int j = 0; j < 8; ++j )
 			{
 				const int ql = col_of( j );
-				if ( ql >= q_lim ) continue;
+				if ( ql >= q_lim || !keep( ql - pl ) ) continue;
 				float px, py, qx, qy;
 				unpack2( accP[i][j], px, py ); unpack2( accQ[i][j], qx, qy );
 				const float sx = cjx ? -1.f : 1.f, sy = cjy ? -1.f : 1.f;

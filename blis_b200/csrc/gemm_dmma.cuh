@@ -47,7 +47,39 @@ struct GemmArgs
 	int      nseg;
 	const T* Xseg[7];
 	const T* Yseg[7];
+	// Triangular D (the gemmt family: frame/3/gemmt/bli_gemmt_{l,u}_ker_var2.c computes only the stored
+	// triangle of C).  tri == 0: full;  tri == 1: only q - p <= tri_off;  tri == 2: only q - p >= tri_off.
+	// Tiles wholly outside are skipped, rows of tiles crossing the diagonal are clipped in the epilogue.
+	int      tri;
+	int64_t  tri_off;
 };
+
+template <typename T>
+__device__ __forceinline__ bool tri_skip_tile( const GemmArgs<T>& g, int64_t p0, int64_t q0, int p_lim, int q_lim )
+{
+	if ( g.tri == 0 ) return false;
+	if ( g.tri == 1 ) return ( q0 - ( p0 + p_lim - 1 ) ) > g.tri_off;     // smallest q - p of the tile
+	return ( q0 + q_lim - 1 - p0 ) < g.tri_off;                           // largest q - p of the tile
+}
+
+template <typename T>
+__device__ __forceinline__ bool tri_tile_interior( const GemmArgs<T>& g, int64_t p0, int64_t q0, int p_lim, int q_lim )
+{
+	if ( g.tri == 0 ) return true;
+	if ( g.tri == 1 ) return ( q0 + q_lim - 1 - p0 ) <= g.tri_off;
+	return ( q0 - ( p0 + p_lim - 1 ) ) >= g.tri_off;
+}
+
+// Element (pl, ql) of the tile at (p0, q0) belongs to the stored triangle iff dlo <= ql - pl <= dhi.
+template <typename T>
+__device__ __forceinline__ void tri_band( const GemmArgs<T>& g, int64_t p0, int64_t q0, int& dlo, int& dhi )
+{
+	constexpr int BIG = 1 << 30;
+	const int64_t d = max( (int64_t)-BIG, min( (int64_t)BIG, p0 - q0 + g.tri_off ) );
+	dlo = ( g.tri == 2 ) ? (int)d : -BIG;
+	dhi = ( g.tri == 1 ) ? (int)d :  BIG;
+}
+__device__ __forceinline__ bool in_band( int d, int dlo, int dhi ) { return d >= dlo && d <= dhi; }
 
 // Tile -> (tp,tq) with a grouped raster so that the ~148 concurrently running
 // tiles form a compact block and share X/Y panels in L2.
@@ -144,6 +176,7 @@ gemm_dmma_kernel( const GemmArgs<T> g )
 		const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
 		const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
 		const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );
+		if ( tri_skip_tile( g, p0, q0, p_lim, q_lim ) ) continue;
 
 		const T* gx = XK ? g.X + p0 * g.ldx : g.X + p0;
 		const T* gy = YK ? g.Y + q0 * g.ldy : g.Y + q0;
@@ -243,6 +276,8 @@ gemm_dmma_kernel( const GemmArgs<T> g )
 		cp_async_wait<0>();
 
 		// ---- epilogue: D = alpha*acc + beta*D   (beta == 0: D is not read)
+		int dlo, dhi;
+		tri_band( g, p0, q0, dlo, dhi );
 		#pragma unroll
 		for ( int i = 0; i < MT; ++i )
 		{
@@ -253,13 +288,14 @@ gemm_dmma_kernel( const GemmArgs<T> g )
 			for ( int j = 0; j < NTL; ++j )
 			{
 				const int ql = wq0 + j * 8 + 2 * t4;
-				if ( ql >= q_lim ) continue;
-				const bool two = ( ql + 1 < q_lim );
+				const bool one = ( ql < q_lim && in_band( ql - pl, dlo, dhi ) );
+				const bool two = ( ql + 1 < q_lim && in_band( ql + 1 - pl, dlo, dhi ) );
+				if ( !one && !two ) continue;
 				if constexpr ( !CPLX )
 				{
 					double r0 = g.alpha * acc[0][i][j][0];
 					double r1 = g.alpha * acc[0][i][j][1];
-					if ( two && g.d_vec_ok )
+					if ( one && two && g.d_vec_ok )
 					{
 						double2* dp = reinterpret_cast<double2*>( drow + ql );
 						if ( !g.beta_is_zero ) { const double2 o = *dp; r0 = fma( g.beta, o.x, r0 ); r1 = fma( g.beta, o.y, r1 ); }
@@ -267,8 +303,11 @@ gemm_dmma_kernel( const GemmArgs<T> g )
 					}
 					else
 					{
-						if ( !g.beta_is_zero ) r0 = fma( g.beta, drow[ql], r0 );
-						drow[ql] = r0;
+						if ( one )
+						{
+							if ( !g.beta_is_zero ) r0 = fma( g.beta, drow[ql], r0 );
+							drow[ql] = r0;
+						}
 						if ( two )
 						{
 							if ( !g.beta_is_zero ) r1 = fma( g.beta, drow[ql + 1], r1 );
@@ -281,7 +320,7 @@ gemm_dmma_kernel( const GemmArgs<T> g )
 					#pragma unroll
 					for ( int e = 0; e < 2; ++e )
 					{
-						if ( e == 1 && !two ) break;
+						if ( e == 0 ? !one : !two ) continue;
 						const double ar = acc[0][i][j][e], ai = acc[1][i][j][e];
 						// ab *= alpha (bli_tscals), then c := ab + beta*c (bli_txpbys)
 						double rr = g.alpha.x * ar - g.alpha.y * ai;

@@ -52,7 +52,7 @@ struct DmmaTmaCfg
 	static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES + BAR_BYTES + 1024;   // + slack for 1 KiB alignment
 };
 
-template <bool XK, bool YK>
+template <bool XK, bool YK, bool TRI = false>
 __global__ void __launch_bounds__( 384, 1 )
 gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy )
 {
@@ -112,6 +112,7 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 			int tp, tq;
 			tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
 			const int p0 = tp * BP, q0 = tq * BQ;
+			if ( TRI && tri_skip_tile( g, p0, q0, (int)min( (int64_t)BP, g.P - p0 ), (int)min( (int64_t)BQ, g.Q - q0 ) ) ) continue;
 			for ( int64_t kt = 0; kt < KT; ++kt )
 			{
 				mbar_wait( empty_bar( stage ), phase ^ 1u );
@@ -187,6 +188,7 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 		const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
 		const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
 		const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );
+		if ( TRI && tri_skip_tile( g, p0, q0, p_lim, q_lim ) ) continue;
 
 		double acc[MT][NTL][2];
 		#pragma unroll
@@ -237,13 +239,17 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 		}
 
 		// ---- epilogue: D = alpha*acc + beta*D   (beta == 0: D is not read)
+		const bool interior = ( !TRI || tri_tile_interior( g, p0, q0, p_lim, q_lim ) );
+		int dlo = 0, dhi = 0;
+		if constexpr ( TRI ) tri_band( g, p0, q0, dlo, dhi );
+		auto keep = [&]( int d ) { if constexpr ( TRI ) return in_band( d, dlo, dhi ); else return true; };
 		#pragma unroll
 		for ( int i = 0; i < MT; ++i )
 		{
 			const int pl = wp0 + i * 8 + gq;
 			if ( pl >= p_lim ) continue;
 			double* drow = g.D + ( p0 + pl ) * g.ldd + q0;
-			if ( g.d_vec_ok && q_lim == BQ )
+			if ( g.d_vec_ok && q_lim == BQ && interior )
 			{
 				double2* __restrict__ dp = reinterpret_cast<double2*>( drow + wq0 + 2 * t4 );
 				double2 o[NTL];
@@ -265,11 +271,13 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 			for ( int j = 0; j < NTL; ++j )
 			{
 				const int ql = wq0 + j * 8 + 2 * t4;
-				if ( ql >= q_lim ) continue;
 				double r0 = g.alpha * acc[i][j][0], r1 = g.alpha * acc[i][j][1];
-				if ( !g.beta_is_zero ) r0 = fma( g.beta, drow[ql], r0 );
-				drow[ql] = r0;
-				if ( ql + 1 < q_lim )
+				if ( ql < q_lim && keep( ql - pl ) )
+				{
+					if ( !g.beta_is_zero ) r0 = fma( g.beta, drow[ql], r0 );
+					drow[ql] = r0;
+				}
+				if ( ql + 1 < q_lim && keep( ql + 1 - pl ) )
 				{
 					if ( !g.beta_is_zero ) r1 = fma( g.beta, drow[ql + 1], r1 );
 					drow[ql + 1] = r1;

@@ -71,7 +71,7 @@ struct DmmaWsCfg : DmmaCfg<T, BP, BQ, BK, WP, WQ, STAGES, XK, YK, AL>
 	static constexpr int REG_CONS = ( NCONS == 128 ) ? 216 : 224;
 };
 
-template <typename T, int BP, int BQ, int BK, int WP, int WQ, int STAGES, bool XK, bool YK, bool AL>
+template <typename T, int BP, int BQ, int BK, int WP, int WQ, int STAGES, bool XK, bool YK, bool AL, bool TRI = false>
 __global__ void __launch_bounds__( WP * WQ * 32 + 128, ( WP * WQ == 4 ) ? 2 : 1 )
 gemm_dmma_ws_kernel( const GemmArgs<T> g )
 {
@@ -139,6 +139,7 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 			const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
 			const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
 			const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );
+			if ( TRI && tri_skip_tile( g, p0, q0, p_lim, q_lim ) ) continue;
 			const int64_t xo = XK ? p0 * g.ldx : p0, yo = YK ? q0 * g.ldy : q0;
 			if ( !g.beta_is_zero )
 			{
@@ -223,6 +224,7 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 		const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
 		const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
 		const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );
+		if ( TRI && tri_skip_tile( g, p0, q0, p_lim, q_lim ) ) continue;
 
 		double acc[CPLX ? 2 : 1][MT][NTL][2];
 		#pragma unroll
@@ -297,7 +299,7 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 		}
 
 		// ---- epilogue: D = alpha*acc + beta*D   (beta == 0: D is not read)
-		if ( g.d_vec_ok && q_lim == BQ )
+		if ( g.d_vec_ok && q_lim == BQ && ( !TRI || tri_tile_interior( g, p0, q0, p_lim, q_lim ) ) )
 		{
 			// Interior tile: all loads of a tile row are issued before the first store, so a lane has
 			// NTL (2*NTL for complex) 16-byte loads in flight instead of one (small-k problems are bound
@@ -353,6 +355,9 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 			}
 			continue;
 		}
+		int dlo = 0, dhi = 0;
+		if constexpr ( TRI ) tri_band( g, p0, q0, dlo, dhi );
+		auto keep = [&]( int d ) { if constexpr ( TRI ) return in_band( d, dlo, dhi ); else return true; };
 		#pragma unroll
 		for ( int i = 0; i < MT; ++i )
 		{
@@ -363,13 +368,14 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 			for ( int j = 0; j < NTL; ++j )
 			{
 				const int ql = wq0 + j * 8 + 2 * t4;
-				if ( ql >= q_lim ) continue;
-				const bool two = ( ql + 1 < q_lim );
+				const bool one = ( ql < q_lim && keep( ql - pl ) );
+				const bool two = ( ql + 1 < q_lim && keep( ql + 1 - pl ) );
+				if ( !one && !two ) continue;
 				if constexpr ( !CPLX )
 				{
 					double r0 = g.alpha * acc[0][i][j][0];
 					double r1 = g.alpha * acc[0][i][j][1];
-					if ( two && g.d_vec_ok )
+					if ( one && two && g.d_vec_ok )
 					{
 						double2* dp = reinterpret_cast<double2*>( drow + ql );
 						if ( !g.beta_is_zero ) { const double2 o = *dp; r0 = fma( g.beta, o.x, r0 ); r1 = fma( g.beta, o.y, r1 ); }
@@ -377,8 +383,11 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 					}
 					else
 					{
-						if ( !g.beta_is_zero ) r0 = fma( g.beta, drow[ql], r0 );
-						drow[ql] = r0;
+						if ( one )
+						{
+							if ( !g.beta_is_zero ) r0 = fma( g.beta, drow[ql], r0 );
+							drow[ql] = r0;
+						}
 						if ( two )
 						{
 							if ( !g.beta_is_zero ) r1 = fma( g.beta, drow[ql + 1], r1 );
@@ -391,7 +400,7 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 					#pragma unroll
 					for ( int e = 0; e < 2; ++e )
 					{
-						if ( e == 1 && !two ) break;
+						if ( e == 0 ? !one : !two ) continue;
 						const double ar = acc[0][i][j][e], ai = acc[1][i][j][e];
 						double rr = g.alpha.x * ar - g.alpha.y * ai;
 						double ri = g.alpha.x * ai + g.alpha.y * ar;

@@ -85,6 +85,7 @@ gemm_ffma_kernel( const GemmArgs<T> g )
 		const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
 		const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
 		const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );
+		if ( tri_skip_tile( g, p0, q0, p_lim, q_lim ) ) continue;
 		const T* gx = XK ? g.X + p0 * g.ldx : g.X + p0;
 		const T* gy = YK ? g.Y + q0 * g.ldy : g.Y + q0;
 
@@ -176,6 +177,8 @@ gemm_ffma_kernel( const GemmArgs<T> g )
 		cp_async_wait<0>();
 
 		// ---- epilogue
+		int dlo, dhi;
+		tri_band( g, p0, q0, dlo, dhi );
 		#pragma unroll
 		for ( int i = 0; i < TP; ++i )
 		{
@@ -195,7 +198,7 @@ gemm_ffma_kernel( const GemmArgs<T> g )
 					if constexpr ( CPLX ) r[e] = make_float2( g.alpha.x * a.x - g.alpha.y * a.y, g.alpha.x * a.y + g.alpha.y * a.x );
 					else                  r[e] = g.alpha * a;
 				}
-				const bool full = ( ql + VE <= q_lim );
+				const bool full = ( ql + VE <= q_lim && in_band( ql - pl, dlo, dhi ) && in_band( ql + VE - 1 - pl, dlo, dhi ) );
 				if ( full && g.d_vec_ok )
 				{
 					float4* dp = reinterpret_cast<float4*>( drow + ql );
@@ -221,7 +224,7 @@ gemm_ffma_kernel( const GemmArgs<T> g )
 					#pragma unroll
 					for ( int e = 0; e < VE; ++e )
 					{
-						if ( ql + e >= q_lim ) break;
+						if ( ql + e >= q_lim || !in_band( ql + e - pl, dlo, dhi ) ) continue;
 						if ( !g.beta_is_zero )
 						{
 							const T o = drow[ql + e];

@@ -57,7 +57,7 @@ struct FfmaTmaCfg
 	static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES + BAR_BYTES + 1024;
 };
 
-template <bool XK, bool YK>
+template <bool XK, bool YK, bool TRI = false>
 __global__ void __launch_bounds__( 384, 1 )
 gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy )
 {
@@ -108,6 +108,7 @@ gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorM
 			int tp, tq;
 			tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
 			const int p0 = tp * BP, q0 = tq * BQ;
+			if ( TRI && tri_skip_tile( g, p0, q0, (int)min( (int64_t)BP, g.P - p0 ), (int)min( (int64_t)BQ, g.Q - q0 ) ) ) continue;
 			for ( int64_t kt = 0; kt < KT; ++kt )
 			{
 				mbar_wait( empty_bar( stage ), phase ^ 1u );
@@ -179,6 +180,7 @@ gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorM
 		const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
 		const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
 		const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );
+		if ( TRI && tri_skip_tile( g, p0, q0, p_lim, q_lim ) ) continue;
 
 		unsigned long long acc2[8][4];             // acc2[i][j2] = ( acc[i][2*j2], acc[i][2*j2+1] )
 		#pragma unroll
@@ -290,6 +292,10 @@ gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorM
 		}
 
 		// ---- epilogue: D = alpha*acc + beta*D (beta == 0: D is not read)
+		const bool interior = ( !TRI || tri_tile_interior( g, p0, q0, p_lim, q_lim ) );
+		int dlo = 0, dhi = 0;
+		if constexpr ( TRI ) tri_band( g, p0, q0, dlo, dhi );
+		auto keep = [&]( int d ) { if constexpr ( TRI ) return in_band( d, dlo, dhi ); else return true; };
 		float acc[8][8];
 		#pragma unroll
 		for ( int i = 0; i < 8; ++i )
@@ -301,7 +307,7 @@ gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorM
 			const int pl = row_of( i );
 			if ( pl >= p_lim ) continue;
 			float* drow = g.D + ( p0 + pl ) * g.ldd + q0;
-			if ( !YK && g.d_vec_ok && q_lim == BQ )
+			if ( !YK && g.d_vec_ok && q_lim == BQ && interior )
 			{
 				float4* __restrict__ dp0 = reinterpret_cast<float4*>( drow + col_of( 0 ) );
 				float4* __restrict__ dp1 = reinterpret_cast<float4*>( drow + col_of( 4 ) );
@@ -325,13 +331,13 @@ gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorM
 			for ( int j = 0; j < 8; ++j )
 			{
 				const int ql = col_of( j );
-				o[j] = ( !g.beta_is_zero && ql < q_lim ) ? drow[ql] : 0.f;
+				o[j] = ( !g.beta_is_zero && ql < q_lim && keep( ql - pl ) ) ? drow[ql] : 0.f;
 			}
 			#pragma unroll
 			for ( int j = 0; j < 8; ++j )
 			{
 				const int ql = col_of( j );
-				if ( ql >= q_lim ) continue;
+				if ( ql >= q_lim || !keep( ql - pl ) ) continue;
 				float r = g.alpha * acc[i][j];
 				if ( !g.beta_is_zero ) r = fmaf( g.beta, o[j], r );
 				drow[ql] = r;

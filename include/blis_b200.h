@@ -158,6 +158,54 @@ B200_DECL_TRSM( d, double )
 B200_DECL_TRSM( c, b200_scomplex )
 B200_DECL_TRSM( z, b200_dcomplex )
 
+/* ---- gemmt family ------------------------------
+ * Updates of ONE triangle (uploc) of the m x m matrix C; the other triangle is
+ * never written.  transa(A) is m x k.
+ *   gemmt:  C := beta*C + alpha * transa(A) * transb(B)            transb(B): k x m
+ *   syrk:   C := beta*C + alpha * transa(A) * transa(A)^T
+ *   herk:   C := beta*C + alpha * transa(A) * transa(A)^H          alpha, beta REAL (float/double)
+ *   syr2k:  C := beta*C + alpha * transa(A) * transb(B)^T + alpha * transb(B) * transa(A)^T        transb(B): m x k
+ *   her2k:  C := beta*C + alpha * transa(A) * transb(B)^H + conj(alpha) * transb(B) * transa(A)^H  beta REAL
+ * herk/her2k set the imaginary parts of C's diagonal to zero afterwards.
+ *
+ * Stand in for bli_gemmt_ex / bli_syrk_ex / bli_herk_ex / bli_syr2k_ex /
+ * bli_her2k_ex (frame/3/bli_l3_oapi_ex.c:151-346); argument order follows the
+ * typed API bli_?gemmt / bli_?syrk / bli_?herk / bli_?syr2k / bli_?her2k
+ * (frame/3/bli_l3_tapi.c:77-296) with the datatype as the first argument. */
+b200_err_t b200_gemmt( int dt, int uploc, int transa, int transb,
+                      b200_dim_t m, b200_dim_t k,
+                      const void* alpha,
+                      const void* a, b200_inc_t rs_a, b200_inc_t cs_a,
+                      const void* b, b200_inc_t rs_b, b200_inc_t cs_b,
+                      const void* beta,
+                      void*       c, b200_inc_t rs_c, b200_inc_t cs_c );
+b200_err_t b200_syrk( int dt, int uploc, int transa,
+                      b200_dim_t m, b200_dim_t k,
+                      const void* alpha,
+                      const void* a, b200_inc_t rs_a, b200_inc_t cs_a,
+                      const void* beta,
+                      void*       c, b200_inc_t rs_c, b200_inc_t cs_c );
+b200_err_t b200_herk( int dt, int uploc, int transa,
+                      b200_dim_t m, b200_dim_t k,
+                      const void* alpha_real,
+                      const void* a, b200_inc_t rs_a, b200_inc_t cs_a,
+                      const void* beta_real,
+                      void*       c, b200_inc_t rs_c, b200_inc_t cs_c );
+b200_err_t b200_syr2k( int dt, int uploc, int transa, int transb,
+                      b200_dim_t m, b200_dim_t k,
+                      const void* alpha,
+                      const void* a, b200_inc_t rs_a, b200_inc_t cs_a,
+                      const void* b, b200_inc_t rs_b, b200_inc_t cs_b,
+                      const void* beta,
+                      void*       c, b200_inc_t rs_c, b200_inc_t cs_c );
+b200_err_t b200_her2k( int dt, int uploc, int transa, int transb,
+                      b200_dim_t m, b200_dim_t k,
+                      const void* alpha,
+                      const void* a, b200_inc_t rs_a, b200_inc_t cs_a,
+                      const void* b, b200_inc_t rs_b, b200_inc_t cs_b,
+                      const void* beta_real,
+                      void*       c, b200_inc_t rs_c, b200_inc_t cs_c );
+
 /* ---- blocksizes ------------------------------------------------------------
  * What bli_cntx_init_b200 registers through bli_cntx_set_blkszs()
  * (config/zen3/bli_cntx_init_zen3.c:37-258 is the pattern): the CTA tile

@@ -1,5 +1,5 @@
 /*
- * blis_oracle.h -- CPU restatement of the reference's gemm/trsm hot path.
+ * blis_oracle.h -- CPU restatement of the reference's gemm/trsm hot path (and the gemmt family next to it).
  *
  * TEST INFRASTRUCTURE ONLY.  This is the checker the CUDA engine is compared
  * against; it is never linked into, called from, or shipped with the product
@@ -70,6 +70,19 @@ void orc_##ch##gemmtrsm_ukr( int upper, dim_t m, dim_t n, dim_t k, const ctype* 
 void orc_##ch##gemm( int transa, int transb, dim_t m, dim_t n, dim_t k, const ctype* alpha, \
                           const ctype* a, inc_t rs_a, inc_t cs_a, const ctype* b, inc_t rs_b, inc_t cs_b, \
                           const ctype* beta, ctype* c, inc_t rs_c, inc_t cs_c ); \
+void orc_##ch##gemmt( int uploc, int transa, int transb, dim_t m, dim_t k, const ctype* alpha, \
+                          const ctype* a, inc_t rs_a, inc_t cs_a, const ctype* b, inc_t rs_b, inc_t cs_b, \
+                          const ctype* beta, ctype* c, inc_t rs_c, inc_t cs_c ); \
+void orc_##ch##syrk( int uploc, int transa, dim_t m, dim_t k, const ctype* alpha, const ctype* a, inc_t rs_a, inc_t cs_a, \
+                          const ctype* beta, ctype* c, inc_t rs_c, inc_t cs_c ); \
+void orc_##ch##herk( int uploc, int transa, dim_t m, dim_t k, const ctype* alpha_r, const ctype* a, inc_t rs_a, inc_t cs_a, \
+                          const ctype* beta_r, ctype* c, inc_t rs_c, inc_t cs_c ); \
+void orc_##ch##syr2k( int uploc, int transa, int transb, dim_t m, dim_t k, const ctype* alpha, \
+                          const ctype* a, inc_t rs_a, inc_t cs_a, const ctype* b, inc_t rs_b, inc_t cs_b, \
+                          const ctype* beta, ctype* c, inc_t rs_c, inc_t cs_c ); \
+void orc_##ch##her2k( int uploc, int transa, int transb, dim_t m, dim_t k, const ctype* alpha, \
+                          const ctype* a, inc_t rs_a, inc_t cs_a, const ctype* b, inc_t rs_b, inc_t cs_b, \
+                          const ctype* beta_r, ctype* c, inc_t rs_c, inc_t cs_c ); \
 void orc_##ch##trsm( int side, int uplo, int transa, int diag, dim_t m, dim_t n, const ctype* alpha, \
                           const ctype* a, inc_t rs_a, inc_t cs_a, ctype* b, inc_t rs_b, inc_t cs_b );
 

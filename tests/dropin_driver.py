@@ -13,7 +13,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "tests"))
 import gen  # noqa: E402
 
-glue = C.CDLL(str(ROOT / "oracle" / "_ref" / "libblis_b200_glue.so"), mode=C.RTLD_GLOBAL)   # first: interposes bli_trsm_ex
+glue = C.CDLL(str(ROOT / "oracle" / "_ref" / "libblis_b200_glue.so"), mode=C.RTLD_GLOBAL)   # first: interposes bli_trsm_ex, bli_gemmt_ex, ...
 from refblis import RefBlis, LEFT, RIGHT, LOWER, UPPER, TRANSPOSE, CONJ_TRANSPOSE, NONUNIT_DIAG, UNIT_DIAG  # noqa: E402
 ref = RefBlis(threads=4)
 glue.bli_plugin_register_b200.restype = C.c_int
@@ -69,5 +69,32 @@ for ch in "sdcz":
     t = np.triu(a).astype(hi).conj().T
     out[f"bli_{ch}trsm"] = float(np.abs(b.astype(hi) @ t - al * b0.astype(hi)).max())
 out["launches_trsm"] = int(eng.b200_launch_count() - before)
+
+# --- gemmt family through dsyrk_ and bli_?gemmt / herk / her2k / syr2k (bli_*_ex interposed by the glue)
+before = eng.b200_launch_count()
+m, k = 230, 90
+a = gen.matrix("d", m, k, 20, "frac"); c = gen.matrix("d", m, m, 21, "frac"); c0 = c.copy(order="K")
+L.dsyrk_(C.c_char_p(b"L"), C.c_char_p(b"N"), i32(m), i32(k), f64(2.0), a.ctypes.data_as(C.c_void_p), i32(a.strides[1] // 8),
+         f64(1.2), c.ctypes.data_as(C.c_void_p), i32(c.strides[1] // 8))
+want = np.where(np.tril(np.ones((m, m), bool)), 1.2 * c0 + 2.0 * (a @ a.T), c0)
+out["dsyrk_"] = float(np.abs(c - want).max())
+b = gen.matrix("d", k, m, 22, "frac"); c = c0.copy(order="K")
+ref.gemmt(UPPER, 0, 0, 2.0, a, b, 1.2, c)
+out["bli_dgemmt"] = float(np.abs(c - np.where(np.triu(np.ones((m, m), bool)), 1.2 * c0 + 2.0 * (a @ b), c0)).max())
+b = gen.matrix("d", m, k, 23, "frac"); c = c0.copy(order="K")
+ref.syr2k(LOWER, 0, 0, 2.0, a, b, 1.2, c)
+out["bli_dsyr2k"] = float(np.abs(c - np.where(np.tril(np.ones((m, m), bool)), 1.2 * c0 + 2.0 * (a @ b.T + b @ a.T), c0)).max())
+for ch in "cz":
+    a = gen.matrix(ch, m, k, 24, "frac"); b = gen.matrix(ch, m, k, 25, "frac"); c0 = gen.matrix(ch, m, m, 26, "frac")
+    hi = np.complex128
+    low = np.tril(np.ones((m, m), bool))
+    c = c0.copy(order="K"); ref.herk(LOWER, 0, 2.0, a, 1.2, c)
+    w = 1.2 * c0.astype(hi) + 2.0 * (a.astype(hi) @ a.astype(hi).conj().T); w[np.diag_indices(m)] = w[np.diag_indices(m)].real
+    out[f"bli_{ch}herk"] = float(np.abs(c - np.where(low, w, c0)).max())
+    c = c0.copy(order="K"); al = 2.0 + 0.2j; ref.her2k(LOWER, 0, 0, al, a, b, 1.2, c)
+    w = 1.2 * c0.astype(hi) + al * (a.astype(hi) @ b.astype(hi).conj().T) + np.conj(al) * (b.astype(hi) @ a.astype(hi).conj().T)
+    w[np.diag_indices(m)] = w[np.diag_indices(m)].real
+    out[f"bli_{ch}her2k"] = float(np.abs(c - np.where(low, w, c0)).max())
+out["launches_gemmt_family"] = int(eng.b200_launch_count() - before)
 out["launches_total"] = int(eng.b200_launch_count() - n0)
 print(json.dumps(out))

@@ -14,6 +14,7 @@ Writes (all small, committed):
                     triangular (lower/upper, unit, inverted diag, conj, ragged) panels
   gemm.npz          bli_?gemm outputs for the cases in `gemm_cases()`
   trsm.npz          bli_?trsm outputs for the cases in `trsm_cases()`
+  gemmt.npz         bli_?gemmt / syrk / herk / syr2k / her2k outputs for `gemmt_cases()` (unstored triangle NaN-poisoned)
 Inputs are not stored: tests rebuild them with tests/gen.py (integer-hash
 generators, platform independent).
 """
@@ -130,6 +131,58 @@ def trsm_cases():
     return cases
 
 
+def gemmt_cases():
+    """(ch, op, kind, m, k, uplo, transa, transb, oa, ob, oc, alpha, beta); op in gemmt/syrk/herk/syr2k/her2k.
+    Scalars as in testsuite/src/test_{gemmt,syrk,herk,syr2k,her2k}.c (alpha 2.0-ish, beta 1.2-ish; herk's alpha and
+    beta and her2k's beta are real)."""
+    cases = []
+    for ch in "sdcz":
+        cx = ch in "cz"
+        al, be = ((2.0 + 0.2j, 1.2 + 0.5j) if cx else (2.0, 1.2))
+        trs = (NO_TRANSPOSE, TRANSPOSE, CONJ_NO_TRANSPOSE, CONJ_TRANSPOSE) if cx else (NO_TRANSPOSE, TRANSPOSE)
+        for op in ("gemmt", "syrk", "herk", "syr2k", "her2k"):
+            a_, b_ = (2.0 if op == "herk" else al), (1.2 if op in ("herk", "her2k") else be)
+            for uplo, ta in itertools.product((LOWER, UPPER), trs):
+                tb = trs[(trs.index(ta) + 1) % len(trs)]
+                cases.append((ch, op, "frac", 21, 13, uplo, ta, tb, "c", "c", "c", a_, b_))
+            cases += [
+                (ch, op, "frac", 100, 100, LOWER, NO_TRANSPOSE, NO_TRANSPOSE, "c", "c", "c", a_, b_),  # input.general.fast size
+                (ch, op, "frac", 45, 300, UPPER, TRANSPOSE, NO_TRANSPOSE, "r", "c", "r", a_, b_),        # k > KC, row-stored C
+                (ch, op, "frac", 33, 9, LOWER, NO_TRANSPOSE, TRANSPOSE, "g", "r", "g", a_, b_),          # general strides
+                (ch, op, "frac", 17, 6, UPPER, NO_TRANSPOSE, NO_TRANSPOSE, "c", "c", "c", a_, 0.0),      # beta == 0
+                (ch, op, "frac", 9, 5, LOWER, NO_TRANSPOSE, NO_TRANSPOSE, "c", "c", "c", 0.0, b_),       # alpha == 0
+                (ch, op, "frac", 1, 4, LOWER, NO_TRANSPOSE, NO_TRANSPOSE, "c", "c", "c", a_, b_),
+                (ch, op, "pow2", 40, 32, LOWER, NO_TRANSPOSE, TRANSPOSE, "c", "c", "c", 2.0, 0.5),       # exact
+                (ch, op, "pow2", 29, 48, UPPER, TRANSPOSE, NO_TRANSPOSE, "r", "c", "r", -1.0, 1.0),      # exact
+            ]
+    return cases
+
+
+def gemmt_inputs(case, idx):
+    """A, B (None for syrk/herk) and C with the triangle that must not be touched filled with NaN."""
+    ch, op, kind, m, k, uplo, ta, tb, oa, ob, oc, al, be = case
+    am, ak = (k, m) if ta & TRANSPOSE else (m, k)
+    a = gen.matrix(ch, am, ak, 19 * idx + 1, kind, oa, pad=3)
+    b = None
+    if op == "gemmt":
+        bm, bn = (m, k) if tb & TRANSPOSE else (k, m)
+        b = gen.matrix(ch, bm, bn, 19 * idx + 2, kind, ob, pad=1)
+    elif op in ("syr2k", "her2k"):
+        bm, bn = (k, m) if tb & TRANSPOSE else (m, k)
+        b = gen.matrix(ch, bm, bn, 19 * idx + 2, kind, ob, pad=1)
+    c = gen.matrix(ch, m, m, 19 * idx + 3, kind, oc, pad=2)
+    gen.poison_unstored(c, uplo == LOWER)
+    return a, b, c
+
+
+def gemmt_run(impl, case, a, b, c):
+    ch, op, kind, m, k, uplo, ta, tb, oa, ob, oc, al, be = case
+    if op in ("syrk", "herk"):
+        getattr(impl, op)(uplo, ta, al, a, be, c)
+    else:
+        getattr(impl, op)(uplo, ta, tb, al, a, b, be, c)
+
+
 def gemm_inputs(case, idx):
     ch, kind, m, n, k, ta, tb, oa, ob, oc, al, be = case
     am, ak = (k, m) if ta & TRANSPOSE else (m, k)
@@ -168,10 +221,30 @@ int main(void){ printf("{\"PACKED_PANELS\":%d,\"TRIANGULAR\":%d,\"GENERAL\":%d,\
                                          env={"LD_LIBRARY_PATH": str(ROOT / "oracle" / "_ref")}).stdout)
 
 
+def write_gemmt(ref):
+    res = {}
+    for idx, cs in enumerate(gemmt_cases()):
+        a, b, c = gemmt_inputs(cs, idx)
+        gemmt_run(ref, cs, a, b, c)
+        m = cs[3]
+        unstored = np.triu(np.ones((m, m), bool), 1) if cs[5] == LOWER else np.tril(np.ones((m, m), bool), -1)
+        assert np.isnan(np.abs(c[unstored])).all() and np.isfinite(np.abs(c[~unstored])).all(), \
+            ("reference touched the unstored triangle of C?", cs)
+        res[f"c{idx}"] = np.ascontiguousarray(c)
+    np.savez_compressed(HERE / "gemmt.npz", **res)
+    return len(res)
+
+
 def main():
     ref = RefBlis(threads=1)
     L = ref.lib
     print("reference sub-configuration:", ref.arch())
+    if len(sys.argv) > 1 and sys.argv[1] == "gemmt":       # add the gemmt-family fixtures without rewriting the others
+        n = write_gemmt(ref)
+        man = json.loads((HERE / "MANIFEST.json").read_text()); man["n_gemmt"] = n
+        (HERE / "MANIFEST.json").write_text(json.dumps(man, indent=1))
+        print("gemmt.npz written:", n, "cases")
+        return
 
     # ---- index arithmetic
     db, tr, p2 = index_cases()
@@ -225,7 +298,8 @@ def main():
     (HERE / "MANIFEST.json").write_text(json.dumps({
         "generated_by": "tests/golden/make_golden.py", "reference_version": "3.0-dev (so 4.0.0)",
         "sub_configuration": ref.arch(), "threads": 1,
-        "n_packm": len(packm_cases()), "n_gemm": len(gemm_cases()), "n_trsm": len(trsm_cases())}, indent=1))
+        "n_packm": len(packm_cases()), "n_gemm": len(gemm_cases()), "n_trsm": len(trsm_cases()),
+        "n_gemmt": write_gemmt(ref)}, indent=1))
     print("golden fixtures written:", sorted(p.name for p in HERE.iterdir()))
 
 

@@ -50,7 +50,39 @@ def build_oracle() -> Path:
     return ORACLE_SO
 
 
-class Oracle:
+class _GemmtFamily:
+    """gemmt / syrk / herk / syr2k / her2k with the typed-API argument lists (frame/3/bli_l3_tapi.c:77-296), in place on
+    numpy arrays with any strides.  `_PREFIX` is "orc_" (restatement) or "bli_" (the real reference)."""
+    _PREFIX = ""
+
+    def _two(self, name, uplo, transa, transb, alpha, a, b, beta, c):
+        ch = CH[c.dtype]
+        m = c.shape[0]
+        k = a.shape[0] if (transa & TRANSPOSE) else a.shape[1]
+        rdt = np.zeros(1, c.dtype).real.dtype
+        al = _scalar(c.dtype, alpha)
+        be = _scalar(rdt if name == "her2k" else c.dtype, beta)
+        getattr(self.lib, f"{self._PREFIX}{ch}{name}")(uplo, transa, transb, m, k, _p(al), _p(a), *_estr(a), _p(b), *_estr(b),
+                                                        _p(be), _p(c), *_estr(c))
+
+    def _one(self, name, uplo, transa, alpha, a, beta, c):
+        ch = CH[c.dtype]
+        m = c.shape[0]
+        k = a.shape[0] if (transa & TRANSPOSE) else a.shape[1]
+        sdt = np.zeros(1, c.dtype).real.dtype if name == "herk" else c.dtype
+        al, be = _scalar(sdt, alpha), _scalar(sdt, beta)
+        getattr(self.lib, f"{self._PREFIX}{ch}{name}")(uplo, transa, m, k, _p(al), _p(a), *_estr(a), _p(be), _p(c), *_estr(c))
+
+    def gemmt(self, uplo, transa, transb, alpha, a, b, beta, c): self._two("gemmt", uplo, transa, transb, alpha, a, b, beta, c)
+    def syr2k(self, uplo, transa, transb, alpha, a, b, beta, c): self._two("syr2k", uplo, transa, transb, alpha, a, b, beta, c)
+    def her2k(self, uplo, transa, transb, alpha, a, b, beta, c): self._two("her2k", uplo, transa, transb, alpha, a, b, beta, c)
+    def syrk(self, uplo, transa, alpha, a, beta, c): self._one("syrk", uplo, transa, alpha, a, beta, c)
+    def herk(self, uplo, transa, alpha, a, beta, c): self._one("herk", uplo, transa, alpha, a, beta, c)
+
+
+class Oracle(_GemmtFamily):
+    _PREFIX = "orc_"
+
     def __init__(self):
         self.lib = C.CDLL(str(build_oracle()))
         L = self.lib
@@ -63,6 +95,10 @@ class Oracle:
         for ch in "sdcz":
             getattr(L, f"orc_{ch}gemm").argtypes = [ci, ci, i64, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
             getattr(L, f"orc_{ch}trsm").argtypes = [ci, ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64]
+            for name in ("gemmt", "syr2k", "her2k"):
+                getattr(L, f"orc_{ch}{name}").argtypes = [ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
+            for name in ("syrk", "herk"):
+                getattr(L, f"orc_{ch}{name}").argtypes = [ci, ci, i64, i64, vp, vp, i64, i64, vp, vp, i64, i64]
             getattr(L, f"orc_{ch}packm_cxk").argtypes = [ci, i64, i64, i64, i64, vp, vp, i64, i64, vp, i64]
             getattr(L, f"orc_{ch}packm_struc_cxk").argtypes = [ci, ci, ci, ci, ci, i64, i64, i64, i64, i64, i64, vp, vp, i64, i64, vp, i64]
             getattr(L, f"orc_{ch}gemm_ukr").argtypes = [i64, i64, i64, vp, vp, vp, vp, vp, i64, i64, i64, i64]
@@ -99,7 +135,9 @@ class Oracle:
         getattr(self.lib, f"orc_{ch}trsm")(side, uplo, transa, diag, m, n, _p(al), _p(a), *_estr(a), _p(b), *_estr(b))
 
 
-class RefBlis:
+class RefBlis(_GemmtFamily):
+    _PREFIX = "bli_"
+
     """The real reference: typed API bli_?gemm / bli_?trsm (frame/3/bli_l3_tapi.c)
     plus the helper functions the oracle restates."""
 
@@ -112,6 +150,10 @@ class RefBlis:
         for ch in "sdcz":
             getattr(L, f"bli_{ch}gemm").argtypes = [ci, ci, i64, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
             getattr(L, f"bli_{ch}trsm").argtypes = [ci, ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64]
+            for name in ("gemmt", "syr2k", "her2k"):
+                getattr(L, f"bli_{ch}{name}").argtypes = [ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
+            for name in ("syrk", "herk"):
+                getattr(L, f"bli_{ch}{name}").argtypes = [ci, ci, i64, i64, vp, vp, i64, i64, vp, vp, i64, i64]
         L.bli_determine_blocksize.argtypes = [ci, i64, i64, i64, i64]; L.bli_determine_blocksize.restype = i64
         L.bli_thread_range_sub.argtypes = [i64, i64, i64, i64, C.c_bool, C.POINTER(i64), C.POINTER(i64)]
         L.bli_thread_partition_2x2.argtypes = [i64, i64, i64, C.POINTER(i64), C.POINTER(i64)]

@@ -125,6 +125,30 @@ def test_trsm_vs_golden(oracle):
             assert rel_err(b, want) <= 20 * TOL[ch], f"trsm case {idx} {cs}: {rel_err(b, want)}"
 
 
+def _tri_masks(m, lower):
+    unstored = np.triu(np.ones((m, m), bool), 1) if lower else np.tril(np.ones((m, m), bool), -1)
+    return ~unstored, unstored
+
+
+def test_gemmt_family_vs_golden(oracle):
+    """gemmt / syrk / herk / syr2k / her2k: the restatement against reference outputs.  The triangle of C that is
+    not stored is NaN in the inputs and must come back untouched (the reference leaves it NaN too)."""
+    gold = np.load(GOLD / "gemmt.npz")
+    for idx, cs in enumerate(G.gemmt_cases()):
+        ch, op, kind, m, uplo = cs[0], cs[1], cs[2], cs[3], cs[5]
+        a, b, c = G.gemmt_inputs(cs, idx)
+        G.gemmt_run(oracle, cs, a, b, c)
+        want = gold[f"c{idx}"]
+        stored, unstored = _tri_masks(m, uplo == G.LOWER)
+        assert np.isnan(np.abs(c[unstored])).all(), f"gemmt case {idx} {cs}: unstored triangle written"
+        if _exact(kind):
+            assert np.array_equal(c[stored], want[stored]), f"gemmt case {idx} {cs} not bit-exact"
+        else:
+            assert rel_err(c[stored], want[stored]) <= TOL[ch], f"gemmt case {idx} {cs}: {rel_err(c[stored], want[stored])}"
+        if op in ("herk", "her2k") and ch in "cz":
+            assert (np.diag(c).imag == 0).all()
+
+
 @pytest.mark.parametrize("ch", list("sdcz"))
 def test_gemm_live_reference_other_blocksizes(oracle, ref, ch):
     """Same algorithm under the haswell-like blocksizes (incl. row preference):

@@ -4,7 +4,7 @@ reference library built by oracle/build_ref.py, and derive its input files.
 TEST INFRASTRUCTURE.  Outputs go to oracle/_ref/testsuite/ (git-ignored, travels to the GPU box):
   test_libblis.x            the reference testsuite driver, linked to libblis_ref.so only
   input.general.<tag>       derived from testsuite/input.general.fast (sizes / datatypes edited)
-  input.operations.l3       derived from testsuite/input.operations.fast: only gemm and trsm enabled
+  input.operations.l3       derived from testsuite/input.operations.fast: only gemm, trsm and the gemmt family enabled
                             (switch value 2), all transa/transb and side/uplo/trans/diag combinations
 On the GPU box the binary is run twice by tests/test_blis_dropin_gpu.py: as is (CPU reference) and with
 LD_PRELOAD=libblis_b200_glue.so BLIS_B200_PLUGIN=1 (gemm/trsm served by the B200 engine).
@@ -22,19 +22,20 @@ ROOT = Path(__file__).resolve().parent.parent
 REF = Path("/root/reference")
 OUT = ROOT / "oracle" / "_ref" / "testsuite"
 EXE = OUT / "test_libblis.x"
+L3_OPS = ("gemm", "trsm", "gemmt", "syrk", "herk", "syr2k", "her2k")      # the operations the engine serves
 
 
 def _derive_inputs():
     gen = (REF / "testsuite" / "input.general.fast").read_text()
     ops = (REF / "testsuite" / "input.operations.fast").read_text().splitlines()
-    # only gemm and trsm of the "Level-3" section, every parameter combination
+    # only the served operations of the "Level-3" section, every parameter combination
     out, in_l3, i = [], False, 0
     while i < len(ops):
         ln = ops[i]
         if ln.startswith("# --- Level-3 ---"):
             in_l3 = True
         m = re.match(r"^(\d)(\s+#\s+)(\w+)\s*$", ln)
-        if in_l3 and m and m.group(3) in ("gemm", "trsm"):
+        if in_l3 and m and m.group(3) in L3_OPS:
             out.append("2" + ln[1:])
             i += 1
             while i < len(ops) and ops[i].strip() and not re.match(r"^\d\s+#\s+\w+\s*$", ops[i]):
@@ -67,6 +68,8 @@ def build(force: bool = False) -> Path:
             return EXE
         raise FileNotFoundError("no /root/reference and no prebuilt testsuite binary")
     if EXE.exists() and not force:
+        OUT.mkdir(parents=True, exist_ok=True)
+        _derive_inputs()
         return EXE
     sys.path.insert(0, str(ROOT / "oracle"))
     import build_ref
