@@ -19,6 +19,7 @@
 #include "trsm.cuh"
 #include "../../include/blis_b200.h"
 #include <algorithm>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -90,6 +91,47 @@ __global__ void scal2d_kernel( R* __restrict__ c, int64_t rs, int64_t cs, int64_
 }
 
 static inline int64_t iabs64( int64_t x ) { return x < 0 ? -x : x; }
+
+// dst[c*ldd + r] = src[r*lds + c]: 32 x 32 tiles through shared memory, both sides coalesced.
+template <typename T>
+__global__ void __launch_bounds__( 256 ) transpose2d_kernel( T* __restrict__ dst, int64_t ldd, const T* __restrict__ src, int64_t lds,
+                                                             int64_t R, int64_t Cn, int tiles_c )
+{
+	__shared__ T tile[32][33];
+	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+	const int64_t ntiles = ( ( R + 31 ) / 32 ) * tiles_c;
+	for ( int64_t t = blockIdx.x; t < ntiles; t += gridDim.x )
+	{
+		const int64_t r0 = ( t / tiles_c ) * 32, c0 = ( t % tiles_c ) * 32;
+		#pragma unroll
+		for ( int i = 0; i < 4; ++i )
+		{
+			const int64_t r = r0 + ty + 8 * i, c = c0 + tx;
+			if ( r < R && c < Cn ) tile[ty + 8 * i][tx] = src[r * lds + c];
+		}
+		__syncthreads();
+		#pragma unroll
+		for ( int i = 0; i < 4; ++i )
+		{
+			const int64_t c = c0 + ty + 8 * i, r = r0 + tx;
+			if ( r < R && c < Cn ) dst[c * ldd + r] = tile[tx][ty + 8 * i];
+		}
+		__syncthreads();
+	}
+}
+
+template <typename T>
+static int transpose2d( T* dst, int64_t ldd, const T* src, int64_t lds, int64_t R, int64_t Cn, cudaStream_t st )
+{
+	const int64_t tiles_c = ( Cn + 31 ) / 32, ntiles = ( ( R + 31 ) / 32 ) * tiles_c;
+	if ( ntiles <= 0 ) return kSuccess;
+	if ( tiles_c >= ( 1ll << 31 ) ) return fail( "transpose2d: matrix too wide" );
+	const int blocks = (int)std::min<int64_t>( ntiles, (int64_t)ctx().num_sms * 32 );
+	transpose2d_kernel<T><<<blocks, 256, 0, st>>>( dst, ldd, src, lds, R, Cn, (int)tiles_c );
+	B200_CUDA( cudaGetLastError() );
+	ctx().launches++;
+	return kSuccess;
+}
 
 template <typename T>
 static int copy2d( T* dst, int64_t rsd, int64_t csd, const T* src, int64_t rss, int64_t css,
@@ -530,6 +572,21 @@ static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T 
 	{
 		if ( dev_alloc( &tmp_y, (size_t)g.Q * k * ES, st ) != kSuccess ) rc = kFailure;
 		else { rc = copy2d( (T*)tmp_y, (int64_t)1, k, g.Y, ys_k, ys_q, k, g.Q, st ); g.Y = (const T*)tmp_y; yk = true; g.ldy = k; }
+	}
+
+	// FP32 kernels pair accumulators along q (packed FFMA2), which a k-contiguous Y can only feed through two
+	// register moves per pair (ncu/SASS: +1000 MOV/IMAD per 1024 FFMA2, 33 instead of 58 TFLOP/s for sgemm "TN").
+	// For problems large enough to notice, Y is transposed once into a q-contiguous temporary instead:
+	// O(K*Q) traffic against O(P*Q*K) flops (0.3 % of the run time at 16384^3).
+	if ( rc == kSuccess && yk && !tmp_y && nseg == 1 && ( std::is_same<T, float>::value || std::is_same<T, float2>::value ) &&
+	     ctx().transpose_y && g.P >= 512 && (double)g.P * (double)g.Q * (double)k >= 1e9 && ( g.Q * ES ) % 16 == 0 )
+	{
+		if ( dev_alloc( &tmp_y, (size_t)g.Q * k * ES, st ) != kSuccess ) rc = kFailure;
+		else
+		{
+			rc = transpose2d( (T*)tmp_y, g.Q, g.Y, g.ldy, g.Q, k, st );
+			g.Y = (const T*)tmp_y; yk = false; g.ldy = g.Q;
+		}
 	}
 
 	if ( rc == kSuccess )
@@ -1097,6 +1154,7 @@ extern "C" b200_err_t b200_set_option( const char* key, long long value )
 	else if ( !strcmp( key, "cgemm_cfg" ) ) c.cgemm_cfg = (int)value;
 	else if ( !strcmp( key, "grid_mult" ) ) c.grid_mult = (int)std::max<long long>( 1, value );
 	else if ( !strcmp( key, "dynamic_tiles" ) ) c.dynamic_tiles = (int)value;
+	else if ( !strcmp( key, "transpose_y" ) ) c.transpose_y = (int)value;
 	else if ( !strcmp( key, "reserve_sms" ) )
 	{
 		// leave SMs free for concurrently running communication kernels (multi-GPU overlap)

@@ -66,6 +66,25 @@ __device__ __forceinline__ void dmma884( double& d0, double& d1, double a, doubl
 __device__ __forceinline__ double flip_sign( double x, bool s ) { return s ? -x : x; }
 __device__ __forceinline__ float  flip_sign( float  x, bool s ) { return s ? -x : x; }
 
+// ---- complex epilogue arithmetic with a FIXED rounding order --------------------
+// ab *= alpha (bli_tscals) and c := ab + beta*c (bli_txpbys).  Written with explicit mul/fma so that the
+// compiler cannot contract the expressions differently in different epilogue paths: the vectorised interior path,
+// the bounds-checked edge path and the triangular (gemmt) path of every kernel round identically.
+__device__ __forceinline__ double mul_rn( double a, double b ) { return __dmul_rn( a, b ); }
+__device__ __forceinline__ float  mul_rn( float  a, float  b ) { return __fmul_rn( a, b ); }
+template <typename R>
+__device__ __forceinline__ void cscal( R ar, R ai, R xr, R xi, R& rr, R& ri )      // (ar + i ai) * (xr + i xi)
+{
+	rr = fma( -ai, xi, mul_rn( ar, xr ) );
+	ri = fma(  ai, xr, mul_rn( ar, xi ) );
+}
+template <typename R>
+__device__ __forceinline__ void cxpby( R br, R bi, R yr, R yi, R& rr, R& ri )      // (rr + i ri) += (br + i bi) * (yr + i yi)
+{
+	rr = fma( br, yr, rr ); rr = fma( -bi, yi, rr );
+	ri = fma( br, yi, ri ); ri = fma(  bi, yr, ri );
+}
+
 // ---- complex arithmetic in the reference's operation order -------------------
 // (frame/include/level0: bli_tdots / bli_tscals / bli_txpbys for c,z)
 template <typename R> struct Cx { R r, i; };

@@ -276,12 +276,11 @@ gemm_cfma_tma_kernel( const GemmArgs<float2> g, const __grid_constant__ CUtensor
 				unpack2( accP[i][j], px, py ); unpack2( accQ[i][j], qx, qy );
 				const float sx = cjx ? -1.f : 1.f, sy = cjy ? -1.f : 1.f;
 				const float ar = px - sx * sy * qy, ai = sy * py + sx * qx;
-				float rr = g.alpha.x * ar - g.alpha.y * ai;
-				float ri = g.alpha.x * ai + g.alpha.y * ar;
+				float rr, ri;
+				cscal( g.alpha.x, g.alpha.y, ar, ai, rr, ri );
 				if ( !g.beta_is_zero )
 				{
-					rr += g.beta.x * o[j].x - g.beta.y * o[j].y;
-					ri += g.beta.x * o[j].y + g.beta.y * o[j].x;
+					cxpby( g.beta.x, g.beta.y, o[j].x, o[j].y, rr, ri );
 				}
 				drow[ql] = make_float2( rr, ri );
 			}

@@ -323,13 +323,12 @@ gemm_dmma_kernel( const GemmArgs<T> g )
 						if ( e == 0 ? !one : !two ) continue;
 						const double ar = acc[0][i][j][e], ai = acc[1][i][j][e];
 						// ab *= alpha (bli_tscals), then c := ab + beta*c (bli_txpbys)
-						double rr = g.alpha.x * ar - g.alpha.y * ai;
-						double ri = g.alpha.x * ai + g.alpha.y * ar;
+						double rr, ri;
+						cscal( g.alpha.x, g.alpha.y, ar, ai, rr, ri );
 						if ( !g.beta_is_zero )
 						{
 							const double2 o = drow[ql + e];
-							rr += g.beta.x * o.x - g.beta.y * o.y;
-							ri += g.beta.x * o.y + g.beta.y * o.x;
+							cxpby( g.beta.x, g.beta.y, o.x, o.y, rr, ri );
 						}
 						drow[ql + e] = make_double2( rr, ri );
 					}

@@ -342,12 +342,11 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 						for ( int e = 0; e < 2; ++e )
 						{
 							const double ar = acc[0][i][j][e], ai = acc[1][i][j][e];
-							double rr = g.alpha.x * ar - g.alpha.y * ai;
-							double ri = g.alpha.x * ai + g.alpha.y * ar;
+							double rr, ri;
+							cscal( g.alpha.x, g.alpha.y, ar, ai, rr, ri );
 							if ( !g.beta_is_zero )
 							{
-								rr += g.beta.x * o[j][e].x - g.beta.y * o[j][e].y;
-								ri += g.beta.x * o[j][e].y + g.beta.y * o[j][e].x;
+								cxpby( g.beta.x, g.beta.y, o[j][e].x, o[j][e].y, rr, ri );
 							}
 							__stcs( dp + j * 8 + e, make_double2( rr, ri ) );
 						}
@@ -402,13 +401,12 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 					{
 						if ( e == 0 ? !one : !two ) continue;
 						const double ar = acc[0][i][j][e], ai = acc[1][i][j][e];
-						double rr = g.alpha.x * ar - g.alpha.y * ai;
-						double ri = g.alpha.x * ai + g.alpha.y * ar;
+						double rr, ri;
+						cscal( g.alpha.x, g.alpha.y, ar, ai, rr, ri );
 						if ( !g.beta_is_zero )
 						{
 							const double2 o = drow[ql + e];
-							rr += g.beta.x * o.x - g.beta.y * o.y;
-							ri += g.beta.x * o.y + g.beta.y * o.x;
+							cxpby( g.beta.x, g.beta.y, o.x, o.y, rr, ri );
 						}
 						drow[ql + e] = make_double2( rr, ri );
 					}

@@ -195,7 +195,7 @@ gemm_ffma_kernel( const GemmArgs<T> g )
 				for ( int e = 0; e < VE; ++e )
 				{
 					const T a = acc[i][gq * VE + e];
-					if constexpr ( CPLX ) r[e] = make_float2( g.alpha.x * a.x - g.alpha.y * a.y, g.alpha.x * a.y + g.alpha.y * a.x );
+					if constexpr ( CPLX ) cscal( g.alpha.x, g.alpha.y, a.x, a.y, r[e].x, r[e].y );
 					else                  r[e] = g.alpha * a;
 				}
 				const bool full = ( ql + VE <= q_lim && in_band( ql - pl, dlo, dhi ) && in_band( ql + VE - 1 - pl, dlo, dhi ) );
@@ -207,8 +207,8 @@ gemm_ffma_kernel( const GemmArgs<T> g )
 						const float4 o = *dp;
 						if constexpr ( CPLX )
 						{
-							r[0].x += g.beta.x * o.x - g.beta.y * o.y; r[0].y += g.beta.x * o.y + g.beta.y * o.x;
-							r[1].x += g.beta.x * o.z - g.beta.y * o.w; r[1].y += g.beta.x * o.w + g.beta.y * o.z;
+							cxpby( g.beta.x, g.beta.y, o.x, o.y, r[0].x, r[0].y );
+							cxpby( g.beta.x, g.beta.y, o.z, o.w, r[1].x, r[1].y );
 						}
 						else
 						{
@@ -228,7 +228,7 @@ gemm_ffma_kernel( const GemmArgs<T> g )
 						if ( !g.beta_is_zero )
 						{
 							const T o = drow[ql + e];
-							if constexpr ( CPLX ) { r[e].x += g.beta.x * o.x - g.beta.y * o.y; r[e].y += g.beta.x * o.y + g.beta.y * o.x; }
+							if constexpr ( CPLX ) cxpby( g.beta.x, g.beta.y, o.x, o.y, r[e].x, r[e].y );
 							else                  r[e] = fmaf( g.beta, o, r[e] );
 						}
 						drow[ql + e] = r[e];

@@ -269,6 +269,36 @@ def test_gemm_aligned_operands_tma_paths(engine, oracle, ch):
                     assert rel_err(got, want) <= TOL[ch], (ch, m, n, k, ta, tb, oc, rel_err(got, want))
 
 
+@pytest.mark.parametrize("ch", list("sc"))
+def test_gemm_fp32_k_contiguous_y_is_transposed_once(engine, ref, ch):
+    """s/c with a k-contiguous second kernel operand (column-major "TN"/"TT", row-major "NT"...) and a problem large
+    enough: the engine transposes that operand once into a q-contiguous temporary and runs the fast orientation.
+    Same results (within TOL) with the transposition switched off, and against the real reference; ragged sizes."""
+    cx = ch == "c"
+    al, be = ((2.0 + 0.2j, 1.2 + 0.5j) if cx else (2.0, 1.2))
+    for idx, (m, n, k, ta, tb, oc) in enumerate(((1028, 1036, 1004, TRANSPOSE, NO_TRANSPOSE, "c"),
+                                                 (1100, 900, 1200, CONJ_TRANSPOSE if cx else TRANSPOSE, TRANSPOSE, "c"),
+                                                 (1024, 1024, 1024, NO_TRANSPOSE, TRANSPOSE, "r"))):
+        am, ak = (k, m) if ta & TRANSPOSE else (m, k)
+        bk, bn = (n, k) if tb & TRANSPOSE else (k, n)
+        a = gen.matrix(ch, am, ak, 4000 + idx, "frac"); b = gen.matrix(ch, bk, bn, 4100 + idx, "frac")
+        c = gen.matrix(ch, m, n, 4200 + idx, "frac", oc)
+        want = c.copy(order="K")
+        ref.gemm(ta, tb, al, a, b, be, want)
+        n0 = engine.launch_count()
+        got = run_gemm(engine, ch, ta, tb, al, a, b, be, c)
+        assert engine.launch_count() - n0 == 2, "expected one transposition + one gemm kernel"
+        assert rel_err(got, want) <= TOL[ch] * 4, (ch, m, n, k, rel_err(got, want))
+        engine.set_option("transpose_y", 0)
+        try:
+            n0 = engine.launch_count()
+            got2 = run_gemm(engine, ch, ta, tb, al, a, b, be, c)
+            assert engine.launch_count() - n0 == 1
+        finally:
+            engine.set_option("transpose_y", 1)
+        assert rel_err(got2, want) <= TOL[ch] * 4
+
+
 def test_gemm_concurrent_host_threads(engine):
     """BLIS is re-entrant (SURVEY 8b 'Threading'): several application threads call gemm at the same time,
     each on its own CUDA stream; the engine's shared state (tile-scheduler counters, workspace pool, staging
