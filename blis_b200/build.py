@@ -18,7 +18,7 @@ CSRC = PKG / "csrc"
 LIB = PKG / "libblis_b200.so"
 STAMP = PKG / ".libblis_b200.stamp"
 
-SOURCES = ["capi.cu", "context.cu", "peaks.cu"]
+SOURCES = ["capi.cu", "gemm_d.cu", "gemm_z.cu", "gemm_s.cu", "gemm_c.cu", "context.cu", "peaks.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -8,19 +8,8 @@
 //   bli_l3_return_early_if_trivial   frame/3/bli_l3_util.c:40-65
 //   bli_trsm_blk_var1 (solve block, then rank-k update of the remaining rows)
 //                 frame/3/trsm/bli_trsm_blk_var1.c:40-188
-#include "context.cuh"
-#include "gemm_dmma.cuh"
-#include "gemm_dmma_ws.cuh"
-#include "gemm_dmma_tma.cuh"
-#include "gemm_ffma_tma.cuh"
-#include "gemm_cfma_tma.cuh"
-#include "gemm_ffma.cuh"
-#include "gemm_ffma_ws.cuh"
+#include "gemm_launch.cuh"
 #include "trsm.cuh"
-#include "../../include/blis_b200.h"
-#include <algorithm>
-#include <type_traits>
-#include <utility>
 #include <vector>
 
 namespace b200 {
@@ -168,225 +157,6 @@ static int scal2d( T* c, int64_t rs, int64_t cs, int64_t m, int64_t n, T beta, c
 	return kSuccess;
 }
 
-// ---- kernel launchers -------------------------------------------------------------
-template <typename KernT>
-static int set_smem( KernT kern, int bytes )
-{
-	B200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes ) );
-	return kSuccess;
-}
-
-template <typename T, int BP, int BQ, int BK, int WP, int WQ, int ST>
-static int launch_dmma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
-{
-	auto go = [&]( auto XKc, auto YKc, auto ALc ) -> int
-	{
-		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
-		using Cfg = DmmaCfg<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
-		auto kern = gemm_dmma_kernel<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
-		static bool attr = false;
-		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
-		kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>( g );
-		B200_CUDA( cudaGetLastError() );
-		ctx().launches++;
-		return kSuccess;
-	};
-	using Tt = std::true_type; using Ff = std::false_type;
-	const int sel = ( xk ? 4 : 0 ) | ( yk ? 2 : 0 ) | ( al ? 1 : 0 );
-	switch ( sel )
-	{
-		case 0: return go( Ff{}, Ff{}, Ff{} );  case 1: return go( Ff{}, Ff{}, Tt{} );
-		case 2: return go( Ff{}, Tt{}, Ff{} );  case 3: return go( Ff{}, Tt{}, Tt{} );
-		case 4: return go( Tt{}, Ff{}, Ff{} );  case 5: return go( Tt{}, Ff{}, Tt{} );
-		case 6: return go( Tt{}, Tt{}, Ff{} );  default: return go( Tt{}, Tt{}, Tt{} );
-	}
-}
-
-template <typename T, int BP, int BQ, int BK, int WP, int WQ, int ST, bool TRI = false>
-static int launch_dmma_ws( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
-{
-	auto go = [&]( auto XKc, auto YKc, auto ALc ) -> int
-	{
-		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
-		using Cfg = DmmaWsCfg<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
-		auto kern = gemm_dmma_ws_kernel<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL, TRI>;
-		static bool attr = false;
-		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
-		kern<<<grid, Cfg::NT_ALL, Cfg::SMEM_BYTES, st>>>( g );
-		B200_CUDA( cudaGetLastError() );
-		ctx().launches++;
-		return kSuccess;
-	};
-	using Tt = std::true_type; using Ff = std::false_type;
-	const int sel = ( xk ? 4 : 0 ) | ( yk ? 2 : 0 ) | ( al ? 1 : 0 );
-	switch ( sel )
-	{
-		case 0: return go( Ff{}, Ff{}, Ff{} );  case 1: return go( Ff{}, Ff{}, Tt{} );
-		case 2: return go( Ff{}, Tt{}, Ff{} );  case 3: return go( Ff{}, Tt{}, Tt{} );
-		case 4: return go( Tt{}, Ff{}, Ff{} );  case 5: return go( Tt{}, Ff{}, Tt{} );
-		case 6: return go( Tt{}, Tt{}, Ff{} );  default: return go( Tt{}, Tt{}, Tt{} );
-	}
-}
-
-// ---- TMA path (dgemm, 16-byte aligned operands) ---------------------------------------------
-typedef CUresult ( *EncodeTiledFn )( CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
-static EncodeTiledFn encode_tiled_fn()
-{
-	static EncodeTiledFn fn = nullptr;
-	if ( !fn )
-	{
-		void* p = nullptr; cudaDriverEntryPointQueryResult q;
-		if ( cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q ) == cudaSuccess && q == cudaDriverEntryPointSuccess )
-			fn = (EncodeTiledFn)p;
-	}
-	return fn;
-}
-// Tensor map of an operand with `rows` rows: k-contiguous (element (r,k) at base[r*ld + k]) -> dims {K, rows}, box {16, 128};
-// row-contiguous (element (r,k) at base[k*ld + r]) -> dims {rows, K}, box {16, 16}.  128-byte swizzle, zero fill out of bounds.
-// (float: the same with 32-element = 128-byte box rows: box {32, 128} resp. {32, 32}.)
-static int make_tmap( CUtensorMap* tm, const void* base, size_t es, bool kmajor, int64_t rows, int64_t K, int64_t ld, int box_rows = 128 )
-{
-	EncodeTiledFn enc = encode_tiled_fn();
-	if ( !enc ) return fail( "cuTensorMapEncodeTiled not available" );
-	const cuuint32_t inner = (cuuint32_t)( 128 / es );
-	cuuint64_t dims[2]    = { (cuuint64_t)( kmajor ? K : rows ), (cuuint64_t)( kmajor ? rows : K ) };
-	cuuint64_t strides[1] = { (cuuint64_t)ld * es };
-	cuuint32_t box[2]     = { inner, (cuuint32_t)( kmajor ? box_rows : inner ) };
-	cuuint32_t estr[2]    = { 1, 1 };
-	const CUresult r = enc( tm, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-	                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-	                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
-	if ( r != CUDA_SUCCESS ) return fail( "cuTensorMapEncodeTiled failed (%d)", (int)r );
-	return kSuccess;
-}
-template <typename T>
-static bool tma_eligible( const GemmArgs<T>& g, bool xk, bool yk, bool al )
-{
-	// TMA needs 16-byte aligned bases and strides (== al), a leading dimension that covers the row, 32-bit box coordinates
-	return al && g.nseg == 1 && g.P < ( 1ll << 31 ) && g.Q < ( 1ll << 31 ) && g.K < ( 1ll << 31 ) &&
-	       g.ldx >= ( xk ? g.K : g.P ) && g.ldy >= ( yk ? g.K : g.Q ) && g.ldx * 8 < ( 1ll << 40 ) && g.ldy * 8 < ( 1ll << 40 );
-}
-template <bool TRI = false>
-static int launch_dmma_tma( const GemmArgs<double>& g, bool xk, bool yk, int grid, cudaStream_t st )
-{
-	CUtensorMap tmx, tmy;
-	if ( make_tmap( &tmx, g.X, 8, xk, g.P, g.K, g.ldx ) != kSuccess ) return kFailure;
-	if ( make_tmap( &tmy, g.Y, 8, yk, g.Q, g.K, g.ldy ) != kSuccess ) return kFailure;
-	auto go = [&]( auto XKc, auto YKc ) -> int
-	{
-		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
-		auto kern = gemm_dmma_tma_kernel<XK, YK, TRI>;
-		static bool attr = false;
-		if ( !attr ) { if ( set_smem( kern, DmmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
-		kern<<<grid, DmmaTmaCfg::NT_ALL, DmmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
-		B200_CUDA( cudaGetLastError() );
-		ctx().launches++;
-		return kSuccess;
-	};
-	using Tt = std::true_type; using Ff = std::false_type;
-	if ( xk ) return yk ? go( Tt{}, Tt{} ) : go( Tt{}, Ff{} );
-	return yk ? go( Ff{}, Tt{} ) : go( Ff{}, Ff{} );
-}
-
-template <bool TRI = false>
-static int launch_ffma_tma( const GemmArgs<float>& g, bool xk, bool yk, int grid, cudaStream_t st )
-{
-	CUtensorMap tmx, tmy;
-	if ( make_tmap( &tmx, g.X, 4, xk, g.P, g.K, g.ldx ) != kSuccess ) return kFailure;
-	if ( make_tmap( &tmy, g.Y, 4, yk, g.Q, g.K, g.ldy ) != kSuccess ) return kFailure;
-	auto go = [&]( auto XKc, auto YKc ) -> int
-	{
-		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
-		auto kern = gemm_ffma_tma_kernel<XK, YK, TRI>;
-		static bool attr = false;
-		if ( !attr ) { if ( set_smem( kern, FfmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
-		kern<<<grid, FfmaTmaCfg::NT_ALL, FfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
-		B200_CUDA( cudaGetLastError() );
-		ctx().launches++;
-		return kSuccess;
-	};
-	using Tt = std::true_type; using Ff = std::false_type;
-	if ( xk ) return yk ? go( Tt{}, Tt{} ) : go( Tt{}, Ff{} );
-	return yk ? go( Ff{}, Tt{} ) : go( Ff{}, Ff{} );
-}
-
-template <bool TRI = false>
-static int launch_cfma_tma( const GemmArgs<float2>& g, bool xk, bool yk, int grid, cudaStream_t st )
-{
-	// float2 elements are moved as opaque 8-byte elements (FLOAT64-typed map; zero fill out of bounds)
-	CUtensorMap tmx, tmy;
-	if ( make_tmap( &tmx, g.X, 8, xk, g.P, g.K, g.ldx, CfmaTmaCfg::BP ) != kSuccess ) return kFailure;
-	if ( make_tmap( &tmy, g.Y, 8, yk, g.Q, g.K, g.ldy, CfmaTmaCfg::BQ ) != kSuccess ) return kFailure;
-	auto go = [&]( auto XKc, auto YKc ) -> int
-	{
-		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
-		auto kern = gemm_cfma_tma_kernel<XK, YK, TRI>;
-		static bool attr = false;
-		if ( !attr ) { if ( set_smem( kern, CfmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
-		kern<<<grid, CfmaTmaCfg::NT_ALL, CfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
-		B200_CUDA( cudaGetLastError() );
-		ctx().launches++;
-		return kSuccess;
-	};
-	using Tt = std::true_type; using Ff = std::false_type;
-	if ( xk ) return yk ? go( Tt{}, Tt{} ) : go( Tt{}, Ff{} );
-	return yk ? go( Ff{}, Tt{} ) : go( Ff{}, Ff{} );
-}
-
-template <typename T, int BP, int BQ, int BK, int TP, int TQ, int ST>
-static int launch_ffma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
-{
-	auto go = [&]( auto XKc, auto YKc, auto ALc ) -> int
-	{
-		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
-		using Cfg = FfmaCfg<T, BP, BQ, BK, TP, TQ, ST>;
-		auto kern = gemm_ffma_kernel<T, BP, BQ, BK, TP, TQ, ST, XK, YK, AL>;
-		static bool attr = false;
-		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
-		kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>( g );
-		B200_CUDA( cudaGetLastError() );
-		ctx().launches++;
-		return kSuccess;
-	};
-	using Tt = std::true_type; using Ff = std::false_type;
-	const int sel = ( xk ? 4 : 0 ) | ( yk ? 2 : 0 ) | ( al ? 1 : 0 );
-	switch ( sel )
-	{
-		case 0: return go( Ff{}, Ff{}, Ff{} );  case 1: return go( Ff{}, Ff{}, Tt{} );
-		case 2: return go( Ff{}, Tt{}, Ff{} );  case 3: return go( Ff{}, Tt{}, Tt{} );
-		case 4: return go( Tt{}, Ff{}, Ff{} );  case 5: return go( Tt{}, Ff{}, Tt{} );
-		case 6: return go( Tt{}, Tt{}, Ff{} );  default: return go( Tt{}, Tt{}, Tt{} );
-	}
-}
-
-template <typename T, int BP, int BQ, int BK, int TP, int TQ, int ST>
-static int launch_ffma_ws( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
-{
-	auto go = [&]( auto XKc, auto YKc, auto ALc ) -> int
-	{
-		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
-		using Cfg = FfmaWsCfg<T, BP, BQ, BK, TP, TQ, ST>;
-		auto kern = gemm_ffma_ws_kernel<T, BP, BQ, BK, TP, TQ, ST, XK, YK, AL>;
-		static bool attr = false;
-		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
-		kern<<<grid, Cfg::NT_ALL, Cfg::SMEM_BYTES, st>>>( g );
-		B200_CUDA( cudaGetLastError() );
-		ctx().launches++;
-		return kSuccess;
-	};
-	using Tt = std::true_type; using Ff = std::false_type;
-	const int sel = ( xk ? 4 : 0 ) | ( yk ? 2 : 0 ) | ( al ? 1 : 0 );
-	switch ( sel )
-	{
-		case 0: return go( Ff{}, Ff{}, Ff{} );  case 1: return go( Ff{}, Ff{}, Tt{} );
-		case 2: return go( Ff{}, Tt{}, Ff{} );  case 3: return go( Ff{}, Tt{}, Tt{} );
-		case 4: return go( Tt{}, Ff{}, Ff{} );  case 5: return go( Tt{}, Ff{}, Tt{} );
-		case 6: return go( Tt{}, Tt{}, Ff{} );  default: return go( Tt{}, Tt{}, Tt{} );
-	}
-}
-
 // Tile shapes per datatype = the "blocksizes" this engine registers
 // (MR/NR become the warp tile, MC/NC the CTA tile, KC the staged k slab).
 template <typename T> struct Tiles;
@@ -394,100 +164,6 @@ template <> struct Tiles<double>  { static constexpr int BP = 128, BQ = 128, BK 
 template <> struct Tiles<double2> { static constexpr int BP = 64,  BQ = 128, BK = 8,  MR = 32, NR = 32; };
 template <> struct Tiles<float>   { static constexpr int BP = 128, BQ = 128, BK = 16, MR = 8,  NR = 8;  };
 template <> struct Tiles<float2>  { static constexpr int BP = 64,  BQ = 128, BK = 16, MR = 4,  NR = 8;  };
-
-template <typename T>
-static int launch_gemm_kernel( GemmArgs<T>& g, bool xk, bool yk, bool al, cudaStream_t st );
-
-template <>
-int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, cudaStream_t st )
-{
-	Context& c = ctx();
-	auto tiles = [&]( int bp, int bq ) {
-		g.tiles_p = (int)( ( g.P + bp - 1 ) / bp ); g.tiles_q = (int)( ( g.Q + bq - 1 ) / bq );
-		return (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
-	};
-	int cfg = c.dgemm_cfg;
-	if ( g.nseg > 1 && ( cfg < 4 ) ) cfg = -1;          // k-panel accumulation needs a warp-specialised kernel
-	if ( g.tri )
-	{
-		// triangular D (gemmt family): the TRI instantiations of the default kernels
-		const int64_t t128 = ( ( g.P + 127 ) / 128 ) * ( ( g.Q + 127 ) / 128 );
-		if ( t128 < 2 * c.num_sms )
-		{
-			const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 128, 64 ); c.grid_mult = gm;
-			return launch_dmma_ws<double, 128, 64, 16, 4, 1, 3, true>( g, xk, yk, al, grid, st );
-		}
-		if ( tma_eligible( g, xk, yk, al ) ) return launch_dmma_tma<true>( g, xk, yk, tiles( 128, 128 ), st );
-		return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5, true>( g, xk, yk, al, tiles( 128, 128 ), st );
-	}
-	if ( cfg < 0 )
-	{
-		// auto: the cooperative 128x128 tile unless it cannot fill the SMs once; then 128x64 tiles, two CTAs per SM
-		const int64_t t128 = ( ( g.P + 127 ) / 128 ) * ( ( g.Q + 127 ) / 128 );
-		cfg = ( t128 < c.num_sms ) ? 7 : ( tma_eligible( g, xk, yk, al ) ? 9 : 6 );
-	}
-	switch ( cfg )
-	{
-		default:
-		case 0: return launch_dmma<double, 128, 128, 16, 2, 4, 4>( g, xk, yk, al, tiles( 128, 128 ), st );
-		case 1: return launch_dmma<double, 128, 128, 16, 4, 2, 4>( g, xk, yk, al, tiles( 128, 128 ), st );
-		case 2: return launch_dmma<double, 128, 128, 8,  2, 4, 6>( g, xk, yk, al, tiles( 128, 128 ), st );
-		case 3: return launch_dmma<double, 128, 128, 32, 2, 4, 3>( g, xk, yk, al, tiles( 128, 128 ), st );
-		case 4: return launch_dmma_ws<double, 128, 128, 16, 2, 4, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
-		case 5: return launch_dmma_ws<double, 128, 128, 32, 2, 4, 3>( g, xk, yk, al, tiles( 128, 128 ), st );
-		case 6: return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
-		case 9: if ( tma_eligible( g, xk, yk, al ) ) return launch_dmma_tma( g, xk, yk, tiles( 128, 128 ), st );
-		        return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
-		case 7: { const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 128, 64 ); c.grid_mult = gm;
-		          return launch_dmma_ws<double, 128, 64, 16, 4, 1, 3>( g, xk, yk, al, grid, st ); }
-		case 8: { const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 64, 128 ); c.grid_mult = gm;
-		          return launch_dmma_ws<double, 64, 128, 16, 1, 4, 3>( g, xk, yk, al, grid, st ); }
-	}
-}
-template <>
-int launch_gemm_kernel<double2>( GemmArgs<double2>& g, bool xk, bool yk, bool al, cudaStream_t st )
-{
-	Context& c = ctx();
-	g.tiles_p = (int)( ( g.P + 63 ) / 64 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
-	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
-	if ( g.tri ) return launch_dmma_ws<double2, 64, 128, 8, 2, 4, 5, true>( g, xk, yk, al, grid, st );
-	if ( c.zgemm_cfg == 1 || g.nseg > 1 ) return launch_dmma_ws<double2, 64, 128, 8, 2, 4, 5>( g, xk, yk, al, grid, st );
-	return launch_dmma<double2, 64, 128, 8, 2, 4, 4>( g, xk, yk, al, grid, st );
-}
-template <>
-int launch_gemm_kernel<float>( GemmArgs<float>& g, bool xk, bool yk, bool al, cudaStream_t st )
-{
-	Context& c = ctx();
-	if ( g.nseg > 1 ) return fail( "b200_gemm_kpanels: only d and z are supported" );
-	g.tiles_p = (int)( ( g.P + 127 ) / 128 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
-	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
-	// default (sgemm_cfg < 0 or 3): TMA + packed-FFMA2 kernel when the operands are 16-byte aligned
-	if ( g.tri )
-	{
-		if ( tma_eligible( g, xk, yk, al ) ) return launch_ffma_tma<true>( g, xk, yk, grid, st );
-		return launch_ffma<float, 128, 128, 16, 8, 8, 4>( g, xk, yk, al, grid, st );       // run-time tri support
-	}
-	if ( ( c.sgemm_cfg < 0 || c.sgemm_cfg == 3 ) && tma_eligible( g, xk, yk, al ) ) return launch_ffma_tma( g, xk, yk, grid, st );
-	if ( c.sgemm_cfg == 1 ) return launch_ffma_ws<float, 128, 128, 16, 8, 8, 5>( g, xk, yk, al, grid, st );
-	if ( c.sgemm_cfg == 2 ) return launch_ffma_ws<float, 128, 128, 32, 8, 8, 4>( g, xk, yk, al, grid, st );
-	return launch_ffma<float, 128, 128, 16, 8, 8, 4>( g, xk, yk, al, grid, st );
-}
-template <>
-int launch_gemm_kernel<float2>( GemmArgs<float2>& g, bool xk, bool yk, bool al, cudaStream_t st )
-{
-	Context& c = ctx();
-	if ( g.nseg > 1 ) return fail( "b200_gemm_kpanels: only d and z are supported" );
-	g.tiles_p = (int)( ( g.P + 63 ) / 64 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
-	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
-	if ( g.tri )
-	{
-		if ( tma_eligible( g, xk, yk, al ) ) return launch_cfma_tma<true>( g, xk, yk, grid, st );
-		return launch_ffma_ws<float2, 64, 128, 16, 4, 8, 5>( g, xk, yk, al, grid, st );     // run-time tri support
-	}
-	if ( ( c.cgemm_cfg < 0 || c.cgemm_cfg == 3 ) && tma_eligible( g, xk, yk, al ) ) return launch_cfma_tma( g, xk, yk, grid, st );
-	if ( c.cgemm_cfg != 0 ) return launch_ffma_ws<float2, 64, 128, 16, 4, 8, 5>( g, xk, yk, al, grid, st );
-	return launch_ffma<float2, 64, 128, 16, 4, 8, 4>( g, xk, yk, al, grid, st );
-}
 
 // ---- gemm on device-resident strided views ------------------------------------
 // C(m x n) := beta*C + alpha * A(m x k) * B(k x n); A/B views already carry any

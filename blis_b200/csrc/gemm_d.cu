@@ -1,0 +1,54 @@
+// gemm_d.cu -- kernel selection and launch for datatype double (see gemm_launch.cuh).
+#define B200_GEMM_LAUNCHERS
+#include "gemm_launch.cuh"
+
+namespace b200 {
+
+template <>
+int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, cudaStream_t st )
+{
+	Context& c = ctx();
+	auto tiles = [&]( int bp, int bq ) {
+		g.tiles_p = (int)( ( g.P + bp - 1 ) / bp ); g.tiles_q = (int)( ( g.Q + bq - 1 ) / bq );
+		return (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
+	};
+	int cfg = c.dgemm_cfg;
+	if ( g.nseg > 1 && ( cfg < 4 ) ) cfg = -1;          // k-panel accumulation needs a warp-specialised kernel
+	if ( g.tri )
+	{
+		// triangular D (gemmt family): the TRI instantiations of the default kernels
+		const int64_t t128 = ( ( g.P + 127 ) / 128 ) * ( ( g.Q + 127 ) / 128 );
+		if ( t128 < 2 * c.num_sms )
+		{
+			const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 128, 64 ); c.grid_mult = gm;
+			return launch_dmma_ws<double, 128, 64, 16, 4, 1, 3, true>( g, xk, yk, al, grid, st );
+		}
+		if ( tma_eligible( g, xk, yk, al ) ) return launch_dmma_tma<true>( g, xk, yk, tiles( 128, 128 ), st );
+		return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5, true>( g, xk, yk, al, tiles( 128, 128 ), st );
+	}
+	if ( cfg < 0 )
+	{
+		// auto: the cooperative 128x128 tile unless it cannot fill the SMs once; then 128x64 tiles, two CTAs per SM
+		const int64_t t128 = ( ( g.P + 127 ) / 128 ) * ( ( g.Q + 127 ) / 128 );
+		cfg = ( t128 < c.num_sms ) ? 7 : ( tma_eligible( g, xk, yk, al ) ? 9 : 6 );
+	}
+	switch ( cfg )
+	{
+		default:
+		case 0: return launch_dmma<double, 128, 128, 16, 2, 4, 4>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 1: return launch_dmma<double, 128, 128, 16, 4, 2, 4>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 2: return launch_dmma<double, 128, 128, 8,  2, 4, 6>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 3: return launch_dmma<double, 128, 128, 32, 2, 4, 3>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 4: return launch_dmma_ws<double, 128, 128, 16, 2, 4, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 5: return launch_dmma_ws<double, 128, 128, 32, 2, 4, 3>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 6: return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 9: if ( tma_eligible( g, xk, yk, al ) ) return launch_dmma_tma( g, xk, yk, tiles( 128, 128 ), st );
+		        return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 7: { const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 128, 64 ); c.grid_mult = gm;
+		          return launch_dmma_ws<double, 128, 64, 16, 4, 1, 3>( g, xk, yk, al, grid, st ); }
+		case 8: { const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 64, 128 ); c.grid_mult = gm;
+		          return launch_dmma_ws<double, 64, 128, 16, 1, 4, 3>( g, xk, yk, al, grid, st ); }
+	}
+}
+
+} // namespace b200

@@ -1,0 +1,252 @@
+// gemm_launch.cuh -- host-side launchers of the gemm kernels (shared by the per-datatype translation units
+// gemm_{d,z,s,c}.cu, which are compiled in parallel) and the kernel-selection entry point used by capi.cu.
+#pragma once
+#include "context.cuh"
+#include "gemm_dmma.cuh"
+#include "gemm_dmma_ws.cuh"
+#include "gemm_dmma_tma.cuh"
+#include "gemm_ffma_tma.cuh"
+#include "gemm_cfma_tma.cuh"
+#include "gemm_ffma.cuh"
+#include "gemm_ffma_ws.cuh"
+#include "../../include/blis_b200.h"
+#include <algorithm>
+#include <type_traits>
+#include <utility>
+
+namespace b200 {
+
+// Picks the kernel for one normalised problem (gemm_dmma.cuh: GemmArgs) and launches it on `st`.
+// One explicit specialisation per datatype, each in its own translation unit.
+template <typename T>
+int launch_gemm_kernel( GemmArgs<T>& g, bool xk, bool yk, bool al, cudaStream_t st );
+template <> int launch_gemm_kernel<double> ( GemmArgs<double>&  g, bool xk, bool yk, bool al, cudaStream_t st );
+template <> int launch_gemm_kernel<double2>( GemmArgs<double2>& g, bool xk, bool yk, bool al, cudaStream_t st );
+template <> int launch_gemm_kernel<float>  ( GemmArgs<float>&   g, bool xk, bool yk, bool al, cudaStream_t st );
+template <> int launch_gemm_kernel<float2> ( GemmArgs<float2>&  g, bool xk, bool yk, bool al, cudaStream_t st );
+
+template <typename KernT>
+static int set_smem( KernT kern, int bytes )
+{
+	B200_CUDA( cudaFuncSetAttribute( kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes ) );
+	return kSuccess;
+}
+
+#ifdef B200_GEMM_LAUNCHERS      // defined by gemm_{d,z,s,c}.cu only: capi.cu does not instantiate any gemm kernel
+
+// ---- kernel launchers -------------------------------------------------------------
+
+template <typename T, int BP, int BQ, int BK, int WP, int WQ, int ST>
+static int launch_dmma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
+{
+	auto go = [&]( auto XKc, auto YKc, auto ALc ) -> int
+	{
+		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
+		using Cfg = DmmaCfg<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
+		auto kern = gemm_dmma_kernel<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
+		static bool attr = false;
+		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>( g );
+		B200_CUDA( cudaGetLastError() );
+		ctx().launches++;
+		return kSuccess;
+	};
+	using Tt = std::true_type; using Ff = std::false_type;
+	const int sel = ( xk ? 4 : 0 ) | ( yk ? 2 : 0 ) | ( al ? 1 : 0 );
+	switch ( sel )
+	{
+		case 0: return go( Ff{}, Ff{}, Ff{} );  case 1: return go( Ff{}, Ff{}, Tt{} );
+		case 2: return go( Ff{}, Tt{}, Ff{} );  case 3: return go( Ff{}, Tt{}, Tt{} );
+		case 4: return go( Tt{}, Ff{}, Ff{} );  case 5: return go( Tt{}, Ff{}, Tt{} );
+		case 6: return go( Tt{}, Tt{}, Ff{} );  default: return go( Tt{}, Tt{}, Tt{} );
+	}
+}
+
+template <typename T, int BP, int BQ, int BK, int WP, int WQ, int ST, bool TRI = false>
+static int launch_dmma_ws( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
+{
+	auto go = [&]( auto XKc, auto YKc, auto ALc ) -> int
+	{
+		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
+		using Cfg = DmmaWsCfg<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
+		auto kern = gemm_dmma_ws_kernel<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL, TRI>;
+		static bool attr = false;
+		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<grid, Cfg::NT_ALL, Cfg::SMEM_BYTES, st>>>( g );
+		B200_CUDA( cudaGetLastError() );
+		ctx().launches++;
+		return kSuccess;
+	};
+	using Tt = std::true_type; using Ff = std::false_type;
+	const int sel = ( xk ? 4 : 0 ) | ( yk ? 2 : 0 ) | ( al ? 1 : 0 );
+	switch ( sel )
+	{
+		case 0: return go( Ff{}, Ff{}, Ff{} );  case 1: return go( Ff{}, Ff{}, Tt{} );
+		case 2: return go( Ff{}, Tt{}, Ff{} );  case 3: return go( Ff{}, Tt{}, Tt{} );
+		case 4: return go( Tt{}, Ff{}, Ff{} );  case 5: return go( Tt{}, Ff{}, Tt{} );
+		case 6: return go( Tt{}, Tt{}, Ff{} );  default: return go( Tt{}, Tt{}, Tt{} );
+	}
+}
+
+// ---- TMA path (dgemm, 16-byte aligned operands) ---------------------------------------------
+typedef CUresult ( *EncodeTiledFn )( CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
+static EncodeTiledFn encode_tiled_fn()
+{
+	static EncodeTiledFn fn = nullptr;
+	if ( !fn )
+	{
+		void* p = nullptr; cudaDriverEntryPointQueryResult q;
+		if ( cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q ) == cudaSuccess && q == cudaDriverEntryPointSuccess )
+			fn = (EncodeTiledFn)p;
+	}
+	return fn;
+}
+// Tensor map of an operand with `rows` rows: k-contiguous (element (r,k) at base[r*ld + k]) -> dims {K, rows}, box {16, 128};
+// row-contiguous (element (r,k) at base[k*ld + r]) -> dims {rows, K}, box {16, 16}.  128-byte swizzle, zero fill out of bounds.
+// (float: the same with 32-element = 128-byte box rows: box {32, 128} resp. {32, 32}.)
+static int make_tmap( CUtensorMap* tm, const void* base, size_t es, bool kmajor, int64_t rows, int64_t K, int64_t ld, int box_rows = 128 )
+{
+	EncodeTiledFn enc = encode_tiled_fn();
+	if ( !enc ) return fail( "cuTensorMapEncodeTiled not available" );
+	const cuuint32_t inner = (cuuint32_t)( 128 / es );
+	cuuint64_t dims[2]    = { (cuuint64_t)( kmajor ? K : rows ), (cuuint64_t)( kmajor ? rows : K ) };
+	cuuint64_t strides[1] = { (cuuint64_t)ld * es };
+	cuuint32_t box[2]     = { inner, (cuuint32_t)( kmajor ? box_rows : inner ) };
+	cuuint32_t estr[2]    = { 1, 1 };
+	const CUresult r = enc( tm, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+	                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+	                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+	if ( r != CUDA_SUCCESS ) return fail( "cuTensorMapEncodeTiled failed (%d)", (int)r );
+	return kSuccess;
+}
+template <typename T>
+static bool tma_eligible( const GemmArgs<T>& g, bool xk, bool yk, bool al )
+{
+	// TMA needs 16-byte aligned bases and strides (== al), a leading dimension that covers the row, 32-bit box coordinates
+	return al && g.nseg == 1 && g.P < ( 1ll << 31 ) && g.Q < ( 1ll << 31 ) && g.K < ( 1ll << 31 ) &&
+	       g.ldx >= ( xk ? g.K : g.P ) && g.ldy >= ( yk ? g.K : g.Q ) && g.ldx * 8 < ( 1ll << 40 ) && g.ldy * 8 < ( 1ll << 40 );
+}
+template <bool TRI = false>
+static int launch_dmma_tma( const GemmArgs<double>& g, bool xk, bool yk, int grid, cudaStream_t st )
+{
+	CUtensorMap tmx, tmy;
+	if ( make_tmap( &tmx, g.X, 8, xk, g.P, g.K, g.ldx ) != kSuccess ) return kFailure;
+	if ( make_tmap( &tmy, g.Y, 8, yk, g.Q, g.K, g.ldy ) != kSuccess ) return kFailure;
+	auto go = [&]( auto XKc, auto YKc ) -> int
+	{
+		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
+		auto kern = gemm_dmma_tma_kernel<XK, YK, TRI>;
+		static bool attr = false;
+		if ( !attr ) { if ( set_smem( kern, DmmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<grid, DmmaTmaCfg::NT_ALL, DmmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
+		B200_CUDA( cudaGetLastError() );
+		ctx().launches++;
+		return kSuccess;
+	};
+	using Tt = std::true_type; using Ff = std::false_type;
+	if ( xk ) return yk ? go( Tt{}, Tt{} ) : go( Tt{}, Ff{} );
+	return yk ? go( Ff{}, Tt{} ) : go( Ff{}, Ff{} );
+}
+
+template <bool TRI = false>
+static int launch_ffma_tma( const GemmArgs<float>& g, bool xk, bool yk, int grid, cudaStream_t st )
+{
+	CUtensorMap tmx, tmy;
+	if ( make_tmap( &tmx, g.X, 4, xk, g.P, g.K, g.ldx ) != kSuccess ) return kFailure;
+	if ( make_tmap( &tmy, g.Y, 4, yk, g.Q, g.K, g.ldy ) != kSuccess ) return kFailure;
+	auto go = [&]( auto XKc, auto YKc ) -> int
+	{
+		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
+		auto kern = gemm_ffma_tma_kernel<XK, YK, TRI>;
+		static bool attr = false;
+		if ( !attr ) { if ( set_smem( kern, FfmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<grid, FfmaTmaCfg::NT_ALL, FfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
+		B200_CUDA( cudaGetLastError() );
+		ctx().launches++;
+		return kSuccess;
+	};
+	using Tt = std::true_type; using Ff = std::false_type;
+	if ( xk ) return yk ? go( Tt{}, Tt{} ) : go( Tt{}, Ff{} );
+	return yk ? go( Ff{}, Tt{} ) : go( Ff{}, Ff{} );
+}
+
+template <bool TRI = false>
+static int launch_cfma_tma( const GemmArgs<float2>& g, bool xk, bool yk, int grid, cudaStream_t st )
+{
+	// float2 elements are moved as opaque 8-byte elements (FLOAT64-typed map; zero fill out of bounds)
+	CUtensorMap tmx, tmy;
+	if ( make_tmap( &tmx, g.X, 8, xk, g.P, g.K, g.ldx, CfmaTmaCfg::BP ) != kSuccess ) return kFailure;
+	if ( make_tmap( &tmy, g.Y, 8, yk, g.Q, g.K, g.ldy, CfmaTmaCfg::BQ ) != kSuccess ) return kFailure;
+	auto go = [&]( auto XKc, auto YKc ) -> int
+	{
+		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
+		auto kern = gemm_cfma_tma_kernel<XK, YK, TRI>;
+		static bool attr = false;
+		if ( !attr ) { if ( set_smem( kern, CfmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<grid, CfmaTmaCfg::NT_ALL, CfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
+		B200_CUDA( cudaGetLastError() );
+		ctx().launches++;
+		return kSuccess;
+	};
+	using Tt = std::true_type; using Ff = std::false_type;
+	if ( xk ) return yk ? go( Tt{}, Tt{} ) : go( Tt{}, Ff{} );
+	return yk ? go( Ff{}, Tt{} ) : go( Ff{}, Ff{} );
+}
+
+template <typename T, int BP, int BQ, int BK, int TP, int TQ, int ST>
+static int launch_ffma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
+{
+	auto go = [&]( auto XKc, auto YKc, auto ALc ) -> int
+	{
+		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
+		using Cfg = FfmaCfg<T, BP, BQ, BK, TP, TQ, ST>;
+		auto kern = gemm_ffma_kernel<T, BP, BQ, BK, TP, TQ, ST, XK, YK, AL>;
+		static bool attr = false;
+		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>( g );
+		B200_CUDA( cudaGetLastError() );
+		ctx().launches++;
+		return kSuccess;
+	};
+	using Tt = std::true_type; using Ff = std::false_type;
+	const int sel = ( xk ? 4 : 0 ) | ( yk ? 2 : 0 ) | ( al ? 1 : 0 );
+	switch ( sel )
+	{
+		case 0: return go( Ff{}, Ff{}, Ff{} );  case 1: return go( Ff{}, Ff{}, Tt{} );
+		case 2: return go( Ff{}, Tt{}, Ff{} );  case 3: return go( Ff{}, Tt{}, Tt{} );
+		case 4: return go( Tt{}, Ff{}, Ff{} );  case 5: return go( Tt{}, Ff{}, Tt{} );
+		case 6: return go( Tt{}, Tt{}, Ff{} );  default: return go( Tt{}, Tt{}, Tt{} );
+	}
+}
+
+template <typename T, int BP, int BQ, int BK, int TP, int TQ, int ST>
+static int launch_ffma_ws( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
+{
+	auto go = [&]( auto XKc, auto YKc, auto ALc ) -> int
+	{
+		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
+		using Cfg = FfmaWsCfg<T, BP, BQ, BK, TP, TQ, ST>;
+		auto kern = gemm_ffma_ws_kernel<T, BP, BQ, BK, TP, TQ, ST, XK, YK, AL>;
+		static bool attr = false;
+		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<grid, Cfg::NT_ALL, Cfg::SMEM_BYTES, st>>>( g );
+		B200_CUDA( cudaGetLastError() );
+		ctx().launches++;
+		return kSuccess;
+	};
+	using Tt = std::true_type; using Ff = std::false_type;
+	const int sel = ( xk ? 4 : 0 ) | ( yk ? 2 : 0 ) | ( al ? 1 : 0 );
+	switch ( sel )
+	{
+		case 0: return go( Ff{}, Ff{}, Ff{} );  case 1: return go( Ff{}, Ff{}, Tt{} );
+		case 2: return go( Ff{}, Tt{}, Ff{} );  case 3: return go( Ff{}, Tt{}, Tt{} );
+		case 4: return go( Tt{}, Ff{}, Ff{} );  case 5: return go( Tt{}, Ff{}, Tt{} );
+		case 6: return go( Tt{}, Tt{}, Ff{} );  default: return go( Tt{}, Tt{}, Tt{} );
+	}
+}
+
+#endif // B200_GEMM_LAUNCHERS
+
+} // namespace b200
