@@ -128,7 +128,47 @@ def _typed_one_operand(dtype, name):
     return f
 
 
+def _typed_hemm(dtype, name):
+    """bli_?hemm / bli_?symm (frame/3/bli_l3_tapi.c:114-155)."""
+    def f(side, uploa, conja, transb, m, n, alpha, a, rs_a, cs_a, b, rs_b, cs_b, beta, c, rs_c, cs_c):
+        lib = _lib.load()
+        _bind_stream(a, b, c)
+        al, be = _scalar_buf(dtype, alpha), _scalar_buf(dtype, beta)
+        rc = getattr(lib, "b200_" + name)(_DT[dtype], int(side), int(uploa), int(conja), int(transb), m, n, C.addressof(al),
+                                          _ptr(a), rs_a, cs_a, _ptr(b), rs_b, cs_b, C.addressof(be), _ptr(c), rs_c, cs_c)
+        check(rc, "bli_" + name)
+    return f
+
+
+def _typed_trmm3(dtype):
+    """bli_?trmm3 (frame/3/bli_l3_tapi.c:298-339)."""
+    def f(side, uploa, transa, diaga, transb, m, n, alpha, a, rs_a, cs_a, b, rs_b, cs_b, beta, c, rs_c, cs_c):
+        lib = _lib.load()
+        _bind_stream(a, b, c)
+        al, be = _scalar_buf(dtype, alpha), _scalar_buf(dtype, beta)
+        rc = lib.b200_trmm3(_DT[dtype], int(side), int(uploa), int(transa), int(diaga), int(transb), m, n, C.addressof(al),
+                            _ptr(a), rs_a, cs_a, _ptr(b), rs_b, cs_b, C.addressof(be), _ptr(c), rs_c, cs_c)
+        check(rc, "bli_trmm3")
+    return f
+
+
+def _typed_trmm(dtype):
+    """bli_?trmm (frame/3/bli_l3_tapi.c, GENTFUNC trmm): in place on B."""
+    def f(side, uploa, transa, diaga, m, n, alpha, a, rs_a, cs_a, b, rs_b, cs_b):
+        lib = _lib.load()
+        _bind_stream(a, b)
+        al = _scalar_buf(dtype, alpha)
+        rc = lib.b200_trmm(_DT[dtype], int(side), int(uploa), int(transa), int(diaga), m, n,
+                           C.addressof(al), _ptr(a), rs_a, cs_a, _ptr(b), rs_b, cs_b)
+        check(rc, "bli_trmm")
+    return f
+
+
 for _ch, _dt in _CH.items():
+    globals()[f"bli_{_ch}hemm"] = _typed_hemm(_dt, "hemm")
+    globals()[f"bli_{_ch}symm"] = _typed_hemm(_dt, "symm")
+    globals()[f"bli_{_ch}trmm3"] = _typed_trmm3(_dt)
+    globals()[f"bli_{_ch}trmm"] = _typed_trmm(_dt)
     for _name in ("gemmt", "syr2k", "her2k"):
         globals()[f"bli_{_ch}{_name}"] = _typed_two_operand(_dt, _name)
     for _name in ("syrk", "herk"):

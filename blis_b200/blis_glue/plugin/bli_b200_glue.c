@@ -266,6 +266,91 @@ void bli_her2k_ex_b200( const obj_t* alpha, const obj_t* a, const obj_t* b, cons
 	if ( r != BLIS_SUCCESS ) bli_b200_die( "her2k" );
 }
 
+/* -- hemm, symm, trmm3, trmm: bli_hemm_ex / bli_symm_ex / bli_trmm3_ex / bli_trmm_ex
+      (frame/3/bli_l3_oapi_ex.c:349-689); no handler slot exists for them either ------------ */
+
+static void bli_b200_struc_mm( int op, side_t side, const obj_t* alpha, const obj_t* a, const obj_t* b,
+                               const obj_t* beta, const obj_t* c, const char* name )
+{
+	bli_b200_same_dt( a, b, c, name );
+	if ( bli_obj_has_zero_dim( c ) ) return;
+	const num_t dt = bli_obj_dt( c );
+	obj_t al, be; bli_b200_scalar( dt, alpha, &al ); bli_b200_scalar( dt, beta, &be );
+	err_t r;
+	if ( op == 0 || op == 1 )
+		r = ( op == 0 ? b200_hemm : b200_symm )( ( int )dt, ( int )side, ( int )bli_obj_uplo( a ),
+		  ( int )bli_obj_conj_status( a ), ( int )bli_obj_conjtrans_status( b ),
+		  bli_obj_length( c ), bli_obj_width( c ), bli_obj_buffer_for_1x1( dt, &al ),
+		  bli_obj_buffer_at_off( a ), bli_obj_row_stride( a ), bli_obj_col_stride( a ),
+		  bli_obj_buffer_at_off( b ), bli_obj_row_stride( b ), bli_obj_col_stride( b ),
+		  bli_obj_buffer_for_1x1( dt, &be ),
+		  bli_obj_buffer_at_off( c ), bli_obj_row_stride( c ), bli_obj_col_stride( c ) );
+	else
+		r = b200_trmm3( ( int )dt, ( int )side, ( int )bli_obj_uplo( a ), ( int )bli_obj_conjtrans_status( a ),
+		  ( int )bli_obj_diag( a ), ( int )bli_obj_conjtrans_status( b ),
+		  bli_obj_length( c ), bli_obj_width( c ), bli_obj_buffer_for_1x1( dt, &al ),
+		  bli_obj_buffer_at_off( a ), bli_obj_row_stride( a ), bli_obj_col_stride( a ),
+		  bli_obj_buffer_at_off( b ), bli_obj_row_stride( b ), bli_obj_col_stride( b ),
+		  bli_obj_buffer_for_1x1( dt, &be ),
+		  bli_obj_buffer_at_off( c ), bli_obj_row_stride( c ), bli_obj_col_stride( c ) );
+	if ( r != BLIS_SUCCESS ) bli_b200_die( name );
+}
+
+void bli_hemm_ex_b200( side_t side, const obj_t* alpha, const obj_t* a, const obj_t* b, const obj_t* beta, const obj_t* c,
+                       const cntx_t* cntx, const rntm_t* rntm )
+{
+	( void )rntm;
+	bli_init_once();
+	if ( bli_error_checking_is_enabled() ) bli_hemm_check( side, alpha, a, b, beta, c, cntx );
+	bli_b200_struc_mm( 0, side, alpha, a, b, beta, c, "hemm" );
+}
+
+void bli_symm_ex_b200( side_t side, const obj_t* alpha, const obj_t* a, const obj_t* b, const obj_t* beta, const obj_t* c,
+                       const cntx_t* cntx, const rntm_t* rntm )
+{
+	( void )rntm;
+	bli_init_once();
+	if ( bli_error_checking_is_enabled() ) bli_symm_check( side, alpha, a, b, beta, c, cntx );
+	bli_b200_struc_mm( 1, side, alpha, a, b, beta, c, "symm" );
+}
+
+void bli_trmm3_ex_b200( side_t side, const obj_t* alpha, const obj_t* a, const obj_t* b, const obj_t* beta, const obj_t* c,
+                        const cntx_t* cntx, const rntm_t* rntm )
+{
+	( void )rntm;
+	bli_init_once();
+	if ( bli_error_checking_is_enabled() ) bli_trmm3_check( side, alpha, a, b, beta, c, cntx );
+	bli_b200_struc_mm( 2, side, alpha, a, b, beta, c, "trmm3" );
+}
+
+void bli_trmm_ex_b200( side_t side, const obj_t* alpha, const obj_t* a, const obj_t* b,
+                       const cntx_t* cntx, const rntm_t* rntm )
+{
+	( void )rntm;
+	bli_init_once();
+	if ( bli_error_checking_is_enabled() ) bli_trmm_check( side, alpha, a, b, cntx );
+	bli_b200_same_dt( a, NULL, b, "trmm" );
+	if ( bli_obj_has_zero_dim( b ) ) return;
+	const num_t dt = bli_obj_dt( b );
+	obj_t al; bli_b200_scalar( dt, alpha, &al );
+	const err_t r = b200_trmm( ( int )dt, ( int )side, ( int )bli_obj_uplo( a ), ( int )bli_obj_conjtrans_status( a ),
+	  ( int )bli_obj_diag( a ), bli_obj_length( b ), bli_obj_width( b ), bli_obj_buffer_for_1x1( dt, &al ),
+	  bli_obj_buffer_at_off( a ), bli_obj_row_stride( a ), bli_obj_col_stride( a ),
+	  bli_obj_buffer_at_off( b ), bli_obj_row_stride( b ), bli_obj_col_stride( b ) );
+	if ( r != BLIS_SUCCESS ) bli_b200_die( "trmm" );
+}
+
+#ifdef BLIS_B200_OVERRIDE_GEMMT_EX
+void bli_hemm_ex( side_t side, const obj_t* alpha, const obj_t* a, const obj_t* b, const obj_t* beta, const obj_t* c, const cntx_t* cntx, const rntm_t* rntm )
+{ bli_hemm_ex_b200( side, alpha, a, b, beta, c, cntx, rntm ); }
+void bli_symm_ex( side_t side, const obj_t* alpha, const obj_t* a, const obj_t* b, const obj_t* beta, const obj_t* c, const cntx_t* cntx, const rntm_t* rntm )
+{ bli_symm_ex_b200( side, alpha, a, b, beta, c, cntx, rntm ); }
+void bli_trmm3_ex( side_t side, const obj_t* alpha, const obj_t* a, const obj_t* b, const obj_t* beta, const obj_t* c, const cntx_t* cntx, const rntm_t* rntm )
+{ bli_trmm3_ex_b200( side, alpha, a, b, beta, c, cntx, rntm ); }
+void bli_trmm_ex( side_t side, const obj_t* alpha, const obj_t* a, const obj_t* b, const cntx_t* cntx, const rntm_t* rntm )
+{ bli_trmm_ex_b200( side, alpha, a, b, cntx, rntm ); }
+#endif
+
 #ifdef BLIS_B200_OVERRIDE_GEMMT_EX
 /* Build-time switch of the config route / LD_PRELOAD demo, as for trsm. */
 void bli_gemmt_ex( const obj_t* alpha, const obj_t* a, const obj_t* b, const obj_t* beta, const obj_t* c, const cntx_t* cntx, const rntm_t* rntm )

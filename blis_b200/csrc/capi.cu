@@ -165,6 +165,8 @@ template <> struct Tiles<double2> { static constexpr int BP = 64,  BQ = 128, BK 
 template <> struct Tiles<float>   { static constexpr int BP = 128, BQ = 128, BK = 16, MR = 8,  NR = 8;  };
 template <> struct Tiles<float2>  { static constexpr int BP = 64,  BQ = 128, BK = 16, MR = 4,  NR = 8;  };
 
+enum { kTriA = 1, kTriB = 2, kTriLower = 4, kTriUpper = 8 };
+
 // ---- gemm on device-resident strided views ------------------------------------
 // C(m x n) := beta*C + alpha * A(m x k) * B(k x n); A/B views already carry any
 // transposition in their strides; conja/conjb request conjugation.
@@ -174,7 +176,9 @@ static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T 
                      const T* b, int64_t rs_b, int64_t cs_b,
                      T beta, T* c, int64_t rs_c, int64_t cs_c, cudaStream_t st,
                      int nseg = 1, const T* const* a_more = nullptr, const T* const* b_more = nullptr,
-                     int uplo_c = 0 )     // 0: all of C; B200_LOWER / B200_UPPER: only that triangle of C is computed and stored
+                     int uplo_c = 0,      // 0: all of C; B200_LOWER / B200_UPPER: only that triangle of C is computed and stored
+                     int tri_operand = 0 ) // 0: none; kTriA/kTriB | kTriLower/kTriUpper: that operand is (effectively) triangular with
+                                           // explicit zeros on the other side -> tiles skip the k range that only multiplies zeros
 {
 	if ( m <= 0 || n <= 0 ) return kSuccess;
 	// bli_l3_return_early_if_trivial: alpha == 0 or k == 0  ->  C := beta*C
@@ -223,6 +227,14 @@ static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T 
 	g.tri = 0; g.tri_off = 0;
 	if ( uplo_c == B200_LOWER ) g.tri = swapped ? 2 : 1;
 	if ( uplo_c == B200_UPPER ) g.tri = swapped ? 1 : 2;
+	g.ktri = 0;
+	if ( tri_operand && ctx().ktri_skip )
+	{
+		const bool on_a = ( tri_operand & kTriA ) != 0, lower = ( tri_operand & kTriLower ) != 0;
+		// a(i,l) lower: zero for l > i.  b(l,j) lower: zero for l < j.  X(p,k)/Y(k,q) as mapped above.
+		if ( on_a ) g.ktri = swapped ? ( lower ? 3 : 4 ) : ( lower ? 1 : 2 );
+		else        g.ktri = swapped ? ( lower ? 2 : 1 ) : ( lower ? 4 : 3 );
+	}
 	g.tile_counter = ctx().dynamic_tiles ? ctx().sched_counters + 2 * ( ctx().sched_next++ % 64 ) : nullptr;
 	for ( int sgm = 1; sgm < nseg; ++sgm )
 	{
@@ -284,7 +296,7 @@ template <typename T>
 static int gemm_front( int transa, int transb, int64_t m, int64_t n, int64_t k,
                        const T* alpha, const T* a, int64_t rs_a, int64_t cs_a,
                        const T* b, int64_t rs_b, int64_t cs_b,
-                       const T* beta, T* c, int64_t rs_c, int64_t cs_c )
+                       const T* beta, T* c, int64_t rs_c, int64_t cs_c, int tri_operand = 0 )
 {
 	if ( ensure_init() != kSuccess ) return kFailure;
 	if ( m < 0 || n < 0 || k < 0 ) return fail( "b200_gemm: negative dimension" );
@@ -311,7 +323,7 @@ static int gemm_front( int transa, int transb, int64_t m, int64_t n, int64_t k,
 	}
 	// Host C of a large problem: pipeline over column blocks of C (and of B when it is a host
 	// operand) so that H2D of block j+1 and D2H of block j-1 run under the kernels of block j.
-	const bool pipelined = c_host && need_ab && n >= 1024 && (double)m * (double)n * (double)k >= 2e9;
+	const bool pipelined = c_host && need_ab && n >= 1024 && (double)m * (double)n * (double)k >= 2e9 && tri_operand == 0;
 	const T* b_host = nullptr; int64_t rs_bh = 0, cs_bh = 0;      // set when B moves block-wise
 	if ( rc == kSuccess && need_ab && classify( b ) != MemKind::Device )
 	{
@@ -328,7 +340,7 @@ static int gemm_front( int transa, int transb, int64_t m, int64_t n, int64_t k,
 		cdev = (T*)dc; rs_cd = 1; cs_cd = m;
 	}
 	if ( rc == kSuccess && !pipelined )
-		rc = gemm_dev<T>( conja, conjb, m, n, k, al, a, rs_a, cs_a, b, rs_b, cs_b, be, cdev, rs_cd, cs_cd, st );
+		rc = gemm_dev<T>( conja, conjb, m, n, k, al, a, rs_a, cs_a, b, rs_b, cs_b, be, cdev, rs_cd, cs_cd, st, 1, nullptr, nullptr, 0, tri_operand );
 	if ( rc == kSuccess && c_host && !pipelined )
 	{
 		rc = stage_to_host( c, rs_c, cs_c, dc, m, n, ES, st );
@@ -708,6 +720,170 @@ extern "C" b200_err_t b200_trsm( int dt, int side, int uploa, int transa, int di
 
 // k-panel accumulation: C := beta*C + alpha * sum_{s<npanels} op(A_s) * op(B_s), every panel k wide, all
 // A panels (resp. B panels) with the same strides.  Device-resident operands, d and z only.
+// ---- hemm, symm, trmm, trmm3 -----------------------------------------------------------------
+// bli_hemm_ex / bli_symm_ex / bli_trmm3_ex / bli_trmm_ex (frame/3/bli_l3_oapi_ex.c:349-689): the gemm control tree
+// with a structured A.  The reference resolves the structure while PACKING (bli_packm_struc_cxk.c:146-301: the
+// unstored side of a Hermitian/symmetric matrix is read from its mirror image, conjugated for Hermitian; the unstored
+// side of a triangular matrix is packed as explicit zeros; ref_kernels/1m/bli_packm_cxc_diag_ref.c:36-98: a unit
+// diagonal is packed as one, a Hermitian diagonal loses its imaginary part) and then runs gemm-shaped macrokernels
+// (trmm ones skip the zero k range).  Here the structure is resolved ONCE into a dense m x m device matrix
+// (O(m^2) traffic against O(m^2 n) flops) and the product is the gemm kernel, trimmed in k for trmm.
+namespace b200 {
+
+enum { kStrucTri = 0, kStrucSym = 1, kStrucHerm = 2 };
+
+template <typename R, int NC>
+__global__ void densify_kernel( R* dst, int64_t ldd, const R* src, int64_t rs, int64_t cs,
+                                int64_t m, int struc, int lower, int unit )
+{
+	const int64_t total = m * m;
+	for ( int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x )
+	{
+		const int64_t i = e % m, j = e / m;
+		const bool stored = lower ? ( i >= j ) : ( i <= j );
+		R re = (R)0, im = (R)0;
+		if ( i == j )
+		{
+			if ( struc == kStrucTri && unit ) re = (R)1;
+			else
+			{
+				const R* p = src + ( i * rs + j * cs ) * NC;
+				re = p[0];
+				if ( NC == 2 && struc != kStrucHerm ) im = p[NC - 1];
+			}
+		}
+		else if ( stored )
+		{
+			const R* p = src + ( i * rs + j * cs ) * NC;
+			re = p[0]; if ( NC == 2 ) im = p[NC - 1];
+		}
+		else if ( struc != kStrucTri )
+		{
+			const R* p = src + ( j * rs + i * cs ) * NC;         // mirror image
+			re = p[0]; if ( NC == 2 ) im = ( struc == kStrucHerm ) ? -p[NC - 1] : p[NC - 1];
+		}
+		R* d = dst + ( i + j * ldd ) * NC;
+		if ( src == dst && stored && i != j ) continue;       // in place (staged copy): stored elements stay
+		d[0] = re; if ( NC == 2 ) d[NC - 1] = im;
+	}
+}
+
+// Dense, structure-resolved copy of the ma x ma matrix A (host or device) in `*da` (column-major, ld = ma).
+template <typename T>
+static int densify_operand( void** da, const T* a, int64_t rs_a, int64_t cs_a, int64_t ma, int struc, int uplo, bool unit, cudaStream_t st )
+{
+	using R = typename Elem<T>::real;
+	constexpr int NC = Elem<T>::cplx ? 2 : 1;
+	*da = nullptr;
+	if ( dev_alloc( da, (size_t)ma * ma * sizeof(T), st ) != kSuccess ) return kFailure;
+	const T* src = a; int64_t rs = rs_a, cs = cs_a;
+	if ( classify( a ) != MemKind::Device )
+	{
+		// the whole array is staged (the unstored triangle may hold anything; it is never used) and resolved in place
+		if ( stage_to_device( *da, a, ma, ma, rs_a, cs_a, sizeof(T), st ) != kSuccess ) return kFailure;
+		src = (const T*)*da; rs = 1; cs = ma;
+	}
+	const int64_t total = ma * ma;
+	const int blocks = (int)std::min<int64_t>( ( total + 255 ) / 256, (int64_t)ctx().num_sms * 16 );
+	densify_kernel<R, NC><<<blocks, 256, 0, st>>>( (R*)*da, ma, (const R*)src, rs, cs, ma, struc, uplo == B200_LOWER ? 1 : 0, unit ? 1 : 0 );
+	B200_CUDA( cudaGetLastError() );
+	ctx().launches++;
+	return kSuccess;
+}
+
+// op: 0 hemm, 1 symm, 2 trmm3, 3 trmm (C == B, beta ignored)
+template <typename T>
+static int struc_mm_front( int op, int side, int uploa, int transa, int diaga, int transb, int64_t m, int64_t n,
+                           const T* alpha, const T* a, int64_t rs_a, int64_t cs_a,
+                           const T* b, int64_t rs_b, int64_t cs_b,
+                           const T* beta, T* c, int64_t rs_c, int64_t cs_c, const char* name )
+{
+	if ( ensure_init() != kSuccess ) return kFailure;
+	if ( m < 0 || n < 0 ) return fail( "%s: negative dimension", name );
+	if ( !alpha || ( op != 3 && !beta ) ) return fail( "%s: alpha/beta must be non-NULL host pointers", name );
+	if ( uploa != B200_LOWER && uploa != B200_UPPER ) return fail( "%s: uplo must be BLIS_LOWER or BLIS_UPPER", name );
+	if ( side != B200_LEFT && side != B200_RIGHT ) return fail( "%s: side must be BLIS_LEFT or BLIS_RIGHT", name );
+	if ( m == 0 || n == 0 ) return kSuccess;
+	cudaStream_t st = cur_stream();
+	const int64_t ma = ( side == B200_LEFT ) ? m : n;
+	const T zero = Scalar<T>::make( 0.0, 0.0 );
+	const T al = *alpha, be = ( op == 3 ) ? zero : *beta;
+	const int struc = ( op == 0 ) ? kStrucHerm : ( op == 1 ) ? kStrucSym : kStrucTri;
+
+	void *da = nullptr, *dt = nullptr;
+	int rc = kSuccess;
+	if ( !Scalar<T>::is_zero( al ) )
+		rc = densify_operand<T>( &da, a, rs_a, cs_a, ma, struc, uploa, diaga == B200_UNIT_DIAG, st );
+	const T* ad = (const T*)da;
+
+	const T* bsrc = b; int64_t rs_bs = rs_b, cs_bs = cs_b; int transb_use = transb;
+	if ( op == 3 )
+	{
+		// trmm is in place: B := alpha * transa(A) * B.  The product reads a copy of B (bli_trmm_ex aliases C = B and
+		// relies on the macrokernel's loop order; a copy costs O(mn) against O(m^2 n)).
+		transb_use = B200_NO_TRANSPOSE;
+		if ( rc == kSuccess && !Scalar<T>::is_zero( al ) )
+		{
+			if ( dev_alloc( &dt, (size_t)m * n * sizeof(T), st ) != kSuccess ) rc = kFailure;
+			else if ( classify( b ) != MemKind::Device ) rc = stage_to_device( dt, b, m, n, rs_b, cs_b, sizeof(T), st );
+			else rc = copy2d( (T*)dt, (int64_t)1, m, b, rs_b, cs_b, m, n, st );
+			bsrc = (const T*)dt; rs_bs = 1; cs_bs = m;
+		}
+	}
+	if ( rc == kSuccess )
+	{
+		// effective triangle of transa(A): transposition mirrors it
+		int tri_operand = 0;
+		if ( struc == kStrucTri )
+		{
+			const bool lower_eff = ( uploa == B200_LOWER ) != ( ( transa & B200_TRANSPOSE ) != 0 );
+			tri_operand = ( side == B200_LEFT ? kTriA : kTriB ) | ( lower_eff ? kTriLower : kTriUpper );
+		}
+		const int ta = ( struc == kStrucTri ) ? transa : ( transa & B200_CONJ_NO_TRANSPOSE );   // hemm/symm: conja only
+		if ( side == B200_LEFT )
+			rc = gemm_front<T>( ta, transb_use, m, n, m, &al, ad, 1, ma, bsrc, rs_bs, cs_bs, &be, c, rs_c, cs_c, tri_operand );
+		else
+			rc = gemm_front<T>( transb_use, ta, m, n, n, &al, bsrc, rs_bs, cs_bs, ad, 1, ma, &be, c, rs_c, cs_c, tri_operand );
+	}
+	dev_free( da, st ); dev_free( dt, st );
+	return rc;
+}
+
+} // namespace b200
+
+static int struc_mm_dt( int dt, int op, int side, int uploa, int transa, int diaga, int transb, int64_t m, int64_t n,
+                        const void* alpha, const void* a, int64_t rs_a, int64_t cs_a, const void* b, int64_t rs_b, int64_t cs_b,
+                        const void* beta, void* c, int64_t rs_c, int64_t cs_c, const char* name )
+{
+	switch ( dt )
+	{
+		case B200_FLOAT:    return struc_mm_front<float>  ( op, side, uploa, transa, diaga, transb, m, n, (const float*)alpha,   (const float*)a,   rs_a, cs_a, (const float*)b,   rs_b, cs_b, (const float*)beta,   (float*)c,   rs_c, cs_c, name );
+		case B200_DOUBLE:   return struc_mm_front<double> ( op, side, uploa, transa, diaga, transb, m, n, (const double*)alpha,  (const double*)a,  rs_a, cs_a, (const double*)b,  rs_b, cs_b, (const double*)beta,  (double*)c,  rs_c, cs_c, name );
+		case B200_SCOMPLEX: return struc_mm_front<float2> ( op, side, uploa, transa, diaga, transb, m, n, (const float2*)alpha,  (const float2*)a,  rs_a, cs_a, (const float2*)b,  rs_b, cs_b, (const float2*)beta,  (float2*)c,  rs_c, cs_c, name );
+		case B200_DCOMPLEX: return struc_mm_front<double2>( op, side, uploa, transa, diaga, transb, m, n, (const double2*)alpha, (const double2*)a, rs_a, cs_a, (const double2*)b, rs_b, cs_b, (const double2*)beta, (double2*)c, rs_c, cs_c, name );
+	}
+	return fail( "%s: unsupported datatype %d", name, dt );
+}
+
+extern "C" b200_err_t b200_hemm( int dt, int side, int uploa, int conja, int transb, b200_dim_t m, b200_dim_t n,
+	const void* alpha, const void* a, b200_inc_t rs_a, b200_inc_t cs_a, const void* b, b200_inc_t rs_b, b200_inc_t cs_b,
+	const void* beta, void* c, b200_inc_t rs_c, b200_inc_t cs_c )
+{ return struc_mm_dt( dt, 0, side, uploa, conja, B200_NONUNIT_DIAG, transb, m, n, alpha, a, rs_a, cs_a, b, rs_b, cs_b, beta, c, rs_c, cs_c, "b200_hemm" ); }
+
+extern "C" b200_err_t b200_symm( int dt, int side, int uploa, int conja, int transb, b200_dim_t m, b200_dim_t n,
+	const void* alpha, const void* a, b200_inc_t rs_a, b200_inc_t cs_a, const void* b, b200_inc_t rs_b, b200_inc_t cs_b,
+	const void* beta, void* c, b200_inc_t rs_c, b200_inc_t cs_c )
+{ return struc_mm_dt( dt, 1, side, uploa, conja, B200_NONUNIT_DIAG, transb, m, n, alpha, a, rs_a, cs_a, b, rs_b, cs_b, beta, c, rs_c, cs_c, "b200_symm" ); }
+
+extern "C" b200_err_t b200_trmm3( int dt, int side, int uploa, int transa, int diaga, int transb, b200_dim_t m, b200_dim_t n,
+	const void* alpha, const void* a, b200_inc_t rs_a, b200_inc_t cs_a, const void* b, b200_inc_t rs_b, b200_inc_t cs_b,
+	const void* beta, void* c, b200_inc_t rs_c, b200_inc_t cs_c )
+{ return struc_mm_dt( dt, 2, side, uploa, transa, diaga, transb, m, n, alpha, a, rs_a, cs_a, b, rs_b, cs_b, beta, c, rs_c, cs_c, "b200_trmm3" ); }
+
+extern "C" b200_err_t b200_trmm( int dt, int side, int uploa, int transa, int diaga, b200_dim_t m, b200_dim_t n,
+	const void* alpha, const void* a, b200_inc_t rs_a, b200_inc_t cs_a, void* b, b200_inc_t rs_b, b200_inc_t cs_b )
+{ return struc_mm_dt( dt, 3, side, uploa, transa, diaga, B200_NO_TRANSPOSE, m, n, alpha, a, rs_a, cs_a, b, rs_b, cs_b, nullptr, b, rs_b, cs_b, "b200_trmm" ); }
+
 // ---- gemmt family C ABI ------------------------------------------------------------------
 // Real-typed scalars of herk (alpha, beta) and her2k (beta) are widened to the matrix datatype (imaginary part 0),
 // as bli_obj_init_finish_1x1( dt_r, ... ) + typecast does in bli_l3_tapi_ex.c:184-185,259-260.
@@ -831,6 +1007,7 @@ extern "C" b200_err_t b200_set_option( const char* key, long long value )
 	else if ( !strcmp( key, "grid_mult" ) ) c.grid_mult = (int)std::max<long long>( 1, value );
 	else if ( !strcmp( key, "dynamic_tiles" ) ) c.dynamic_tiles = (int)value;
 	else if ( !strcmp( key, "transpose_y" ) ) c.transpose_y = (int)value;
+	else if ( !strcmp( key, "ktri_skip" ) ) c.ktri_skip = (int)value;
 	else if ( !strcmp( key, "reserve_sms" ) )
 	{
 		// leave SMs free for concurrently running communication kernels (multi-GPU overlap)

@@ -11,7 +11,7 @@ int launch_gemm_kernel<float2>( GemmArgs<float2>& g, bool xk, bool yk, bool al, 
 	if ( g.nseg > 1 ) return fail( "b200_gemm_kpanels: only d and z are supported" );
 	g.tiles_p = (int)( ( g.P + 63 ) / 64 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
 	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
-	if ( g.tri )
+	if ( g.tri || g.ktri )
 	{
 		if ( tma_eligible( g, xk, yk, al ) ) return launch_cfma_tma<true>( g, xk, yk, grid, st );
 		return launch_ffma_ws<float2, 64, 128, 16, 4, 8, 5>( g, xk, yk, al, grid, st );     // run-time tri support

@@ -86,7 +86,9 @@ gemm_cfma_tma_kernel( const GemmArgs<float2> g, const __grid_constant__ CUtensor
 			tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
 			const int p0 = tp * BP, q0 = tq * BQ;
 			if ( TRI && tri_skip_tile( g, p0, q0, (int)min( (int64_t)BP, g.P - p0 ), (int)min( (int64_t)BQ, g.Q - q0 ) ) ) continue;
-			for ( int64_t kt = 0; kt < KT; ++kt )
+			int64_t kt0 = 0, kt1 = KT;
+			if constexpr ( TRI ) tile_k_range( g, p0, (int)min( (int64_t)BP, g.P - p0 ), q0, (int)min( (int64_t)BQ, g.Q - q0 ), BK, KT, kt0, kt1 );
+			for ( int64_t kt = kt0; kt < kt1; ++kt )
 			{
 				mbar_wait( empty_bar( stage ), phase ^ 1u );
 				const uint32_t xs = sbase + (uint32_t)stage * Cfg::STAGE_BYTES, ys = xs + Cfg::X_BYTES;
@@ -236,7 +238,9 @@ gemm_cfma_tma_kernel( const GemmArgs<float2> g, const __grid_constant__ CUtensor
 		};
 
 		float2 xa[4][2], ya[8][2];
-		for ( int64_t kt = 0; kt < KT; ++kt )
+		int64_t kt0 = 0, kt1 = KT;
+		if constexpr ( TRI ) tile_k_range( g, p0, p_lim, q0, q_lim, BK, KT, kt0, kt1 );
+		for ( int64_t kt = kt0; kt < kt1; ++kt )
 		{
 			mbar_wait( full_bar( stage ), phase );
 			#pragma unroll

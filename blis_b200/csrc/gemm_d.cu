@@ -14,7 +14,7 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 	};
 	int cfg = c.dgemm_cfg;
 	if ( g.nseg > 1 && ( cfg < 4 ) ) cfg = -1;          // k-panel accumulation needs a warp-specialised kernel
-	if ( g.tri )
+	if ( g.tri || g.ktri )
 	{
 		// triangular D (gemmt family): the TRI instantiations of the default kernels
 		const int64_t t128 = ( ( g.P + 127 ) / 128 ) * ( ( g.Q + 127 ) / 128 );

@@ -52,7 +52,29 @@ struct GemmArgs
 	// Tiles wholly outside are skipped, rows of tiles crossing the diagonal are clipped in the epilogue.
 	int      tri;
 	int64_t  tri_off;
+	// Triangular OPERAND (trmm, trmm3: frame/3/trmm/bli_trmm_{ll,lu,rl,ru}_ker_var2.c skip the k range where the
+	// packed triangular panel is identically zero).  The operand itself holds explicit zeros on its unstored side
+	// (as bli_packm_struc_cxk.c:185-196,262-273 packs them), so this only trims the k loop of a tile:
+	//   ktri == 1: X(p,k) == 0 for k > p   -> k < p0 + p_lim      ktri == 2: X(p,k) == 0 for k < p -> k >= p0
+	//   ktri == 3: Y(k,q) == 0 for k > q   -> k < q0 + q_lim      ktri == 4: Y(k,q) == 0 for k < q -> k >= q0
+	int      ktri;
 };
+
+// k-tile range [kt0, kt1) a tile has to visit (all of [0, KT) unless an operand is triangular).
+template <typename T>
+__device__ __forceinline__ void tile_k_range( const GemmArgs<T>& g, int64_t p0, int p_lim, int64_t q0, int q_lim,
+                                              int BK, int64_t KT, int64_t& kt0, int64_t& kt1 )
+{
+	kt0 = 0; kt1 = KT;
+	switch ( g.ktri )
+	{
+		case 1: kt1 = min( KT, ( p0 + p_lim + BK - 1 ) / BK ); break;
+		case 2: kt0 = p0 / BK; break;
+		case 3: kt1 = min( KT, ( q0 + q_lim + BK - 1 ) / BK ); break;
+		case 4: kt0 = q0 / BK; break;
+		default: break;
+	}
+}
 
 template <typename T>
 __device__ __forceinline__ bool tri_skip_tile( const GemmArgs<T>& g, int64_t p0, int64_t q0, int p_lim, int q_lim )

@@ -113,7 +113,9 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 			tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
 			const int p0 = tp * BP, q0 = tq * BQ;
 			if ( TRI && tri_skip_tile( g, p0, q0, (int)min( (int64_t)BP, g.P - p0 ), (int)min( (int64_t)BQ, g.Q - q0 ) ) ) continue;
-			for ( int64_t kt = 0; kt < KT; ++kt )
+			int64_t kt0 = 0, kt1 = KT;
+			if constexpr ( TRI ) tile_k_range( g, p0, (int)min( (int64_t)BP, g.P - p0 ), q0, (int)min( (int64_t)BQ, g.Q - q0 ), BK, KT, kt0, kt1 );
+			for ( int64_t kt = kt0; kt < kt1; ++kt )
 			{
 				mbar_wait( empty_bar( stage ), phase ^ 1u );
 				const uint32_t xs = sbase + (uint32_t)stage * Cfg::STAGE_BYTES, ys = xs + Cfg::OPER_BYTES;
@@ -209,7 +211,9 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 					dmma884( acc[i][j][0], acc[i][j][1], xf[i], yf[j] );
 		};
 
-		for ( int64_t kt = 0; kt < KT; ++kt )
+		int64_t kt0 = 0, kt1 = KT;
+		if constexpr ( TRI ) tile_k_range( g, p0, p_lim, q0, q_lim, BK, KT, kt0, kt1 );
+		for ( int64_t kt = kt0; kt < kt1; ++kt )
 		{
 			#pragma unroll
 			for ( int kk = 0; kk < KS; kk += 2 )
@@ -225,7 +229,7 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 				{
 					int ns = stage + 1; uint32_t nph = phase;
 					if ( ns == STAGES ) { ns = 0; nph ^= 1u; }
-					if ( kt + 1 < KT )
+					if ( kt + 1 < kt1 )
 					{
 						mbar_wait( full_bar( ns ), nph );
 						load_frags( xa, ya, ns, 0 );

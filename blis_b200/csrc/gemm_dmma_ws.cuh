@@ -159,7 +159,9 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 			{
 			const T* gx = ( seg == 0 ? g.X : g.Xseg[seg - 1] ) + xo;
 			const T* gy = ( seg == 0 ? g.Y : g.Yseg[seg - 1] ) + yo;
-			for ( int64_t kt = 0; kt < KT_SEG; ++kt )
+			int64_t kt0 = 0, kt1 = KT_SEG;
+			if constexpr ( TRI ) tile_k_range( g, p0, p_lim, q0, q_lim, BK, KT_SEG, kt0, kt1 );    // nseg == 1 with a triangular operand
+			for ( int64_t kt = kt0; kt < kt1; ++kt )
 			{
 				mbar_wait( empty_bar( stage ), phase ^ 1u );
 				const int k_lim = (int)min( (int64_t)BK, g.K - kt * BK );
@@ -267,7 +269,9 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 			}
 		};
 
-		for ( int64_t kt = 0; kt < KT; ++kt )
+		int64_t kt0 = 0, kt1 = KT;
+		if constexpr ( TRI ) tile_k_range( g, p0, p_lim, q0, q_lim, BK, KT, kt0, kt1 );
+		for ( int64_t kt = kt0; kt < kt1; ++kt )
 		{
 			// KS k4-steps per stage, fragments double-buffered (a <-> b); KS is even
 			#pragma unroll
@@ -285,7 +289,7 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 					// last step of this stage: prefetch step 0 of the next stage first
 					int ns = stage + 1; uint32_t nph = phase;
 					if ( ns == STAGES ) { ns = 0; nph ^= 1u; }
-					if ( kt + 1 < KT )
+					if ( kt + 1 < kt1 )
 					{
 						mbar_wait( full_bar( ns ), nph );
 						load_frags( xa, ya, ns, 0 );

@@ -109,7 +109,9 @@ gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorM
 			tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
 			const int p0 = tp * BP, q0 = tq * BQ;
 			if ( TRI && tri_skip_tile( g, p0, q0, (int)min( (int64_t)BP, g.P - p0 ), (int)min( (int64_t)BQ, g.Q - q0 ) ) ) continue;
-			for ( int64_t kt = 0; kt < KT; ++kt )
+			int64_t kt0 = 0, kt1 = KT;
+			if constexpr ( TRI ) tile_k_range( g, p0, (int)min( (int64_t)BP, g.P - p0 ), q0, (int)min( (int64_t)BQ, g.Q - q0 ), BK, KT, kt0, kt1 );
+			for ( int64_t kt = kt0; kt < kt1; ++kt )
 			{
 				mbar_wait( empty_bar( stage ), phase ^ 1u );
 				const uint32_t xs = sbase + (uint32_t)stage * Cfg::STAGE_BYTES, ys = xs + Cfg::OPER_BYTES;
@@ -262,7 +264,9 @@ gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorM
 		float xa[8][4], ya[8][4], xb[8][4], yb[8][4];
 		mbar_wait( full_bar( stage ), phase );
 		load_group( xa, ya, stage, 0 );
-		for ( int64_t kt = 0; kt < KT; ++kt )
+		int64_t kt0 = 0, kt1 = KT;
+		if constexpr ( TRI ) tile_k_range( g, p0, p_lim, q0, q_lim, BK, KT, kt0, kt1 );
+		for ( int64_t kt = kt0; kt < kt1; ++kt )
 		{
 			#pragma unroll
 			for ( int kg = 0; kg < BK / 4; kg += 2 )
@@ -278,7 +282,7 @@ gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorM
 				{
 					int ns = stage + 1; uint32_t nph = phase;
 					if ( ns == STAGES ) { ns = 0; nph ^= 1u; }
-					if ( kt + 1 < KT )
+					if ( kt + 1 < kt1 )
 					{
 						mbar_wait( full_bar( ns ), nph );
 						load_group( xa, ya, ns, 0 );

@@ -90,7 +90,9 @@ gemm_ffma_ws_kernel( const GemmArgs<T> g )
 			if ( tri_skip_tile( g, p0, q0, p_lim, q_lim ) ) continue;
 			const T* gx = XK ? g.X + p0 * g.ldx : g.X + p0;
 			const T* gy = YK ? g.Y + q0 * g.ldy : g.Y + q0;
-			for ( int64_t kt = 0; kt < KT; ++kt )
+			int64_t kt0, kt1;
+			tile_k_range( g, p0, p_lim, q0, q_lim, BK, KT, kt0, kt1 );
+			for ( int64_t kt = kt0; kt < kt1; ++kt )
 			{
 				mbar_wait( empty_bar( stage ), phase ^ 1u );
 				const int k_lim = (int)min( (int64_t)BK, g.K - kt * BK );
@@ -200,7 +202,9 @@ gemm_ffma_ws_kernel( const GemmArgs<T> g )
 		mbar_wait( full_bar( stage ), phase );
 		load_vecs( xa, ya, stage, 0 );
 
-		for ( int64_t kt = 0; kt < KT; ++kt )
+		int64_t kt0, kt1;
+		tile_k_range( g, p0, p_lim, q0, q_lim, BK, KT, kt0, kt1 );
+		for ( int64_t kt = kt0; kt < kt1; ++kt )
 		{
 			#pragma unroll
 			for ( int k = 0; k < BK; k += 2 )
@@ -216,7 +220,7 @@ gemm_ffma_ws_kernel( const GemmArgs<T> g )
 				{
 					int ns = stage + 1; uint32_t nph = phase;
 					if ( ns == STAGES ) { ns = 0; nph ^= 1u; }
-					if ( kt + 1 < KT )
+					if ( kt + 1 < kt1 )
 					{
 						mbar_wait( full_bar( ns ), nph );
 						load_vecs( xa, ya, ns, 0 );

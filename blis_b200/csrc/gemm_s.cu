@@ -12,7 +12,7 @@ int launch_gemm_kernel<float>( GemmArgs<float>& g, bool xk, bool yk, bool al, cu
 	g.tiles_p = (int)( ( g.P + 127 ) / 128 ); g.tiles_q = (int)( ( g.Q + 127 ) / 128 );
 	const int grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
 	// default (sgemm_cfg < 0 or 3): TMA + packed-FFMA2 kernel when the operands are 16-byte aligned
-	if ( g.tri )
+	if ( g.tri || g.ktri )
 	{
 		if ( tma_eligible( g, xk, yk, al ) ) return launch_ffma_tma<true>( g, xk, yk, grid, st );
 		return launch_ffma<float, 128, 128, 16, 8, 8, 4>( g, xk, yk, al, grid, st );       // run-time tri support

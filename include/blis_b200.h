@@ -206,6 +206,46 @@ b200_err_t b200_her2k( int dt, int uploc, int transa, int transb,
                       const void* beta_real,
                       void*       c, b200_inc_t rs_c, b200_inc_t cs_c );
 
+/* ---- hemm, symm, trmm, trmm3 --------------------
+ * A is m x m (side = left) or n x n (side = right); only its uploa triangle is read.
+ *   hemm:  C := beta*C + alpha * conja(A) * transb(B)   or   alpha * transb(B) * conja(A)     A Hermitian
+ *   symm:  the same with A symmetric
+ *   trmm3: C := beta*C + alpha * transa(A) * transb(B)  or   alpha * transb(B) * transa(A)    A triangular (diaga)
+ *   trmm:  B := alpha * transa(A) * B                   or   alpha * B * transa(A)            in place
+ * The imaginary part of a Hermitian diagonal is ignored, a unit diagonal is not read
+ * (ref_kernels/1m/bli_packm_cxc_diag_ref.c:36-98).
+ *
+ * Stand in for bli_hemm_ex / bli_symm_ex / bli_trmm3_ex / bli_trmm_ex
+ * (frame/3/bli_l3_oapi_ex.c:349-689); argument order follows the typed API bli_?hemm / bli_?symm
+ * (frame/3/bli_l3_tapi.c:114-155), bli_?trmm3 (:298-339) and bli_?trmm (GENTFUNC trmm) with the
+ * datatype as the first argument. */
+b200_err_t b200_hemm( int dt, int side, int uploa, int conja, int transb,
+                      b200_dim_t m, b200_dim_t n,
+                      const void* alpha,
+                      const void* a, b200_inc_t rs_a, b200_inc_t cs_a,
+                      const void* b, b200_inc_t rs_b, b200_inc_t cs_b,
+                      const void* beta,
+                      void*       c, b200_inc_t rs_c, b200_inc_t cs_c );
+b200_err_t b200_symm( int dt, int side, int uploa, int conja, int transb,
+                      b200_dim_t m, b200_dim_t n,
+                      const void* alpha,
+                      const void* a, b200_inc_t rs_a, b200_inc_t cs_a,
+                      const void* b, b200_inc_t rs_b, b200_inc_t cs_b,
+                      const void* beta,
+                      void*       c, b200_inc_t rs_c, b200_inc_t cs_c );
+b200_err_t b200_trmm3( int dt, int side, int uploa, int transa, int diaga, int transb,
+                      b200_dim_t m, b200_dim_t n,
+                      const void* alpha,
+                      const void* a, b200_inc_t rs_a, b200_inc_t cs_a,
+                      const void* b, b200_inc_t rs_b, b200_inc_t cs_b,
+                      const void* beta,
+                      void*       c, b200_inc_t rs_c, b200_inc_t cs_c );
+b200_err_t b200_trmm( int dt, int side, int uploa, int transa, int diaga,
+                      b200_dim_t m, b200_dim_t n,
+                      const void* alpha,
+                      const void* a, b200_inc_t rs_a, b200_inc_t cs_a,
+                      void*       b, b200_inc_t rs_b, b200_inc_t cs_b );
+
 /* ---- blocksizes ------------------------------------------------------------
  * What bli_cntx_init_b200 registers through bli_cntx_set_blkszs()
  * (config/zen3/bli_cntx_init_zen3.c:37-258 is the pattern): the CTA tile

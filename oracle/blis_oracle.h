@@ -83,6 +83,17 @@ void orc_##ch##syr2k( int uploc, int transa, int transb, dim_t m, dim_t k, const
 void orc_##ch##her2k( int uploc, int transa, int transb, dim_t m, dim_t k, const ctype* alpha, \
                           const ctype* a, inc_t rs_a, inc_t cs_a, const ctype* b, inc_t rs_b, inc_t cs_b, \
                           const ctype* beta_r, ctype* c, inc_t rs_c, inc_t cs_c ); \
+void orc_##ch##hemm( int side, int uplo, int conja, int transb, dim_t m, dim_t n, const ctype* alpha, \
+                          const ctype* a, inc_t rs_a, inc_t cs_a, const ctype* b, inc_t rs_b, inc_t cs_b, \
+                          const ctype* beta, ctype* c, inc_t rs_c, inc_t cs_c ); \
+void orc_##ch##symm( int side, int uplo, int conja, int transb, dim_t m, dim_t n, const ctype* alpha, \
+                          const ctype* a, inc_t rs_a, inc_t cs_a, const ctype* b, inc_t rs_b, inc_t cs_b, \
+                          const ctype* beta, ctype* c, inc_t rs_c, inc_t cs_c ); \
+void orc_##ch##trmm3( int side, int uplo, int transa, int diag, int transb, dim_t m, dim_t n, const ctype* alpha, \
+                          const ctype* a, inc_t rs_a, inc_t cs_a, const ctype* b, inc_t rs_b, inc_t cs_b, \
+                          const ctype* beta, ctype* c, inc_t rs_c, inc_t cs_c ); \
+void orc_##ch##trmm( int side, int uplo, int transa, int diag, dim_t m, dim_t n, const ctype* alpha, \
+                          const ctype* a, inc_t rs_a, inc_t cs_a, ctype* b, inc_t rs_b, inc_t cs_b ); \
 void orc_##ch##trsm( int side, int uplo, int transa, int diag, dim_t m, dim_t n, const ctype* alpha, \
                           const ctype* a, inc_t rs_a, inc_t cs_a, ctype* b, inc_t rs_b, inc_t cs_b );
 

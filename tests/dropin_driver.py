@@ -96,5 +96,19 @@ for ch in "cz":
     w[np.diag_indices(m)] = w[np.diag_indices(m)].real
     out[f"bli_{ch}her2k"] = float(np.abs(c - np.where(low, w, c0)).max())
 out["launches_gemmt_family"] = int(eng.b200_launch_count() - before)
+
+# --- symm / trmm through the Fortran BLAS layer (bli_symm_ex / bli_trmm_ex interposed by the glue)
+before = eng.b200_launch_count()
+m, n = 210, 130
+a = gen.matrix("d", m, m, 30, "frac"); b = gen.matrix("d", m, n, 31, "frac"); c = gen.matrix("d", m, n, 32, "frac"); c0 = c.copy(order="K")
+asym = np.tril(a) + np.tril(a, -1).T
+L.dsymm_(C.c_char_p(b"L"), C.c_char_p(b"L"), i32(m), i32(n), f64(2.0), a.ctypes.data_as(C.c_void_p), i32(a.strides[1] // 8),
+         b.ctypes.data_as(C.c_void_p), i32(b.strides[1] // 8), f64(1.2), c.ctypes.data_as(C.c_void_p), i32(c.strides[1] // 8))
+out["dsymm_"] = float(np.abs(c - (1.2 * c0 + 2.0 * (asym @ b))).max())
+b0 = b.copy(order="K")
+L.dtrmm_(C.c_char_p(b"L"), C.c_char_p(b"U"), C.c_char_p(b"T"), C.c_char_p(b"N"), i32(m), i32(n), f64(2.0),
+         a.ctypes.data_as(C.c_void_p), i32(a.strides[1] // 8), b.ctypes.data_as(C.c_void_p), i32(b.strides[1] // 8))
+out["dtrmm_"] = float(np.abs(b - 2.0 * (np.triu(a).T @ b0)).max())
+out["launches_symm_trmm"] = int(eng.b200_launch_count() - before)
 out["launches_total"] = int(eng.b200_launch_count() - n0)
 print(json.dumps(out))

@@ -14,6 +14,7 @@ Writes (all small, committed):
                     triangular (lower/upper, unit, inverted diag, conj, ragged) panels
   gemm.npz          bli_?gemm outputs for the cases in `gemm_cases()`
   trsm.npz          bli_?trsm outputs for the cases in `trsm_cases()`
+  strucmm.npz       bli_?hemm / symm / trmm3 / trmm outputs for `strucmm_cases()` (unstored triangle of A NaN-poisoned)
   gemmt.npz         bli_?gemmt / syrk / herk / syr2k / her2k outputs for `gemmt_cases()` (unstored triangle NaN-poisoned)
 Inputs are not stored: tests rebuild them with tests/gen.py (integer-hash
 generators, platform independent).
@@ -183,6 +184,60 @@ def gemmt_run(impl, case, a, b, c):
         getattr(impl, op)(uplo, ta, tb, al, a, b, be, c)
 
 
+def strucmm_cases():
+    """(ch, op, kind, m, n, side, uplo, transa, diag, transb, oa, ob, oc, alpha, beta); op in hemm/symm/trmm3/trmm.
+    For hemm/symm transa carries conja only and diag is ignored; trmm ignores transb, ob/oc describe B, beta unused."""
+    cases = []
+    for ch in "sdcz":
+        cx = ch in "cz"
+        al, be = ((2.0 + 0.2j, 1.2 + 0.5j) if cx else (2.0, 1.2))
+        trs = (NO_TRANSPOSE, TRANSPOSE, CONJ_NO_TRANSPOSE, CONJ_TRANSPOSE) if cx else (NO_TRANSPOSE, TRANSPOSE)
+        for op in ("hemm", "symm", "trmm3", "trmm"):
+            tas = trs if op in ("trmm3", "trmm") else ((NO_TRANSPOSE, CONJ_NO_TRANSPOSE) if cx else (NO_TRANSPOSE,))
+            for side, uplo, ta in itertools.product((LEFT, RIGHT), (LOWER, UPPER), tas):
+                tb = trs[(trs.index(ta) + 1) % len(trs)] if ta in trs else NO_TRANSPOSE
+                dg = UNIT_DIAG if (uplo == UPPER) == (side == LEFT) else NONUNIT_DIAG
+                cases.append((ch, op, "frac", 23, 11, side, uplo, ta, dg, tb, "c", "c", "c", al, be))
+            cases += [
+                (ch, op, "frac", *((100, 100) if ch == "d" else (36, 44)), LEFT, LOWER, NO_TRANSPOSE, NONUNIT_DIAG, NO_TRANSPOSE, "c", "c", "c", al, be),   # d: input.general.fast size
+                (ch, op, "frac", 12, 300, RIGHT, UPPER, NO_TRANSPOSE, NONUNIT_DIAG, TRANSPOSE, "r", "c", "r", al, be),       # n > KC on the structured side
+                (ch, op, "frac", 33, 9, LEFT, UPPER, NO_TRANSPOSE, UNIT_DIAG, NO_TRANSPOSE, "g", "r", "g", al, be),          # general strides
+                (ch, op, "frac", 17, 6, RIGHT, LOWER, NO_TRANSPOSE, NONUNIT_DIAG, NO_TRANSPOSE, "c", "c", "c", al, 0.0),     # beta == 0
+                (ch, op, "frac", 9, 5, LEFT, LOWER, NO_TRANSPOSE, NONUNIT_DIAG, NO_TRANSPOSE, "c", "c", "c", 0.0, be),       # alpha == 0
+                (ch, op, "frac", 1, 4, LEFT, LOWER, NO_TRANSPOSE, NONUNIT_DIAG, NO_TRANSPOSE, "c", "c", "c", al, be),
+                (ch, op, "pow2", 40, 32, LEFT, LOWER, NO_TRANSPOSE, NONUNIT_DIAG, TRANSPOSE, "c", "c", "c", 2.0, 0.5),       # exact
+                (ch, op, "pow2", 29, 48, RIGHT, UPPER, TRANSPOSE, UNIT_DIAG, NO_TRANSPOSE, "r", "c", "r", -1.0, 1.0),        # exact
+            ]
+    return cases
+
+
+def strucmm_inputs(case, idx):
+    """A (only the uplo triangle valid: the other one is NaN), B and C; for trmm C is None (B is updated in place)."""
+    ch, op, kind, m, n, side, uplo, ta, dg, tb, oa, ob, oc, al, be = case
+    ma = m if side == LEFT else n
+    a = gen.matrix(ch, ma, ma, 23 * idx + 1, kind, oa, pad=1)
+    gen.poison_unstored(a, uplo == LOWER)
+    if op == "trmm":
+        return a, gen.matrix(ch, m, n, 23 * idx + 2, kind, oc, pad=2), None
+    bm, bn = (n, m) if tb & TRANSPOSE else (m, n)
+    b = gen.matrix(ch, bm, bn, 23 * idx + 2, kind, ob, pad=1)
+    c = gen.matrix(ch, m, n, 23 * idx + 3, kind, oc, pad=2)
+    return a, b, c
+
+
+def strucmm_run(impl, case, a, b, c):
+    """Runs the case; returns the array that holds the result (C, or B for trmm)."""
+    ch, op, kind, m, n, side, uplo, ta, dg, tb, oa, ob, oc, al, be = case
+    if op in ("hemm", "symm"):
+        getattr(impl, op)(side, uplo, ta & CONJ_NO_TRANSPOSE, tb, al, a, b, be, c)
+    elif op == "trmm3":
+        impl.trmm3(side, uplo, ta, dg, tb, al, a, b, be, c)
+    else:
+        impl.trmm(side, uplo, ta, dg, al, a, b)
+        return b
+    return c
+
+
 def gemm_inputs(case, idx):
     ch, kind, m, n, k, ta, tb, oa, ob, oc, al, be = case
     am, ak = (k, m) if ta & TRANSPOSE else (m, k)
@@ -235,15 +290,26 @@ def write_gemmt(ref):
     return len(res)
 
 
+def write_strucmm(ref):
+    res = {}
+    for idx, cs in enumerate(strucmm_cases()):
+        a, b, c = strucmm_inputs(cs, idx)
+        out = strucmm_run(ref, cs, a, b, c)
+        assert np.isfinite(np.abs(out)).all(), ("reference read the unstored triangle of A?", cs)
+        res[f"c{idx}"] = np.ascontiguousarray(out)
+    np.savez_compressed(HERE / "strucmm.npz", **res)
+    return len(res)
+
+
 def main():
     ref = RefBlis(threads=1)
     L = ref.lib
     print("reference sub-configuration:", ref.arch())
-    if len(sys.argv) > 1 and sys.argv[1] == "gemmt":       # add the gemmt-family fixtures without rewriting the others
-        n = write_gemmt(ref)
-        man = json.loads((HERE / "MANIFEST.json").read_text()); man["n_gemmt"] = n
+    if len(sys.argv) > 1 and sys.argv[1] in ("gemmt", "strucmm"):   # add one family's fixtures without rewriting the others
+        n = write_gemmt(ref) if sys.argv[1] == "gemmt" else write_strucmm(ref)
+        man = json.loads((HERE / "MANIFEST.json").read_text()); man["n_" + sys.argv[1]] = n
         (HERE / "MANIFEST.json").write_text(json.dumps(man, indent=1))
-        print("gemmt.npz written:", n, "cases")
+        print(sys.argv[1] + ".npz written:", n, "cases")
         return
 
     # ---- index arithmetic
@@ -299,7 +365,7 @@ def main():
         "generated_by": "tests/golden/make_golden.py", "reference_version": "3.0-dev (so 4.0.0)",
         "sub_configuration": ref.arch(), "threads": 1,
         "n_packm": len(packm_cases()), "n_gemm": len(gemm_cases()), "n_trsm": len(trsm_cases()),
-        "n_gemmt": write_gemmt(ref)}, indent=1))
+        "n_gemmt": write_gemmt(ref), "n_strucmm": write_strucmm(ref)}, indent=1))
     print("golden fixtures written:", sorted(p.name for p in HERE.iterdir()))
 
 

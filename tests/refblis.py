@@ -73,6 +73,22 @@ class _GemmtFamily:
         al, be = _scalar(sdt, alpha), _scalar(sdt, beta)
         getattr(self.lib, f"{self._PREFIX}{ch}{name}")(uplo, transa, m, k, _p(al), _p(a), *_estr(a), _p(be), _p(c), *_estr(c))
 
+    def _mm(self, name, head, alpha, a, b, beta, c):
+        ch = CH[c.dtype]
+        m, n = c.shape
+        al, be = _scalar(c.dtype, alpha), _scalar(c.dtype, beta)
+        getattr(self.lib, f"{self._PREFIX}{ch}{name}")(*head, m, n, _p(al), _p(a), *_estr(a), _p(b), *_estr(b), _p(be), _p(c), *_estr(c))
+
+    def hemm(self, side, uplo, conja, transb, alpha, a, b, beta, c): self._mm("hemm", (side, uplo, conja, transb), alpha, a, b, beta, c)
+    def symm(self, side, uplo, conja, transb, alpha, a, b, beta, c): self._mm("symm", (side, uplo, conja, transb), alpha, a, b, beta, c)
+    def trmm3(self, side, uplo, transa, diag, transb, alpha, a, b, beta, c): self._mm("trmm3", (side, uplo, transa, diag, transb), alpha, a, b, beta, c)
+
+    def trmm(self, side, uplo, transa, diag, alpha, a, b):
+        ch = CH[b.dtype]
+        m, n = b.shape
+        al = _scalar(b.dtype, alpha)
+        getattr(self.lib, f"{self._PREFIX}{ch}trmm")(side, uplo, transa, diag, m, n, _p(al), _p(a), *_estr(a), _p(b), *_estr(b))
+
     def gemmt(self, uplo, transa, transb, alpha, a, b, beta, c): self._two("gemmt", uplo, transa, transb, alpha, a, b, beta, c)
     def syr2k(self, uplo, transa, transb, alpha, a, b, beta, c): self._two("syr2k", uplo, transa, transb, alpha, a, b, beta, c)
     def her2k(self, uplo, transa, transb, alpha, a, b, beta, c): self._two("her2k", uplo, transa, transb, alpha, a, b, beta, c)
@@ -99,6 +115,10 @@ class Oracle(_GemmtFamily):
                 getattr(L, f"orc_{ch}{name}").argtypes = [ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
             for name in ("syrk", "herk"):
                 getattr(L, f"orc_{ch}{name}").argtypes = [ci, ci, i64, i64, vp, vp, i64, i64, vp, vp, i64, i64]
+            for name in ("hemm", "symm"):
+                getattr(L, f"orc_{ch}{name}").argtypes = [ci, ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
+            getattr(L, f"orc_{ch}trmm3").argtypes = [ci, ci, ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
+            getattr(L, f"orc_{ch}trmm").argtypes = [ci, ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64]
             getattr(L, f"orc_{ch}packm_cxk").argtypes = [ci, i64, i64, i64, i64, vp, vp, i64, i64, vp, i64]
             getattr(L, f"orc_{ch}packm_struc_cxk").argtypes = [ci, ci, ci, ci, ci, i64, i64, i64, i64, i64, i64, vp, vp, i64, i64, vp, i64]
             getattr(L, f"orc_{ch}gemm_ukr").argtypes = [i64, i64, i64, vp, vp, vp, vp, vp, i64, i64, i64, i64]
@@ -154,6 +174,10 @@ class RefBlis(_GemmtFamily):
                 getattr(L, f"bli_{ch}{name}").argtypes = [ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
             for name in ("syrk", "herk"):
                 getattr(L, f"bli_{ch}{name}").argtypes = [ci, ci, i64, i64, vp, vp, i64, i64, vp, vp, i64, i64]
+            for name in ("hemm", "symm"):
+                getattr(L, f"bli_{ch}{name}").argtypes = [ci, ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
+            getattr(L, f"bli_{ch}trmm3").argtypes = [ci, ci, ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
+            getattr(L, f"bli_{ch}trmm").argtypes = [ci, ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64]
         L.bli_determine_blocksize.argtypes = [ci, i64, i64, i64, i64]; L.bli_determine_blocksize.restype = i64
         L.bli_thread_range_sub.argtypes = [i64, i64, i64, i64, C.c_bool, C.POINTER(i64), C.POINTER(i64)]
         L.bli_thread_partition_2x2.argtypes = [i64, i64, i64, C.POINTER(i64), C.POINTER(i64)]

@@ -5,7 +5,7 @@ oracle/build_ref.py) with the glue of blis_b200/blis_glue/ on top.
    (dgemm_, cblas_dgemm, bli_?gemm, dtrsm_, bli_?trsm) are called on host arrays: results must be
    right AND must have been computed by the engine (b200_launch_count grows);
 2. the reference's own testsuite binary (testsuite/src, unmodified) is run with
-   LD_PRELOAD=libblis_b200_glue.so BLIS_B200_PLUGIN=1: every gemm/trsm/gemmt/syrk/herk/syr2k/her2k line must say PASS
+   LD_PRELOAD=libblis_b200_glue.so BLIS_B200_PLUGIN=1: every line of the eleven served level-3 operations must say PASS
    (thresholds testsuite/src/test_gemm.c:44-47, test_trsm.c:44-47), same count as the CPU run.
 """
 import json
@@ -45,6 +45,9 @@ def test_reference_entry_points_run_on_the_engine():
     for k in ("dsyrk_", "bli_dgemmt", "bli_zherk", "bli_zher2k", "bli_dsyr2k"):
         assert out[k] < 1e-11, (k, out[k])
     assert out["bli_cherk"] < 2e-3
+    assert out["launches_symm_trmm"] >= 4, "symm/trmm did not reach the CUDA engine"
+    for k in ("dsymm_", "dtrmm_"):
+        assert out[k] < 1e-11, (k, out[k])
 
 
 def _run_testsuite(general, preload):
@@ -53,7 +56,7 @@ def _run_testsuite(general, preload):
         env.update(LD_PRELOAD=str(GLUE), BLIS_B200_PLUGIN="1", BLIS_B200_VERBOSE="1")
     r = subprocess.run([str(TS / "test_libblis.x"), "-g", str(TS / general), "-o", str(TS / "input.operations.l3")],
                        capture_output=True, text=True, timeout=1200, env=env, cwd=str(TS))
-    lines = [ln for ln in r.stdout.splitlines() if re.match(r"^blis_[sdcz](gemm|trsm|gemmt|syrk|herk|syr2k|her2k)_", ln)]
+    lines = [ln for ln in r.stdout.splitlines() if re.match(r"^blis_[sdcz](gemm|trsm|gemmt|syrk|herk|syr2k|her2k|hemm|symm|trmm|trmm3)_", ln)]
     return r, lines
 
 

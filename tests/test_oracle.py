@@ -130,6 +130,21 @@ def _tri_masks(m, lower):
     return ~unstored, unstored
 
 
+def test_hemm_symm_trmm_vs_golden(oracle):
+    """hemm / symm / trmm3 / trmm: the restatement against reference outputs; the unstored triangle of A is NaN, so a
+    finite result also proves that it is never read."""
+    gold = np.load(GOLD / "strucmm.npz")
+    for idx, cs in enumerate(G.strucmm_cases()):
+        ch, kind = cs[0], cs[2]
+        a, b, c = G.strucmm_inputs(cs, idx)
+        out = G.strucmm_run(oracle, cs, a, b, c)
+        want = gold[f"c{idx}"]
+        if _exact(kind):
+            assert np.array_equal(np.ascontiguousarray(out), want), f"strucmm case {idx} {cs} not bit-exact"
+        else:
+            assert rel_err(out, want) <= TOL[ch], f"strucmm case {idx} {cs}: {rel_err(out, want)}"
+
+
 def test_gemmt_family_vs_golden(oracle):
     """gemmt / syrk / herk / syr2k / her2k: the restatement against reference outputs.  The triangle of C that is
     not stored is NaN in the inputs and must come back untouched (the reference leaves it NaN too)."""

@@ -22,7 +22,7 @@ ROOT = Path(__file__).resolve().parent.parent
 REF = Path("/root/reference")
 OUT = ROOT / "oracle" / "_ref" / "testsuite"
 EXE = OUT / "test_libblis.x"
-L3_OPS = ("gemm", "trsm", "gemmt", "syrk", "herk", "syr2k", "her2k")      # the operations the engine serves
+L3_OPS = ("gemm", "trsm", "gemmt", "syrk", "herk", "syr2k", "her2k", "hemm", "symm", "trmm", "trmm3")      # the operations the engine serves
 
 
 def _derive_inputs():
