@@ -159,8 +159,9 @@ def test_trmm_large_k_range_skipping_is_exact(engine, ch, m, n):
         ma = m if side == LEFT else n
         a, b, c0 = rnd(ma, ma), rnd(m, n), rnd(m, n)
         a_tri = (torch.tril(a) if uplo == LOWER else torch.triu(a)).t().contiguous().t()      # explicit zeros, column-major
-        a_nan = torch.where(a_tri != 0, a_tri, torch.full_like(a_tri, float("nan")))
-        a_nan = a_nan.t().contiguous().t()
+        ones = torch.ones(ma, ma, dtype=torch.bool, device=dev)
+        a_nan = torch.where(torch.tril(ones) if uplo == LOWER else torch.triu(ones), a, torch.full_like(a, float("nan")))
+        a_nan = a_nan.t().contiguous().t()                 # unstored triangle NaN (by index: a stored value may be exactly 0)
         full = c0.clone()
         if side == LEFT:
             gemm(0, 0, m, n, m, al, a_tri, 1, ma, b, 1, m, be, full, 1, m)
