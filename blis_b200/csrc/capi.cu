@@ -227,6 +227,7 @@ static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T 
 	g.tri = 0; g.tri_off = 0;
 	if ( uplo_c == B200_LOWER ) g.tri = swapped ? 2 : 1;
 	if ( uplo_c == B200_UPPER ) g.tri = swapped ? 1 : 2;
+	g.raster = ctx().raster_group;
 	g.ktri = 0;
 	if ( tri_operand && ctx().ktri_skip )
 	{
@@ -1008,6 +1009,8 @@ extern "C" b200_err_t b200_set_option( const char* key, long long value )
 	else if ( !strcmp( key, "dynamic_tiles" ) ) c.dynamic_tiles = (int)value;
 	else if ( !strcmp( key, "transpose_y" ) ) c.transpose_y = (int)value;
 	else if ( !strcmp( key, "ktri_skip" ) ) c.ktri_skip = (int)value;
+	else if ( !strcmp( key, "tma_l2_promotion" ) ) c.tma_l2_promotion = (int)std::min<long long>( 3, std::max<long long>( 0, value ) );
+	else if ( !strcmp( key, "raster_group" ) ) c.raster_group = (int)std::max<long long>( 1, value );
 	else if ( !strcmp( key, "reserve_sms" ) )
 	{
 		// leave SMs free for concurrently running communication kernels (multi-GPU overlap)

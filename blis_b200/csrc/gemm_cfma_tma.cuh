@@ -83,7 +83,7 @@ gemm_cfma_tma_kernel( const GemmArgs<float2> g, const __grid_constant__ CUtensor
 			mbar_arrive( sched_full( slot ) );
 			if ( tile >= num_tiles ) break;
 			int tp, tq;
-			tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
+			tile_coords( tile, g.tiles_p, g.tiles_q, g.raster, tp, tq );
 			const int p0 = tp * BP, q0 = tq * BQ;
 			if ( TRI && tri_skip_tile( g, p0, q0, (int)min( (int64_t)BP, g.P - p0 ), (int)min( (int64_t)BQ, g.Q - q0 ) ) ) continue;
 			int64_t kt0 = 0, kt1 = KT;
@@ -151,7 +151,7 @@ gemm_cfma_tma_kernel( const GemmArgs<float2> g, const __grid_constant__ CUtensor
 		if ( lane == 0 ) mbar_arrive( sched_empty( slot ) );
 		if ( tile >= num_tiles ) break;
 		int tp, tq;
-		tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
+		tile_coords( tile, g.tiles_p, g.tiles_q, g.raster, tp, tq );
 		const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
 		const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
 		const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );

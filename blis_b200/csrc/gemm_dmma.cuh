@@ -58,6 +58,7 @@ struct GemmArgs
 	//   ktri == 1: X(p,k) == 0 for k > p   -> k < p0 + p_lim      ktri == 2: X(p,k) == 0 for k < p -> k >= p0
 	//   ktri == 3: Y(k,q) == 0 for k > q   -> k < q0 + q_lim      ktri == 4: Y(k,q) == 0 for k < q -> k >= q0
 	int      ktri;
+	int      raster;            // tile rows per raster group (tile_coords); 8 unless tuned
 };
 
 // k-tile range [kt0, kt1) a tile has to visit (all of [0, KT) unless an operand is triangular).
@@ -105,9 +106,8 @@ __device__ __forceinline__ bool in_band( int d, int dlo, int dhi ) { return d >=
 
 // Tile -> (tp,tq) with a grouped raster so that the ~148 concurrently running
 // tiles form a compact block and share X/Y panels in L2.
-__device__ __forceinline__ void tile_coords( int tile, int tiles_p, int tiles_q, int& tp, int& tq )
+__device__ __forceinline__ void tile_coords( int tile, int tiles_p, int tiles_q, int GROUP, int& tp, int& tq )
 {
-	constexpr int GROUP = 8;
 	const int per_group = GROUP * tiles_q;
 	const int grp   = tile / per_group;
 	const int first = grp * GROUP;
@@ -194,7 +194,7 @@ gemm_dmma_kernel( const GemmArgs<T> g )
 	for ( int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x )
 	{
 		int tp, tq;
-		tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
+		tile_coords( tile, g.tiles_p, g.tiles_q, g.raster, tp, tq );
 		const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
 		const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
 		const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );

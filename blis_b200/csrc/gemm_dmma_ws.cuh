@@ -135,7 +135,7 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 			const int tile = sched_tile[slot];
 			if ( tile >= num_tiles ) break;
 			int tp, tq;
-			tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
+			tile_coords( tile, g.tiles_p, g.tiles_q, g.raster, tp, tq );
 			const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
 			const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
 			const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );
@@ -222,7 +222,7 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 		if ( lane == 0 ) mbar_arrive( sched_empty( slot ) );
 		if ( tile >= num_tiles ) break;
 		int tp, tq;
-		tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
+		tile_coords( tile, g.tiles_p, g.tiles_q, g.raster, tp, tq );
 		const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
 		const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
 		const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );

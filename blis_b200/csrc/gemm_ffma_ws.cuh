@@ -83,7 +83,7 @@ gemm_ffma_ws_kernel( const GemmArgs<T> g )
 		for ( int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x )
 		{
 			int tp, tq;
-			tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
+			tile_coords( tile, g.tiles_p, g.tiles_q, g.raster, tp, tq );
 			const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
 			const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
 			const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );
@@ -136,7 +136,7 @@ gemm_ffma_ws_kernel( const GemmArgs<T> g )
 	for ( int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x )
 	{
 		int tp, tq;
-		tile_coords( tile, g.tiles_p, g.tiles_q, tp, tq );
+		tile_coords( tile, g.tiles_p, g.tiles_q, g.raster, tp, tq );
 		const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
 		const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
 		const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );

@@ -116,7 +116,7 @@ static int make_tmap( CUtensorMap* tm, const void* base, size_t es, bool kmajor,
 	cuuint32_t box[2]     = { inner, (cuuint32_t)( kmajor ? box_rows : inner ) };
 	cuuint32_t estr[2]    = { 1, 1 };
 	const CUresult r = enc( tm, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-	                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+	                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, (CUtensorMapL2promotion)ctx().tma_l2_promotion,
 	                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
 	if ( r != CUDA_SUCCESS ) return fail( "cuTensorMapEncodeTiled failed (%d)", (int)r );
 	return kSuccess;
