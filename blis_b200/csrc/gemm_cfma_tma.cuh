@@ -88,6 +88,7 @@ gemm_cfma_tma_kernel( const GemmArgs<float2> g, const __grid_constant__ CUtensor
 			if ( TRI && tri_skip_tile( g, p0, q0, (int)min( (int64_t)BP, g.P - p0 ), (int)min( (int64_t)BQ, g.Q - q0 ) ) ) continue;
 			int64_t kt0 = 0, kt1 = KT;
 			if constexpr ( TRI ) tile_k_range( g, p0, (int)min( (int64_t)BP, g.P - p0 ), q0, (int)min( (int64_t)BQ, g.Q - q0 ), BK, KT, kt0, kt1 );
+			prefetch_d_tile_l2( g, p0, q0, BP, BQ );
 			for ( int64_t kt = kt0; kt < kt1; ++kt )
 			{
 				mbar_wait( empty_bar( stage ), phase ^ 1u );

@@ -41,6 +41,20 @@ __device__ __forceinline__ void tma_load_2d( uint32_t dst, const CUtensorMap* ma
 	              :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory" );
 }
 
+// Producer side: ask L2 for the BP x BQ tile of D at (p0, q0) now (one bulk prefetch per row); the consumers' epilogue
+// reads it after the k loop.  Needs 16-byte aligned rows (d_vec_ok); nothing is requested when beta == 0.
+template <typename T>
+__device__ __forceinline__ void prefetch_d_tile_l2( const GemmArgs<T>& g, int p0, int q0, int BP, int BQ )
+{
+	if ( g.beta_is_zero || !g.d_vec_ok ) return;
+	const int rows = (int)min( (int64_t)BP, g.P - p0 );
+	const uint32_t bytes = (uint32_t)( min( (int64_t)BQ, g.Q - q0 ) * (int64_t)sizeof(T) ) & ~15u;
+	const T* dt = g.D + (int64_t)p0 * g.ldd + q0;
+	if ( bytes == 0 ) return;
+	for ( int r = 0; r < rows; ++r )
+		asm volatile( "cp.async.bulk.prefetch.L2.global [%0], %1;\n" :: "l"(dt + (int64_t)r * g.ldd), "r"(bytes) : "memory" );
+}
+
 struct DmmaTmaCfg
 {
 	static constexpr int BP = 128, BQ = 128, BK = 16, WP = 4, WQ = 2, STAGES = 6;
@@ -115,6 +129,7 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 			if ( TRI && tri_skip_tile( g, p0, q0, (int)min( (int64_t)BP, g.P - p0 ), (int)min( (int64_t)BQ, g.Q - q0 ) ) ) continue;
 			int64_t kt0 = 0, kt1 = KT;
 			if constexpr ( TRI ) tile_k_range( g, p0, (int)min( (int64_t)BP, g.P - p0 ), q0, (int)min( (int64_t)BQ, g.Q - q0 ), BK, KT, kt0, kt1 );
+			prefetch_d_tile_l2( g, p0, q0, BP, BQ );
 			for ( int64_t kt = kt0; kt < kt1; ++kt )
 			{
 				mbar_wait( empty_bar( stage ), phase ^ 1u );
@@ -247,30 +262,46 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 		int dlo = 0, dhi = 0;
 		if constexpr ( TRI ) tri_band( g, p0, q0, dlo, dhi );
 		auto keep = [&]( int d ) { if constexpr ( TRI ) return in_band( d, dlo, dhi ); else return true; };
+		if ( g.d_vec_ok && q_lim == BQ && interior )
+		{
+			// Interior tile.  The rows a lane owns are software pipelined: the next loads are in flight while the
+			// previous ones are scaled and stored (small-k problems are bound by exactly this read-modify-write of C; the producer
+			// has already asked L2 for the tile).
+			// (half rows: NTL/2 16-byte loads per lane in flight while the previous half row is scaled and stored)
+			constexpr int HJ = NTL / 2;
+			double2 o[2][HJ];
+			auto half_ptr = [&]( int h ) { return reinterpret_cast<double2*>( g.D + ( p0 + wp0 + ( h >> 1 ) * 8 + gq ) * g.ldd + q0 + wq0 + 2 * t4 ) + ( h & 1 ) * HJ * 4; };
+			auto load_half = [&]( int h )
+			{
+				if ( g.beta_is_zero || wp0 + ( h >> 1 ) * 8 + gq >= p_lim ) return;
+				const double2* dp = half_ptr( h );
+				#pragma unroll
+				for ( int j = 0; j < HJ; ++j ) o[h & 1][j] = __ldcs( dp + j * 4 );
+			};
+			load_half( 0 );
+			#pragma unroll
+			for ( int h = 0; h < 2 * MT; ++h )
+			{
+				if ( h + 1 < 2 * MT ) load_half( h + 1 );
+				if ( wp0 + ( h >> 1 ) * 8 + gq >= p_lim ) continue;
+				double2* dp = half_ptr( h );
+				#pragma unroll
+				for ( int j = 0; j < HJ; ++j )
+				{
+					const int i = h >> 1, jj = ( h & 1 ) * HJ + j;
+					double r0 = g.alpha * acc[i][jj][0], r1 = g.alpha * acc[i][jj][1];
+					if ( !g.beta_is_zero ) { r0 = fma( g.beta, o[h & 1][j].x, r0 ); r1 = fma( g.beta, o[h & 1][j].y, r1 ); }
+					__stcs( dp + j * 4, make_double2( r0, r1 ) );
+				}
+			}
+			continue;
+		}
 		#pragma unroll
 		for ( int i = 0; i < MT; ++i )
 		{
 			const int pl = wp0 + i * 8 + gq;
 			if ( pl >= p_lim ) continue;
 			double* drow = g.D + ( p0 + pl ) * g.ldd + q0;
-			if ( g.d_vec_ok && q_lim == BQ && interior )
-			{
-				double2* __restrict__ dp = reinterpret_cast<double2*>( drow + wq0 + 2 * t4 );
-				double2 o[NTL];
-				if ( !g.beta_is_zero )
-				{
-					#pragma unroll
-					for ( int j = 0; j < NTL; ++j ) o[j] = __ldcs( dp + j * 4 );
-				}
-				#pragma unroll
-				for ( int j = 0; j < NTL; ++j )
-				{
-					double r0 = g.alpha * acc[i][j][0], r1 = g.alpha * acc[i][j][1];
-					if ( !g.beta_is_zero ) { r0 = fma( g.beta, o[j].x, r0 ); r1 = fma( g.beta, o[j].y, r1 ); }
-					__stcs( dp + j * 4, make_double2( r0, r1 ) );
-				}
-				continue;
-			}
 			#pragma unroll
 			for ( int j = 0; j < NTL; ++j )
 			{

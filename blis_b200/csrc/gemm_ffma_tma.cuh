@@ -111,6 +111,7 @@ gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorM
 			if ( TRI && tri_skip_tile( g, p0, q0, (int)min( (int64_t)BP, g.P - p0 ), (int)min( (int64_t)BQ, g.Q - q0 ) ) ) continue;
 			int64_t kt0 = 0, kt1 = KT;
 			if constexpr ( TRI ) tile_k_range( g, p0, (int)min( (int64_t)BP, g.P - p0 ), q0, (int)min( (int64_t)BQ, g.Q - q0 ), BK, KT, kt0, kt1 );
+			prefetch_d_tile_l2( g, p0, q0, BP, BQ );
 			for ( int64_t kt = kt0; kt < kt1; ++kt )
 			{
 				mbar_wait( empty_bar( stage ), phase ^ 1u );
@@ -305,31 +306,41 @@ gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorM
 		for ( int i = 0; i < 8; ++i )
 			#pragma unroll
 			for ( int j = 0; j < 4; ++j ) unpack2( acc2[i][j], acc[i][2 * j], acc[i][2 * j + 1] );
+		if ( !YK && g.d_vec_ok && q_lim == BQ && interior )
+		{
+			// Interior tile, q-contiguous ownership: two 16-byte accesses per row; the loads of row i+1 are in flight
+			// while row i is scaled and stored (the producer has already asked L2 for the tile).
+			float4 o[2][2];
+			auto ptr = [&]( int i, int h ) { return reinterpret_cast<float4*>( g.D + ( p0 + row_of( i ) ) * g.ldd + q0 + col_of( 4 * h ) ); };
+			auto load_row = [&]( int i )
+			{
+				if ( g.beta_is_zero || row_of( i ) >= p_lim ) return;
+				o[i & 1][0] = __ldcs( ptr( i, 0 ) ); o[i & 1][1] = __ldcs( ptr( i, 1 ) );
+			};
+			load_row( 0 );
+			#pragma unroll
+			for ( int i = 0; i < 8; ++i )
+			{
+				if ( i + 1 < 8 ) load_row( i + 1 );
+				if ( row_of( i ) >= p_lim ) continue;
+				float4 r0 = make_float4( g.alpha * acc[i][0], g.alpha * acc[i][1], g.alpha * acc[i][2], g.alpha * acc[i][3] );
+				float4 r1 = make_float4( g.alpha * acc[i][4], g.alpha * acc[i][5], g.alpha * acc[i][6], g.alpha * acc[i][7] );
+				if ( !g.beta_is_zero )
+				{
+					const float4 o0 = o[i & 1][0], o1 = o[i & 1][1];
+					r0.x = fmaf( g.beta, o0.x, r0.x ); r0.y = fmaf( g.beta, o0.y, r0.y ); r0.z = fmaf( g.beta, o0.z, r0.z ); r0.w = fmaf( g.beta, o0.w, r0.w );
+					r1.x = fmaf( g.beta, o1.x, r1.x ); r1.y = fmaf( g.beta, o1.y, r1.y ); r1.z = fmaf( g.beta, o1.z, r1.z ); r1.w = fmaf( g.beta, o1.w, r1.w );
+				}
+				__stcs( ptr( i, 0 ), r0 ); __stcs( ptr( i, 1 ), r1 );
+			}
+			continue;
+		}
 		#pragma unroll
 		for ( int i = 0; i < 8; ++i )
 		{
 			const int pl = row_of( i );
 			if ( pl >= p_lim ) continue;
 			float* drow = g.D + ( p0 + pl ) * g.ldd + q0;
-			if ( !YK && g.d_vec_ok && q_lim == BQ && interior )
-			{
-				float4* __restrict__ dp0 = reinterpret_cast<float4*>( drow + col_of( 0 ) );
-				float4* __restrict__ dp1 = reinterpret_cast<float4*>( drow + col_of( 4 ) );
-				float4 o0 = make_float4( 0.f, 0.f, 0.f, 0.f ), o1 = o0;
-				if ( !g.beta_is_zero ) { o0 = __ldcs( dp0 ); o1 = __ldcs( dp1 ); }
-				float4 r0, r1;
-				r0.x = fmaf( g.beta, o0.x, g.alpha * acc[i][0] ); r0.y = fmaf( g.beta, o0.y, g.alpha * acc[i][1] );
-				r0.z = fmaf( g.beta, o0.z, g.alpha * acc[i][2] ); r0.w = fmaf( g.beta, o0.w, g.alpha * acc[i][3] );
-				r1.x = fmaf( g.beta, o1.x, g.alpha * acc[i][4] ); r1.y = fmaf( g.beta, o1.y, g.alpha * acc[i][5] );
-				r1.z = fmaf( g.beta, o1.z, g.alpha * acc[i][6] ); r1.w = fmaf( g.beta, o1.w, g.alpha * acc[i][7] );
-				if ( g.beta_is_zero )
-				{
-					r0 = make_float4( g.alpha * acc[i][0], g.alpha * acc[i][1], g.alpha * acc[i][2], g.alpha * acc[i][3] );
-					r1 = make_float4( g.alpha * acc[i][4], g.alpha * acc[i][5], g.alpha * acc[i][6], g.alpha * acc[i][7] );
-				}
-				__stcs( dp0, r0 ); __stcs( dp1, r1 );
-				continue;
-			}
 			float o[8];
 			#pragma unroll
 			for ( int j = 0; j < 8; ++j )
