@@ -264,33 +264,26 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 		auto keep = [&]( int d ) { if constexpr ( TRI ) return in_band( d, dlo, dhi ); else return true; };
 		if ( g.d_vec_ok && q_lim == BQ && interior )
 		{
-			// Interior tile.  The rows a lane owns are software pipelined: the next loads are in flight while the
-			// previous ones are scaled and stored (small-k problems are bound by exactly this read-modify-write of C; the producer
-			// has already asked L2 for the tile).
-			// (half rows: NTL/2 16-byte loads per lane in flight while the previous half row is scaled and stored)
-			constexpr int HJ = NTL / 2;
-			double2 o[2][HJ];
-			auto half_ptr = [&]( int h ) { return reinterpret_cast<double2*>( g.D + ( p0 + wp0 + ( h >> 1 ) * 8 + gq ) * g.ldd + q0 + wq0 + 2 * t4 ) + ( h & 1 ) * HJ * 4; };
-			auto load_half = [&]( int h )
-			{
-				if ( g.beta_is_zero || wp0 + ( h >> 1 ) * 8 + gq >= p_lim ) return;
-				const double2* dp = half_ptr( h );
-				#pragma unroll
-				for ( int j = 0; j < HJ; ++j ) o[h & 1][j] = __ldcs( dp + j * 4 );
-			};
-			load_half( 0 );
+			// Interior tile: all loads of a row are issued before its first store (NTL 16-byte loads per lane in flight;
+			// the producer has already asked L2 for the tile).  Keeping two rows in flight would double the read rate of
+			// small-k problems but needs 64 more registers than the 232 a consumer can have (ptxas spills the loaded
+			// values; measured slower), see DESIGN.md section 10.
 			#pragma unroll
-			for ( int h = 0; h < 2 * MT; ++h )
+			for ( int i = 0; i < MT; ++i )
 			{
-				if ( h + 1 < 2 * MT ) load_half( h + 1 );
-				if ( wp0 + ( h >> 1 ) * 8 + gq >= p_lim ) continue;
-				double2* dp = half_ptr( h );
-				#pragma unroll
-				for ( int j = 0; j < HJ; ++j )
+				if ( wp0 + i * 8 + gq >= p_lim ) continue;
+				double2* __restrict__ dp = reinterpret_cast<double2*>( g.D + ( p0 + wp0 + i * 8 + gq ) * g.ldd + q0 + wq0 + 2 * t4 );
+				double2 o[NTL];
+				if ( !g.beta_is_zero )
 				{
-					const int i = h >> 1, jj = ( h & 1 ) * HJ + j;
-					double r0 = g.alpha * acc[i][jj][0], r1 = g.alpha * acc[i][jj][1];
-					if ( !g.beta_is_zero ) { r0 = fma( g.beta, o[h & 1][j].x, r0 ); r1 = fma( g.beta, o[h & 1][j].y, r1 ); }
+					#pragma unroll
+					for ( int j = 0; j < NTL; ++j ) o[j] = __ldcs( dp + j * 4 );
+				}
+				#pragma unroll
+				for ( int j = 0; j < NTL; ++j )
+				{
+					double r0 = g.alpha * acc[i][j][0], r1 = g.alpha * acc[i][j][1];
+					if ( !g.beta_is_zero ) { r0 = fma( g.beta, o[j].x, r0 ); r1 = fma( g.beta, o[j].y, r1 ); }
 					__stcs( dp + j * 4, make_double2( r0, r1 ) );
 				}
 			}
