@@ -224,13 +224,32 @@ def bli_gemm(alpha, a: Obj, b: Obj, beta, c: Obj) -> None:
     Checks follow bli_gemm_check (frame/3/bli_l3_check.c:37-63): conformal
     dimensions and one datatype; mixed-datatype gemm is out of scope here."""
     if not (a.dt == b.dt == c.dt):
-        raise EngineError("bli_gemm: mixed-datatype operands are out of scope for the b200 engine")
+        return bli_gemm_md(alpha, a, b, beta, c)
     ma, ka = a.dims_after_trans()
     kb, nb = b.dims_after_trans()
     if (ma, nb) != (c.m, c.n) or ka != kb:
         raise EngineError("bli_gemm: non-conformal dimensions")
     _typed_gemm(c.dt)(a.conjtrans, b.conjtrans, c.m, c.n, ka, alpha,
                       a.buf, a.rs, a.cs, b.buf, b.rs, b.cs, beta, c.buf, c.rs, c.cs)
+
+
+def bli_gemm_md(alpha, a: Obj, b: Obj, beta, c: Obj, comp_prec=None) -> None:
+    """Mixed-datatype gemm on objects (bli_gemm with operands of different dt, docs/MixedDatatypes.md);
+    comp_prec: torch.float32 / torch.float64, default = the precision of C (bli_obj_comp_prec's default)."""
+    ma, ka = a.dims_after_trans()
+    kb, nb = b.dims_after_trans()
+    if (ma, nb) != (c.m, c.n) or ka != kb:
+        raise EngineError("bli_gemm: non-conformal dimensions")
+    if comp_prec is None:
+        comp_prec = _REAL[c.dt]
+    lib = _lib.load()
+    _bind_stream(a.buf, b.buf, c.buf)
+    al, be = complex(alpha), complex(beta)
+    alb, beb = (C.c_double * 2)(al.real, al.imag), (C.c_double * 2)(be.real, be.imag)
+    rc = lib.b200_gemm_md(_DT[a.dt], _DT[b.dt], _DT[c.dt], 0 if comp_prec == torch.float32 else 2, int(a.conjtrans), int(b.conjtrans),
+                          c.m, c.n, ka, C.addressof(alb), _ptr(a.buf), a.rs, a.cs, _ptr(b.buf), b.rs, b.cs, C.addressof(beb),
+                          _ptr(c.buf), c.rs, c.cs)
+    check(rc, "bli_gemm (mixed datatype)")
 
 
 def bli_trsm(side: int, alpha, a: Obj, b: Obj) -> None:

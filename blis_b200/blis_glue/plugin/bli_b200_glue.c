@@ -365,6 +365,49 @@ void bli_her2k_ex( const obj_t* alpha, const obj_t* a, const obj_t* b, const obj
 { bli_her2k_ex_b200( alpha, a, b, beta, c, cntx, rntm ); }
 #endif
 
+/* -- mixed-datatype gemm: bli_gemm_ex itself ------------------------------------------------
+   bli_gemmsup rejects operands of different datatype or a computation precision other than C's before it
+   reaches the handler (frame/3/bli_l3_sup.c:60-75), so mixed-datatype problems would run on the CPU control tree
+   (frame/3/gemm/bli_gemm_cntl.c:87-392).  bli_gemm_ex_b200 has bli_gemm_ex's parameter list; homogeneous problems
+   go to b200_gemm, everything else to b200_gemm_md.  Bound like trsm (-DBLIS_B200_OVERRIDE_GEMM_EX). */
+void bli_gemm_ex_b200( const obj_t* alpha, const obj_t* a, const obj_t* b, const obj_t* beta, const obj_t* c,
+                       const cntx_t* cntx, const rntm_t* rntm )
+{
+	( void )rntm;
+	bli_init_once();
+	if ( bli_error_checking_is_enabled() ) bli_gemm_check( alpha, a, b, beta, c, cntx );
+	if ( bli_obj_has_zero_dim( c ) ) return;
+	const num_t dt_a = bli_obj_dt( a ), dt_b = bli_obj_dt( b ), dt_c = bli_obj_dt( c );
+	const prec_t cp = bli_obj_comp_prec( c );
+	obj_t al, be;
+	if ( dt_a == dt_c && dt_b == dt_c && cp == bli_dt_prec( dt_c ) )
+	{
+		bli_b200_scalar( dt_c, alpha, &al ); bli_b200_scalar( dt_c, beta, &be );
+		const err_t r = b200_gemm( ( int )dt_c, ( int )bli_obj_conjtrans_status( a ), ( int )bli_obj_conjtrans_status( b ),
+		  bli_obj_length( c ), bli_obj_width( c ), bli_obj_width_after_trans( a ), bli_obj_buffer_for_1x1( dt_c, &al ),
+		  bli_obj_buffer_at_off( a ), bli_obj_row_stride( a ), bli_obj_col_stride( a ),
+		  bli_obj_buffer_at_off( b ), bli_obj_row_stride( b ), bli_obj_col_stride( b ), bli_obj_buffer_for_1x1( dt_c, &be ),
+		  bli_obj_buffer_at_off( c ), bli_obj_row_stride( c ), bli_obj_col_stride( c ) );
+		if ( r != BLIS_SUCCESS ) bli_b200_die( "gemm" );
+		return;
+	}
+	bli_b200_scalar( BLIS_DCOMPLEX, alpha, &al ); bli_b200_scalar( BLIS_DCOMPLEX, beta, &be );
+	const err_t r = b200_gemm_md( ( int )dt_a, ( int )dt_b, ( int )dt_c, ( int )cp,
+	  ( int )bli_obj_conjtrans_status( a ), ( int )bli_obj_conjtrans_status( b ),
+	  bli_obj_length( c ), bli_obj_width( c ), bli_obj_width_after_trans( a ),
+	  ( const double* )bli_obj_buffer_for_1x1( BLIS_DCOMPLEX, &al ),
+	  bli_obj_buffer_at_off( a ), bli_obj_row_stride( a ), bli_obj_col_stride( a ),
+	  bli_obj_buffer_at_off( b ), bli_obj_row_stride( b ), bli_obj_col_stride( b ),
+	  ( const double* )bli_obj_buffer_for_1x1( BLIS_DCOMPLEX, &be ),
+	  bli_obj_buffer_at_off( c ), bli_obj_row_stride( c ), bli_obj_col_stride( c ) );
+	if ( r != BLIS_SUCCESS ) bli_b200_die( "gemm (mixed datatype)" );
+}
+
+#ifdef BLIS_B200_OVERRIDE_GEMM_EX
+void bli_gemm_ex( const obj_t* alpha, const obj_t* a, const obj_t* b, const obj_t* beta, const obj_t* c, const cntx_t* cntx, const rntm_t* rntm )
+{ bli_gemm_ex_b200( alpha, a, b, beta, c, cntx, rntm ); }
+#endif
+
 /* -- registration ----------------------------------------------------------- */
 
 /* Install the engine into one context: tile shapes as blocksizes, thresholds

@@ -246,6 +246,23 @@ b200_err_t b200_trmm( int dt, int side, int uploa, int transa, int diaga,
                       const void* a, b200_inc_t rs_a, b200_inc_t cs_a,
                       void*       b, b200_inc_t rs_b, b200_inc_t cs_b );
 
+/* ---- mixed-datatype gemm -----------------------
+ * C := beta*C + alpha*transa(A)*transb(B) with A, B, C of ANY of the four datatypes and a
+ * computation precision comp_prec (BLIS prec_t: 0 = single, 2 = double): what bli_gemm_ex does
+ * for operands of different domain/precision (docs/MixedDatatypes.md;
+ * frame/3/gemm/bli_gemm_cntl.c:87-392).  A and B are typecast to the computation precision, the
+ * product runs in the smallest domain that holds it, the result is typecast and accumulated into C
+ * with beta in C's datatype.  alpha and beta point to dcomplex values {real, imag} in host memory
+ * (the imaginary part of alpha is ignored when A, B and C are all real, that of beta when C is real).
+ * Reached from the BLIS side through bli_gemm_ex_b200 when bli_obj_dt()/bli_obj_comp_prec() differ. */
+b200_err_t b200_gemm_md( int dt_a, int dt_b, int dt_c, int comp_prec, int transa, int transb,
+                      b200_dim_t m, b200_dim_t n, b200_dim_t k,
+                      const double* alpha,
+                      const void* a, b200_inc_t rs_a, b200_inc_t cs_a,
+                      const void* b, b200_inc_t rs_b, b200_inc_t cs_b,
+                      const double* beta,
+                      void*       c, b200_inc_t rs_c, b200_inc_t cs_c );
+
 /* ---- blocksizes ------------------------------------------------------------
  * What bli_cntx_init_b200 registers through bli_cntx_set_blkszs()
  * (config/zen3/bli_cntx_init_zen3.c:37-258 is the pattern): the CTA tile

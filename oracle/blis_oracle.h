@@ -102,4 +102,10 @@ ORC_DECL( d, double )
 ORC_DECL( c, float )    /* pointers to interleaved (re,im) pairs */
 ORC_DECL( z, double )
 
+/* mixed-datatype gemm (docs/MixedDatatypes.md; bli_gemm_cntl.c:87-392): dt_* are num_t values, comp_prec is 0 (single)
+   or 2 (double), alpha and beta point to {real, imag} doubles */
+void orc_gemm_md( int dt_a, int dt_b, int dt_c, int comp_prec, int transa, int transb, dim_t m, dim_t n, dim_t k,
+                  const double* alpha, const void* a, inc_t rs_a, inc_t cs_a, const void* b, inc_t rs_b, inc_t cs_b,
+                  const double* beta, void* c, inc_t rs_c, inc_t cs_c );
+
 #endif

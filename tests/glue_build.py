@@ -28,11 +28,33 @@ def build(force: bool = False) -> Path:
     build_ref.build()
     incs = [f"-I{d}" for d in build_ref._inc_dirs()] + [f"-I{ROOT / 'include'}"]
     cmd = ["gcc", "-std=c99", "-O2", "-fPIC", "-shared", "-D_POSIX_C_SOURCE=200809L", "-Wall", "-Wno-unused-function",
-           "-DBLIS_B200_OVERRIDE_TRSM_EX", "-DBLIS_B200_OVERRIDE_GEMMT_EX", *incs, str(GLUE_SRC), "-o", str(GLUE_SO),
+           "-DBLIS_B200_OVERRIDE_TRSM_EX", "-DBLIS_B200_OVERRIDE_GEMMT_EX", "-DBLIS_B200_OVERRIDE_GEMM_EX", *incs, str(GLUE_SRC), "-o", str(GLUE_SO),
            f"-L{ROOT / 'blis_b200'}", "-lblis_b200", f"-L{GLUE_SO.parent}", "-lblis_ref",
            "-Wl,-rpath,$ORIGIN/../../blis_b200", "-Wl,-rpath,$ORIGIN"]
     subprocess.run(cmd, check=True)
     return GLUE_SO
+
+
+SHIM_SRC = ROOT / "tests" / "ref_shim.c"
+SHIM_SO = ROOT / "oracle" / "_ref" / "libref_shim.so"
+
+
+def build_shim(force: bool = False) -> Path:
+    """tests/ref_shim.c -> oracle/_ref/libref_shim.so (object-API calls into the real reference)."""
+    if not Path("/root/reference").exists():
+        if SHIM_SO.exists():
+            return SHIM_SO
+        raise FileNotFoundError("no /root/reference and no prebuilt reference shim")
+    if SHIM_SO.exists() and not force and SHIM_SO.stat().st_mtime >= SHIM_SRC.stat().st_mtime:
+        return SHIM_SO
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import build_ref
+    build_ref.build()
+    incs = [f"-I{d}" for d in build_ref._inc_dirs()]
+    cmd = ["gcc", "-std=c99", "-O2", "-fPIC", "-shared", "-D_POSIX_C_SOURCE=200809L", "-Wall", "-Wno-unused-function", *incs,
+           str(SHIM_SRC), "-o", str(SHIM_SO), f"-L{SHIM_SO.parent}", "-lblis_ref", "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True)
+    return SHIM_SO
 
 
 def syntax_check_config() -> None:
@@ -48,3 +70,4 @@ def syntax_check_config() -> None:
 
 if __name__ == "__main__":
     print(build(force=True))
+    print(build_shim(force=True))

@@ -14,6 +14,7 @@ Writes (all small, committed):
                     triangular (lower/upper, unit, inverted diag, conj, ragged) panels
   gemm.npz          bli_?gemm outputs for the cases in `gemm_cases()`
   trsm.npz          bli_?trsm outputs for the cases in `trsm_cases()`
+  gemm_md.npz       bli_gemm on objects of mixed datatypes (tests/ref_shim.c) for `gemm_md_cases()`
   strucmm.npz       bli_?hemm / symm / trmm3 / trmm outputs for `strucmm_cases()` (unstored triangle of A NaN-poisoned)
   gemmt.npz         bli_?gemmt / syrk / herk / syr2k / her2k outputs for `gemmt_cases()` (unstored triangle NaN-poisoned)
 Inputs are not stored: tests rebuild them with tests/gen.py (integer-hash
@@ -238,6 +239,40 @@ def strucmm_run(impl, case, a, b, c):
     return c
 
 
+def gemm_md_cases():
+    """(cha, chb, chc, comp_prec, kind, m, n, k, transa, transb, oc, alpha, beta): every combination of the four storage
+    datatypes for A, B, C and both computation precisions (docs/MixedDatatypes.md; testsuite/input.operations.mixed)."""
+    cases = []
+    for cha, chb, chc in itertools.product("sdcz", repeat=3):
+        for cp in (0, 2):
+            i = len(cases)
+            ta = (NO_TRANSPOSE, TRANSPOSE, CONJ_NO_TRANSPOSE, CONJ_TRANSPOSE)[i % 4]
+            tb = (NO_TRANSPOSE, CONJ_TRANSPOSE, TRANSPOSE, CONJ_NO_TRANSPOSE)[(i // 4) % 4]
+            cases.append((cha, chb, chc, cp, "frac", 13, 9, 21, ta, tb, "cr"[i % 2], 2.0 + 0.2j, 1.2 + 0.5j))
+            cases.append((cha, chb, chc, cp, "pow2", 10, 12, 16, tb, ta, "rc"[i % 2], 0.5 - 0.25j, 2.0 + 0.5j))
+    for chs in (("s", "s", "d"), ("d", "s", "z"), ("c", "z", "s"), ("z", "d", "c")):
+        cases.append((*chs, 2, "frac", 40, 30, 300, NO_TRANSPOSE, NO_TRANSPOSE, "c", 2.0, 1.2))      # k > KC
+        cases.append((*chs, 0, "frac", 9, 7, 5, NO_TRANSPOSE, NO_TRANSPOSE, "c", 2.0 + 0.2j, 0.0))    # beta == 0
+        cases.append((*chs, 0, "frac", 6, 5, 4, NO_TRANSPOSE, NO_TRANSPOSE, "c", 0.0, 1.2 + 0.5j))    # alpha == 0
+    return cases
+
+
+def gemm_md_inputs(case, idx):
+    cha, chb, chc, cp, kind, m, n, k, ta, tb, oc, al, be = case
+    am, ak = (k, m) if ta & TRANSPOSE else (m, k)
+    bk, bn = (n, k) if tb & TRANSPOSE else (k, n)
+    a = gen.matrix(cha, am, ak, 29 * idx + 1, kind, "c", pad=1)
+    b = gen.matrix(chb, bk, bn, 29 * idx + 2, kind, "r", pad=2)
+    c = gen.matrix(chc, m, n, 29 * idx + 3, kind, oc, pad=1)
+    return a, b, c
+
+
+def md_tol(case):
+    """Elementwise tolerance: that of the lowest precision involved."""
+    from util import TOL
+    return TOL["s"] if (case[3] == 0 or any(ch in "sc" for ch in case[:3])) else TOL["d"]
+
+
 def gemm_inputs(case, idx):
     ch, kind, m, n, k, ta, tb, oa, ob, oc, al, be = case
     am, ak = (k, m) if ta & TRANSPOSE else (m, k)
@@ -301,12 +336,23 @@ def write_strucmm(ref):
     return len(res)
 
 
+def write_gemm_md():
+    from refblis import ref_gemm_md
+    res = {}
+    for idx, cs in enumerate(gemm_md_cases()):
+        a, b, c = gemm_md_inputs(cs, idx)
+        ref_gemm_md(cs[8], cs[9], cs[11], a, b, cs[12], c, cs[3])
+        res[f"c{idx}"] = np.ascontiguousarray(c)
+    np.savez_compressed(HERE / "gemm_md.npz", **res)
+    return len(res)
+
+
 def main():
     ref = RefBlis(threads=1)
     L = ref.lib
     print("reference sub-configuration:", ref.arch())
-    if len(sys.argv) > 1 and sys.argv[1] in ("gemmt", "strucmm"):   # add one family's fixtures without rewriting the others
-        n = write_gemmt(ref) if sys.argv[1] == "gemmt" else write_strucmm(ref)
+    if len(sys.argv) > 1 and sys.argv[1] in ("gemmt", "strucmm", "gemm_md"):   # add one family's fixtures without rewriting the others
+        n = {"gemmt": lambda: write_gemmt(ref), "strucmm": lambda: write_strucmm(ref), "gemm_md": write_gemm_md}[sys.argv[1]]()
         man = json.loads((HERE / "MANIFEST.json").read_text()); man["n_" + sys.argv[1]] = n
         (HERE / "MANIFEST.json").write_text(json.dumps(man, indent=1))
         print(sys.argv[1] + ".npz written:", n, "cases")
@@ -365,7 +411,8 @@ def main():
         "generated_by": "tests/golden/make_golden.py", "reference_version": "3.0-dev (so 4.0.0)",
         "sub_configuration": ref.arch(), "threads": 1,
         "n_packm": len(packm_cases()), "n_gemm": len(gemm_cases()), "n_trsm": len(trsm_cases()),
-        "n_gemmt": write_gemmt(ref), "n_strucmm": write_strucmm(ref)}, indent=1))
+        "n_gemmt": write_gemmt(ref), "n_strucmm": write_strucmm(ref),
+        "n_gemm_md": write_gemm_md()}, indent=1))
     print("golden fixtures written:", sorted(p.name for p in HERE.iterdir()))
 
 

@@ -221,5 +221,40 @@ class RefBlis(_GemmtFamily):
         getattr(self.lib, f"bli_{ch}trsm")(side, uplo, transa, diag, m, n, _p(al), _p(a), *_estr(a), _p(b), *_estr(b))
 
 
+SHIM_SO = ROOT / "oracle" / "_ref" / "libref_shim.so"
+_MD_ARGS = [ci, ci, ci, ci, ci, ci, i64, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
+
+
+def _gemm_md(fn, transa, transb, alpha, a, b, beta, c, comp_prec):
+    """Common driver of the mixed-datatype checkers: numpy arrays of any of the four datatypes."""
+    m, n = c.shape
+    k = a.shape[0] if (transa & TRANSPOSE) else a.shape[1]
+    if comp_prec is None:
+        comp_prec = 0 if c.dtype in (np.float32, np.complex64) else 2
+    al = np.array([complex(alpha).real, complex(alpha).imag], dtype=np.float64)
+    be = np.array([complex(beta).real, complex(beta).imag], dtype=np.float64)
+    fn(DT[CH[a.dtype]], DT[CH[b.dtype]], DT[CH[c.dtype]], comp_prec, transa, transb, m, n, k, _p(al), _p(a), *_estr(a),
+       _p(b), *_estr(b), _p(be), _p(c), *_estr(c))
+
+
+def oracle_gemm_md(oracle, transa, transb, alpha, a, b, beta, c, comp_prec=None):
+    f = oracle.lib.orc_gemm_md
+    f.argtypes = _MD_ARGS; f.restype = None
+    _gemm_md(f, transa, transb, alpha, a, b, beta, c, comp_prec)
+
+
+_shim = None
+
+
+def ref_gemm_md(transa, transb, alpha, a, b, beta, c, comp_prec=None):
+    """bli_gemm of the REAL reference on objects of different datatypes (through tests/ref_shim.c)."""
+    global _shim
+    if _shim is None:
+        C.CDLL(str(REF_SO), mode=C.RTLD_GLOBAL)
+        _shim = C.CDLL(str(SHIM_SO))
+        _shim.ref_gemm_md.argtypes = _MD_ARGS; _shim.ref_gemm_md.restype = None
+    _gemm_md(_shim.ref_gemm_md, transa, transb, alpha, a, b, beta, c, comp_prec)
+
+
 def have_ref() -> bool:
     return REF_SO.exists()

@@ -145,6 +145,22 @@ def test_hemm_symm_trmm_vs_golden(oracle):
             assert rel_err(out, want) <= TOL[ch], f"strucmm case {idx} {cs}: {rel_err(out, want)}"
 
 
+def test_gemm_mixed_datatype_vs_golden(oracle):
+    """All 4 x 4 x 4 storage datatype combinations x both computation precisions: the restatement of
+    bli_gemm_cntl.c's mixed-domain / mixed-precision rules against reference outputs (bit-exact on power-of-two data;
+    one reference artefact, a denormal left in a real C by the real-only packing path, is tolerated below 1e-300)."""
+    from refblis import oracle_gemm_md
+    gold = np.load(GOLD / "gemm_md.npz")
+    for idx, cs in enumerate(G.gemm_md_cases()):
+        a, b, c = G.gemm_md_inputs(cs, idx)
+        oracle_gemm_md(oracle, cs[8], cs[9], cs[11], a, b, cs[12], c, cs[3])
+        want = gold[f"c{idx}"]
+        if _exact(cs[4]):
+            assert float(np.abs(np.ascontiguousarray(c) - want).max()) < 1e-300, f"gemm_md case {idx} {cs} not bit-exact"
+        else:
+            assert rel_err(c, want) <= G.md_tol(cs), f"gemm_md case {idx} {cs}: {rel_err(c, want)}"
+
+
 def test_gemmt_family_vs_golden(oracle):
     """gemmt / syrk / herk / syr2k / her2k: the restatement against reference outputs.  The triangle of C that is
     not stored is NaN in the inputs and must come back untouched (the reference leaves it NaN too)."""
