@@ -50,11 +50,11 @@ def test_reference_entry_points_run_on_the_engine():
         assert out[k] < 1e-11, (k, out[k])
 
 
-def _run_testsuite(general, preload):
+def _run_testsuite(general, preload, operations="input.operations.l3"):
     env = dict(os.environ)
     if preload:
         env.update(LD_PRELOAD=str(GLUE), BLIS_B200_PLUGIN="1", BLIS_B200_VERBOSE="1")
-    r = subprocess.run([str(TS / "test_libblis.x"), "-g", str(TS / general), "-o", str(TS / "input.operations.l3")],
+    r = subprocess.run([str(TS / "test_libblis.x"), "-g", str(TS / general), "-o", str(TS / operations)],
                        capture_output=True, text=True, timeout=1200, env=env, cwd=str(TS))
     lines = [ln for ln in r.stdout.splitlines() if re.match(r"^blis_[sdcz](gemm|trsm|gemmt|syrk|herk|syr2k|her2k|hemm|symm|trmm|trmm3)_", ln)]
     return r, lines
@@ -75,3 +75,21 @@ def test_reference_testsuite_passes_on_the_engine(general):
     assert [ln.split()[0] for ln in lines] == [ln.split()[0] for ln in cpu_lines]
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / f"testsuite_{general}.b200.txt").write_text("\n".join(lines) + "\n" + (m.group(0) if m else ""))
+
+
+def test_reference_testsuite_mixed_datatype_gemm_on_the_engine():
+    """The reference testsuite's mixed-domain + mixed-precision gemm sweep (every A/B/C datatype combination and both
+    computation precisions, testsuite/src/test_gemm.c) with bli_gemm_ex bound to the engine: all PASS, same experiments
+    as the CPU run."""
+    general = "input.general.n100mixed"
+    _need(GLUE, TS / "test_libblis.x", TS / general, TS / "input.operations.gemm")
+    r, lines = _run_testsuite(general, preload=True, operations="input.operations.gemm")
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if re.match(r"^blis_[sdcz]+gemm_", ln)]
+    m = re.search(r"libblis \(b200\): (\d+) CUDA kernels", r.stderr)
+    assert m and int(m.group(1)) > len(lines), "the engine was not used: " + r.stderr[-500:]
+    assert len(lines) > 10000, r.stdout[-2000:]
+    bad = [ln for ln in lines if not ln.rstrip().endswith("PASS")]
+    assert not bad, "\n".join(bad[:10])
+    (ROOT / "gpurun_out").mkdir(exist_ok=True)
+    (ROOT / "gpurun_out" / "testsuite_mixed.b200.txt").write_text("\n".join(lines[::97]) + f"\n{len(lines)} experiments, all PASS\n" + m.group(0))

@@ -50,8 +50,11 @@ def _derive_inputs():
         i += 1
     (OUT / "input.operations.l3").write_text("\n".join(out) + "\n")
 
-    def general(tag, size, dts):
+    def general(tag, size, dts, mixed=False):
         g = gen
+        if mixed:
+            g = re.sub(r"^0(\s+# Test gemm with mixed-domain operands\?)", "1\\1", g, flags=re.M)
+            g = re.sub(r"^0(\s+# Test gemm with mixed-precision operands\?)", "1\\1", g, flags=re.M)
         g = re.sub(r"^\d+(\s+# Problem size: first to test)", f"{size}\\1", g, flags=re.M)
         g = re.sub(r"^\d+(\s+# Problem size: maximum to test)", f"{size}\\1", g, flags=re.M)
         g = re.sub(r"^\d+(\s+# Problem size: increment between experiments)", f"{size}\\1", g, flags=re.M)
@@ -60,6 +63,18 @@ def _derive_inputs():
         (OUT / f"input.general.{tag}").write_text(g)
     general("n100", 100, "sdcz")
     general("n1000d", 1000, "d")
+    general("n100mixed", 100, "sdcz", mixed=True)
+    # gemm only, for the mixed-datatype run (the other operations have no mixed-datatype variants)
+    l3 = (OUT / "input.operations.l3").read_text().splitlines()
+    keep, in_l3 = [], False
+    for ln in l3:
+        if ln.startswith("# --- Level-3 ---"):
+            in_l3 = True
+        m = re.match(r"^(\d)(\s+#\s+)(\w+)\s*$", ln)
+        if in_l3 and m and m.group(3) != "gemm":
+            ln = "0" + ln[1:]
+        keep.append(ln)
+    (OUT / "input.operations.gemm").write_text("\n".join(keep) + "\n")
 
 
 def build(force: bool = False) -> Path:
