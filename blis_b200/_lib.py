@@ -26,7 +26,7 @@ EXPORTS = [
     "b200_gemm", "b200_gemm_kpanels", "b200_sgemm", "b200_dgemm", "b200_cgemm", "b200_zgemm",
     "b200_trsm", "b200_strsm", "b200_dtrsm", "b200_ctrsm", "b200_ztrsm",
     "b200_gemmt", "b200_syrk", "b200_herk", "b200_syr2k", "b200_her2k",
-    "b200_hemm", "b200_symm", "b200_trmm3", "b200_trmm", "b200_gemm_md",
+    "b200_hemm", "b200_symm", "b200_trmm3", "b200_trmm", "b200_gemm_md", "b200_gemm_batch",
     "b200_blksz", "b200_measure_peak", "b200_launch_count", "b200_set_option",
 ]
 
@@ -79,6 +79,7 @@ def load() -> C.CDLL:
     lib.b200_trmm.argtypes = [ci, ci, ci, ci, ci] + trsm_tail; lib.b200_trmm.restype = ci        # dt side uplo transa diag
     lib.b200_gemm_md.argtypes = [ci, ci, ci, ci, ci, ci, i64, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
     lib.b200_gemm_md.restype = ci
+    lib.b200_gemm_batch.argtypes = [ci, ci] + [vp] * 17; lib.b200_gemm_batch.restype = ci
     lib.b200_blksz.argtypes = [ci, ci]; lib.b200_blksz.restype = i64
     lib.b200_measure_peak.argtypes = [ci, ci]; lib.b200_measure_peak.restype = C.c_double
     lib.b200_launch_count.argtypes = []; lib.b200_launch_count.restype = C.c_ulonglong

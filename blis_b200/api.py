@@ -252,6 +252,31 @@ def bli_gemm_md(alpha, a: Obj, b: Obj, beta, c: Obj, comp_prec=None) -> None:
     check(rc, "bli_gemm (mixed datatype)")
 
 
+def gemm_batch(dtype, groups) -> None:
+    """Batched gemm (?gemm_batch_, frame/compat/extra/bla_gemm_batch.c).  `groups` is a list of dicts
+    {transa, transb, m, n, k, alpha, beta, a: [tensors], b: [tensors], c: [tensors]}; every tensor of a group has the
+    same strides (taken from the first one).  Device problems run concurrently on the engine's stream pool."""
+    import numpy as np
+    lib = _lib.load()
+    first = groups[0]["c"][0]
+    _bind_stream(first)
+    ng = len(groups)
+    I32, I64 = C.c_int * ng, C.c_int64 * ng
+    gs = I32(*[len(g["c"]) for g in groups])
+    ta, tb = I32(*[int(g["transa"]) for g in groups]), I32(*[int(g["transb"]) for g in groups])
+    mm, nn, kk = I64(*[g["m"] for g in groups]), I64(*[g["n"] for g in groups]), I64(*[g["k"] for g in groups])
+    npdt = {torch.float32: np.float32, torch.float64: np.float64, torch.complex64: np.complex64, torch.complex128: np.complex128}[dtype]
+    al = np.array([g["alpha"] for g in groups], dtype=npdt); be = np.array([g["beta"] for g in groups], dtype=npdt)
+    def strides(key, which): return I64(*[g[key][0].stride(which) for g in groups])
+    total = sum(len(g["c"]) for g in groups)
+    P = C.c_void_p * total
+    pa = P(*[_ptr(t) for g in groups for t in g["a"]]); pb = P(*[_ptr(t) for g in groups for t in g["b"]])
+    pc = P(*[_ptr(t) for g in groups for t in g["c"]])
+    rc = lib.b200_gemm_batch(_DT[dtype], ng, gs, ta, tb, mm, nn, kk, al.ctypes.data, pa, strides("a", 0), strides("a", 1),
+                             pb, strides("b", 0), strides("b", 1), be.ctypes.data, pc, strides("c", 0), strides("c", 1))
+    check(rc, "gemm_batch")
+
+
 def bli_trsm(side: int, alpha, a: Obj, b: Obj) -> None:
     """Solve trans(A) X = alpha B (left) or X trans(A) = alpha B (right), B := X
     (bli_trsm, frame/3/bli_l3_oapi.c; checks as bli_trsm_check)."""

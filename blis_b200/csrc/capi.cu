@@ -1211,6 +1211,83 @@ extern "C" b200_err_t b200_gemm_md( int dt_a, int dt_b, int dt_c, int comp_prec,
 	return gemm_md_front( dt_a, dt_b, dt_c, comp_prec, transa, transb, m, n, k, alpha, a, rs_a, cs_a, b, rs_b, cs_b, beta, c, rs_c, cs_c );
 }
 
+// ---- batched gemm --------------------------------------------------------
+// ?gemm_batch_ / cblas_?gemm_batch (frame/compat/extra/bla_gemm_batch.c:44-131): group i holds group_size[i]
+// independent problems with the same shape, transposition and scalars; the reference loops over them calling
+// bli_?gemm_ex one after the other.  Here the problems of a batch whose operands are device resident (or pinned)
+// are issued round-robin on a pool of streams, so that small problems, which cannot fill 148 SMs one at a time,
+// run side by side; problems with pageable host operands take the ordinary (synchronous, staged) path.
+namespace b200 {
+
+template <typename T>
+static int gemm_batch_front( int group_count, const int* group_size, const int* transa, const int* transb,
+                             const int64_t* m, const int64_t* n, const int64_t* k, const T* alpha,
+                             const T* const* a, const int64_t* rs_a, const int64_t* cs_a,
+                             const T* const* b, const int64_t* rs_b, const int64_t* cs_b,
+                             const T* beta, T* const* c, const int64_t* rs_c, const int64_t* cs_c )
+{
+	if ( ensure_init() != kSuccess ) return kFailure;
+	if ( group_count < 0 ) return fail( "b200_gemm_batch: negative group count" );
+	if ( group_count == 0 ) return kSuccess;
+	if ( !group_size || !transa || !transb || !m || !n || !k || !alpha || !beta || !a || !b || !c ||
+	     !rs_a || !cs_a || !rs_b || !cs_b || !rs_c || !cs_c ) return fail( "b200_gemm_batch: NULL argument array" );
+	Context& cx = ctx();
+	cudaStream_t st = cur_stream();
+	std::lock_guard<std::mutex> lock( cx.batch_mu );          // one batch at a time owns the stream pool
+	int rc = kSuccess;
+	B200_CUDA( cudaEventRecord( cx.batch_fork, st ) );
+	for ( int s = 0; s < Context::kBatchStreams; ++s ) B200_CUDA( cudaStreamWaitEvent( cx.batch_streams[s], cx.batch_fork, 0 ) );
+	int64_t idx = 0; int next = 0;
+	for ( int g = 0; g < group_count && rc == kSuccess; ++g )
+	{
+		if ( group_size[g] < 0 || m[g] < 0 || n[g] < 0 || k[g] < 0 ) { rc = fail( "b200_gemm_batch: negative size in group %d", g ); break; }
+		int64_t ra = rs_a[g], ca = cs_a[g], rb = rs_b[g], cb = cs_b[g];
+		if ( transa[g] & B200_TRANSPOSE ) std::swap( ra, ca );
+		if ( transb[g] & B200_TRANSPOSE ) std::swap( rb, cb );
+		const bool conja = Elem<T>::cplx && ( transa[g] & B200_CONJ_NO_TRANSPOSE ), conjb = Elem<T>::cplx && ( transb[g] & B200_CONJ_NO_TRANSPOSE );
+		const bool need_ab = ( k[g] > 0 && !Scalar<T>::is_zero( alpha[g] ) );
+		for ( int j = 0; j < group_size[g] && rc == kSuccess; ++j, ++idx )
+		{
+			if ( m[g] == 0 || n[g] == 0 ) continue;
+			const bool on_device = classify( c[idx] ) == MemKind::Device &&
+			                       ( !need_ab || ( classify( a[idx] ) == MemKind::Device && classify( b[idx] ) == MemKind::Device ) );
+			if ( on_device )
+			{
+				cudaStream_t bs = cx.batch_streams[next]; next = ( next + 1 ) % Context::kBatchStreams;
+				rc = gemm_dev<T>( conja, conjb, m[g], n[g], k[g], alpha[g], a[idx], ra, ca, b[idx], rb, cb, beta[g], c[idx], rs_c[g], cs_c[g], bs );
+			}
+			else
+				rc = gemm_front<T>( transa[g], transb[g], m[g], n[g], k[g], alpha + g, a[idx], rs_a[g], cs_a[g], b[idx], rs_b[g], cs_b[g],
+				                    beta + g, c[idx], rs_c[g], cs_c[g] );
+		}
+	}
+	// join: the caller's stream continues after every pool stream has drained
+	for ( int s = 0; s < Context::kBatchStreams; ++s )
+	{
+		cudaEventRecord( cx.batch_join[s], cx.batch_streams[s] );
+		cudaStreamWaitEvent( st, cx.batch_join[s], 0 );
+	}
+	return rc;
+}
+
+} // namespace b200
+
+extern "C" b200_err_t b200_gemm_batch( int dt, int group_count, const int* group_size, const int* transa, const int* transb,
+	const b200_dim_t* m, const b200_dim_t* n, const b200_dim_t* k, const void* alpha,
+	const void* const* a, const b200_inc_t* rs_a, const b200_inc_t* cs_a,
+	const void* const* b, const b200_inc_t* rs_b, const b200_inc_t* cs_b,
+	const void* beta, void* const* c, const b200_inc_t* rs_c, const b200_inc_t* cs_c )
+{
+	switch ( dt )
+	{
+		case B200_FLOAT:    return gemm_batch_front<float>  ( group_count, group_size, transa, transb, m, n, k, (const float*)alpha,   (const float* const*)a,   rs_a, cs_a, (const float* const*)b,   rs_b, cs_b, (const float*)beta,   (float* const*)c,   rs_c, cs_c );
+		case B200_DOUBLE:   return gemm_batch_front<double> ( group_count, group_size, transa, transb, m, n, k, (const double*)alpha,  (const double* const*)a,  rs_a, cs_a, (const double* const*)b,  rs_b, cs_b, (const double*)beta,  (double* const*)c,  rs_c, cs_c );
+		case B200_SCOMPLEX: return gemm_batch_front<float2> ( group_count, group_size, transa, transb, m, n, k, (const float2*)alpha,  (const float2* const*)a,  rs_a, cs_a, (const float2* const*)b,  rs_b, cs_b, (const float2*)beta,  (float2* const*)c,  rs_c, cs_c );
+		case B200_DCOMPLEX: return gemm_batch_front<double2>( group_count, group_size, transa, transb, m, n, k, (const double2*)alpha, (const double2* const*)a, rs_a, cs_a, (const double2* const*)b, rs_b, cs_b, (const double2*)beta, (double2* const*)c, rs_c, cs_c );
+	}
+	return fail( "b200_gemm_batch: unsupported datatype %d", dt );
+}
+
 template <typename T>
 static int kpanels_front( int transa, int transb, int64_t m, int64_t n, int64_t k, int npanels, const T* alpha,
                           const T* const* a, int64_t rs_a, int64_t cs_a, const T* const* b, int64_t rs_b, int64_t cs_b,

@@ -41,6 +41,12 @@ static int do_init( int device )
 	B200_CUDA( cudaStreamCreateWithFlags( &c.stream, cudaStreamNonBlocking ) );
 	B200_CUDA( cudaStreamCreateWithFlags( &c.copy_stream, cudaStreamNonBlocking ) );
 	B200_CUDA( cudaStreamCreateWithFlags( &c.d2h_stream, cudaStreamNonBlocking ) );
+	for ( int i = 0; i < Context::kBatchStreams; ++i )
+	{
+		B200_CUDA( cudaStreamCreateWithFlags( &c.batch_streams[i], cudaStreamNonBlocking ) );
+		B200_CUDA( cudaEventCreateWithFlags( &c.batch_join[i], cudaEventDisableTiming ) );
+	}
+	B200_CUDA( cudaEventCreateWithFlags( &c.batch_fork, cudaEventDisableTiming ) );
 	// keep freed workspace cached in the pool instead of returning it to the OS
 	cudaMemPool_t pool;
 	if ( cudaDeviceGetDefaultMemPool( &pool, device ) == cudaSuccess )

@@ -37,6 +37,10 @@ struct Context
 	cudaStream_t stream  = nullptr;       // engine-owned default stream
 	cudaStream_t copy_stream = nullptr;   // host->device staging of pipelined calls
 	cudaStream_t d2h_stream  = nullptr;   // device->host of pipelined calls
+	static constexpr int kBatchStreams = 8;
+	cudaStream_t batch_streams[kBatchStreams] = {};   // b200_gemm_batch: independent small problems run concurrently
+	cudaEvent_t  batch_fork = nullptr, batch_join[kBatchStreams] = {};
+	std::mutex   batch_mu;
 	// pinned staging ring for pageable host operands
 	static constexpr int    kStageBufs  = 2;
 	static constexpr size_t kStageBytes = (size_t)64 << 20;

@@ -263,6 +263,23 @@ b200_err_t b200_gemm_md( int dt_a, int dt_b, int dt_c, int comp_prec, int transa
                       const double* beta,
                       void*       c, b200_inc_t rs_c, b200_inc_t cs_c );
 
+/* ---- batched gemm ------------------------------
+ * group_count groups; group i holds group_size[i] independent problems
+ *   C_j := beta[i]*C_j + alpha[i]*transa[i](A_j)*transb[i](B_j),   C_j is m[i] x n[i], inner dimension k[i],
+ * all with the strides rs/cs_{a,b,c}[i]; the matrix pointers of all groups are concatenated in a[], b[], c[]
+ * (sum of group_size entries); alpha/beta are arrays of group_count elements of datatype dt in HOST memory.
+ * Parameter order follows ?gemm_batch_ (frame/compat/extra/bla_gemm_batch.c:44-60) with BLIS strides instead of
+ * leading dimensions.  Device-resident problems run concurrently on a pool of streams and are ordered after the
+ * work already queued on the calling thread's stream; the call returns without synchronising in that case. */
+b200_err_t b200_gemm_batch( int dt, int group_count, const int* group_size,
+                      const int* transa, const int* transb,
+                      const b200_dim_t* m, const b200_dim_t* n, const b200_dim_t* k,
+                      const void* alpha,
+                      const void* const* a, const b200_inc_t* rs_a, const b200_inc_t* cs_a,
+                      const void* const* b, const b200_inc_t* rs_b, const b200_inc_t* cs_b,
+                      const void* beta,
+                      void* const*       c, const b200_inc_t* rs_c, const b200_inc_t* cs_c );
+
 /* ---- blocksizes ------------------------------------------------------------
  * What bli_cntx_init_b200 registers through bli_cntx_set_blkszs()
  * (config/zen3/bli_cntx_init_zen3.c:37-258 is the pattern): the CTA tile
