@@ -30,7 +30,10 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 	{
 		// auto: the cooperative 128x128 tile unless it cannot fill the SMs once; then 128x64 tiles, two CTAs per SM
 		const int64_t t128 = ( ( g.P + 127 ) / 128 ) * ( ( g.Q + 127 ) / 128 );
-		cfg = ( t128 < c.num_sms ) ? 7 : ( tma_eligible( g, xk, yk, al ) ? 9 : 6 );
+		const int64_t t64 = ( ( g.P + 63 ) / 64 ) * ( ( g.Q + 63 ) / 64 );
+		// ... and 64x64 tiles when even 128x64 tiles leave SMs idle (1024^3: 64 -> 256 tiles)
+		cfg = ( t128 < c.num_sms ) ? ( ( 2 * t128 < c.num_sms && g.nseg == 1 ) ? 10 : 7 ) : ( tma_eligible( g, xk, yk, al ) ? 9 : 6 );
+		(void)t64;
 	}
 	switch ( cfg )
 	{
@@ -46,6 +49,8 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 		        return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
 		case 7: { const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 128, 64 ); c.grid_mult = gm;
 		          return launch_dmma_ws<double, 128, 64, 16, 4, 1, 3>( g, xk, yk, al, grid, st ); }
+		case 10: { const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 64, 64 ); c.grid_mult = gm;
+		           return launch_dmma_ws<double, 64, 64, 16, 2, 2, 4>( g, xk, yk, al, grid, st ); }
 		case 8: { const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 64, 128 ); c.grid_mult = gm;
 		          return launch_dmma_ws<double, 64, 128, 16, 1, 4, 3>( g, xk, yk, al, grid, st ); }
 	}

@@ -17,6 +17,17 @@ int launch_gemm_kernel<float>( GemmArgs<float>& g, bool xk, bool yk, bool al, cu
 		if ( tma_eligible( g, xk, yk, al ) ) return launch_ffma_tma<true>( g, xk, yk, grid, st );
 		return launch_ffma<float, 128, 128, 16, 8, 8, 4>( g, xk, yk, al, grid, st );       // run-time tri support
 	}
+	const int64_t t128 = (int64_t)g.tiles_p * g.tiles_q;
+	if ( ( c.sgemm_cfg < 0 && t128 < c.num_sms ) || c.sgemm_cfg == 4 || c.sgemm_cfg == 5 )
+	{
+		// problems that cannot fill the SMs with 128x128 tiles: 64x128 tiles, or 64x64 when those are still too few
+		// (cp.async kernel, several CTAs per SM)
+		const bool tiny = ( c.sgemm_cfg == 5 ) || ( c.sgemm_cfg < 0 && 2 * t128 < c.num_sms );
+		g.tiles_p = (int)( ( g.P + 63 ) / 64 ); g.tiles_q = (int)( ( g.Q + ( tiny ? 63 : 127 ) ) / ( tiny ? 64 : 128 ) );
+		const int small_grid = (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * 4 );
+		if ( tiny ) return launch_ffma<float, 64, 64, 16, 4, 4, 4>( g, xk, yk, al, small_grid, st );
+		return launch_ffma<float, 64, 128, 16, 4, 8, 4>( g, xk, yk, al, small_grid, st );
+	}
 	if ( ( c.sgemm_cfg < 0 || c.sgemm_cfg == 3 ) && tma_eligible( g, xk, yk, al ) ) return launch_ffma_tma( g, xk, yk, grid, st );
 	if ( c.sgemm_cfg == 1 ) return launch_ffma_ws<float, 128, 128, 16, 8, 8, 5>( g, xk, yk, al, grid, st );
 	if ( c.sgemm_cfg == 2 ) return launch_ffma_ws<float, 128, 128, 32, 8, 8, 4>( g, xk, yk, al, grid, st );
