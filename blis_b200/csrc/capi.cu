@@ -316,15 +316,19 @@ static int gemm_front( int transa, int transb, int64_t m, int64_t n, int64_t k,
 	void *da = nullptr, *db = nullptr, *dc = nullptr;
 	int rc = kSuccess;
 	const bool c_host = ( classify( c ) != MemKind::Device );
-	if ( need_ab && classify( a ) != MemKind::Device )
-	{
-		if ( dev_alloc( &da, (size_t)m * k * ES, st ) != kSuccess ) return kFailure;
-		rc = stage_to_device( da, a, m, k, rs_a, cs_a, ES, st );
-		a = (const T*)da; rs_a = 1; cs_a = m;
-	}
 	// Host C of a large problem: pipeline over column blocks of C (and of B when it is a host
 	// operand) so that H2D of block j+1 and D2H of block j-1 run under the kernels of block j.
 	const bool pipelined = c_host && need_ab && n >= 1024 && (double)m * (double)n * (double)k >= 2e9 && tri_operand == 0;
+	// A host-resident A is needed by every column block.  Pipelined calls move it in k panels behind the first B/C block
+	// and start computing that block panel by panel (k-panel accumulation) instead of waiting for all of A.
+	const T* a_host = nullptr; int64_t rs_ah = 0, cs_ah = 0;
+	if ( need_ab && classify( a ) != MemKind::Device )
+	{
+		if ( dev_alloc( &da, (size_t)m * k * ES, st ) != kSuccess ) return kFailure;
+		if ( pipelined && k >= 2048 ) { a_host = a; rs_ah = rs_a; cs_ah = cs_a; }
+		else rc = stage_to_device( da, a, m, k, rs_a, cs_a, ES, st );
+		a = (const T*)da; rs_a = 1; cs_a = m;
+	}
 	const T* b_host = nullptr; int64_t rs_bh = 0, cs_bh = 0;      // set when B moves block-wise
 	if ( rc == kSuccess && need_ab && classify( b ) != MemKind::Device )
 	{
@@ -349,7 +353,7 @@ static int gemm_front( int transa, int transb, int64_t m, int64_t n, int64_t k,
 	}
 	if ( rc == kSuccess && pipelined )
 	{
-		// A is needed in full by every block and was staged above; B and C move block-wise.
+		// B and C move block-wise; a host-resident A moves in k panels under the first block (see a_host above).
 		Context& cx = ctx();
 		cudaStream_t s_in = cx.copy_stream, s_out = cx.d2h_stream;
 		const int64_t nb = std::max<int64_t>( 512, ( ( n + 7 ) / 8 + 127 ) / 128 * 128 );
@@ -380,6 +384,25 @@ static int gemm_front( int transa, int transb, int64_t m, int64_t n, int64_t k,
 		{
 			const int64_t j0 = (int64_t)j * nb, w = std::min( nb, n - j0 );
 			cudaStreamWaitEvent( st, ev_in[j], 0 );
+			if ( j == 0 && a_host )
+			{
+				// first block: C_0 := beta*C_0 + alpha * sum_p A(:, panel p) * B_0(panel p, :), each step waiting only for its panel of A
+				const int64_t kb = std::max<int64_t>( 512, ( ( k + 7 ) / 8 + 127 ) / 128 * 128 );
+				const T one = Scalar<T>::make( 1.0, 0.0 );
+				for ( int64_t p0 = 0; p0 < k && rc == kSuccess; p0 += kb )
+				{
+					const int64_t kw = std::min( kb, k - p0 );
+					rc = stage_to_device( (T*)da + p0 * m, a_host + p0 * cs_ah, m, kw, rs_ah, cs_ah, ES, s_in );
+					cudaEvent_t ev_a; cudaEventCreateWithFlags( &ev_a, cudaEventDisableTiming );
+					cudaEventRecord( ev_a, s_in );
+					cudaStreamWaitEvent( st, ev_a, 0 );
+					cudaEventDestroy( ev_a );
+					if ( rc == kSuccess )
+						rc = gemm_dev<T>( conja, conjb, m, w, kw, al, a + p0 * cs_a, rs_a, cs_a, b + p0 * rs_b, rs_b, cs_b,
+						                  p0 == 0 ? be : one, (T*)dc, 1, m, st );
+				}
+			}
+			else
 			rc = gemm_dev<T>( conja, conjb, m, w, k, al, a, rs_a, cs_a, b + j0 * cs_b, rs_b, cs_b, be,
 			                  (T*)dc + j0 * m, 1, m, st );
 			cudaEventRecord( ev_done[j], st );

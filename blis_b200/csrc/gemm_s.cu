@@ -18,7 +18,9 @@ int launch_gemm_kernel<float>( GemmArgs<float>& g, bool xk, bool yk, bool al, cu
 		return launch_ffma<float, 128, 128, 16, 8, 8, 4>( g, xk, yk, al, grid, st );       // run-time tri support
 	}
 	const int64_t t128 = (int64_t)g.tiles_p * g.tiles_q;
-	if ( ( c.sgemm_cfg < 0 && t128 < c.num_sms ) || c.sgemm_cfg == 4 || c.sgemm_cfg == 5 )
+	// [B200] 1024^3 (64 tiles of 128x128): 18.7 -> 23.8 TFLOP/s, 768^3: 9.8 -> 16.8, 512^3: 3.8 -> 6.6; at 1536^3 (144 tiles) the
+	// 128x128 TMA kernel is better again (45.8 vs 31.7), hence the 55 % threshold
+	if ( ( c.sgemm_cfg < 0 && 20 * t128 < 11 * c.num_sms ) || c.sgemm_cfg == 4 || c.sgemm_cfg == 5 )
 	{
 		// problems that cannot fill the SMs with 128x128 tiles: 64x128 tiles, or 64x64 when those are still too few
 		// (cp.async kernel, several CTAs per SM)

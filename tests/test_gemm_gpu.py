@@ -223,6 +223,18 @@ def test_gemm_host_operands_pipelined_blocks(engine, pin):
             tc_.fill_(float("nan"))
         engine.bli_dgemm(0, 0, m, n, k, 2.0, ta_, *estr(a), tb_, *estr(b), beta, tc_, *estr(c))
         assert rel_err(to_numpy(tc_), want) <= TOL["d"], (pin, beta)
+    # k >= 2048: a host-resident A also moves in k panels and the first column block is accumulated panel by panel
+    # (ragged last panel, transposed A, row-stored B)
+    m, n, k = 900, 1100, 2500
+    a = gen.matrix("d", k, m, 74, "frac", pad=2); b = gen.matrix("d", k, n, 75, "frac", "r")
+    for beta in (1.2, 0.0):
+        c = gen.matrix("d", m, n, 76, "frac")
+        want = beta * c + 2.0 * (a.T @ b)
+        ta_, tb_, tc_ = (to_torch(x, "cpu", pin=pin) for x in (a, b, c))
+        if beta == 0.0:
+            tc_.fill_(float("nan"))
+        engine.bli_dgemm(TRANSPOSE, 0, m, n, k, 2.0, ta_, *estr(a), tb_, *estr(b), beta, tc_, *estr(c))
+        assert rel_err(to_numpy(tc_), want) <= TOL["d"], (pin, beta, "k panels")
 
 
 @pytest.mark.parametrize("ch", ["d", "z"])
