@@ -46,7 +46,13 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 		case 4: return launch_dmma_ws<double, 128, 128, 16, 2, 4, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
 		case 5: return launch_dmma_ws<double, 128, 128, 32, 2, 4, 3>( g, xk, yk, al, tiles( 128, 128 ), st );
 		case 6: return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
-		case 9: if ( tma_eligible( g, xk, yk, al ) ) return launch_dmma_tma( g, xk, yk, tiles( 128, 128 ), st );
+		case 9: if ( tma_eligible( g, xk, yk, al ) )
+		        {
+		        	// small k: the read-modify-write of D is staged through the TMA ring as well (gemm_dmma_tma.cuh, CST)
+		        	if ( c.dmma_cst && !g.beta_is_zero && g.d_vec_ok && g.K <= c.dmma_cst && g.ldd >= g.Q && g.ldd * 8 < ( 1ll << 40 ) )
+		        		return launch_dmma_tma<false, true>( g, xk, yk, tiles( 128, 128 ), st );
+		        	return launch_dmma_tma( g, xk, yk, tiles( 128, 128 ), st );
+		        }
 		        return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
 		case 7: { const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 128, 64 ); c.grid_mult = gm;
 		          return launch_dmma_ws<double, 128, 64, 16, 4, 1, 3>( g, xk, yk, al, grid, st ); }

@@ -66,9 +66,17 @@ struct DmmaTmaCfg
 	static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES + BAR_BYTES + 1024;   // + slack for 1 KiB alignment
 };
 
-template <bool XK, bool YK, bool TRI = false>
+// CST ("C staged"): for small k the epilogue's read-modify-write of D dominates (k = 64: 8.4 us of DMMA per tile against
+// ~4 us of exposed global-load latency, ncu: 37 % of the stall samples behind the last DMMA).  With CST the producer also
+// TMA-loads the D tile, as FOUR extra ring stages of 32 rows x 128 columns (eight 128B-swizzled {16, 32} boxes = one
+// 32 KiB stage) issued right behind the tile's k stages, and the consumers take D from shared memory: warp row-group r
+// (rows 32r..32r+31) reads exactly extra stage r.  The loads travel through the same full/empty ring, so they are in
+// flight while the k loop runs and no register is spent on latency hiding.  Used when beta != 0, D rows are 16-byte
+// aligned and K <= 1024 (gemm_d.cu); the default instantiation is untouched.
+template <bool XK, bool YK, bool TRI = false, bool CST = false>
 __global__ void __launch_bounds__( 384, 1 )
-gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy )
+gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
+                      const __grid_constant__ CUtensorMap tmd )
 {
 	using Cfg = DmmaTmaCfg;
 	constexpr int BP = Cfg::BP, BQ = Cfg::BQ, BK = Cfg::BK, WQ = Cfg::WQ, STAGES = Cfg::STAGES;
@@ -129,7 +137,7 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 			if ( TRI && tri_skip_tile( g, p0, q0, (int)min( (int64_t)BP, g.P - p0 ), (int)min( (int64_t)BQ, g.Q - q0 ) ) ) continue;
 			int64_t kt0 = 0, kt1 = KT;
 			if constexpr ( TRI ) tile_k_range( g, p0, (int)min( (int64_t)BP, g.P - p0 ), q0, (int)min( (int64_t)BQ, g.Q - q0 ), BK, KT, kt0, kt1 );
-			prefetch_d_tile_l2( g, p0, q0, BP, BQ );
+			if constexpr ( !CST ) prefetch_d_tile_l2( g, p0, q0, BP, BQ );
 			for ( int64_t kt = kt0; kt < kt1; ++kt )
 			{
 				mbar_wait( empty_bar( stage ), phase ^ 1u );
@@ -150,6 +158,20 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 					for ( int b = 0; b < BQ / 16; ++b ) tma_load_2d( ys + b * 2048, &tmy, q0 + b * 16, k0, fb );
 				}
 				if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
+			}
+			if constexpr ( CST )
+			{
+				#pragma unroll 1
+				for ( int qd = 0; qd < BP / 32; ++qd )
+				{
+					mbar_wait( empty_bar( stage ), phase ^ 1u );
+					const uint32_t cs = sbase + (uint32_t)stage * Cfg::STAGE_BYTES;
+					const uint32_t fb = full_bar( stage );
+					mbar_arrive_expect_tx( fb, (uint32_t)Cfg::STAGE_BYTES );
+					#pragma unroll
+					for ( int b = 0; b < BQ / 16; ++b ) tma_load_2d( cs + b * 4096, &tmd, q0 + b * 16, p0 + qd * 32, fb );
+					if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
+				}
 			}
 		}
 		if ( g.tile_counter )
@@ -262,6 +284,40 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 		int dlo = 0, dhi = 0;
 		if constexpr ( TRI ) tri_band( g, p0, q0, dlo, dhi );
 		auto keep = [&]( int d ) { if constexpr ( TRI ) return in_band( d, dlo, dhi ); else return true; };
+		if constexpr ( CST )
+		{
+			// the four D stages of this tile: row-group r = warp / WQ takes its 32 rows from stage r; every warp walks the ring
+			const bool fast = ( g.d_vec_ok && q_lim == BQ && interior );
+			#pragma unroll 1
+			for ( int qd = 0; qd < BP / 32; ++qd )
+			{
+				mbar_wait( full_bar( stage ), phase );
+				if ( fast && qd == warp / WQ )
+				{
+					const unsigned char* cs = smem + (size_t)stage * Cfg::STAGE_BYTES + ( wq0 >> 4 ) * 4096 + gq * 128;
+					#pragma unroll
+					for ( int i = 0; i < MT; ++i )
+					{
+						if ( wp0 + i * 8 + gq >= p_lim ) continue;
+						double2* __restrict__ dp = reinterpret_cast<double2*>( g.D + ( p0 + wp0 + i * 8 + gq ) * g.ldd + q0 + wq0 + 2 * t4 );
+						double2 o[NTL];
+						#pragma unroll
+						for ( int j = 0; j < NTL; ++j )
+							o[j] = *reinterpret_cast<const double2*>( cs + ( j >> 1 ) * 4096 + i * 1024 + ( ( ( ( ( j & 1 ) << 2 ) | t4 ) ^ gq ) << 4 ) );
+						#pragma unroll
+						for ( int j = 0; j < NTL; ++j )
+						{
+							const double r0 = fma( g.beta, o[j].x, g.alpha * acc[i][j][0] ), r1 = fma( g.beta, o[j].y, g.alpha * acc[i][j][1] );
+							__stcs( dp + j * 4, make_double2( r0, r1 ) );
+						}
+					}
+				}
+				__syncwarp();
+				if ( lane == 0 ) mbar_arrive( empty_bar( stage ) );
+				if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
+			}
+			if ( fast ) continue;
+		}
 		if ( g.d_vec_ok && q_lim == BQ && interior )
 		{
 			// Interior tile: all loads of a row are issued before its first store (NTL 16-byte loads per lane in flight;

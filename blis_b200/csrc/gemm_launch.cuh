@@ -128,19 +128,22 @@ static bool tma_eligible( const GemmArgs<T>& g, bool xk, bool yk, bool al )
 	return al && g.nseg == 1 && g.P < ( 1ll << 31 ) && g.Q < ( 1ll << 31 ) && g.K < ( 1ll << 31 ) &&
 	       g.ldx >= ( xk ? g.K : g.P ) && g.ldy >= ( yk ? g.K : g.Q ) && g.ldx * 8 < ( 1ll << 40 ) && g.ldy * 8 < ( 1ll << 40 );
 }
-template <bool TRI = false>
+template <bool TRI = false, bool CST = false>
 static int launch_dmma_tma( const GemmArgs<double>& g, bool xk, bool yk, int grid, cudaStream_t st )
 {
-	CUtensorMap tmx, tmy;
+	CUtensorMap tmx, tmy, tmd;
 	if ( make_tmap( &tmx, g.X, 8, xk, g.P, g.K, g.ldx ) != kSuccess ) return kFailure;
 	if ( make_tmap( &tmy, g.Y, 8, yk, g.Q, g.K, g.ldy ) != kSuccess ) return kFailure;
+	// D as {16 columns, 32 rows} boxes (CST: the epilogue reads D from shared memory); a copy of tmx when unused
+	if ( CST ) { if ( make_tmap( &tmd, g.D, 8, true, g.P, g.Q, g.ldd, 32 ) != kSuccess ) return kFailure; }
+	else tmd = tmx;
 	auto go = [&]( auto XKc, auto YKc ) -> int
 	{
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
-		auto kern = gemm_dmma_tma_kernel<XK, YK, TRI>;
+		auto kern = gemm_dmma_tma_kernel<XK, YK, TRI, CST>;
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, DmmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
-		kern<<<grid, DmmaTmaCfg::NT_ALL, DmmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
+		kern<<<grid, DmmaTmaCfg::NT_ALL, DmmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy, tmd );
 		B200_CUDA( cudaGetLastError() );
 		ctx().launches++;
 		return kSuccess;
