@@ -408,6 +408,48 @@ void bli_gemm_ex( const obj_t* alpha, const obj_t* a, const obj_t* b, const obj_
 { bli_gemm_ex_b200( alpha, a, b, beta, c, cntx, rntm ); }
 #endif
 
+/* -- batched gemm: ?gemm_batch_ (frame/compat/extra/bla_gemm_batch.c:44-131) ------------------
+   The reference loops over the problems calling bli_?gemm_ex; these wrappers hand the whole batch to
+   b200_gemm_batch (device-resident problems run concurrently; host problems are staged one by one). */
+#ifdef BLIS_B200_OVERRIDE_GEMM_BATCH
+#include <stdlib.h>
+static void bli_b200_gemm_batch( num_t dt, const f77_char* ta, const f77_char* tb, const f77_int* m, const f77_int* n, const f77_int* k,
+                                 const void* alpha, const void** a, const f77_int* lda, const void** b, const f77_int* ldb,
+                                 const void* beta, void** c, const f77_int* ldc, const f77_int* group_count, const f77_int* group_size )
+{
+	const int ng = ( int )*group_count;
+	bli_init_auto();
+	if ( ng <= 0 ) return;
+	int*        gs  = malloc( sizeof( int ) * 3 * ( size_t )ng );
+	b200_dim_t* dim = malloc( sizeof( b200_dim_t ) * 9 * ( size_t )ng );
+	int *tra = gs + ng, *trb = gs + 2 * ng;
+	b200_dim_t *mm = dim, *nn = dim + ng, *kk = dim + 2 * ng, *rsa = dim + 3 * ng, *csa = dim + 4 * ng,
+	           *rsb = dim + 5 * ng, *csb = dim + 6 * ng, *rsc = dim + 7 * ng, *csc = dim + 8 * ng;
+	for ( int i = 0; i < ng; ++i )
+	{
+		trans_t t;
+		gs[i] = ( int )group_size[i];
+		bli_param_map_netlib_to_blis_trans( ta[i], &t ); tra[i] = ( int )t;
+		bli_param_map_netlib_to_blis_trans( tb[i], &t ); trb[i] = ( int )t;
+		mm[i] = m[i]; nn[i] = n[i]; kk[i] = k[i];
+		rsa[i] = 1; csa[i] = lda[i]; rsb[i] = 1; csb[i] = ldb[i]; rsc[i] = 1; csc[i] = ldc[i];
+	}
+	const err_t r = b200_gemm_batch( ( int )dt, ng, gs, tra, trb, mm, nn, kk, alpha, ( const void* const* )a, rsa, csa,
+	                                 ( const void* const* )b, rsb, csb, beta, ( void* const* )c, rsc, csc );
+	free( gs ); free( dim );
+	if ( r != BLIS_SUCCESS || b200_sync() != BLIS_SUCCESS ) bli_b200_die( "gemm_batch" );
+}
+#define BLI_B200_GEMM_BATCH( ch, ftype, dt ) \
+void ch##gemm_batch_( const f77_char* ta, const f77_char* tb, const f77_int* m, const f77_int* n, const f77_int* k, \
+                      const ftype* alpha, const ftype** a, const f77_int* lda, const ftype** b, const f77_int* ldb, \
+                      const ftype* beta, ftype** c, const f77_int* ldc, const f77_int* group_count, const f77_int* group_size ) \
+{ bli_b200_gemm_batch( dt, ta, tb, m, n, k, alpha, ( const void** )a, lda, ( const void** )b, ldb, beta, ( void** )c, ldc, group_count, group_size ); }
+BLI_B200_GEMM_BATCH( s, float,    BLIS_FLOAT )
+BLI_B200_GEMM_BATCH( d, double,   BLIS_DOUBLE )
+BLI_B200_GEMM_BATCH( c, scomplex, BLIS_SCOMPLEX )
+BLI_B200_GEMM_BATCH( z, dcomplex, BLIS_DCOMPLEX )
+#endif
+
 /* -- registration ----------------------------------------------------------- */
 
 /* Install the engine into one context: tile shapes as blocksizes, thresholds

@@ -110,5 +110,25 @@ L.dtrmm_(C.c_char_p(b"L"), C.c_char_p(b"U"), C.c_char_p(b"T"), C.c_char_p(b"N"),
          a.ctypes.data_as(C.c_void_p), i32(a.strides[1] // 8), b.ctypes.data_as(C.c_void_p), i32(b.strides[1] // 8))
 out["dtrmm_"] = float(np.abs(b - 2.0 * (np.triu(a).T @ b0)).max())
 out["launches_symm_trmm"] = int(eng.b200_launch_count() - before)
+
+# --- dgemm_batch_ (BLAS extension, frame/compat/extra/bla_gemm_batch.c) interposed by the glue: two groups on host arrays
+before = eng.b200_launch_count()
+shapes = [(40, 30, 20, 3), (65, 17, 50, 2)]
+As, Bs, Cs, wants = [], [], [], []
+for gi, (m_, n_, k_, cnt) in enumerate(shapes):
+    for j in range(cnt):
+        A_ = gen.matrix("d", m_, k_, 40 + 7 * gi + j, "frac"); B_ = gen.matrix("d", k_, n_, 60 + 7 * gi + j, "frac"); C_ = gen.matrix("d", m_, n_, 80 + 7 * gi + j, "frac")
+        A_, B_, C_ = (np.asfortranarray(x) for x in (A_, B_, C_))
+        wants.append((1.0 + gi) * (A_ @ B_) + 0.5 * C_)
+        As.append(A_); Bs.append(B_); Cs.append(C_)
+ng = len(shapes)
+I32 = C.c_int * ng
+P = C.c_void_p * len(As)
+glue.dgemm_batch_(C.c_char_p(b"NN"), C.c_char_p(b"NN"), I32(*[s_[0] for s_ in shapes]), I32(*[s_[1] for s_ in shapes]), I32(*[s_[2] for s_ in shapes]),
+               (C.c_double * ng)(1.0, 2.0), P(*[x.ctypes.data for x in As]), I32(*[s_[0] for s_ in shapes]),
+               P(*[x.ctypes.data for x in Bs]), I32(*[s_[2] for s_ in shapes]), (C.c_double * ng)(0.5, 0.5),
+               P(*[x.ctypes.data for x in Cs]), I32(*[s_[0] for s_ in shapes]), C.byref(C.c_int(ng)), I32(*[s_[3] for s_ in shapes]))
+out["dgemm_batch_"] = float(max(np.abs(c_ - w_).max() for c_, w_ in zip(Cs, wants)))
+out["launches_gemm_batch"] = int(eng.b200_launch_count() - before)
 out["launches_total"] = int(eng.b200_launch_count() - n0)
 print(json.dumps(out))

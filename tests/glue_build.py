@@ -28,7 +28,7 @@ def build(force: bool = False) -> Path:
     build_ref.build()
     incs = [f"-I{d}" for d in build_ref._inc_dirs()] + [f"-I{ROOT / 'include'}"]
     cmd = ["gcc", "-std=c99", "-O2", "-fPIC", "-shared", "-D_POSIX_C_SOURCE=200809L", "-Wall", "-Wno-unused-function",
-           "-DBLIS_B200_OVERRIDE_TRSM_EX", "-DBLIS_B200_OVERRIDE_GEMMT_EX", "-DBLIS_B200_OVERRIDE_GEMM_EX", *incs, str(GLUE_SRC), "-o", str(GLUE_SO),
+           "-DBLIS_B200_OVERRIDE_TRSM_EX", "-DBLIS_B200_OVERRIDE_GEMMT_EX", "-DBLIS_B200_OVERRIDE_GEMM_EX", "-DBLIS_B200_OVERRIDE_GEMM_BATCH", *incs, str(GLUE_SRC), "-o", str(GLUE_SO),
            f"-L{ROOT / 'blis_b200'}", "-lblis_b200", f"-L{GLUE_SO.parent}", "-lblis_ref",
            "-Wl,-rpath,$ORIGIN/../../blis_b200", "-Wl,-rpath,$ORIGIN"]
     subprocess.run(cmd, check=True)

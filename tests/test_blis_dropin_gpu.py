@@ -46,6 +46,7 @@ def test_reference_entry_points_run_on_the_engine():
         assert out[k] < 1e-11, (k, out[k])
     assert out["bli_cherk"] < 2e-3
     assert out["launches_symm_trmm"] >= 4, "symm/trmm did not reach the CUDA engine"
+    assert out["launches_gemm_batch"] >= 5 and out["dgemm_batch_"] < 1e-11, ("dgemm_batch_", out["launches_gemm_batch"], out["dgemm_batch_"])
     for k in ("dsymm_", "dtrmm_"):
         assert out[k] < 1e-11, (k, out[k])
 
