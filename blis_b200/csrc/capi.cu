@@ -292,6 +292,111 @@ static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T 
 	return rc;
 }
 
+// C(i,j) += beta * S(i,j) on dense column-major device blocks (the host C of a k-panel pipelined call is added once,
+// after its alpha*A*B part has been accumulated)
+template <typename R, int NC>
+__global__ void add_scaled_kernel( R* __restrict__ c, const R* __restrict__ s, int64_t total, R br, R bi )
+{
+	for ( int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x )
+	{
+		if ( NC == 1 ) c[e] = fma( br, s[e], c[e] );
+		else
+		{
+			const R sr = s[2 * e], si = s[2 * e + 1];
+			c[2 * e]     += br * sr - bi * si;
+			c[2 * e + 1] += br * si + bi * sr;
+		}
+	}
+}
+
+// ---- host operands, long k: pipeline over k PANELS -------------------------------------------------------------
+// C := beta*C + alpha*A*B with every operand in host memory costs 8(mk + kn + 2mn) bytes of PCIe traffic.  The column
+// block pipeline of gemm_front cannot start the second block before ALL of A has arrived.  Here the product is
+// accumulated panel by panel over k (the pc loop of bli_gemm_blk_var3): round p needs only A(:, panel p) and
+// B(panel p, :), 1/np of the traffic, and is one full-size launch; the host C is staged meanwhile into a separate buffer
+// and merged (beta) during the last round, which runs per column block so that each finished block of C leaves on the
+// D2H stream under the kernels of the next one.  Exposed transfer: the first pair of panels and the last block of C.
+template <typename T>
+static int gemm_host_kpipe( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T al, const T* a, int64_t rs_a, int64_t cs_a,
+                            const T* b, int64_t rs_b, int64_t cs_b, T be, T* c, int64_t rs_c, int64_t cs_c, cudaStream_t st )
+{
+	using R = typename Elem<T>::real;
+	constexpr int NC = Elem<T>::cplx ? 2 : 1;
+	constexpr size_t ES = sizeof(T);
+	Context& cx = ctx();
+	cudaStream_t s_in = cx.copy_stream, s_out = cx.d2h_stream;
+	const bool a_host = classify( a ) != MemKind::Device, b_host = classify( b ) != MemKind::Device;
+	const bool load_c = !Scalar<T>::is_zero( be );
+	const int64_t kb = std::max<int64_t>( 512, ( ( k + 7 ) / 8 + 127 ) / 128 * 128 );
+	const int np = (int)( ( k + kb - 1 ) / kb );
+	const int64_t nb = std::max<int64_t>( 512, ( ( n + 7 ) / 8 + 127 ) / 128 * 128 );
+	const int nblk = (int)( ( n + nb - 1 ) / nb );
+	void *da = nullptr, *db = nullptr, *dc = nullptr, *ds = nullptr;
+	int rc = kSuccess;
+	if ( ( a_host && dev_alloc( &da, (size_t)m * k * ES, st ) != kSuccess ) || ( b_host && dev_alloc( &db, (size_t)k * n * ES, st ) != kSuccess ) ||
+	     dev_alloc( &dc, (size_t)m * n * ES, st ) != kSuccess || ( load_c && dev_alloc( &ds, (size_t)m * n * ES, st ) != kSuccess ) ) rc = kFailure;
+	std::vector<cudaEvent_t> ev( np + 2 * nblk + 1 );
+	for ( auto& e : ev ) cudaEventCreateWithFlags( &e, cudaEventDisableTiming );
+	cudaEvent_t* ev_p = ev.data(); cudaEvent_t* ev_c = ev.data() + np; cudaEvent_t* ev_done = ev.data() + np + nblk; cudaEvent_t ev_alloc = ev.back();
+	cudaEventRecord( ev_alloc, st );
+	cudaStreamWaitEvent( s_in, ev_alloc, 0 ); cudaStreamWaitEvent( s_out, ev_alloc, 0 );
+	const T one = Scalar<T>::make( 1.0, 0.0 ), zero = Scalar<T>::make( 0.0, 0.0 );
+	int c_sent = 0;                                  // column blocks of the host C already queued for staging
+	auto send_c = [&]( int upto ) -> int
+	{
+		int r = kSuccess;
+		for ( ; c_sent < upto && c_sent < nblk && r == kSuccess; ++c_sent )
+		{
+			const int64_t j0 = (int64_t)c_sent * nb, w = std::min( nb, n - j0 );
+			if ( load_c ) r = stage_to_device( (T*)ds + j0 * m, c + j0 * cs_c, m, w, rs_c, cs_c, ES, s_in );
+			cudaEventRecord( ev_c[c_sent], s_in );
+		}
+		return r;
+	};
+	for ( int p = 0; p < np && rc == kSuccess; ++p )
+	{
+		const int64_t p0 = (int64_t)p * kb, kw = std::min( kb, k - p0 );
+		// panel p of A (m x kw, stored densely at da + p0*m) and of B (kw x n, stored densely at db + p0*n)
+		if ( a_host ) rc = stage_to_device( (T*)da + p0 * m, a + p0 * cs_a, m, kw, rs_a, cs_a, ES, s_in );
+		if ( rc == kSuccess && b_host ) rc = stage_to_device( (T*)db + p0 * n, b + p0 * rs_b, kw, n, rs_b, cs_b, ES, s_in );
+		cudaEventRecord( ev_p[p], s_in );
+		if ( rc == kSuccess ) rc = send_c( ( ( p + 1 ) * nblk ) / np );          // the host C trickles in behind the panels
+		const T* ap = a_host ? (const T*)da + p0 * m : a + p0 * cs_a;  const int64_t rs_ap = a_host ? 1 : rs_a, cs_ap = a_host ? m : cs_a;
+		const T* bp = b_host ? (const T*)db + p0 * n : b + p0 * rs_b;  const int64_t rs_bp = b_host ? 1 : rs_b, cs_bp = b_host ? kw : cs_b;
+		cudaStreamWaitEvent( st, ev_p[p], 0 );
+		if ( rc != kSuccess ) break;
+		if ( p + 1 < np )
+			rc = gemm_dev<T>( conja, conjb, m, n, kw, al, ap, rs_ap, cs_ap, bp, rs_bp, cs_bp, p == 0 ? zero : one, (T*)dc, 1, m, st );
+		else
+		{
+			rc = send_c( nblk );
+			for ( int j = 0; j < nblk && rc == kSuccess; ++j )
+			{
+				const int64_t j0 = (int64_t)j * nb, w = std::min( nb, n - j0 );
+				rc = gemm_dev<T>( conja, conjb, m, w, kw, al, ap, rs_ap, cs_ap, bp + j0 * cs_bp, rs_bp, cs_bp, p == 0 ? zero : one, (T*)dc + j0 * m, 1, m, st );
+				if ( rc == kSuccess && load_c )
+				{
+					cudaStreamWaitEvent( st, ev_c[j], 0 );
+					const int64_t total = m * w;
+					const int blocks = (int)std::min<int64_t>( ( total + 255 ) / 256, (int64_t)cx.num_sms * 16 );
+					R br, bi; if constexpr ( Elem<T>::cplx ) { br = be.x; bi = be.y; } else { br = be; bi = 0; }
+					add_scaled_kernel<R, NC><<<blocks, 256, 0, st>>>( (R*)( (T*)dc + j0 * m ), (const R*)( (const T*)ds + j0 * m ), total, br, bi );
+					if ( cudaGetLastError() != cudaSuccess ) rc = fail( "b200_gemm: launch failed" );
+					cx.launches++;
+				}
+				cudaEventRecord( ev_done[j], st );
+				cudaStreamWaitEvent( s_out, ev_done[j], 0 );
+				if ( rc == kSuccess ) rc = stage_to_host( c + j0 * cs_c, rs_c, cs_c, (T*)dc + j0 * m, m, w, ES, s_out );
+			}
+		}
+	}
+	if ( cudaStreamSynchronize( s_out ) != cudaSuccess || cudaStreamSynchronize( s_in ) != cudaSuccess || cudaStreamSynchronize( st ) != cudaSuccess )
+		rc = fail( "b200_gemm: stream sync failed: %s", cudaGetErrorString( cudaGetLastError() ) );
+	for ( auto& e : ev ) cudaEventDestroy( e );
+	dev_free( da, st ); dev_free( db, st ); dev_free( dc, st ); dev_free( ds, st );
+	return rc;
+}
+
 // ---- gemm front end: transposition bits + host operand staging ---------------------
 template <typename T>
 static int gemm_front( int transa, int transb, int64_t m, int64_t n, int64_t k,
@@ -316,6 +421,10 @@ static int gemm_front( int transa, int transb, int64_t m, int64_t n, int64_t k,
 	void *da = nullptr, *db = nullptr, *dc = nullptr;
 	int rc = kSuccess;
 	const bool c_host = ( classify( c ) != MemKind::Device );
+	// long k, everything large: accumulate over k panels (gemm_host_kpipe above)
+	if ( c_host && need_ab && tri_operand == 0 && ctx().host_kpipe && k >= 4096 && n >= 2048 && m >= 512 &&
+	     (double)m * (double)n * (double)k >= 6e10 && ( classify( a ) != MemKind::Device || classify( b ) != MemKind::Device ) )
+		return gemm_host_kpipe<T>( conja, conjb, m, n, k, al, a, rs_a, cs_a, b, rs_b, cs_b, be, c, rs_c, cs_c, st );
 	// Host C of a large problem: pipeline over column blocks of C (and of B when it is a host
 	// operand) so that H2D of block j+1 and D2H of block j-1 run under the kernels of block j.
 	const bool pipelined = c_host && need_ab && n >= 1024 && (double)m * (double)n * (double)k >= 2e9 && tri_operand == 0;
@@ -1377,6 +1486,7 @@ extern "C" b200_err_t b200_set_option( const char* key, long long value )
 	else if ( !strcmp( key, "dynamic_tiles" ) ) c.dynamic_tiles = (int)value;
 	else if ( !strcmp( key, "transpose_y" ) ) c.transpose_y = (int)value;
 	else if ( !strcmp( key, "ktri_skip" ) ) c.ktri_skip = (int)value;
+	else if ( !strcmp( key, "host_kpipe" ) ) c.host_kpipe = (int)value;
 	else if ( !strcmp( key, "dmma_cst" ) ) c.dmma_cst = (int)value;
 	else if ( !strcmp( key, "tma_l2_promotion" ) ) c.tma_l2_promotion = (int)std::min<long long>( 3, std::max<long long>( 0, value ) );
 	else if ( !strcmp( key, "raster_group" ) ) c.raster_group = (int)std::max<long long>( 1, value );

@@ -237,6 +237,37 @@ def test_gemm_host_operands_pipelined_blocks(engine, pin):
         assert rel_err(to_numpy(tc_), want) <= TOL["d"], (pin, beta, "k panels")
 
 
+@pytest.mark.parametrize("pin", [False, True])
+def test_gemm_host_operands_k_panel_pipeline(engine, pin):
+    """Long k with host operands: the engine accumulates over k panels (A and B move panel by panel, the host C is staged
+    separately and merged in the last round, finished column blocks leave under the next block's kernels).  Ragged last
+    panel and last column block, transposed A, beta != 0 and beta == 0, pageable and pinned memory; same result with the
+    k-panel pipeline switched off (column-block pipeline)."""
+    m, n, k = 1800, 4100 + 28, 8200 + 40
+    rng = np.random.default_rng(5)
+    a = np.asfortranarray(rng.uniform(-1, 1, (k, m))); b = np.asfortranarray(rng.uniform(-1, 1, (k, n)))
+    ab = torch.from_numpy(a).t() @ torch.from_numpy(b)
+    for beta in (1.2, 0.0):
+        c = np.asfortranarray(rng.uniform(-1, 1, (m, n)))
+        want = (beta * torch.from_numpy(c) + 2.0 * ab).numpy()
+        outs = []
+        for kpipe in (1, 0):
+            engine.set_option("host_kpipe", kpipe)
+            try:
+                ta_, tb_, tc_ = (to_torch(x, "cpu", pin=pin) for x in (a, b, c))
+                if beta == 0.0:
+                    tc_.fill_(float("nan"))
+                n0 = engine.launch_count()
+                engine.bli_dgemm(TRANSPOSE, 0, m, n, k, 2.0, ta_, *estr(a), tb_, *estr(b), beta, tc_, *estr(c))
+                launches = engine.launch_count() - n0
+            finally:
+                engine.set_option("host_kpipe", 1)
+            outs.append(to_numpy(tc_))
+            assert rel_err(outs[-1], want) <= 4 * TOL["d"], (pin, beta, kpipe)
+            if kpipe:
+                assert launches >= 8 + 8, ("k-panel pipeline not taken", launches)
+
+
 @pytest.mark.parametrize("ch", ["d", "z"])
 def test_gemm_kpanels_accumulates_like_blk_var3(engine, oracle, ch):
     """b200_gemm_kpanels == the reference's pc loop: one rank-k update per panel with beta reset
