@@ -265,7 +265,7 @@ def test_gemm_host_operands_k_panel_pipeline(engine, pin):
             outs.append(to_numpy(tc_))
             assert rel_err(outs[-1], want) <= 4 * TOL["d"], (pin, beta, kpipe)
             if kpipe:
-                assert launches >= 8 + 8, ("k-panel pipeline not taken", launches)
+                assert launches == (7 + 7 + (7 if beta != 0.0 else 0)), ("k-panel pipeline: 7 full rounds + 7 column blocks (+ 7 merges of C)", launches)
 
 
 @pytest.mark.parametrize("ch", ["d", "z"])
