@@ -327,10 +327,20 @@ static int gemm_host_kpipe( bool conja, bool conjb, int64_t m, int64_t n, int64_
 	cudaStream_t s_in = cx.copy_stream, s_out = cx.d2h_stream;
 	const bool a_host = classify( a ) != MemKind::Device, b_host = classify( b ) != MemKind::Device;
 	const bool load_c = !Scalar<T>::is_zero( be );
+	// panel / block boundaries: uniform eighths, except that the FIRST k panel and the LAST column block are quartered so
+	// that the exposed head (first pair of panels) and tail (last block of C going home) are short
 	const int64_t kb = std::max<int64_t>( 512, ( ( k + 7 ) / 8 + 127 ) / 128 * 128 );
-	const int np = (int)( ( k + kb - 1 ) / kb );
 	const int64_t nb = std::max<int64_t>( 512, ( ( n + 7 ) / 8 + 127 ) / 128 * 128 );
-	const int nblk = (int)( ( n + nb - 1 ) / nb );
+	std::vector<int64_t> pk{ 0 }, pn{ 0 };
+	{
+		const int64_t k0 = std::max<int64_t>( 512, ( kb / 4 + 127 ) / 128 * 128 );
+		if ( k0 < kb && k > kb ) pk.push_back( k0 );
+		while ( pk.back() < k ) pk.push_back( std::min( k, pk.back() + kb ) );
+		while ( pn.back() < n ) pn.push_back( std::min( n, pn.back() + nb ) );
+		const int64_t n0 = std::max<int64_t>( 512, ( nb / 4 + 127 ) / 128 * 128 );
+		if ( pn.size() > 2 && n - pn[pn.size() - 2] > n0 ) pn.insert( pn.end() - 1, n - n0 );
+	}
+	const int np = (int)pk.size() - 1, nblk = (int)pn.size() - 1;
 	void *da = nullptr, *db = nullptr, *dc = nullptr, *ds = nullptr;
 	int rc = kSuccess;
 	if ( ( a_host && dev_alloc( &da, (size_t)m * k * ES, st ) != kSuccess ) || ( b_host && dev_alloc( &db, (size_t)k * n * ES, st ) != kSuccess ) ||
@@ -347,7 +357,7 @@ static int gemm_host_kpipe( bool conja, bool conjb, int64_t m, int64_t n, int64_
 		int r = kSuccess;
 		for ( ; c_sent < upto && c_sent < nblk && r == kSuccess; ++c_sent )
 		{
-			const int64_t j0 = (int64_t)c_sent * nb, w = std::min( nb, n - j0 );
+			const int64_t j0 = pn[c_sent], w = pn[c_sent + 1] - j0;
 			if ( load_c ) r = stage_to_device( (T*)ds + j0 * m, c + j0 * cs_c, m, w, rs_c, cs_c, ES, s_in );
 			cudaEventRecord( ev_c[c_sent], s_in );
 		}
@@ -355,7 +365,7 @@ static int gemm_host_kpipe( bool conja, bool conjb, int64_t m, int64_t n, int64_
 	};
 	for ( int p = 0; p < np && rc == kSuccess; ++p )
 	{
-		const int64_t p0 = (int64_t)p * kb, kw = std::min( kb, k - p0 );
+		const int64_t p0 = pk[p], kw = pk[p + 1] - p0;
 		// panel p of A (m x kw, stored densely at da + p0*m) and of B (kw x n, stored densely at db + p0*n)
 		if ( a_host ) rc = stage_to_device( (T*)da + p0 * m, a + p0 * cs_a, m, kw, rs_a, cs_a, ES, s_in );
 		if ( rc == kSuccess && b_host ) rc = stage_to_device( (T*)db + p0 * n, b + p0 * rs_b, kw, n, rs_b, cs_b, ES, s_in );
@@ -372,7 +382,7 @@ static int gemm_host_kpipe( bool conja, bool conjb, int64_t m, int64_t n, int64_
 			rc = send_c( nblk );
 			for ( int j = 0; j < nblk && rc == kSuccess; ++j )
 			{
-				const int64_t j0 = (int64_t)j * nb, w = std::min( nb, n - j0 );
+				const int64_t j0 = pn[j], w = pn[j + 1] - j0;
 				rc = gemm_dev<T>( conja, conjb, m, w, kw, al, ap, rs_ap, cs_ap, bp + j0 * cs_bp, rs_bp, cs_bp, p == 0 ? zero : one, (T*)dc + j0 * m, 1, m, st );
 				if ( rc == kSuccess && load_c )
 				{
