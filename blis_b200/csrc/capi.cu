@@ -370,7 +370,9 @@ static int gemm_host_kpipe( bool conja, bool conjb, int64_t m, int64_t n, int64_
 		if ( a_host ) rc = stage_to_device( (T*)da + p0 * m, a + p0 * cs_a, m, kw, rs_a, cs_a, ES, s_in );
 		if ( rc == kSuccess && b_host ) rc = stage_to_device( (T*)db + p0 * n, b + p0 * rs_b, kw, n, rs_b, cs_b, ES, s_in );
 		cudaEventRecord( ev_p[p], s_in );
-		if ( rc == kSuccess ) rc = send_c( ( ( p + 1 ) * nblk ) / np );          // the host C trickles in behind the panels
+		// the host C trickles in behind the panels -- but not behind the (short) first one, whose round would otherwise
+		// finish before the second pair of panels has arrived
+		if ( rc == kSuccess && p >= 1 ) rc = send_c( np > 1 ? ( p * nblk ) / ( np - 1 ) : nblk );
 		const T* ap = a_host ? (const T*)da + p0 * m : a + p0 * cs_a;  const int64_t rs_ap = a_host ? 1 : rs_a, cs_ap = a_host ? m : cs_a;
 		const T* bp = b_host ? (const T*)db + p0 * n : b + p0 * rs_b;  const int64_t rs_bp = b_host ? 1 : rs_b, cs_bp = b_host ? kw : cs_b;
 		cudaStreamWaitEvent( st, ev_p[p], 0 );
