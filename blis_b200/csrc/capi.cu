@@ -327,14 +327,13 @@ static int gemm_host_kpipe( bool conja, bool conjb, int64_t m, int64_t n, int64_
 	cudaStream_t s_in = cx.copy_stream, s_out = cx.d2h_stream;
 	const bool a_host = classify( a ) != MemKind::Device, b_host = classify( b ) != MemKind::Device;
 	const bool load_c = !Scalar<T>::is_zero( be );
-	// panel / block boundaries: uniform eighths, except that the FIRST k panel and the LAST column block are quartered so
-	// that the exposed head (first pair of panels) and tail (last block of C going home) are short
+	// panel / block boundaries: uniform eighths, except that the LAST column block is quartered so that the exposed tail
+	// (last block of C going home) is short.  (A short FIRST k panel was measured slower: a row panel of a column-major B
+	// is a 2-D copy whose chunks are kw*8 bytes, and 4 KiB chunks move at a fraction of the PCIe rate.)
 	const int64_t kb = std::max<int64_t>( 512, ( ( k + 7 ) / 8 + 127 ) / 128 * 128 );
 	const int64_t nb = std::max<int64_t>( 512, ( ( n + 7 ) / 8 + 127 ) / 128 * 128 );
 	std::vector<int64_t> pk{ 0 }, pn{ 0 };
 	{
-		const int64_t k0 = std::max<int64_t>( 512, ( kb / 4 + 127 ) / 128 * 128 );
-		if ( k0 < kb && k > kb ) pk.push_back( k0 );
 		while ( pk.back() < k ) pk.push_back( std::min( k, pk.back() + kb ) );
 		while ( pn.back() < n ) pn.push_back( std::min( n, pn.back() + nb ) );
 		const int64_t n0 = std::max<int64_t>( 512, ( nb / 4 + 127 ) / 128 * 128 );
@@ -370,8 +369,7 @@ static int gemm_host_kpipe( bool conja, bool conjb, int64_t m, int64_t n, int64_
 		if ( a_host ) rc = stage_to_device( (T*)da + p0 * m, a + p0 * cs_a, m, kw, rs_a, cs_a, ES, s_in );
 		if ( rc == kSuccess && b_host ) rc = stage_to_device( (T*)db + p0 * n, b + p0 * rs_b, kw, n, rs_b, cs_b, ES, s_in );
 		cudaEventRecord( ev_p[p], s_in );
-		// the host C trickles in behind the panels -- but not behind the (short) first one, whose round would otherwise
-		// finish before the second pair of panels has arrived
+		// the host C trickles in behind the panels, starting behind the second pair so that round 1 is never kept waiting
 		if ( rc == kSuccess && p >= 1 ) rc = send_c( np > 1 ? ( p * nblk ) / ( np - 1 ) : nblk );
 		const T* ap = a_host ? (const T*)da + p0 * m : a + p0 * cs_a;  const int64_t rs_ap = a_host ? 1 : rs_a, cs_ap = a_host ? m : cs_a;
 		const T* bp = b_host ? (const T*)db + p0 * n : b + p0 * rs_b;  const int64_t rs_bp = b_host ? 1 : rs_b, cs_bp = b_host ? kw : cs_b;
