@@ -57,9 +57,13 @@ struct FfmaTmaCfg
 	static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES + BAR_BYTES + 1024;
 };
 
-template <bool XK, bool YK, bool TRI = false>
+// CST: as in gemm_dmma_tma.cuh, small-k problems stage the D tile through the ring: two extra stages per tile, each
+// 64 rows x 128 columns of D as four 128B-swizzled {32 floats, 64 rows} boxes; warp row-group r (rows 32r..32r+31) takes
+// its rows from extra stage r / 2.  Only the q-contiguous ownership (!YK) has the vector epilogue that uses it.
+template <bool XK, bool YK, bool TRI = false, bool CST = false>
 __global__ void __launch_bounds__( 384, 1 )
-gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy )
+gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
+                      const __grid_constant__ CUtensorMap tmd )
 {
 	using Cfg = FfmaTmaCfg;
 	constexpr int BP = Cfg::BP, BQ = Cfg::BQ, BK = Cfg::BK, STAGES = Cfg::STAGES;
@@ -111,7 +115,7 @@ gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorM
 			if ( TRI && tri_skip_tile( g, p0, q0, (int)min( (int64_t)BP, g.P - p0 ), (int)min( (int64_t)BQ, g.Q - q0 ) ) ) continue;
 			int64_t kt0 = 0, kt1 = KT;
 			if constexpr ( TRI ) tile_k_range( g, p0, (int)min( (int64_t)BP, g.P - p0 ), q0, (int)min( (int64_t)BQ, g.Q - q0 ), BK, KT, kt0, kt1 );
-			prefetch_d_tile_l2( g, p0, q0, BP, BQ );
+			if constexpr ( !CST ) prefetch_d_tile_l2( g, p0, q0, BP, BQ );
 			for ( int64_t kt = kt0; kt < kt1; ++kt )
 			{
 				mbar_wait( empty_bar( stage ), phase ^ 1u );
@@ -132,6 +136,20 @@ gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorM
 					for ( int b = 0; b < BQ / 32; ++b ) tma_load_2d( ys + b * 4096, &tmy, q0 + b * 32, k0, fb );
 				}
 				if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
+			}
+			if constexpr ( CST )
+			{
+				#pragma unroll 1
+				for ( int qd = 0; qd < BP / 64; ++qd )
+				{
+					mbar_wait( empty_bar( stage ), phase ^ 1u );
+					const uint32_t cs = sbase + (uint32_t)stage * Cfg::STAGE_BYTES;
+					const uint32_t fb = full_bar( stage );
+					mbar_arrive_expect_tx( fb, (uint32_t)Cfg::STAGE_BYTES );
+					#pragma unroll
+					for ( int b = 0; b < BQ / 32; ++b ) tma_load_2d( cs + b * 8192, &tmd, q0 + b * 32, p0 + qd * 64, fb );
+					if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
+				}
 			}
 		}
 		if ( g.tile_counter )
@@ -306,6 +324,41 @@ gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorM
 		for ( int i = 0; i < 8; ++i )
 			#pragma unroll
 			for ( int j = 0; j < 4; ++j ) unpack2( acc2[i][j], acc[i][2 * j], acc[i][2 * j + 1] );
+		if constexpr ( CST )
+		{
+			// the two D stages of this tile; every warp walks the ring, row-group wr0 / 64 reads its rows
+			const bool fast = ( !YK && g.d_vec_ok && q_lim == BQ && interior );
+			#pragma unroll 1
+			for ( int qd = 0; qd < BP / 64; ++qd )
+			{
+				mbar_wait( full_bar( stage ), phase );
+				if ( fast && qd == ( wr0 >> 6 ) )
+				{
+					const unsigned char* cs = smem + (size_t)stage * Cfg::STAGE_BYTES + ( wc0 >> 5 ) * 8192;
+					#pragma unroll
+					for ( int i = 0; i < 8; ++i )
+					{
+						const int pl = row_of( i );
+						if ( pl >= p_lim ) continue;
+						const int r = pl & 63;
+						const unsigned char* rowp = cs + r * 128 + ( ( tx ^ ( r & 7 ) ) << 4 );
+						const float4 o0 = *reinterpret_cast<const float4*>( rowp ), o1 = *reinterpret_cast<const float4*>( rowp + 8192 );
+						float4* dp0 = reinterpret_cast<float4*>( g.D + ( p0 + pl ) * g.ldd + q0 + col_of( 0 ) );
+						float4* dp1 = reinterpret_cast<float4*>( g.D + ( p0 + pl ) * g.ldd + q0 + col_of( 4 ) );
+						float4 r0, r1;
+						r0.x = fmaf( g.beta, o0.x, g.alpha * acc[i][0] ); r0.y = fmaf( g.beta, o0.y, g.alpha * acc[i][1] );
+						r0.z = fmaf( g.beta, o0.z, g.alpha * acc[i][2] ); r0.w = fmaf( g.beta, o0.w, g.alpha * acc[i][3] );
+						r1.x = fmaf( g.beta, o1.x, g.alpha * acc[i][4] ); r1.y = fmaf( g.beta, o1.y, g.alpha * acc[i][5] );
+						r1.z = fmaf( g.beta, o1.z, g.alpha * acc[i][6] ); r1.w = fmaf( g.beta, o1.w, g.alpha * acc[i][7] );
+						__stcs( dp0, r0 ); __stcs( dp1, r1 );
+					}
+				}
+				__syncwarp();
+				if ( lane == 0 ) mbar_arrive( empty_bar( stage ) );
+				if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
+			}
+			if ( fast ) continue;
+		}
 		if ( !YK && g.d_vec_ok && q_lim == BQ && interior )
 		{
 			// Interior tile, q-contiguous ownership: two 16-byte accesses per row; the loads of row i+1 are in flight

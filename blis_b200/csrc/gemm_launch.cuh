@@ -153,19 +153,22 @@ static int launch_dmma_tma( const GemmArgs<double>& g, bool xk, bool yk, int gri
 	return yk ? go( Ff{}, Tt{} ) : go( Ff{}, Ff{} );
 }
 
-template <bool TRI = false>
+template <bool TRI = false, bool CST = false>
 static int launch_ffma_tma( const GemmArgs<float>& g, bool xk, bool yk, int grid, cudaStream_t st )
 {
-	CUtensorMap tmx, tmy;
+	CUtensorMap tmx, tmy, tmd;
 	if ( make_tmap( &tmx, g.X, 4, xk, g.P, g.K, g.ldx ) != kSuccess ) return kFailure;
 	if ( make_tmap( &tmy, g.Y, 4, yk, g.Q, g.K, g.ldy ) != kSuccess ) return kFailure;
+	// D as {32 columns, 64 rows} boxes (CST: the epilogue reads D from shared memory); a copy of tmx when unused
+	if ( CST ) { if ( make_tmap( &tmd, g.D, 4, true, g.P, g.Q, g.ldd, 64 ) != kSuccess ) return kFailure; }
+	else tmd = tmx;
 	auto go = [&]( auto XKc, auto YKc ) -> int
 	{
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
-		auto kern = gemm_ffma_tma_kernel<XK, YK, TRI>;
+		auto kern = gemm_ffma_tma_kernel<XK, YK, TRI, CST>;
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, FfmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
-		kern<<<grid, FfmaTmaCfg::NT_ALL, FfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
+		kern<<<grid, FfmaTmaCfg::NT_ALL, FfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy, tmd );
 		B200_CUDA( cudaGetLastError() );
 		ctx().launches++;
 		return kSuccess;

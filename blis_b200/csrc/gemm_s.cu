@@ -30,7 +30,13 @@ int launch_gemm_kernel<float>( GemmArgs<float>& g, bool xk, bool yk, bool al, cu
 		if ( tiny ) return launch_ffma<float, 64, 64, 16, 4, 4, 4>( g, xk, yk, al, small_grid, st );
 		return launch_ffma<float, 64, 128, 16, 4, 8, 4>( g, xk, yk, al, small_grid, st );
 	}
-	if ( ( c.sgemm_cfg < 0 || c.sgemm_cfg == 3 ) && tma_eligible( g, xk, yk, al ) ) return launch_ffma_tma( g, xk, yk, grid, st );
+	if ( ( c.sgemm_cfg < 0 || c.sgemm_cfg == 3 ) && tma_eligible( g, xk, yk, al ) )
+	{
+		// small k: the read-modify-write of D is staged through the TMA ring as well (gemm_ffma_tma.cuh, CST)
+		if ( c.dmma_cst && !yk && !g.beta_is_zero && g.d_vec_ok && g.K <= c.dmma_cst && g.ldd >= g.Q && g.ldd * 4 < ( 1ll << 40 ) )
+			return launch_ffma_tma<false, true>( g, xk, yk, grid, st );
+		return launch_ffma_tma( g, xk, yk, grid, st );
+	}
 	if ( c.sgemm_cfg == 1 ) return launch_ffma_ws<float, 128, 128, 16, 8, 8, 5>( g, xk, yk, al, grid, st );
 	if ( c.sgemm_cfg == 2 ) return launch_ffma_ws<float, 128, 128, 32, 8, 8, 4>( g, xk, yk, al, grid, st );
 	return launch_ffma<float, 128, 128, 16, 8, 8, 4>( g, xk, yk, al, grid, st );
