@@ -16,7 +16,13 @@ int launch_gemm_kernel<float2>( GemmArgs<float2>& g, bool xk, bool yk, bool al, 
 		if ( tma_eligible( g, xk, yk, al ) ) return launch_cfma_tma<true>( g, xk, yk, grid, st );
 		return launch_ffma_ws<float2, 64, 128, 16, 4, 8, 5>( g, xk, yk, al, grid, st );     // run-time tri support
 	}
-	if ( ( c.cgemm_cfg < 0 || c.cgemm_cfg == 3 ) && tma_eligible( g, xk, yk, al ) ) return launch_cfma_tma( g, xk, yk, grid, st );
+	if ( ( c.cgemm_cfg < 0 || c.cgemm_cfg == 3 ) && tma_eligible( g, xk, yk, al ) )
+	{
+		// small k: the read-modify-write of D is staged through the TMA ring as well (gemm_cfma_tma.cuh, CST)
+		if ( c.dmma_cst && !yk && !g.beta_is_zero && g.d_vec_ok && g.K <= c.dmma_cst && g.ldd >= g.Q && g.ldd * 8 < ( 1ll << 40 ) )
+			return launch_cfma_tma<false, true>( g, xk, yk, grid, st );
+		return launch_cfma_tma( g, xk, yk, grid, st );
+	}
 	if ( c.cgemm_cfg != 0 ) return launch_ffma_ws<float2, 64, 128, 16, 4, 8, 5>( g, xk, yk, al, grid, st );
 	return launch_ffma<float2, 64, 128, 16, 4, 8, 4>( g, xk, yk, al, grid, st );
 }

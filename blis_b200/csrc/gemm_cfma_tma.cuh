@@ -34,9 +34,13 @@ struct CfmaTmaCfg
 	static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES + BAR_BYTES + 1024;
 };
 
-template <bool XK, bool YK, bool TRI = false>
+// CST: small-k problems stage the D tile through the ring as in gemm_dmma_tma.cuh: four extra stages per tile, each
+// 16 rows x 128 columns of D as eight 128B-swizzled {16 complex, 16 rows} boxes (16 KiB of the 24 KiB stage); warp
+// row-group r (rows 16r..16r+15) takes its rows from extra stage r.  Used with the q-contiguous ownership (!YK).
+template <bool XK, bool YK, bool TRI = false, bool CST = false>
 __global__ void __launch_bounds__( 384, 1 )
-gemm_cfma_tma_kernel( const GemmArgs<float2> g, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy )
+gemm_cfma_tma_kernel( const GemmArgs<float2> g, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
+                      const __grid_constant__ CUtensorMap tmd )
 {
 	using Cfg = CfmaTmaCfg;
 	constexpr int BP = Cfg::BP, BQ = Cfg::BQ, BK = Cfg::BK, STAGES = Cfg::STAGES;
@@ -88,7 +92,7 @@ gemm_cfma_tma_kernel( const GemmArgs<float2> g, const __grid_constant__ CUtensor
 			if ( TRI && tri_skip_tile( g, p0, q0, (int)min( (int64_t)BP, g.P - p0 ), (int)min( (int64_t)BQ, g.Q - q0 ) ) ) continue;
 			int64_t kt0 = 0, kt1 = KT;
 			if constexpr ( TRI ) tile_k_range( g, p0, (int)min( (int64_t)BP, g.P - p0 ), q0, (int)min( (int64_t)BQ, g.Q - q0 ), BK, KT, kt0, kt1 );
-			prefetch_d_tile_l2( g, p0, q0, BP, BQ );
+			if constexpr ( !CST ) prefetch_d_tile_l2( g, p0, q0, BP, BQ );
 			for ( int64_t kt = kt0; kt < kt1; ++kt )
 			{
 				mbar_wait( empty_bar( stage ), phase ^ 1u );
@@ -109,6 +113,20 @@ gemm_cfma_tma_kernel( const GemmArgs<float2> g, const __grid_constant__ CUtensor
 					for ( int b = 0; b < BQ / 16; ++b ) tma_load_2d( ys + b * 2048, &tmy, q0 + b * 16, k0, fb );
 				}
 				if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
+			}
+			if constexpr ( CST )
+			{
+				#pragma unroll 1
+				for ( int qd = 0; qd < BP / 16; ++qd )
+				{
+					mbar_wait( empty_bar( stage ), phase ^ 1u );
+					const uint32_t cs = sbase + (uint32_t)stage * Cfg::STAGE_BYTES;
+					const uint32_t fb = full_bar( stage );
+					mbar_arrive_expect_tx( fb, 16u * 1024u );
+					#pragma unroll
+					for ( int b = 0; b < BQ / 16; ++b ) tma_load_2d( cs + b * 2048, &tmd, q0 + b * 16, p0 + qd * 16, fb );
+					if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
+				}
 			}
 		}
 		if ( g.tile_counter )
@@ -259,6 +277,52 @@ gemm_cfma_tma_kernel( const GemmArgs<float2> g, const __grid_constant__ CUtensor
 		int dlo = 0, dhi = 0;
 		if constexpr ( TRI ) tri_band( g, p0, q0, dlo, dhi );
 		auto keep = [&]( int d ) { if constexpr ( TRI ) return in_band( d, dlo, dhi ); else return true; };
+		if constexpr ( CST )
+		{
+			// the four D stages of this tile; every warp walks the ring, row-group wr0 / 16 reads its rows
+			const bool fast = ( !YK && g.d_vec_ok && q_lim == BQ );
+			const float sx = cjx ? -1.f : 1.f, sy = cjy ? -1.f : 1.f;
+			#pragma unroll 1
+			for ( int qd = 0; qd < BP / 16; ++qd )
+			{
+				mbar_wait( full_bar( stage ), phase );
+				if ( fast && qd == ( wr0 >> 4 ) )
+				{
+					const unsigned char* cs = smem + (size_t)stage * Cfg::STAGE_BYTES + ( wc0 >> 4 ) * 2048;
+					#pragma unroll
+					for ( int i = 0; i < 4; ++i )
+					{
+						const int pl = row_of( i );
+						if ( pl >= p_lim ) continue;
+						const int r = pl & 15;
+						const unsigned char* rowp = cs + r * 128 + ( ( tx ^ ( r & 7 ) ) << 4 );
+						float4* dp = reinterpret_cast<float4*>( g.D + ( p0 + pl ) * g.ldd + q0 + col_of( 0 ) );
+						#pragma unroll
+						for ( int h = 0; h < 4; ++h )
+						{
+							const float4 o = *reinterpret_cast<const float4*>( rowp + h * 2048 );      // two complex elements
+							float4 res;
+							#pragma unroll
+							for ( int e = 0; e < 2; ++e )
+							{
+								float px, py, qx, qy;
+								unpack2( accP[i][2 * h + e], px, py ); unpack2( accQ[i][2 * h + e], qx, qy );
+								const float ar = px - sx * sy * qy, ai = sy * py + sx * qx;
+								float rr, ri;
+								cscal( g.alpha.x, g.alpha.y, ar, ai, rr, ri );
+								cxpby( g.beta.x, g.beta.y, e ? o.z : o.x, e ? o.w : o.y, rr, ri );
+								if ( e ) { res.z = rr; res.w = ri; } else { res.x = rr; res.y = ri; }
+							}
+							__stcs( dp + h * 8, res );       // 16 complex columns = 8 float4 further
+						}
+					}
+				}
+				__syncwarp();
+				if ( lane == 0 ) mbar_arrive( empty_bar( stage ) );
+				if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
+			}
+			if ( fast ) continue;
+		}
 		#pragma unroll
 		for ( int i = 0; i < 4; ++i )
 		{

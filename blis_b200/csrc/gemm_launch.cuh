@@ -178,20 +178,22 @@ static int launch_ffma_tma( const GemmArgs<float>& g, bool xk, bool yk, int grid
 	return yk ? go( Ff{}, Tt{} ) : go( Ff{}, Ff{} );
 }
 
-template <bool TRI = false>
+template <bool TRI = false, bool CST = false>
 static int launch_cfma_tma( const GemmArgs<float2>& g, bool xk, bool yk, int grid, cudaStream_t st )
 {
 	// float2 elements are moved as opaque 8-byte elements (FLOAT64-typed map; zero fill out of bounds)
-	CUtensorMap tmx, tmy;
+	CUtensorMap tmx, tmy, tmd;
+	if ( CST ) { if ( make_tmap( &tmd, g.D, 8, true, g.P, g.Q, g.ldd, 16 ) != kSuccess ) return kFailure; }
 	if ( make_tmap( &tmx, g.X, 8, xk, g.P, g.K, g.ldx, CfmaTmaCfg::BP ) != kSuccess ) return kFailure;
 	if ( make_tmap( &tmy, g.Y, 8, yk, g.Q, g.K, g.ldy, CfmaTmaCfg::BQ ) != kSuccess ) return kFailure;
 	auto go = [&]( auto XKc, auto YKc ) -> int
 	{
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
-		auto kern = gemm_cfma_tma_kernel<XK, YK, TRI>;
+		auto kern = gemm_cfma_tma_kernel<XK, YK, TRI, CST>;
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, CfmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
-		kern<<<grid, CfmaTmaCfg::NT_ALL, CfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
+		if ( !CST ) tmd = tmx;
+		kern<<<grid, CfmaTmaCfg::NT_ALL, CfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy, tmd );
 		B200_CUDA( cudaGetLastError() );
 		ctx().launches++;
 		return kSuccess;
