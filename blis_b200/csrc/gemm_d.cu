@@ -30,11 +30,9 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 	{
 		// auto: the cooperative 128x128 tile unless it cannot fill the SMs once; then 128x64 tiles, two CTAs per SM
 		const int64_t t128 = ( ( g.P + 127 ) / 128 ) * ( ( g.Q + 127 ) / 128 );
-		const int64_t t64 = ( ( g.P + 63 ) / 64 ) * ( ( g.Q + 63 ) / 64 );
 		// ... and 64x64 tiles when even 128x64 tiles leave SMs idle (1024^3: 64 -> 256 tiles)
 		// [B200] 1536^3 (144 tiles): 128x128 wins; 1024^3 (64 tiles): 13 -> 21.4; 768^3: 11.1 (128x64) -> 17.0 (64x64); 512^3: 4.4 -> 6.4
 		cfg = ( 4 * t128 < 3 * c.num_sms ) ? ( ( 2 * t128 < c.num_sms && g.nseg == 1 ) ? 10 : 7 ) : ( tma_eligible( g, xk, yk, al ) ? 9 : 6 );
-		(void)t64;
 	}
 	switch ( cfg )
 	{
