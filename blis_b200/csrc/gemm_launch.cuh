@@ -7,6 +7,7 @@
 #include "gemm_dmma_tma.cuh"
 #include "gemm_ffma_tma.cuh"
 #include "gemm_cfma_tma.cuh"
+#include "gemm_zmma_tma.cuh"
 #include "gemm_ffma.cuh"
 #include "gemm_ffma_ws.cuh"
 #include "../../include/blis_b200.h"
@@ -194,6 +195,50 @@ static int launch_cfma_tma( const GemmArgs<float2>& g, bool xk, bool yk, int gri
 		if ( !attr ) { if ( set_smem( kern, CfmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		if ( !CST ) tmd = tmx;
 		kern<<<grid, CfmaTmaCfg::NT_ALL, CfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy, tmd );
+		B200_CUDA( cudaGetLastError() );
+		ctx().launches++;
+		return kSuccess;
+	};
+	using Tt = std::true_type; using Ff = std::false_type;
+	if ( xk ) return yk ? go( Tt{}, Tt{} ) : go( Tt{}, Ff{} );
+	return yk ? go( Ff{}, Tt{} ) : go( Ff{}, Ff{} );
+}
+
+// zgemm: FLOAT64-typed maps with two elements per complex number; k-contiguous: dims {2K, rows}, box {16, box_rows};
+// row-contiguous: dims {2 rows, K}, box {16, 8} (eight complex rows x eight k lines).  128-byte swizzle, zero fill.
+static int make_tmap_z( CUtensorMap* tm, const void* base, bool kmajor, int64_t rows, int64_t K, int64_t ld, int box_rows )
+{
+	EncodeTiledFn enc = encode_tiled_fn();
+	if ( !enc ) return fail( "cuTensorMapEncodeTiled not available" );
+	cuuint64_t dims[2]    = { (cuuint64_t)( kmajor ? 2 * K : 2 * rows ), (cuuint64_t)( kmajor ? rows : K ) };
+	cuuint64_t strides[1] = { (cuuint64_t)ld * 16 };
+	cuuint32_t box[2]     = { 16, (cuuint32_t)( kmajor ? box_rows : 8 ) };
+	cuuint32_t estr[2]    = { 1, 1 };
+	const CUresult r = enc( tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr,
+	                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, (CUtensorMapL2promotion)ctx().tma_l2_promotion,
+	                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+	if ( r != CUDA_SUCCESS ) return fail( "cuTensorMapEncodeTiled failed (%d)", (int)r );
+	return kSuccess;
+}
+static bool tma_eligible_z( const GemmArgs<double2>& g, bool xk, bool yk )
+{
+	return g.nseg == 1 && ( (uintptr_t)g.X % 16 == 0 ) && ( (uintptr_t)g.Y % 16 == 0 ) &&
+	       g.P < ( 1ll << 30 ) && g.Q < ( 1ll << 30 ) && g.K < ( 1ll << 30 ) &&
+	       g.ldx >= ( xk ? g.K : g.P ) && g.ldy >= ( yk ? g.K : g.Q ) && g.ldx * 16 < ( 1ll << 40 ) && g.ldy * 16 < ( 1ll << 40 );
+}
+template <bool TRI = false>
+static int launch_zmma_tma( const GemmArgs<double2>& g, bool xk, bool yk, int grid, cudaStream_t st )
+{
+	CUtensorMap tmx, tmy;
+	if ( make_tmap_z( &tmx, g.X, xk, g.P, g.K, g.ldx, ZmmaTmaCfg::BP ) != kSuccess ) return kFailure;
+	if ( make_tmap_z( &tmy, g.Y, yk, g.Q, g.K, g.ldy, ZmmaTmaCfg::BQ ) != kSuccess ) return kFailure;
+	auto go = [&]( auto XKc, auto YKc ) -> int
+	{
+		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
+		auto kern = gemm_zmma_tma_kernel<XK, YK, TRI>;
+		static bool attr = false;
+		if ( !attr ) { if ( set_smem( kern, ZmmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<grid, ZmmaTmaCfg::NT_ALL, ZmmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
 		B200_CUDA( cudaGetLastError() );
 		ctx().launches++;
 		return kSuccess;
