@@ -252,20 +252,28 @@ gemm_dmma_ws_kernel( const GemmArgs<T> g )
 			}
 			else
 			{
+				// the two DMMAs into one accumulator are issued a whole pass apart (see gemm_zmma_tma.cuh)
+				double xi[MT], yi[NTL];
+				#pragma unroll
+				for ( int i = 0; i < MT; ++i ) xi[i] = flip_sign( xf[i].y, cjx );
+				#pragma unroll
+				for ( int j = 0; j < NTL; ++j ) yi[j] = flip_sign( yf[j].y, cjy );
 				#pragma unroll
 				for ( int j = 0; j < NTL; ++j )
-				{
-					const double yr = yf[j].x, yi = flip_sign( yf[j].y, cjy );
 					#pragma unroll
 					for ( int i = 0; i < MT; ++i )
 					{
-						const double xr = xf[i].x, xi = flip_sign( xf[i].y, cjx );
-						dmma884( acc[0][i][j][0], acc[0][i][j][1], xr,  yr );
-						dmma884( acc[1][i][j][0], acc[1][i][j][1], xr,  yi );
-						dmma884( acc[0][i][j][0], acc[0][i][j][1], -xi, yi );
-						dmma884( acc[1][i][j][0], acc[1][i][j][1], xi,  yr );
+						dmma884( acc[0][i][j][0], acc[0][i][j][1], xf[i].x, yf[j].x );
+						dmma884( acc[1][i][j][0], acc[1][i][j][1], xf[i].x, yi[j] );
 					}
-				}
+				#pragma unroll
+				for ( int j = 0; j < NTL; ++j )
+					#pragma unroll
+					for ( int i = 0; i < MT; ++i )
+					{
+						dmma884( acc[0][i][j][0], acc[0][i][j][1], -xi[i], yi[j] );
+						dmma884( acc[1][i][j][0], acc[1][i][j][1], xi[i],  yf[j].x );
+					}
 			}
 		};
 

@@ -176,20 +176,30 @@ gemm_zmma_tma_kernel( const GemmArgs<double2> g, const __grid_constant__ CUtenso
 
 		auto mma_step = [&]( double2 ( &xf )[MT], double2 ( &yf )[NTL] )
 		{
+			// re += xr*yr - xi*yi, im += xr*yi + xi*yr.  The two DMMAs into one accumulator are issued a whole pass apart
+			// (32 independent DMMAs in between) so that the second never waits for the first; per accumulator the order
+			// of the additions is unchanged.
+			double xi[MT], yi[NTL];
+			#pragma unroll
+			for ( int i = 0; i < MT; ++i ) xi[i] = flip_sign( xf[i].y, cjx );
+			#pragma unroll
+			for ( int j = 0; j < NTL; ++j ) yi[j] = flip_sign( yf[j].y, cjy );
 			#pragma unroll
 			for ( int j = 0; j < NTL; ++j )
-			{
-				const double yr = yf[j].x, yi = flip_sign( yf[j].y, cjy );
 				#pragma unroll
 				for ( int i = 0; i < MT; ++i )
 				{
-					const double xr = xf[i].x, xi = flip_sign( xf[i].y, cjx );
-					dmma884( acc[0][i][j][0], acc[0][i][j][1], xr,  yr );
-					dmma884( acc[1][i][j][0], acc[1][i][j][1], xr,  yi );
-					dmma884( acc[0][i][j][0], acc[0][i][j][1], -xi, yi );
-					dmma884( acc[1][i][j][0], acc[1][i][j][1], xi,  yr );
+					dmma884( acc[0][i][j][0], acc[0][i][j][1], xf[i].x, yf[j].x );
+					dmma884( acc[1][i][j][0], acc[1][i][j][1], xf[i].x, yi[j] );
 				}
-			}
+			#pragma unroll
+			for ( int j = 0; j < NTL; ++j )
+				#pragma unroll
+				for ( int i = 0; i < MT; ++i )
+				{
+					dmma884( acc[0][i][j][0], acc[0][i][j][1], -xi[i], yi[j] );
+					dmma884( acc[1][i][j][0], acc[1][i][j][1], xi[i],  yf[j].x );
+				}
 		};
 
 		int64_t kt0 = 0, kt1 = KT;

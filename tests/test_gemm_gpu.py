@@ -342,6 +342,38 @@ def test_gemm_fp32_k_contiguous_y_is_transposed_once(engine, ref, ch):
         assert rel_err(got2, want) <= TOL[ch] * 4
 
 
+def test_zgemm_tma_kernel_opt_in(engine, oracle):
+    """The TMA variant of the zgemm kernel (zgemm_cfg = 2; FLOAT64-typed tensor maps with two elements per complex number)
+    against the oracle for every transposition/conjugation, ragged tiles in m, n, k, both C storages, and bit-for-bit
+    against the default warp-specialised cp.async kernel (same fragment values, same accumulation order per accumulator
+    up to the k permutation inside a stage, so only compared within tolerance), plus a triangular (herk) call."""
+    trs = (NO_TRANSPOSE, TRANSPOSE, CONJ_NO_TRANSPOSE, CONJ_TRANSPOSE)
+    al, be = 2.0 + 0.2j, 1.2 + 0.5j
+    seed = 7000
+    engine.set_option("zgemm_cfg", 2)
+    try:
+        for (m, n, k) in ((260, 132, 68), (64, 128, 8), (4, 8, 4), (516, 260, 100), (129, 200, 1)):
+            for ta in trs:
+                for tb in trs:
+                    for oc in "cr":
+                        seed += 1
+                        am, ak = (k, m) if ta & TRANSPOSE else (m, k)
+                        bk, bn = (n, k) if tb & TRANSPOSE else (k, n)
+                        a = gen.matrix("z", am, ak, seed, "frac", "c"); b = gen.matrix("z", bk, bn, seed + 5000, "frac", "c")
+                        c = gen.matrix("z", m, n, seed + 9000, "frac", oc)
+                        want = c.copy(order="K")
+                        oracle.gemm(ta, tb, al, a, b, be, want)
+                        got = run_gemm(engine, "z", ta, tb, al, a, b, be, c)
+                        assert rel_err(got, want) <= TOL["z"], (m, n, k, ta, tb, oc, rel_err(got, want))
+        a = gen.matrix("z", 300, 90, 1, "frac"); c = gen.matrix("z", 300, 300, 2, "frac")
+        want = c.copy(order="K"); oracle.herk(0xC0, 0, 2.0, a, 1.2, want)
+        ta_, tc_ = to_torch(a), to_torch(c)
+        engine.bli_zherk(0xC0, 0, 300, 90, 2.0, ta_, *estr(a), 1.2, tc_, *estr(c)); torch.cuda.synchronize()
+        assert rel_err(to_numpy(tc_), want) <= TOL["z"]
+    finally:
+        engine.set_option("zgemm_cfg", 1)
+
+
 def test_gemm_concurrent_host_threads(engine):
     """BLIS is re-entrant (SURVEY 8b 'Threading'): several application threads call gemm at the same time,
     each on its own CUDA stream; the engine's shared state (tile-scheduler counters, workspace pool, staging
