@@ -50,8 +50,12 @@ def _derive_inputs():
         i += 1
     (OUT / "input.operations.l3").write_text("\n".join(out) + "\n")
 
-    def general(tag, size, dts, mixed=False):
+    def general(tag, size, dts, mixed=False, app_threads=1):
         g = gen
+        if app_threads != 1:
+            # "Simulate application-level threading" (testsuite/src/test_libblis.c: n testsuite threads share the
+            # experiments; every thread calls the BLIS API concurrently)
+            g = re.sub(r"^1(\s+# Simulate application-level threading:)", f"{app_threads}\\1", g, flags=re.M)
         if mixed:
             g = re.sub(r"^0(\s+# Test gemm with mixed-domain operands\?)", "1\\1", g, flags=re.M)
             g = re.sub(r"^0(\s+# Test gemm with mixed-precision operands\?)", "1\\1", g, flags=re.M)
@@ -64,6 +68,7 @@ def _derive_inputs():
     general("n100", 100, "sdcz")
     general("n1000d", 1000, "d")
     general("n100mixed", 100, "sdcz", mixed=True)
+    general("n100t4", 100, "sdcz", app_threads=4)
     # gemm only, for the mixed-datatype run (the other operations have no mixed-datatype variants)
     l3 = (OUT / "input.operations.l3").read_text().splitlines()
     keep, in_l3 = [], False
