@@ -220,6 +220,13 @@ extern "C" void b200_finalize( void )
 	}
 	cudaStreamDestroy( c.stream ); cudaStreamDestroy( c.copy_stream ); cudaStreamDestroy( c.d2h_stream );
 	c.stream = c.copy_stream = c.d2h_stream = nullptr;
+	for ( int i = 0; i < Context::kBatchStreams; ++i )
+	{
+		if ( c.batch_streams[i] ) { cudaStreamDestroy( c.batch_streams[i] ); c.batch_streams[i] = nullptr; }
+		if ( c.batch_join[i] )    { cudaEventDestroy( c.batch_join[i] );     c.batch_join[i] = nullptr; }
+	}
+	if ( c.batch_fork ) { cudaEventDestroy( c.batch_fork ); c.batch_fork = nullptr; }
+	if ( c.sched_counters ) { cudaFree( c.sched_counters ); c.sched_counters = nullptr; }
 	c.ready = false;
 }
 
@@ -245,8 +252,8 @@ extern "C" int b200_device_count( void )
 
 extern "C" const char* b200_info( void )
 {
-	return "blis_b200 0.1 (sm_100a; d/z: DMMA.8x8x4 tiles, s/c: FFMA register tiles; "
-	       "cp.async multi-stage staging; persistent tile scheduler)";
+	return "blis_b200 0.1 (sm_100a; d/z: DMMA.8x8x4 tiles, s/c: FFMA2 register tiles; "
+	       "TMA (cp.async for unaligned views) multi-stage staging; persistent dynamic tile scheduler)";
 }
 
 extern "C" void b200_set_stream( void* stream )

@@ -31,7 +31,7 @@ int fail( const char* fmt, ... );
 // ---- context --------------------------------------------------------------------
 struct Context
 {
-	bool         ready   = false;
+	std::atomic<bool> ready{false};        // set last by do_init (release), read by every entry point (acquire)
 	int          device  = -1;
 	int          num_sms = kNumSMs;
 	cudaStream_t stream  = nullptr;       // engine-owned default stream
