@@ -325,29 +325,23 @@ def main():
                    "how": "bli_dgemm on pinned host operands: H2D of A,B,C + kernel + D2H of C per step, host wall clock"}
 
         # ---- e2e at N > 1: every rank keeps its shards (block-cyclic k panels of A and B, its block of C) in pinned HOST
-        # memory; a step uploads them, runs the distributed product and brings the C block home.  All ranks agree first
-        # that their pinned buffers exist, so that no rank can leave the others waiting inside a collective.
+        # memory; a step is DistGemm.step_host: shards uploaded in the order the k steps use them, C in column blocks under
+        # the first k step, finished column blocks of C read back under the last one (blis_b200/dist.py: summa_host).
+        # All ranks agree first that their pinned buffers exist, so that no rank can leave the others inside a collective.
         if not args.no_e2e and world > 1 and args.op == "dgemm" and args.workload == "headline":
             try:
-                hosts = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (job.a_loc, job.b_loc, job.c.t())]
-                ok = 1
+                hosts, ok = job.host_shards(), 1
             except Exception as exc:                                     # noqa: BLE001 (pinning can fail on a small host)
                 print(f"[rank {rank}] e2e skipped: {exc}", file=sys.stderr)
                 hosts, ok = None, 0
             flag = torch.tensor([ok], dtype=torch.int32, device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if int(flag.item()) == 1:
-                devs = (job.a_loc, job.b_loc, job.c.t())                # job.c is the transposed view of a dense tensor
-                for h, d in zip(hosts, devs):
-                    h.copy_(d)
                 h2d = sum(h.numel() * h.element_size() for h in hosts)
                 d2h = hosts[2].numel() * hosts[2].element_size()
 
                 def e2e_step():
-                    for h, d in zip(hosts, devs):
-                        d.copy_(h, non_blocking=True)
-                    job.step()
-                    hosts[2].copy_(devs[2], non_blocking=True)
+                    job.step_host(hosts)
                     torch.cuda.synchronize()                             # C is back in host memory
                 e2e_steps = max(2, min(args.steps, 3))
                 e2e_step()                                               # warm-up
@@ -362,8 +356,9 @@ def main():
                 dt = float(tmax[0].item())
                 e2e = {"value": total_flops / dt / 1e9, "unit": "GFLOPS", "h2d_bytes_per_step": int(tt[1].item()),
                        "d2h_bytes_per_step": int(tt[2].item()), "ms_per_step": dt * 1e3,
-                       "how": "every rank uploads its pinned host shards of A, B and C, runs the distributed dgemm step and reads "
-                              "its C block back; host wall clock between barriers, max over ranks; bytes summed over ranks"}
+                       "how": "DistGemm.step_host: every rank's shards of A, B and C live in pinned host memory; H2D in k-step order, "
+                              "C in column blocks under the first k step, C blocks read back under the last; host wall clock "
+                              "between barriers, max over ranks; bytes summed over ranks"}
 
     cpu = None
     if rank == 0 and not args.no_cpu and world == 1:

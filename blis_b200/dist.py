@@ -150,6 +150,91 @@ def summa(plan: SummaPlan, ex: PanelExchange, gemm_panel, n_steps=None, gemm_ste
               " ".join(f"({e[0].elapsed_time(e[1]):.1f},{e[1].elapsed_time(e[2]):.1f})" for e in trace), flush=True)
 
 
+class _NoStream:
+    """Stand-in for CUDA streams/events on CPU tensors (tests/test_dist_cpu.py): everything is already ordered."""
+    def wait_stream(self, other): pass
+    def wait_event(self, ev): pass
+    def record_event(self): return None
+    def __enter__(self): return self
+    def __exit__(self, *exc): return False
+
+
+class _CudaStream:
+    """The three operations summa_host needs from a stream, on a torch.cuda stream."""
+    def __init__(self, stream): self.s = stream
+    def wait_stream(self, other): self.s.wait_stream(other.s)
+    def wait_event(self, ev): self.s.wait_event(ev)
+
+    def record_event(self):
+        ev = torch.cuda.Event(); ev.record(self.s); return ev
+
+    def __enter__(self):
+        self._ctx = torch.cuda.stream(self.s); self._ctx.__enter__(); return self
+
+    def __exit__(self, *exc): return self._ctx.__exit__(*exc)
+
+
+def col_blocks(n_loc: int, nblk: int, bf: int = 128):
+    """Column blocks of the local C block, split as bli_thread_range_sub does (multiples of bf, edge on the last)."""
+    out = [partition.thread_range_sub(j, nblk, n_loc, bf) for j in range(nblk)]
+    return [(j0, j1) for j0, j1 in out if j1 > j0]
+
+
+def summa_host(plan: SummaPlan, ex: PanelExchange, hosts, c_dense: torch.Tensor, gemm_cols, cur, s_in, s_out, nblk: int = 4,
+               bf: int = 128):
+    """One distributed product whose shards live in (pinned) HOST memory: the host-pointer path of the multi-GPU gemm.
+
+    hosts = (a_h, b_h, c_h): host images of ex.a_loc [na, kb, m_loc], ex.b_loc [nb, n_loc, kb] and of the dense
+    [n_loc, m_loc] tensor behind the rank's column-major C block (row j of it = column j of C).
+    gemm_cols(first, a_ts, b_ts, j0, j1) accumulates the step's panels into columns [j0, j1) of C.
+    Pipeline (cur = compute stream, s_in = H2D stream, s_out = D2H stream):
+      * s_in uploads the shards in the order the k steps use them; the all-gather of step s is ordered behind upload s;
+      * the host C arrives in column blocks right behind the first step's shards, and the FIRST k step runs block by
+        block, each launch waiting only for its block of C;
+      * the LAST k step runs block by block as well, and every finished block goes home on s_out under the next one.
+    Exposed transfer: the first step's shards + one block of C in, one block of C out."""
+    a_h, b_h, c_h = hosts
+    p, steps = plan, plan.steps
+    blocks = col_blocks(p.n_loc, nblk, bf)
+    s_in.wait_stream(cur)                       # the previous product has finished with the device shards
+    s_out.wait_stream(cur)
+    ev_up, ev_c = [], []
+    with s_in:
+        for s in range(steps):
+            ex.a_loc[s * ex.qa:(s + 1) * ex.qa].copy_(a_h[s * ex.qa:(s + 1) * ex.qa], non_blocking=True)
+            ex.b_loc[s * ex.qb:(s + 1) * ex.qb].copy_(b_h[s * ex.qb:(s + 1) * ex.qb], non_blocking=True)
+            ev_up.append(s_in.record_event())
+            if s == 0:
+                for j0, j1 in blocks:
+                    c_dense[j0:j1].copy_(c_h[j0:j1], non_blocking=True)
+                    ev_c.append(s_in.record_event())
+    works = {}
+
+    def start(s):
+        cur.wait_event(ev_up[s])
+        works[s] = ex.start(s)
+    start(0)
+    if steps > 1:
+        start(1)
+    for s in range(steps):
+        for w in works.pop(s):
+            w.wait()
+        ps = list(ex.panels(s))
+        a_ts, b_ts = [q[1] for q in ps], [q[2] for q in ps]
+        last = s == steps - 1
+        for jb, (j0, j1) in enumerate(blocks if (s == 0 or last) else [(0, p.n_loc)]):
+            if s == 0:
+                cur.wait_event(ev_c[jb])
+            gemm_cols(s == 0, a_ts, b_ts, j0, j1)
+            if last:
+                s_out.wait_event(cur.record_event())
+                with s_out:
+                    c_h[j0:j1].copy_(c_dense[j0:j1], non_blocking=True)
+        if s + 2 < steps:
+            start(s + 2)
+    cur.wait_stream(s_out)                      # whoever synchronises `cur` has C at home
+
+
 class DistGemm:
     """C := beta*C + alpha*A*B on a Pr x Pc grid of GPUs; every rank holds its block of C and its
     block-cyclic k-panels of A's row panel / B's column panel (synthetic data generated in place)."""
@@ -191,6 +276,32 @@ class DistGemm:
 
     def step(self):
         summa(self.plan, self.ex, self._panel, gemm_step=self._step_panels)
+
+    # ---- shards in pinned host memory ------------------------------------------------------------------------------
+    def host_shards(self):
+        """Pinned host images of this rank's shards (A panels, B panels, dense tensor behind the C block), filled from
+        the device."""
+        hosts = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in (self.a_loc, self.b_loc, self.c.t())]
+        for h, d in zip(hosts, (self.a_loc, self.b_loc, self.c.t())):
+            h.copy_(d)
+        return hosts
+
+    def _cols(self, first, a_ts, b_ts, j0, j1):
+        """The step's panels accumulated into columns [j0, j1) of C_ij: one launch per 8 panels."""
+        p = self.plan
+        c_blk = self.c[:, j0:j1]                             # column-major m_loc x w view
+        b_blk = [b[j0:j1] for b in b_ts]                     # [w, kb] rows of a panel == column-major kb x w
+        for lo in range(0, len(a_ts), 8):
+            self.api.bli_gemm_kpanels(torch.float64, 0, 0, p.m_loc, j1 - j0, p.kb, self.alpha, a_ts[lo:lo + 8], 1, p.m_loc,
+                                      b_blk[lo:lo + 8], 1, p.kb, self.beta if (first and lo == 0) else 1.0, c_blk, 1, p.m_loc)
+
+    def step_host(self, hosts, nblk: int = 4):
+        """One product with the shards in pinned host memory (summa_host); returns with the work queued: synchronise the
+        current stream (or the device) to have the C block back in hosts[2]."""
+        if not hasattr(self, "_s_in"):
+            self._s_in, self._s_out = torch.cuda.Stream(self.c.device), torch.cuda.Stream(self.c.device)
+        cur = _CudaStream(torch.cuda.current_stream(self.c.device))
+        summa_host(self.plan, self.ex, hosts, self.c.t(), self._cols, cur, _CudaStream(self._s_in), _CudaStream(self._s_out), nblk)
 
 
 class WeakScalingGemm(DistGemm):

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from blis_b200 import partition
-from blis_b200.dist import PanelExchange, SummaPlan, summa, trsm_column_block
+from blis_b200.dist import PanelExchange, SummaPlan, _NoStream, col_blocks, summa, summa_host, trsm_column_block
 
 
 def _free_port():
@@ -50,6 +50,60 @@ def _worker(rank, world, port, M, N, K, kb, q):
         q.put((rank, repr(e), -1, None))
     finally:
         dist.destroy_process_group()
+
+
+def _worker_host(rank, world, port, M, N, K, kb, q):
+    """summa_host: shards start in 'host' tensors, the device shards are poisoned, C must come home complete."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p = SummaPlan(world, rank, M, N, K, kb)
+        A, B, C = _global(M, N, K)
+        Ai, Bj = A[p.m0:p.m1], B[:, p.n0:p.n1]
+        a_h = torch.stack([Ai[:, t * kb:(t + 1) * kb].t().contiguous() for t in p.a_panels()])
+        b_h = torch.stack([Bj[t * kb:(t + 1) * kb].t().contiguous() for t in p.b_panels()])
+        c_h = C[p.m0:p.m1, p.n0:p.n1].t().contiguous()                                  # dense [n_loc, m_loc]
+        a_loc, b_loc, c_dense = (torch.full_like(x, float("nan")) for x in (a_h, b_h, c_h))
+        ex = PanelExchange(p, a_loc, b_loc)
+        calls = []
+
+        def gemm_cols(first, a_ts, b_ts, j0, j1):
+            acc = sum(b_t[j0:j1] @ a_t for a_t, b_t in zip(a_ts, b_ts))                    # (A_t B_t)^T restricted to the block
+            c_dense[j0:j1] = (1.2 * c_dense[j0:j1] if first else c_dense[j0:j1]) + 2.0 * acc
+            calls.append((first, j0, j1))
+        ns = _NoStream()
+        for _ in range(2):                                                               # twice: C is re-read from the host image
+            c_h.copy_(C[p.m0:p.m1, p.n0:p.n1].t())
+            summa_host(p, ex, (a_h, b_h, c_h), c_dense, gemm_cols, ns, ns, ns, nblk=3, bf=2)
+        want = 1.2 * C[p.m0:p.m1, p.n0:p.n1] + 2.0 * (Ai @ Bj)
+        q.put((rank, float((c_h.t() - want).abs().max()), calls, p.steps, col_blocks(p.n_loc, 3, 2)))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, repr(e), None, None, None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("K", [64, 16])          # 4 k steps; 1 k step (first == last)
+def test_summa_host_shards_two_ranks_gloo(K):
+    world, M, N, kb = 2, 48, 20, 8
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_host, args=(r, world, port, M, N, K, kb, q)) for r in range(world)]
+    for p in procs: p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs: p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, err, calls, steps, blocks in res:
+        assert not isinstance(err, str), err
+        assert err < 1e-12, (rank, err)
+        assert len(blocks) > 1 and blocks[0][0] == 0
+        per = calls[:len(calls) // 2]
+        # first and last k step run block by block, the others as one launch over all columns
+        want_calls = [(True, *b) for b in blocks]
+        if steps > 1:
+            want_calls += [(False, 0, blocks[-1][1])] * (steps - 2) + [(False, *b) for b in blocks]
+        assert per == want_calls, (per, want_calls)
 
 
 def test_summa_two_ranks_gloo():
