@@ -181,14 +181,17 @@ def col_blocks(n_loc: int, nblk: int, bf: int = 128):
 
 
 def summa_host(plan: SummaPlan, ex: PanelExchange, hosts, c_dense: torch.Tensor, gemm_cols, cur, s_in, s_out, nblk: int = 4,
-               bf: int = 128):
+               bf: int = 128, s_nc=None):
     """One distributed product whose shards live in (pinned) HOST memory: the host-pointer path of the multi-GPU gemm.
 
     hosts = (a_h, b_h, c_h): host images of ex.a_loc [na, kb, m_loc], ex.b_loc [nb, n_loc, kb] and of the dense
     [n_loc, m_loc] tensor behind the rank's column-major C block (row j of it = column j of C).
     gemm_cols(first, a_ts, b_ts, j0, j1) accumulates the step's panels into columns [j0, j1) of C.
-    Pipeline (cur = compute stream, s_in = H2D stream, s_out = D2H stream):
-      * s_in uploads the shards in the order the k steps use them; the all-gather of step s is ordered behind upload s;
+    Pipeline (cur = compute stream, s_in = H2D stream, s_out = D2H stream, s_nc = the stream the all-gathers are issued
+    from; cur if None):
+      * s_in uploads the shards in the order the k steps use them; the all-gather of step s is ordered behind upload s
+        -- on s_nc, not on cur: a wait for upload s+1 queued on the compute stream ahead of step s's kernels would hold
+        them back until the whole of C (which travels between the two uploads) has arrived (measured: 70 ms);
       * the host C arrives in column blocks right behind the first step's shards, and the FIRST k step runs block by
         block, each launch waiting only for its block of C;
       * the LAST k step runs block by block as well, and every finished block goes home on s_out under the next one.
@@ -209,10 +212,17 @@ def summa_host(plan: SummaPlan, ex: PanelExchange, hosts, c_dense: torch.Tensor,
                     c_dense[j0:j1].copy_(c_h[j0:j1], non_blocking=True)
                     ev_c.append(s_in.record_event())
     works = {}
+    if s_nc is None:
+        s_nc = cur
+    else:
+        s_nc.wait_stream(cur)
 
-    def start(s):
-        cur.wait_event(ev_up[s])
-        works[s] = ex.start(s)
+    def start(s, buffer_free=None):
+        with s_nc:
+            s_nc.wait_event(ev_up[s])
+            if buffer_free is not None:
+                s_nc.wait_event(buffer_free)     # the kernels that read gather buffer s % 2 have finished
+            works[s] = ex.start(s)
     start(0)
     if steps > 1:
         start(1)
@@ -231,7 +241,7 @@ def summa_host(plan: SummaPlan, ex: PanelExchange, hosts, c_dense: torch.Tensor,
                 with s_out:
                     c_h[j0:j1].copy_(c_dense[j0:j1], non_blocking=True)
         if s + 2 < steps:
-            start(s + 2)
+            start(s + 2, cur.record_event())
     cur.wait_stream(s_out)                      # whoever synchronises `cur` has C at home
 
 
@@ -299,9 +309,10 @@ class DistGemm:
         """One product with the shards in pinned host memory (summa_host); returns with the work queued: synchronise the
         current stream (or the device) to have the C block back in hosts[2]."""
         if not hasattr(self, "_s_in"):
-            self._s_in, self._s_out = torch.cuda.Stream(self.c.device), torch.cuda.Stream(self.c.device)
+            self._s_in, self._s_out, self._s_nc = (torch.cuda.Stream(self.c.device) for _ in range(3))
         cur = _CudaStream(torch.cuda.current_stream(self.c.device))
-        summa_host(self.plan, self.ex, hosts, self.c.t(), self._cols, cur, _CudaStream(self._s_in), _CudaStream(self._s_out), nblk)
+        summa_host(self.plan, self.ex, hosts, self.c.t(), self._cols, cur, _CudaStream(self._s_in), _CudaStream(self._s_out), nblk,
+                   s_nc=_CudaStream(self._s_nc))
 
 
 class WeakScalingGemm(DistGemm):

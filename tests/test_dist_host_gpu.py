@@ -1,5 +1,6 @@
-"""DistGemm.step_host (shards in pinned host memory) == DistGemm.step (device-resident shards), bit for bit, on one GPU
-with a one-rank process group; tests/dist_host_driver.py is the same check under torchrun at any world size."""
+"""DistGemm.step_host (shards in pinned host memory) == DistGemm.step (device-resident shards) to 1e-14 absolute on O(1)
+data (one ulp of epilogue rounding when another tile shape is selected for the column blocks), on one GPU with a one-rank
+process group; tests/dist_host_driver.py is the same check under torchrun at any world size."""
 import json
 import os
 import socket
@@ -22,4 +23,4 @@ def test_step_host_matches_device_resident_step():
     assert out["4steps_steps"] >= 4 and out["1step_steps"] >= 1
     for tag in ("4steps", "1step"):
         for rep in range(2):
-            assert out[f"{tag}_rep{rep}_bit_exact"], out
+            assert out[f"{tag}_rep{rep}_maxdiff"] <= 1e-14, out
