@@ -83,7 +83,7 @@ def _worker_host(rank, world, port, M, N, K, kb, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("K", [64, 16])          # 4 k steps; 1 k step (first == last)
+@pytest.mark.parametrize("K", [64, 32, 16])      # 4 k steps; 2 (first, last: the N=8 bench shape); 1 (first == last)
 def test_summa_host_shards_two_ranks_gloo(K):
     world, M, N, kb = 2, 48, 20, 8
     ctx = mp.get_context("spawn")
