@@ -136,11 +136,12 @@ static void gather_elems( char* dst, const char* src, int64_t m, int64_t j0, int
 		}
 }
 
-// dense column-major device (ld = m)  <->  host (rs, cs)
+// column-major device block (leading dimension ldd >= m elements)  <->  host (rs, cs)
 static int stage_xfer( void* dev, void* host, int64_t m, int64_t n, int64_t rs, int64_t cs, size_t es,
-                       cudaStream_t st, bool to_host )
+                       cudaStream_t st, bool to_host, int64_t ldd = 0 )
 {
 	if ( m <= 0 || n <= 0 ) return kSuccess;
+	if ( ldd <= 0 ) ldd = m;
 	Context& c = ctx();
 	const MemKind kind = classify( host );
 	// Dense device image is column-major m x n.  If the host matrix is
@@ -149,8 +150,8 @@ static int stage_xfer( void* dev, void* host, int64_t m, int64_t n, int64_t rs, 
 	const bool row_lines = ( !col_lines && cs == 1 );
 	if ( kind == MemKind::HostPinned && col_lines )
 	{
-		if ( !to_host ) B200_CUDA( cudaMemcpy2DAsync( dev, m * es, host, cs * es, m * es, n, cudaMemcpyHostToDevice, st ) );
-		else            B200_CUDA( cudaMemcpy2DAsync( host, cs * es, dev, m * es, m * es, n, cudaMemcpyDeviceToHost, st ) );
+		if ( !to_host ) B200_CUDA( cudaMemcpy2DAsync( dev, ldd * es, host, cs * es, m * es, n, cudaMemcpyHostToDevice, st ) );
+		else            B200_CUDA( cudaMemcpy2DAsync( host, cs * es, dev, ldd * es, m * es, n, cudaMemcpyDeviceToHost, st ) );
 		return kSuccess;
 	}
 	(void)row_lines;
@@ -167,18 +168,21 @@ static int stage_xfer( void* dev, void* host, int64_t m, int64_t n, int64_t rs, 
 	{
 		const int64_t j1 = std::min( n, j0 + cols_per );
 		char* pin = (char*)c.stage[buf];
-		char* d   = (char*)dev + (size_t)j0 * colb;
+		char* d   = (char*)dev + (size_t)j0 * (size_t)ldd * es;
+		const size_t dpitch = (size_t)ldd * es;        // == colb for a dense image
 		B200_CUDA( cudaEventSynchronize( c.stage_free[buf] ) );
 		if ( !to_host )
 		{
 			if ( col_lines ) copy_lines( pin, colb, (const char*)host + (size_t)j0 * cs * es, (size_t)cs * es, colb, (size_t)( j1 - j0 ) );
 			else             gather_elems( pin, (const char*)host, m, j0, j1, rs, cs, es, false );
-			B200_CUDA( cudaMemcpyAsync( d, pin, colb * ( j1 - j0 ), cudaMemcpyHostToDevice, st ) );
+			if ( dpitch == colb ) B200_CUDA( cudaMemcpyAsync( d, pin, colb * ( j1 - j0 ), cudaMemcpyHostToDevice, st ) );
+			else                  B200_CUDA( cudaMemcpy2DAsync( d, dpitch, pin, colb, colb, (size_t)( j1 - j0 ), cudaMemcpyHostToDevice, st ) );
 			B200_CUDA( cudaEventRecord( c.stage_free[buf], st ) );
 		}
 		else
 		{
-			B200_CUDA( cudaMemcpyAsync( pin, d, colb * ( j1 - j0 ), cudaMemcpyDeviceToHost, st ) );
+			if ( dpitch == colb ) B200_CUDA( cudaMemcpyAsync( pin, d, colb * ( j1 - j0 ), cudaMemcpyDeviceToHost, st ) );
+			else                  B200_CUDA( cudaMemcpy2DAsync( pin, colb, d, dpitch, colb, (size_t)( j1 - j0 ), cudaMemcpyDeviceToHost, st ) );
 			B200_CUDA( cudaStreamSynchronize( st ) );
 			if ( col_lines ) copy_lines( (char*)host + (size_t)j0 * cs * es, (size_t)cs * es, pin, colb, colb, (size_t)( j1 - j0 ) );
 			else             gather_elems( (char*)host, pin, m, j0, j1, rs, cs, es, true );
@@ -194,6 +198,25 @@ int stage_to_device( void* dst, const void* src, int64_t m, int64_t n, int64_t r
 int stage_to_host( void* dst, int64_t rs, int64_t cs, const void* src, int64_t m, int64_t n, size_t es, cudaStream_t st )
 {
 	return stage_xfer( const_cast<void*>( src ), dst, m, n, rs, cs, es, st, true );
+}
+
+// Only the stored triangle of a host-resident triangular matrix travels (the reference's packm never reads the other one
+// either: bli_packm_struc_cxk.c:155-301).  The matrix is cut into column panels and each panel into the rows the
+// triangle reaches there -- [p0, m) for a lower, [0, p1) for an upper triangle --, so (np + 1) / (2 np) of the square
+// moves: 53 % with 16 panels.  The rest of the device image stays uninitialised; the kernels never read it.
+int stage_tri_to_device( void* dst, const void* src, int64_t m, int64_t rs, int64_t cs, bool upper, size_t es, cudaStream_t st )
+{
+	if ( m < 2048 ) return stage_xfer( dst, const_cast<void*>( src ), m, m, rs, cs, es, st, false );
+	const int64_t pw = ( ( m + 15 ) / 16 + 63 ) / 64 * 64;
+	for ( int64_t p0 = 0; p0 < m; p0 += pw )
+	{
+		const int64_t p1 = std::min( m, p0 + pw );
+		const int64_t r0 = upper ? 0 : p0, r1 = upper ? p1 : m;
+		const char* h = (const char*)src + ( r0 * rs + p0 * cs ) * (int64_t)es;
+		char*       d = (char*)dst + ( r0 + p0 * m ) * (int64_t)es;
+		if ( stage_xfer( d, const_cast<char*>( h ), r1 - r0, p1 - p0, rs, cs, es, st, false, m ) != kSuccess ) return kFailure;
+	}
+	return kSuccess;
 }
 
 } // namespace b200

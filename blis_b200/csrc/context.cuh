@@ -84,5 +84,8 @@ int stage_to_device( void* dst, const void* src, int64_t m, int64_t n, int64_t r
                      size_t es, cudaStream_t st );
 int stage_to_host( void* dst, int64_t rs, int64_t cs, const void* src, int64_t m, int64_t n,
                    size_t es, cudaStream_t st );
+// m x m triangular host matrix -> dense column-major device image (ld = m); only the stored triangle is transferred.
+int stage_tri_to_device( void* dst, const void* src, int64_t m, int64_t rs, int64_t cs, bool upper,
+                         size_t es, cudaStream_t st );
 
 } // namespace b200

@@ -123,7 +123,7 @@ static int trsm_front( int side, int uplo, int transa, int diag, int64_t m, int6
 		if ( rc == kSuccess && classify( a ) != MemKind::Device )
 		{
 			if ( dev_alloc( &da, (size_t)m * m * ES, st ) != kSuccess ) rc = kFailure;
-			else rc = stage_to_device( da, a, m, m, rs_a, cs_a, ES, st );
+			else rc = stage_tri_to_device( da, a, m, rs_a, cs_a, upper, ES, st );     // (rs_a, cs_a, upper): the effective view
 			a = (const T*)da; rs_a = 1; cs_a = m;
 		}
 		if ( rc == kSuccess )

@@ -122,6 +122,34 @@ def test_trsm_special_cases(engine, oracle):
     assert torch.equal(tb_, tb2)
 
 
+@pytest.mark.parametrize("pin", [False, True])
+def test_trsm_host_a_only_stored_triangle_travels(engine, oracle, pin):
+    """Host-resident A with m >= 2048: the engine uploads column panels cut at the diagonal (stage_tri_to_device), so the
+    other triangle -- NaN here -- neither travels nor is read; pageable and pinned, column- and row-stored, every
+    uplo/trans (the effective triangle flips with trans), a ragged last panel."""
+    m, n, seed = 2100, 72, 40
+    b0 = gen.matrix("d", m, n, 7, "frac", "c")
+    for oa in ("c", "r"):
+        for uplo in (LOWER, UPPER):
+            for tr in (NO_TRANSPOSE, TRANSPOSE):
+                seed += 1
+                a = gen.triangular("d", m, seed, "frac", oa)
+                gen.poison_unstored(a, uplo == LOWER)
+                want = b0.copy(order="K")
+                oracle.trsm(LEFT, uplo, tr, NONUNIT_DIAG, 2.0, a, want)
+                ta_, tb_ = to_torch(a, "cpu", pin=pin), to_torch(b0, "cpu", pin=pin)
+                engine.bli_dtrsm(LEFT, uplo, tr, NONUNIT_DIAG, m, n, 2.0, ta_, *estr(a), tb_, *estr(b0))
+                err = rel_err(to_numpy(tb_), want)
+                assert err <= 20 * TOL["d"], (oa, uplo, tr, pin, err)
+    # complex, conjugate-transposed, right side: A is n x n
+    a = gen.triangular("z", 2050, 77, "frac", "c"); gen.poison_unstored(a, False)
+    b = gen.matrix("z", 40, 2050, 78, "frac", "c")
+    want = b.copy(order="K"); oracle.trsm(RIGHT, UPPER, CONJ_TRANSPOSE, UNIT_DIAG, 2.0 + 0.3j, a, want)
+    ta_, tb_ = to_torch(a, "cpu", pin=pin), to_torch(b, "cpu", pin=pin)
+    engine.bli_ztrsm(RIGHT, UPPER, CONJ_TRANSPOSE, UNIT_DIAG, 40, 2050, 2.0 + 0.3j, ta_, *estr(a), tb_, *estr(b))
+    assert rel_err(to_numpy(tb_), want) <= 20 * TOL["z"]
+
+
 def test_trsm_full_size_testsuite_residual(engine):
     """BASELINE config #4: dtrsm left/lower/notrans/nonunit m=32768 n=8192.
     resid = || B t - alpha inv(A) (B0 t) ||  ==  || A (X t) - alpha B0 t || scaled, via a triangular
