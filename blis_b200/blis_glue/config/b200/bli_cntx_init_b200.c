@@ -13,9 +13,11 @@
        bli_family_b200.h raises BLIS_STACK_BUF_MAX_SIZE for the MR x NR tile.
        bli_info / bli_cntx queries therefore describe the GPU tiling truthfully.
      * the whole-operation gemm handler + thresholds (bli_b200_install).
-   The gemm/gemmtrsm microkernel slots keep the reference kernels: with the
-   handler installed no homogeneous gemm reaches them, and mixed-datatype gemm
-   (out of scope) still works on the CPU through them.
+   The gemm/gemmtrsm microkernel slots keep the reference kernels, which serve
+   only operations outside this engine's scope (level-1/2, 1m): with the
+   handler installed no homogeneous gemm reaches them, and mixed-datatype gemm,
+   trsm and the other level-3 operations are taken by the bli_*_ex_b200
+   overrides of the glue before any control tree is built.
 */
 #include "blis.h"
 #include "blis_b200.h"
