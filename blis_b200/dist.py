@@ -325,6 +325,79 @@ class WeakScalingGemm(DistGemm):
         assert (self.plan.pr, self.plan.pc) == (pr, pc)
 
 
+def trsm_host_blocks(solve_cols, b_dev: torch.Tensor, b_host: torch.Tensor, blocks, cur, s_in, s_out):
+    """X := alpha * inv(op(A)) * B for a column block of B that lives in (pinned) HOST memory.
+
+    Columns of B are independent in trsm -- the reference's only parallel trsm loops run over them
+    (frame/3/trsm/bli_trsm_cntl.c:446-451, bli_trsm_ll_ker_var2.c:209-212) -- so the block is cut into column sub-blocks:
+    sub-block j+1 travels to the device on s_in and sub-block j-1 travels home on s_out while sub-block j is solved on cur.
+    b_dev / b_host: the dense [n_loc, m] tensors behind the column-major m x n_loc block (row j = column j of B);
+    solve_cols(j0, j1) solves columns [j0, j1) in place on the device.  Exposed transfer: the first sub-block in, the last
+    one out."""
+    s_in.wait_stream(cur)
+    s_out.wait_stream(cur)
+    ev_in = []
+    with s_in:
+        for j0, j1 in blocks:
+            b_dev[j0:j1].copy_(b_host[j0:j1], non_blocking=True)
+            ev_in.append(s_in.record_event())
+    for jb, (j0, j1) in enumerate(blocks):
+        cur.wait_event(ev_in[jb])
+        solve_cols(j0, j1)
+        s_out.wait_event(cur.record_event())
+        with s_out:
+            b_host[j0:j1].copy_(b_dev[j0:j1], non_blocking=True)
+    cur.wait_stream(s_out)
+
+
+class DistTrsm:
+    """Left-side trsm on `world` GPUs: B (and X) split into column blocks by bli_thread_range_sub, the triangular A
+    replicated, no data-path collective.  Every rank holds A and its block of B (synthetic data generated in place)."""
+
+    def __init__(self, m: int, n: int, world: int, rank: int, device, alpha=2.0, uplo=0xC0, trans=0, diag=0, seed=0xB200):
+        from . import api
+        self.api, self.m, self.alpha, self.uplo, self.trans, self.diag = api, m, alpha, uplo, trans, diag
+        self.j0, self.j1 = trsm_column_block(rank, world, n)
+        self.n_loc = self.j1 - self.j0
+        g = torch.Generator(device=device); g.manual_seed(seed)
+        a = torch.rand(m, m, dtype=torch.float64, device=device, generator=g) * 2 - 1
+        a = a / float(a.abs().sum(dim=1).max()); a.diagonal().add_(2.0)     # testsuite: random, then diag += 2
+        self.a = a.t()                                                      # column-major m x m
+        g.manual_seed(seed + 1 + rank)
+        self.b0 = torch.rand(self.n_loc, m, dtype=torch.float64, device=device, generator=g) * 2 - 1   # dense image of B
+        self.b = self.b0.clone()
+        self.flops = 1.0 * m * m * self.n_loc
+        self.total_flops = 1.0 * m * m * n
+
+    def _solve_cols(self, j0, j1):
+        bv = self.b[j0:j1].t()                                # column-major m x w view
+        self.api.bli_dtrsm(0, self.uplo, self.trans, self.diag, self.m, j1 - j0, self.alpha, self.a, 1, self.m, bv, 1, self.m)
+
+    def step(self):
+        self.b.copy_(self.b0)
+        self._solve_cols(0, self.n_loc)
+
+    def host_block(self):
+        h = torch.empty(self.b0.shape, dtype=self.b0.dtype).pin_memory()
+        h.copy_(self.b0)
+        return h
+
+    def step_host(self, b_host, nblk: int | None = None):
+        """The rank's block of B lives in pinned host memory and X comes back to it (trsm_host_blocks); returns with the
+        work queued.  The diagonal-block solves are latency bound and do not get faster for fewer columns, so every
+        extra sub-block repeats their cost: measured on a B200 at m=8192, n=4096, four sub-blocks take 26.4 ms against
+        21.0 ms for upload -> solve -> download in sequence (11.6 ms device-resident; profiles/r01_dist_trsm_host_check.json).
+        Default: one block (sequential) unless the block is large enough for two halves to hide more transfer than the
+        second pass over the diagonal costs."""
+        if nblk is None:
+            nblk = 2 if (self.m >= 16384 and self.n_loc >= 4096) else 1
+        if not hasattr(self, "_s_in"):
+            self._s_in, self._s_out = torch.cuda.Stream(self.b.device), torch.cuda.Stream(self.b.device)
+        cur = _CudaStream(torch.cuda.current_stream(self.b.device))
+        trsm_host_blocks(self._solve_cols, self.b, b_host, col_blocks(self.n_loc, nblk), cur, _CudaStream(self._s_in),
+                         _CudaStream(self._s_out))
+
+
 def trsm_column_block(rank: int, world: int, n: int, nr: int = 128):
     """Columns [start, end) of B that `rank` solves (multi-GPU trsm: B split by column blocks)."""
     return partition.thread_range_sub(rank, world, n, nr)

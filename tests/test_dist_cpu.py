@@ -11,7 +11,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from blis_b200 import partition
-from blis_b200.dist import PanelExchange, SummaPlan, _NoStream, col_blocks, summa, summa_host, trsm_column_block
+from blis_b200.dist import (PanelExchange, SummaPlan, _NoStream, col_blocks, summa, summa_host, trsm_column_block,
+                            trsm_host_blocks)
 
 
 def _free_port():
@@ -152,3 +153,24 @@ def test_trsm_column_blocks_follow_thread_range():
         assert blocks[0][0] == 0 and blocks[-1][1] == n
         assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
         assert blocks == [partition.thread_range_sub(r, world, n, 128) for r in range(world)]
+
+
+def test_trsm_host_blocks_order_and_result():
+    """trsm_host_blocks on CPU tensors: every column sub-block is uploaded, solved once, and brought home."""
+    m, n_loc = 24, 20
+    g = torch.Generator(); g.manual_seed(7)
+    a = torch.tril(torch.rand(m, m, dtype=torch.float64, generator=g)) + 2.0 * torch.eye(m, dtype=torch.float64)
+    b_host = torch.rand(n_loc, m, dtype=torch.float64, generator=g)               # dense image: row j = column j of B
+    want = torch.linalg.solve_triangular(a, 2.0 * b_host.t(), upper=False).t()
+    b_dev = torch.full_like(b_host, float("nan"))
+    blocks = col_blocks(n_loc, 3, 4)
+    assert len(blocks) == 3 and blocks[0][0] == 0 and blocks[-1][1] == n_loc
+    calls = []
+
+    def solve_cols(j0, j1):
+        b_dev[j0:j1] = torch.linalg.solve_triangular(a, 2.0 * b_dev[j0:j1].t(), upper=False).t()
+        calls.append((j0, j1))
+    ns = _NoStream()
+    trsm_host_blocks(solve_cols, b_dev, b_host, blocks, ns, ns, ns)
+    assert calls == blocks
+    assert float((b_host - want).abs().max()) < 1e-12
