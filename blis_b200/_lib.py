@@ -27,7 +27,7 @@ EXPORTS = [
     "b200_trsm", "b200_strsm", "b200_dtrsm", "b200_ctrsm", "b200_ztrsm",
     "b200_gemmt", "b200_syrk", "b200_herk", "b200_syr2k", "b200_her2k",
     "b200_hemm", "b200_symm", "b200_trmm3", "b200_trmm", "b200_gemm_md", "b200_gemm_batch",
-    "b200_blksz", "b200_measure_peak", "b200_launch_count", "b200_set_option",
+    "b200_blksz", "b200_measure_peak", "b200_launch_count", "b200_set_option", "b200_last_kernel", "b200_kernel_stats",
 ]
 
 _lib = None
@@ -84,6 +84,8 @@ def load() -> C.CDLL:
     lib.b200_measure_peak.argtypes = [ci, ci]; lib.b200_measure_peak.restype = C.c_double
     lib.b200_launch_count.argtypes = []; lib.b200_launch_count.restype = C.c_ulonglong
     lib.b200_set_option.argtypes = [C.c_char_p, C.c_longlong]; lib.b200_set_option.restype = ci
+    lib.b200_last_kernel.argtypes = []; lib.b200_last_kernel.restype = C.c_char_p
+    lib.b200_kernel_stats.argtypes = [C.c_char_p, C.c_size_t, ci]; lib.b200_kernel_stats.restype = C.c_size_t
     _lib = lib
     return lib
 

@@ -371,5 +371,24 @@ def launch_count() -> int:
     return int(_lib.load().b200_launch_count())
 
 
+def last_kernel() -> str:
+    """Name of the last kernel this thread launched through the engine."""
+    return _lib.load().b200_last_kernel().decode()
+
+
+def kernel_stats(reset: bool = False) -> dict:
+    """{kernel name: launches} since the last reset."""
+    lib = _lib.load()
+    n = int(lib.b200_kernel_stats(None, 0, 0))
+    buf = C.create_string_buffer(n + 1)
+    lib.b200_kernel_stats(buf, n + 1, 1 if reset else 0)
+    out = {}
+    for ln in buf.value.decode().splitlines():
+        k, _, v = ln.rpartition("\t")
+        if k:
+            out[k] = int(v)
+    return out
+
+
 def sync() -> None:
     check(_lib.load().b200_sync(), "b200_sync")

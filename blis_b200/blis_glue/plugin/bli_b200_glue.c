@@ -278,13 +278,20 @@ static void bli_b200_struc_mm( int op, side_t side, const obj_t* alpha, const ob
 	obj_t al, be; bli_b200_scalar( dt, alpha, &al ); bli_b200_scalar( dt, beta, &be );
 	err_t r;
 	if ( op == 0 || op == 1 )
+	{
+		/* A transposition bit on the structured operand (object API only): A^T == conj(A) for a Hermitian A and
+		   A^T == A for a symmetric one, which is how the reference's packm resolves it
+		   (frame/1m/packm/bli_packm_struc_cxk.c:146-301 reads the stored triangle through the toggled strides). */
+		conj_t conja = bli_obj_conj_status( a );
+		if ( op == 0 && bli_obj_has_trans( a ) ) conja = ( conja == BLIS_CONJUGATE ? BLIS_NO_CONJUGATE : BLIS_CONJUGATE );
 		r = ( op == 0 ? b200_hemm : b200_symm )( ( int )dt, ( int )side, ( int )bli_obj_uplo( a ),
-		  ( int )bli_obj_conj_status( a ), ( int )bli_obj_conjtrans_status( b ),
+		  ( int )conja, ( int )bli_obj_conjtrans_status( b ),
 		  bli_obj_length( c ), bli_obj_width( c ), bli_obj_buffer_for_1x1( dt, &al ),
 		  bli_obj_buffer_at_off( a ), bli_obj_row_stride( a ), bli_obj_col_stride( a ),
 		  bli_obj_buffer_at_off( b ), bli_obj_row_stride( b ), bli_obj_col_stride( b ),
 		  bli_obj_buffer_for_1x1( dt, &be ),
 		  bli_obj_buffer_at_off( c ), bli_obj_row_stride( c ), bli_obj_col_stride( c ) );
+	}
 	else
 		r = b200_trmm3( ( int )dt, ( int )side, ( int )bli_obj_uplo( a ), ( int )bli_obj_conjtrans_status( a ),
 		  ( int )bli_obj_diag( a ), ( int )bli_obj_conjtrans_status( b ),

@@ -2,7 +2,10 @@
 #include "context.cuh"
 #include "../../include/blis_b200.h"
 #include <algorithm>
+#include <map>
+#include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 namespace b200 {
@@ -21,6 +24,42 @@ int fail( const char* fmt, ... )
 
 Context& ctx() { static Context c; return c; }
 static std::mutex g_init_mu;
+
+// ---- launch bookkeeping ---------------------------------------------------------------------
+static thread_local const char* t_last_kernel = "";
+static std::mutex g_stats_mu;
+static std::map<std::string, unsigned long long> g_kernel_stats;
+
+void note_launch( const char* name )
+{
+	ctx().launches++;
+	t_last_kernel = name;
+	std::lock_guard<std::mutex> lk( g_stats_mu );
+	g_kernel_stats[name]++;
+}
+
+// ---- tile-scheduler counters ------------------------------------------------------------------
+// Every launch of a persistent gemm kernel draws its tiles from a {next tile, finished CTAs} pair that the last CTA
+// re-arms (gemm_dmma_ws.cuh).  Two kernels running at the same time must never share a pair, so pairs are owned by
+// STREAMS: kernels of one stream execute one after the other (the engine does not use programmatic dependent launch),
+// and different streams -- the caller's threads (b200_set_stream), the 8-stream batch pool -- get different pairs.
+// A stream handle that is destroyed and reused simply inherits the (re-armed) pair.
+static std::mutex g_sched_mu;
+static std::unordered_map<cudaStream_t, int> g_sched_of_stream;
+
+int* sched_slot( cudaStream_t st )
+{
+	Context& c = ctx();
+	if ( !c.dynamic_tiles || !c.sched_counters ) return nullptr;
+	std::lock_guard<std::mutex> lk( g_sched_mu );
+	auto it = g_sched_of_stream.find( st );
+	if ( it == g_sched_of_stream.end() )
+	{
+		if ( (int)g_sched_of_stream.size() >= Context::kSchedSlots ) return nullptr;      // static schedule from here on
+		it = g_sched_of_stream.emplace( st, (int)g_sched_of_stream.size() ).first;
+	}
+	return c.sched_counters + 2 * it->second;
+}
 
 static int do_init( int device )
 {
@@ -54,16 +93,27 @@ static int do_init( int device )
 		uint64_t thresh = UINT64_MAX;
 		cudaMemPoolSetAttribute( pool, cudaMemPoolAttrReleaseThreshold, &thresh );
 	}
-	B200_CUDA( cudaMalloc( (void**)&c.sched_counters, 128 * sizeof(int) ) );
-	B200_CUDA( cudaMemset( c.sched_counters, 0, 128 * sizeof(int) ) );
+	B200_CUDA( cudaMalloc( (void**)&c.sched_counters, 2 * Context::kSchedSlots * sizeof(int) ) );
+	B200_CUDA( cudaMemset( c.sched_counters, 0, 2 * Context::kSchedSlots * sizeof(int) ) );
+	{ std::lock_guard<std::mutex> lk2( g_sched_mu ); g_sched_of_stream.clear(); }
 	c.ready = true;
 	return kSuccess;
 }
 
 int ensure_init()
 {
-	if ( ctx().ready ) return kSuccess;
-	return do_init( -1 );
+	if ( !ctx().ready && do_init( -1 ) != kSuccess ) return kFailure;
+	// every calling thread must have the engine's device current: streams, events and the workspace pool belong to it
+	// (a fresh host thread starts on device 0)
+	static thread_local int t_device = -1;
+	const int dev = ctx().device;
+	if ( t_device != dev )
+	{
+		int cur = -1;
+		if ( cudaGetDevice( &cur ) != cudaSuccess || cur != dev ) B200_CUDA( cudaSetDevice( dev ) );
+		t_device = dev;
+	}
+	return kSuccess;
 }
 
 cudaStream_t cur_stream()
@@ -148,8 +198,16 @@ static int stage_xfer( void* dev, void* host, int64_t m, int64_t n, int64_t rs, 
 	// row-stored (cs == 1) we view the transposed problem: lines are rows.
 	const bool col_lines = ( rs == 1 );
 	const bool row_lines = ( !col_lines && cs == 1 );
-	if ( kind == MemKind::HostPinned && col_lines )
+	// the direct 2-D copy needs a pitch that covers the line (BLIS also allows m x 1 operands with cs < m and negative
+	// strides: those take the ring / gather path below)
+	if ( kind == MemKind::HostPinned && col_lines && ( cs >= m || n == 1 ) )
 	{
+		if ( n == 1 )
+		{
+			if ( !to_host ) B200_CUDA( cudaMemcpyAsync( dev, host, m * es, cudaMemcpyHostToDevice, st ) );
+			else            B200_CUDA( cudaMemcpyAsync( host, dev, m * es, cudaMemcpyDeviceToHost, st ) );
+			return kSuccess;
+		}
 		if ( !to_host ) B200_CUDA( cudaMemcpy2DAsync( dev, ldd * es, host, cs * es, m * es, n, cudaMemcpyHostToDevice, st ) );
 		else            B200_CUDA( cudaMemcpy2DAsync( host, cs * es, dev, ldd * es, m * es, n, cudaMemcpyDeviceToHost, st ) );
 		return kSuccess;
@@ -254,6 +312,18 @@ extern "C" void b200_finalize( void )
 }
 
 extern "C" const char* b200_last_error( void ) { return g_err; }
+
+extern "C" const char* b200_last_kernel( void ) { return t_last_kernel; }
+
+extern "C" size_t b200_kernel_stats( char* buf, size_t len, int reset )
+{
+	std::lock_guard<std::mutex> lk( g_stats_mu );
+	std::string out;
+	for ( const auto& kv : g_kernel_stats ) { out += kv.first; out += '\t'; out += std::to_string( kv.second ); out += '\n'; }
+	if ( buf && len ) { const size_t nb = std::min( len - 1, out.size() ); memcpy( buf, out.data(), nb ); buf[nb] = 0; }
+	if ( reset ) g_kernel_stats.clear();
+	return out.size();
+}
 
 // BLIS_MALLOC_USER / BLIS_FREE_USER hooks of config/b200 (bli_family_b200.h):
 // page-locked host memory for matrices created by bli_obj_create().

@@ -54,8 +54,10 @@ struct Context
 	int          cgemm_cfg = -1;         // auto: TMA + FFMA2 kernel when aligned, cp.async ws kernel otherwise
 	int          trsm_nb   = 0;           // 0 = default
 	int          grid_mult = 1;           // persistent CTAs per SM
-	int*         sched_counters = nullptr;   // 64 self-resetting {tile, done} pairs for dynamic tile scheduling
-	std::atomic<unsigned> sched_next{0};
+	// dynamic tile scheduling: self re-arming {tile, done} pairs, ONE PAIR PER STREAM (kernels of one stream run one
+	// after the other, so a stream's pair is never shared by two running kernels; see sched_slot)
+	static constexpr int kSchedSlots = 2048;
+	int*         sched_counters = nullptr;
 	int          dynamic_tiles = 1;
 	int          raster_group = 8;      // tile rows per raster group: the ~148 running tiles form a raster_group x 148/raster_group block
 	int          tma_l2_promotion = 2;  // CUtensorMapL2promotion: 0 none, 1 64 B, 2 128 B, 3 256 B
@@ -67,7 +69,12 @@ struct Context
 };
 
 Context& ctx();
-int ensure_init();                         // lazy init; returns kSuccess/kFailure
+int ensure_init();                         // lazy init + cudaSetDevice(engine device) for the calling thread; kSuccess/kFailure
+// Counts one kernel launch and records its name (per-thread "last kernel" and a per-name histogram: b200_last_kernel,
+// b200_kernel_stats).  `name` must have static storage duration.
+void note_launch( const char* name );
+// The {tile, done} counter pair dynamic tile scheduling uses on stream `st` (nullptr: none left -> static schedule).
+int* sched_slot( cudaStream_t st );
 cudaStream_t cur_stream();                 // thread's selected stream or the engine's
 
 // ---- pointer classification ------------------------------------------------------

@@ -8,9 +8,10 @@ template <>
 int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, cudaStream_t st )
 {
 	Context& c = ctx();
-	auto tiles = [&]( int bp, int bq ) {
+	// grid = min( tiles, SMs x resident CTAs per SM ); `per_sm` = 2 for the kernels with one consumer warpgroup
+	auto tiles = [&]( int bp, int bq, int per_sm = 1 ) {
 		g.tiles_p = (int)( ( g.P + bp - 1 ) / bp ); g.tiles_q = (int)( ( g.Q + bq - 1 ) / bq );
-		return (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult );
+		return (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult * per_sm );
 	};
 	int cfg = c.dgemm_cfg;
 	if ( g.nseg > 1 && ( cfg < 4 ) ) cfg = -1;          // k-panel accumulation needs a warp-specialised kernel
@@ -20,8 +21,7 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 		const int64_t t128 = ( ( g.P + 127 ) / 128 ) * ( ( g.Q + 127 ) / 128 );
 		if ( t128 < 2 * c.num_sms )
 		{
-			const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 128, 64 ); c.grid_mult = gm;
-			return launch_dmma_ws<double, 128, 64, 16, 4, 1, 3, true>( g, xk, yk, al, grid, st );
+			return launch_dmma_ws<double, 128, 64, 16, 4, 1, 3, true>( g, xk, yk, al, tiles( 128, 64, 2 ), st );
 		}
 		if ( tma_eligible( g, xk, yk, al ) ) return launch_dmma_tma<true>( g, xk, yk, tiles( 128, 128 ), st );
 		return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5, true>( g, xk, yk, al, tiles( 128, 128 ), st );
@@ -52,12 +52,9 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 		        	return launch_dmma_tma( g, xk, yk, tiles( 128, 128 ), st );
 		        }
 		        return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
-		case 7: { const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 128, 64 ); c.grid_mult = gm;
-		          return launch_dmma_ws<double, 128, 64, 16, 4, 1, 3>( g, xk, yk, al, grid, st ); }
-		case 10: { const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 64, 64 ); c.grid_mult = gm;
-		           return launch_dmma_ws<double, 64, 64, 16, 2, 2, 4>( g, xk, yk, al, grid, st ); }
-		case 8: { const int gm = c.grid_mult; c.grid_mult = 2 * gm; const int grid = tiles( 64, 128 ); c.grid_mult = gm;
-		          return launch_dmma_ws<double, 64, 128, 16, 1, 4, 3>( g, xk, yk, al, grid, st ); }
+		case 7:  return launch_dmma_ws<double, 128, 64, 16, 4, 1, 3>( g, xk, yk, al, tiles( 128, 64, 2 ), st );
+		case 10: return launch_dmma_ws<double, 64, 64, 16, 2, 2, 4>( g, xk, yk, al, tiles( 64, 64, 2 ), st );
+		case 8:  return launch_dmma_ws<double, 64, 128, 16, 1, 4, 3>( g, xk, yk, al, tiles( 64, 128, 2 ), st );
 	}
 }
 

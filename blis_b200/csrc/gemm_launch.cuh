@@ -12,6 +12,7 @@
 #include "gemm_ffma_ws.cuh"
 #include "../../include/blis_b200.h"
 #include <algorithm>
+#include <string>
 #include <type_traits>
 #include <utility>
 
@@ -25,6 +26,17 @@ template <> int launch_gemm_kernel<double> ( GemmArgs<double>&  g, bool xk, bool
 template <> int launch_gemm_kernel<double2>( GemmArgs<double2>& g, bool xk, bool yk, bool al, cudaStream_t st );
 template <> int launch_gemm_kernel<float>  ( GemmArgs<float>&   g, bool xk, bool yk, bool al, cudaStream_t st );
 template <> int launch_gemm_kernel<float2> ( GemmArgs<float2>&  g, bool xk, bool yk, bool al, cudaStream_t st );
+
+// printf-style kernel name with static lifetime (one per template instantiation of the calling lambda)
+static std::string kfmt( const char* fmt, ... )
+{
+	char buf[160]; va_list ap; va_start( ap, fmt ); vsnprintf( buf, sizeof( buf ), fmt, ap ); va_end( ap );
+	return std::string( buf );
+}
+template <typename T> static const char* tname()
+{
+	return std::is_same<T, double>::value ? "double" : std::is_same<T, float>::value ? "float" : std::is_same<T, float2>::value ? "float2" : "double2";
+}
 
 template <typename KernT>
 static int set_smem( KernT kern, int bytes )
@@ -45,11 +57,12 @@ static int launch_dmma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int gri
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
 		using Cfg = DmmaCfg<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
 		auto kern = gemm_dmma_kernel<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
+		static const std::string kname = kfmt( "gemm_dmma_kernel<%s,%dx%dx%d,%dst,XK=%d,YK=%d,AL=%d>", tname<T>(), BP, BQ, BK, ST, XK, YK, AL );
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>( g );
 		B200_CUDA( cudaGetLastError() );
-		ctx().launches++;
+		note_launch( kname.c_str() );
 		return kSuccess;
 	};
 	using Tt = std::true_type; using Ff = std::false_type;
@@ -71,11 +84,12 @@ static int launch_dmma_ws( const GemmArgs<T>& g, bool xk, bool yk, bool al, int 
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
 		using Cfg = DmmaWsCfg<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
 		auto kern = gemm_dmma_ws_kernel<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL, TRI>;
+		static const std::string kname = kfmt( "gemm_dmma_ws_kernel<%s,%dx%dx%d,%dst,XK=%d,YK=%d,AL=%d,TRI=%d>", tname<T>(), BP, BQ, BK, ST, XK, YK, AL, TRI );
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, Cfg::NT_ALL, Cfg::SMEM_BYTES, st>>>( g );
 		B200_CUDA( cudaGetLastError() );
-		ctx().launches++;
+		note_launch( kname.c_str() );
 		return kSuccess;
 	};
 	using Tt = std::true_type; using Ff = std::false_type;
@@ -142,11 +156,12 @@ static int launch_dmma_tma( const GemmArgs<double>& g, bool xk, bool yk, int gri
 	{
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
 		auto kern = gemm_dmma_tma_kernel<XK, YK, TRI, CST>;
+		static const std::string kname = kfmt( "gemm_dmma_tma_kernel<XK=%d,YK=%d,TRI=%d,CST=%d>", XK, YK, TRI, CST );
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, DmmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, DmmaTmaCfg::NT_ALL, DmmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy, tmd );
 		B200_CUDA( cudaGetLastError() );
-		ctx().launches++;
+		note_launch( kname.c_str() );
 		return kSuccess;
 	};
 	using Tt = std::true_type; using Ff = std::false_type;
@@ -167,11 +182,12 @@ static int launch_ffma_tma( const GemmArgs<float>& g, bool xk, bool yk, int grid
 	{
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
 		auto kern = gemm_ffma_tma_kernel<XK, YK, TRI, CST>;
+		static const std::string kname = kfmt( "gemm_ffma_tma_kernel<XK=%d,YK=%d,TRI=%d,CST=%d>", XK, YK, TRI, CST );
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, FfmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, FfmaTmaCfg::NT_ALL, FfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy, tmd );
 		B200_CUDA( cudaGetLastError() );
-		ctx().launches++;
+		note_launch( kname.c_str() );
 		return kSuccess;
 	};
 	using Tt = std::true_type; using Ff = std::false_type;
@@ -191,12 +207,13 @@ static int launch_cfma_tma( const GemmArgs<float2>& g, bool xk, bool yk, int gri
 	{
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
 		auto kern = gemm_cfma_tma_kernel<XK, YK, TRI, CST>;
+		static const std::string kname = kfmt( "gemm_cfma_tma_kernel<XK=%d,YK=%d,TRI=%d,CST=%d>", XK, YK, TRI, CST );
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, CfmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		if ( !CST ) tmd = tmx;
 		kern<<<grid, CfmaTmaCfg::NT_ALL, CfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy, tmd );
 		B200_CUDA( cudaGetLastError() );
-		ctx().launches++;
+		note_launch( kname.c_str() );
 		return kSuccess;
 	};
 	using Tt = std::true_type; using Ff = std::false_type;
@@ -236,11 +253,12 @@ static int launch_zmma_tma( const GemmArgs<double2>& g, bool xk, bool yk, int gr
 	{
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
 		auto kern = gemm_zmma_tma_kernel<XK, YK, TRI>;
+		static const std::string kname = kfmt( "gemm_zmma_tma_kernel<XK=%d,YK=%d,TRI=%d>", XK, YK, TRI );
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, ZmmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, ZmmaTmaCfg::NT_ALL, ZmmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
 		B200_CUDA( cudaGetLastError() );
-		ctx().launches++;
+		note_launch( kname.c_str() );
 		return kSuccess;
 	};
 	using Tt = std::true_type; using Ff = std::false_type;
@@ -256,11 +274,12 @@ static int launch_ffma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int gri
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
 		using Cfg = FfmaCfg<T, BP, BQ, BK, TP, TQ, ST>;
 		auto kern = gemm_ffma_kernel<T, BP, BQ, BK, TP, TQ, ST, XK, YK, AL>;
+		static const std::string kname = kfmt( "gemm_ffma_kernel<%s,%dx%dx%d,XK=%d,YK=%d,AL=%d>", tname<T>(), BP, BQ, BK, XK, YK, AL );
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>( g );
 		B200_CUDA( cudaGetLastError() );
-		ctx().launches++;
+		note_launch( kname.c_str() );
 		return kSuccess;
 	};
 	using Tt = std::true_type; using Ff = std::false_type;
@@ -282,11 +301,12 @@ static int launch_ffma_ws( const GemmArgs<T>& g, bool xk, bool yk, bool al, int 
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
 		using Cfg = FfmaWsCfg<T, BP, BQ, BK, TP, TQ, ST>;
 		auto kern = gemm_ffma_ws_kernel<T, BP, BQ, BK, TP, TQ, ST, XK, YK, AL>;
+		static const std::string kname = kfmt( "gemm_ffma_ws_kernel<%s,%dx%dx%d,XK=%d,YK=%d,AL=%d>", tname<T>(), BP, BQ, BK, XK, YK, AL );
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, Cfg::NT_ALL, Cfg::SMEM_BYTES, st>>>( g );
 		B200_CUDA( cudaGetLastError() );
-		ctx().launches++;
+		note_launch( kname.c_str() );
 		return kSuccess;
 	};
 	using Tt = std::true_type; using Ff = std::false_type;

@@ -75,7 +75,7 @@ static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T 
 		if ( on_a ) g.ktri = swapped ? ( lower ? 3 : 4 ) : ( lower ? 1 : 2 );
 		else        g.ktri = swapped ? ( lower ? 2 : 1 ) : ( lower ? 4 : 3 );
 	}
-	g.tile_counter = ctx().dynamic_tiles ? ctx().sched_counters + 2 * ( ctx().sched_next++ % 64 ) : nullptr;
+	g.tile_counter = sched_slot( st );
 	for ( int sgm = 1; sgm < nseg; ++sgm )
 	{
 		g.Xseg[sgm - 1] = swapped ? b_more[sgm - 1] : a_more[sgm - 1];
@@ -231,7 +231,7 @@ static int gemm_host_kpipe( bool conja, bool conjb, int64_t m, int64_t n, int64_
 					R br, bi; if constexpr ( Elem<T>::cplx ) { br = be.x; bi = be.y; } else { br = be; bi = 0; }
 					add_scaled_kernel<R, NC><<<blocks, 256, 0, st>>>( (R*)( (T*)dc + j0 * m ), (const R*)( (const T*)ds + j0 * m ), total, br, bi );
 					if ( cudaGetLastError() != cudaSuccess ) rc = fail( "b200_gemm: launch failed" );
-					cx.launches++;
+					note_launch( "add_scaled_kernel" );
 				}
 				cudaEventRecord( ev_done[j], st );
 				cudaStreamWaitEvent( s_out, ev_done[j], 0 );

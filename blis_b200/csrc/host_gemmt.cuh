@@ -118,7 +118,7 @@ static int gemmt_family_front( int op, int uploc, int transa, int transb, int64_
 			const int blocks = (int)std::min<int64_t>( ( m + 255 ) / 256, (int64_t)ctx().num_sms * 4 );
 			zero_diag_imag_kernel<R><<<blocks, 256, 0, st>>>( (R*)cdev, rs_cd + cs_cd, m );
 			if ( cudaGetLastError() != cudaSuccess ) rc = fail( "%s: launch failed", name );
-			ctx().launches++;
+			note_launch( "zero_diag_imag_kernel" );
 		}
 	}
 	if ( rc == kSuccess && c_host )

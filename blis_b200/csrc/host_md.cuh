@@ -115,7 +115,7 @@ static int md_convert( void* dst, int dt_d, int64_t rs_d, int64_t cs_d, const vo
 	const int single = ( dt_d == B200_FLOAT || dt_d == B200_SCOMPLEX ) ? 1 : 0;
 	md_convert_kernel<<<blocks, 256, 0, st>>>( dst, dt_d, rs_d, cs_d, src, dt_s, rs_s, cs_s, m, n, conj ? 1 : 0, use_kappa ? 1 : 0, kr, ki, neg_imag ? 1 : 0, single );
 	B200_CUDA( cudaGetLastError() );
-	ctx().launches++;
+	note_launch( "md_convert_kernel" );
 	return kSuccess;
 }
 
@@ -172,7 +172,7 @@ static int gemm_md_front( int dt_a, int dt_b, int dt_c, int comp_prec, int trans
 			const int blocks = (int)std::min<int64_t>( ( m * n + 255 ) / 256, (int64_t)ctx().num_sms * 16 );
 			md_combine_kernel<<<blocks, 256, 0, st>>>( cdev, dt_c, rs_cd, cs_cd, cdev, dt_c, rs_cd, cs_cd, m, n, 0.0, 0.0, br, bi, beta_zero ? 1 : 0 );
 			if ( cudaGetLastError() != cudaSuccess ) rc = fail( "b200_gemm_md: launch failed" );
-			ctx().launches++;
+			note_launch( "md_combine_kernel" );
 		}
 	}
 	else
@@ -250,7 +250,7 @@ static int gemm_md_front( int dt_a, int dt_b, int dt_c, int comp_prec, int trans
 			const int blocks = (int)std::min<int64_t>( ( m * n + 255 ) / 256, (int64_t)ctx().num_sms * 16 );
 			md_combine_kernel<<<blocks, 256, 0, st>>>( cdev, dt_c, rs_cd, cs_cd, pt, dt_t, rs_t, cs_t, m, n, car, cai, br, bi, beta_zero ? 1 : 0 );
 			if ( cudaGetLastError() != cudaSuccess ) rc = fail( "b200_gemm_md: launch failed" );
-			ctx().launches++;
+			note_launch( "md_combine_kernel" );
 		}
 	}
 	if ( rc == kSuccess && c_host )

@@ -70,7 +70,7 @@ static int densify_operand( void** da, const T* a, int64_t rs_a, int64_t cs_a, i
 	const int blocks = (int)std::min<int64_t>( ( total + 255 ) / 256, (int64_t)ctx().num_sms * 16 );
 	densify_kernel<R, NC><<<blocks, 256, 0, st>>>( (R*)*da, ma, (const R*)src, rs, cs, ma, struc, uplo == B200_LOWER ? 1 : 0, unit ? 1 : 0 );
 	B200_CUDA( cudaGetLastError() );
-	ctx().launches++;
+	note_launch( "densify_kernel" );
 	return kSuccess;
 }
 

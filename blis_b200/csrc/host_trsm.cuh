@@ -38,7 +38,7 @@ static int trsm_base( const TrsmPlan<T>& p, int64_t i0, int mb, T alpha )
 	const int64_t grid = ( p.n + CN - 1 ) / CN;
 	kern<<<(unsigned)grid, NT, smem, p.st>>>( a );
 	B200_CUDA( cudaGetLastError() );
-	ctx().launches++;
+	note_launch( "trsm_base_kernel" );
 	return kSuccess;
 }
 

@@ -109,7 +109,7 @@ static int transpose2d( T* dst, int64_t ldd, const T* src, int64_t lds, int64_t 
 	const int blocks = (int)std::min<int64_t>( ntiles, (int64_t)ctx().num_sms * 32 );
 	transpose2d_kernel<T><<<blocks, 256, 0, st>>>( dst, ldd, src, lds, R, Cn, (int)tiles_c );
 	B200_CUDA( cudaGetLastError() );
-	ctx().launches++;
+	note_launch( "transpose2d_kernel" );
 	return kSuccess;
 }
 
@@ -126,7 +126,7 @@ static int copy2d( T* dst, int64_t rsd, int64_t csd, const T* src, int64_t rss, 
 	const int blocks = (int)std::min<int64_t>( ( total + 255 ) / 256, (int64_t)ctx().num_sms * 16 );
 	copy2d_kernel<R, NC><<<blocks, 256, 0, st>>>( (R*)dst, rsd, csd, (const R*)src, rss, css, m, n, inner_is_row, tri );
 	B200_CUDA( cudaGetLastError() );
-	ctx().launches++;
+	note_launch( "copy2d_kernel" );
 	return kSuccess;
 }
 
@@ -144,7 +144,7 @@ static int scal2d( T* c, int64_t rs, int64_t cs, int64_t m, int64_t n, T beta, c
 	const int blocks = (int)std::min<int64_t>( ( total + 255 ) / 256, (int64_t)ctx().num_sms * 16 );
 	scal2d_kernel<R, NC><<<blocks, 256, 0, st>>>( (R*)c, rs, cs, m, n, br, bi, Scalar<T>::is_zero( beta ) ? 1 : 0, inner_is_row, tri );
 	B200_CUDA( cudaGetLastError() );
-	ctx().launches++;
+	note_launch( "scal2d_kernel" );
 	return kSuccess;
 }
 

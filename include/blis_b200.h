@@ -76,6 +76,14 @@ int         b200_device_count( void );
  * (frame/base/bli_info.c). */
 const char* b200_info( void );
 
+/* Name of the last kernel the calling thread launched (e.g. "gemm_dmma_tma_kernel<XK=1,YK=0,TRI=0,CST=0>"), and a
+ * histogram "name\tcount\n..." of every kernel launched since the last reset, written to buf (NUL terminated, truncated
+ * to len); returns the untruncated length.  The reference reports which microkernel a context holds through
+ * bli_info_get_gemm_ukr_impl_string() (frame/base/bli_info.c:180-215); here tests and bench.py read which tile kernel
+ * actually served a call. */
+const char* b200_last_kernel( void );
+size_t      b200_kernel_stats( char* buf, size_t len, int reset );
+
 /* All work of the calling thread is issued on this CUDA stream
  * (cudaStream_t passed as void*); NULL selects the engine's own stream.
  * The torch harness passes torch's current stream so CUDA events see it. */
