@@ -53,6 +53,7 @@ struct Context
 	int          sgemm_cfg = -1;         // auto: TMA + FFMA2 kernel when aligned, cp.async kernel otherwise
 	int          cgemm_cfg = -1;         // auto: TMA + FFMA2 kernel when aligned, cp.async ws kernel otherwise
 	int          trsm_nb   = 0;           // 0 = default
+	int          trsm_fused = 1;          // dtrsm: fused 256-row diagonal-panel kernel (trsm_panel.cuh); 0 = 64-row block solves + gemm updates
 	int          grid_mult = 1;           // persistent CTAs per SM
 	// dynamic tile scheduling: self re-arming {tile, done} pairs, ONE PAIR PER STREAM (kernels of one stream run one
 	// after the other, so a stream's pair is never shared by two running kernels; see sched_slot)

@@ -3,6 +3,7 @@
 #pragma once
 #include "host_gemm.cuh"
 #include "trsm.cuh"
+#include "trsm_panel.cuh"
 namespace b200 {
 
 // ---- trsm -----------------------------------------------------------------------------
@@ -42,6 +43,29 @@ static int trsm_base( const TrsmPlan<T>& p, int64_t i0, int mb, T alpha )
 	return kSuccess;
 }
 
+// Fused diagonal-panel solve (trsm_panel.cuh): rows [i0, i0+mb), mb <= 256, all n columns, one launch.
+static int trsm_panel( const TrsmPlan<double>& p, int64_t i0, int mb, double alpha )
+{
+	TrsmPanelArgs a;
+	a.A = p.A + i0 * ( p.rs_a + p.cs_a ); a.rs_a = p.rs_a; a.cs_a = p.cs_a;
+	a.B = p.B + i0 * p.rs_b;              a.rs_b = p.rs_b; a.cs_b = p.cs_b;
+	a.n = p.n; a.pb = mb; a.upper = p.upper; a.unit = p.unit; a.alpha = alpha;
+	static bool attr = false;
+	if ( !attr ) { if ( set_smem( trsm_panel_kernel, TrsmPanelCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+	const int64_t grid = ( p.n + TrsmPanelCfg::CN - 1 ) / TrsmPanelCfg::CN;
+	trsm_panel_kernel<<<(unsigned)grid, TrsmPanelCfg::NT, TrsmPanelCfg::SMEM_BYTES, p.st>>>( a );
+	B200_CUDA( cudaGetLastError() );
+	note_launch( "trsm_panel_kernel<double,256x64>" );
+	return kSuccess;
+}
+template <typename T> static int trsm_leaf_rows() { return TrsmBlk<T>::NB; }
+template <> int trsm_leaf_rows<double>() { return ctx().trsm_fused ? TrsmPanelCfg::PB : TrsmBlk<double>::NB; }
+template <typename T> static int trsm_leaf( const TrsmPlan<T>& p, int64_t i0, int mb, T alpha ) { return trsm_base( p, i0, mb, alpha ); }
+template <> int trsm_leaf<double>( const TrsmPlan<double>& p, int64_t i0, int mb, double alpha )
+{
+	return mb > TrsmBlk<double>::NB ? trsm_panel( p, i0, mb, alpha ) : trsm_base( p, i0, mb, alpha );
+}
+
 // Recursive blocked solve of rows [i0, i0+mb): solve one half, rank-k update of
 // the other half with the gemm kernel, solve the other half.  alpha is applied
 // exactly once to every row (either by the base kernel or as the update's beta,
@@ -49,8 +73,8 @@ static int trsm_base( const TrsmPlan<T>& p, int64_t i0, int mb, T alpha )
 template <typename T>
 static int trsm_rec( const TrsmPlan<T>& p, int64_t i0, int64_t mb, T alpha )
 {
-	constexpr int NB = TrsmBlk<T>::NB;
-	if ( mb <= NB ) return trsm_base( p, i0, (int)mb, alpha );
+	const int NB = trsm_leaf_rows<T>();
+	if ( mb <= NB ) return trsm_leaf<T>( p, i0, (int)mb, alpha );
 	const int64_t nblk = ( mb + NB - 1 ) / NB;
 	const int64_t m1 = ( ( nblk + 1 ) / 2 ) * NB, m2 = mb - m1;
 	const T one = Scalar<T>::make( 1.0, 0.0 ), mone = Scalar<T>::make( -1.0, 0.0 );

@@ -287,6 +287,54 @@ class DistGemm:
     def step(self):
         summa(self.plan, self.ex, self._panel, gemm_step=self._step_panels)
 
+    # ---- parity of the distributed result ----------------------------------------------------------------------------
+    def verify(self, hosts=None) -> dict:
+        """Post-timing check of ONE distributed product, run on every rank (collective):
+
+        * bit_equal -- the rank's block of C after `step()` equals, bit for bit, the block the single-GPU engine computes
+          when it replays the same k-panel schedule (same b200_gemm_kpanels calls, beta then 1) on panels gathered
+          INDEPENDENTLY of PanelExchange (whole-shard all_gather in the row/column group, re-indexed by panel number).
+          k is never split across GPUs (frame/3/gemm/bli_gemm_blk_var3.c:110-112: the reference never splits k across
+          threads either), so a wrong slot mapping, a buffer-reuse race between the gather of step s+2 and the kernels of
+          step s, or a panel-segment bug shows up as a bit difference.
+        * resid -- the reference testsuite's randomized residual of that block, || C t - (beta C0 t + alpha A (B t)) ||
+          (testsuite/src/test_gemm.c:393-401; pass threshold 1e-14 at :44-47), computed with torch mat-vecs.
+        * host_bit_equal (when `hosts` is given) -- step_host() from the same C0 in pinned host memory gives the same bits."""
+        p, ex = self.plan, self.ex
+        cd = self.c.t()                                       # dense [n_loc, m_loc] tensor behind the column-major block
+        c0 = cd.clone()
+        self.step()
+        torch.cuda.synchronize()
+        c_dist = cd.clone()
+        a_all = [torch.empty_like(self.a_loc) for _ in range(p.pc)]
+        b_all = [torch.empty_like(self.b_loc) for _ in range(p.pr)]
+        dist.all_gather(a_all, self.a_loc, group=ex.row_pg)
+        dist.all_gather(b_all, self.b_loc, group=ex.col_pg)
+        a_of = lambda t: a_all[t % p.pc][t // p.pc]           # noqa: E731  panel t of A: owner column t % Pc, local index t // Pc
+        b_of = lambda t: b_all[t % p.pr][t // p.pr]           # noqa: E731
+        cd.copy_(c0)
+        for s in range(p.steps):
+            ts = range(s * p.L, (s + 1) * p.L)
+            self._step_panels(s == 0, [a_of(t) for t in ts], [b_of(t) for t in ts])
+        torch.cuda.synchronize()
+        bit_equal = bool(torch.equal(cd, c_dist))
+        g = torch.Generator(device=cd.device); g.manual_seed(7 + p.rank)
+        tv = (torch.rand(p.n_loc, dtype=cd.dtype, device=cd.device, generator=g) * 2 - 1) / p.N
+        z = self.beta * (c0.t() @ tv)
+        for t in range(p.T):
+            z += self.alpha * (a_of(t).t() @ (b_of(t).t() @ tv))
+        resid = float(torch.linalg.vector_norm(c_dist.t() @ tv - z))
+        out = {"bit_equal": bit_equal, "resid": resid,
+               "how": "C_ij after step() vs the same b200_gemm_kpanels schedule replayed on whole-shard all_gather'ed panels (bit for bit), "
+                      "and the testsuite residual ||C t - (beta C0 t + alpha A (B t))|| of the distributed block"}
+        if hosts is not None:
+            hosts[2].copy_(c0)
+            self.step_host(hosts)
+            torch.cuda.synchronize()
+            out["host_bit_equal"] = bool(torch.equal(hosts[2].to(cd.device), c_dist))
+        cd.copy_(c_dist)
+        return out
+
     # ---- shards in pinned host memory ------------------------------------------------------------------------------
     def host_shards(self):
         """Pinned host images of this rank's shards (A panels, B panels, dense tensor behind the C block), filled from

@@ -15,7 +15,7 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def _run(rank: int, world: int = 2, timeout: int = 300):
-    env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
+    env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), B200_REF_BUDGET="3")    # bounded sample: CPU-only container
     return subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", str(world), "--steps", "1",
                            "--warmup", "3"], capture_output=True, text=True, timeout=timeout, env=env, cwd=str(ROOT))
 
@@ -38,3 +38,6 @@ def test_rank0_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    # both halves of the metric: dtrsm (T1) rides in the same line
+    assert line["dtrsm"]["value"] > 0 and line["dtrsm"]["cpu_baseline"]["kind"] == "reference"
+    assert "sub-config" in line["cpu_baseline"]["sample"]

@@ -175,3 +175,60 @@ def test_trsm_full_size_testsuite_residual(engine):
     assert resid <= 1e-14, resid
     back = float(torch.linalg.vector_norm(a @ xt - bt))
     assert back <= 1e-13, back
+
+
+def test_trsm_fused_panel_kernel(engine, oracle):
+    """dtrsm's fused 256-row diagonal-panel kernel (trsm_panel.cuh: in-panel DMMA updates + warp-shuffle substitution),
+    proven by name to be the kernel that ran: ragged panels and ragged column tiles, every side/uplo/trans/diag, row-,
+    column- and general-stride B, row-/column-stored A, unstored triangle NaN-poisoned -- against the oracle; same result
+    (to tolerance) as the 64-row block-solve path it replaces."""
+    seed = 9000
+    for (m, n) in ((65, 8), (130, 70), (256, 64), (255, 129), (300, 65), (513, 200), (1000, 96)):
+        for side in (LEFT, RIGHT):
+            for uplo in (LOWER, UPPER):
+                for tr in (NO_TRANSPOSE, TRANSPOSE):
+                    for dg in (NONUNIT_DIAG, UNIT_DIAG):
+                        for (oa, ob) in (("c", "c"), ("r", "r"), ("c", "g")):
+                            if m * n > 30000 and ((oa, ob) != ("c", "c") or dg == UNIT_DIAG):
+                                continue
+                            seed += 1
+                            mm, nn = (m, n) if side == LEFT else (n, m)
+                            a = gen.triangular("d", m, seed, "frac", oa)
+                            gen.poison_unstored(a, uplo == LOWER)
+                            b = gen.matrix("d", mm, nn, seed + 7000, "frac", ob, pad=1)
+                            want = b.copy(order="K")
+                            oracle.trsm(side, uplo, tr, dg, 2.0, a, want)
+                            engine.kernel_stats(reset=True)
+                            got = run_trsm(engine, "d", side, uplo, tr, dg, 2.0, a, b)
+                            ks = engine.kernel_stats()
+                            assert any(k.startswith("trsm_panel_kernel") for k in ks), ks
+                            assert rel_err(got, want) <= 20 * TOL["d"], (m, n, side, uplo, tr, dg, oa, ob, rel_err(got, want))
+                            engine.set_option("trsm_fused", 0)
+                            try:
+                                got2 = run_trsm(engine, "d", side, uplo, tr, dg, 2.0, a, b)
+                            finally:
+                                engine.set_option("trsm_fused", 1)
+                            assert rel_err(got, got2) <= 20 * TOL["d"]
+
+
+def test_trsm_fused_panel_integer_system_bit_exact(engine, oracle):
+    """Integer-valued banded systems (sub-diagonals 1 and 67, entries +-1, diagonal +-1): every intermediate is an exact
+    integer, so the fused kernel (tensor-pipe updates, shuffled substitution, any summation order) must reproduce the
+    reference's bits, lower and upper, across panel and block boundaries."""
+    m, n = 600, 80
+    i = np.arange(m)
+    for idx, (uplo, tr) in enumerate(((LOWER, NO_TRANSPOSE), (UPPER, NO_TRANSPOSE), (LOWER, TRANSPOSE), (UPPER, TRANSPOSE))):
+        a = np.zeros((m, m), order="F")
+        a[i, i] = 1.0 - 2.0 * (i % 2)
+        a[i[1:], i[:-1]] = 1.0 - 2.0 * ((i[1:] // 3) % 2)
+        a[i[67:], i[:-67]] = 1.0 - 2.0 * ((i[67:] // 5) % 2)
+        if uplo == UPPER:
+            a = np.asfortranarray(a.T)
+        gen.poison_unstored(a, uplo == LOWER)
+        b = gen.matrix("d", m, n, 650 + idx, "ints")
+        want = b.copy(order="K"); oracle.trsm(LEFT, uplo, tr, NONUNIT_DIAG, 2.0, a, want)
+        assert np.isfinite(want).all() and np.abs(want).max() < 2.0 ** 50
+        engine.kernel_stats(reset=True)
+        got = run_trsm(engine, "d", LEFT, uplo, tr, NONUNIT_DIAG, 2.0, a, b)
+        assert any(k.startswith("trsm_panel_kernel") for k in engine.kernel_stats())
+        assert np.array_equal(got, want), (uplo, tr, np.abs(got - want).max())

@@ -1,0 +1,55 @@
+#!/bin/bash
+# One GPU session, parameterised by stage names (replaces the round-1 one-off scripts):
+#   tools/gpu_session.sh [stage ...]       stages run in the order given; outputs land in gpurun_out/
+# Stages:
+#   newtests   the parity tests added this round (TMA paths, skinny shapes, tile counters, fused trsm)
+#   pytest     the whole -m gpu suite
+#   smoke      __graft_entry__.smoke()
+#   sanitize   compute-sanitizer memcheck + racecheck over tools/sanitize_driver.py
+#   bench      both bench arms (reference first)
+#   dtrsm      bench.py --op dtrsm
+#   launches   ncu launch list of the default bench command
+#   ncu_dgemm / ncu_trsm / ncu_skinny   one `ncu --set full` capture of that kernel + tools/ncu_key.py summary
+#   sweep      configs[2] sweep (s/d/c/z squares + k=64)
+mkdir -p gpurun_out
+nvidia-smi > gpurun_out/nvidia-smi.txt 2>&1
+lscpu | head -25 > gpurun_out/lscpu.txt
+for stage in "$@"; do
+echo "=== stage $stage ($(date +%T))"
+case "$stage" in
+newtests)
+	( time timeout 1500 python -m pytest tests -x -q -m gpu -k "fused or tma_paths or large_ragged or skinny_k64 or tile_counters" ) > gpurun_out/pytest_new.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_new.log
+	tail -12 gpurun_out/pytest_new.log ;;
+pytest)
+	( time timeout 2400 python -m pytest tests -x -q -m gpu ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+	tail -8 gpurun_out/pytest_gpu.log ;;
+smoke)
+	timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log ;;
+sanitize)
+	timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_driver.py > gpurun_out/sanitize_memcheck.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_memcheck.log
+	tail -4 gpurun_out/sanitize_memcheck.log
+	timeout 1200 compute-sanitizer --tool racecheck --print-limit 20 python tools/sanitize_driver.py > gpurun_out/sanitize_racecheck.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_racecheck.log
+	tail -4 gpurun_out/sanitize_racecheck.log ;;
+bench)
+	timeout 600 python bench.py --impl reference --steps 2 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 600 gpurun_out/bench_ref.json
+	timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err ;;
+dtrsm)
+	timeout 600 python bench.py --op dtrsm --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_dtrsm.json 2> gpurun_out/bench_dtrsm.err; cat gpurun_out/bench_dtrsm.json; tail -3 gpurun_out/bench_dtrsm.err ;;
+launches)
+	timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-peak > gpurun_out/bench_under_ncu.log 2>&1 ;;
+ncu_dgemm)
+	ncu --set full --clock-control none --import-source on -k regex:gemm_dmma -s 3 -c 1 -o gpurun_out/dgemm_full -f python bench.py --op dgemm --steps 2 --warmup 3 --no-cpu --no-e2e --no-peak > gpurun_out/ncu_full.log 2>&1
+	python tools/ncu_key.py gpurun_out/dgemm_full.ncu-rep > gpurun_out/ncu_dgemm_16384.txt 2>&1; head -12 gpurun_out/ncu_dgemm_16384.txt ;;
+ncu_trsm)
+	ncu --set full --clock-control none --import-source on -k regex:trsm_ -s 40 -c 1 -o gpurun_out/trsm_full -f python bench.py --op dtrsm --steps 1 --warmup 3 --no-cpu --no-e2e --no-peak > gpurun_out/ncu_trsm.log 2>&1
+	python tools/ncu_key.py gpurun_out/trsm_full.ncu-rep > gpurun_out/ncu_trsm_panel.txt 2>&1; head -12 gpurun_out/ncu_trsm_panel.txt ;;
+ncu_skinny)
+	ncu --set full --clock-control none --import-source on -k regex:gemm_ -s 1 -c 1 -o gpurun_out/skinny_full -f python -m tools.one_gemm d 16384 64 -1 2 > /dev/null 2>&1
+	python tools/ncu_key.py gpurun_out/skinny_full.ncu-rep > gpurun_out/ncu_dgemm_k64.txt 2>&1; head -12 gpurun_out/ncu_dgemm_k64.txt ;;
+sweep)
+	for ch in d s c z; do timeout 400 python -m tools.gpu_probe2 $ch -1 512,1024,2048,4096,8192,16384,512x64,4096x64,16384x64 > gpurun_out/sweep_$ch.log 2>&1; tail -1 gpurun_out/sweep_$ch.log; done ;;
+*)
+	echo "unknown stage $stage" ;;
+esac
+done
+ls -la gpurun_out | head -40

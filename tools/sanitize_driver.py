@@ -1,0 +1,87 @@
+#!/usr/bin/env python3
+"""Small problems through every production gemm/trsm kernel family, for compute-sanitizer (memcheck / racecheck / synccheck).
+
+    compute-sanitizer --tool memcheck  python tools/sanitize_driver.py
+    compute-sanitizer --tool racecheck python tools/sanitize_driver.py
+
+Each case is checked against torch and the name of the kernel that ran is printed, so the sanitizer log shows which
+kernels were covered: TMA (d/s/c/z), CST, warp-specialised cp.async, k-panel accumulation, triangular schedules, trsm.
+"""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from blis_b200 import api  # noqa: E402
+
+dev = "cuda"
+torch.cuda.set_device(0)
+g = torch.Generator(device=dev); g.manual_seed(1)
+
+
+def rnd(m, n, dt):
+    x = torch.rand(n, m, dtype=torch.float64, device=dev, generator=g) * 2 - 1
+    if dt.is_complex:
+        x = torch.complex(x, torch.rand(n, m, dtype=torch.float64, device=dev, generator=g) * 2 - 1)
+    return x.to(dt).t()                                     # column-major m x n
+
+
+def check(name, got, want, tol):
+    err = float((got - want).abs().max() / max(1.0, float(want.abs().max())))
+    print(f"{name:28s} {api.last_kernel():70s} err={err:.2e}", flush=True)
+    assert err <= tol, (name, err)
+
+
+GEMM = {torch.float64: api.bli_dgemm, torch.float32: api.bli_sgemm, torch.complex64: api.bli_cgemm, torch.complex128: api.bli_zgemm}
+FORCE = {torch.float64: ("dgemm_cfg", 9, -1), torch.float32: ("sgemm_cfg", 3, -1), torch.complex64: ("cgemm_cfg", 3, -1),
+         torch.complex128: ("zgemm_cfg", 2, 1)}
+
+for dt, tol in ((torch.float64, 1e-12), (torch.float32, 5e-5), (torch.complex64, 5e-5), (torch.complex128, 1e-12)):
+    m, n, k = 260, 388, 100
+    a, b, c = rnd(m, k, dt), rnd(k, n, dt), rnd(m, n, dt)
+    at = rnd(k, m, dt)
+    key, forced, default = FORCE[dt]
+    for label, opt in (("default", default), ("tma", forced)):
+        api.set_option(key, opt)
+        for beta in (1.2, 0.0):
+            c1 = c.clone(memory_format=torch.preserve_format)
+            GEMM[dt](0, 0, m, n, k, 2.0, a, 1, m, b, 1, k, beta, c1, 1, m); torch.cuda.synchronize()
+            check(f"gemm NN {label} beta={beta}", c1, beta * c + 2.0 * (a @ b), tol)
+        c1 = c.clone(memory_format=torch.preserve_format)
+        GEMM[dt](8, 0, m, n, k, 2.0, at, 1, k, b, 1, k, 1.2, c1, 1, m); torch.cuda.synchronize()
+        check(f"gemm TN {label}", c1, 1.2 * c + 2.0 * (at.t() @ b), tol)
+        # unaligned view (offset by one element): cp.async kernels
+        big = rnd(m + 1, k, dt)
+        a_un = big[1:, :]
+        c1 = c.clone(memory_format=torch.preserve_format)
+        GEMM[dt](0, 0, m, n, k, 2.0, a_un, 1, m + 1, b, 1, k, 1.2, c1, 1, m); torch.cuda.synchronize()
+        check(f"gemm unaligned {label}", c1, 1.2 * c + 2.0 * (a_un @ b), tol)
+    api.set_option(key, default)
+
+# k-panel accumulation (d): 3 panels in one launch
+m, n, k = 260, 260, 64
+ap = [rnd(m, k, torch.float64) for _ in range(3)]; bp = [rnd(k, n, torch.float64) for _ in range(3)]
+c = rnd(m, n, torch.float64); c1 = c.clone(memory_format=torch.preserve_format)
+api.bli_gemm_kpanels(torch.float64, 0, 0, m, n, k, 2.0, ap, 1, m, bp, 1, k, 1.2, c1, 1, m); torch.cuda.synchronize()
+check("kpanels", c1, 1.2 * c + 2.0 * sum(x @ y for x, y in zip(ap, bp)), 1e-12)
+
+# triangular schedules: syrk (TRI), trmm (ktri), and trsm (all variants of the solve kernels)
+a = rnd(300, 90, torch.float64); c = rnd(300, 300, torch.float64); c1 = c.clone(memory_format=torch.preserve_format)
+api.bli_dsyrk(0xC0, 0, 300, 90, 2.0, a, 1, 300, 1.2, c1, 1, 300); torch.cuda.synchronize()
+check("syrk lower", torch.tril(c1), torch.tril(1.2 * c + 2.0 * (a @ a.t())), 1e-12)
+for dt, tol in ((torch.float64, 1e-11), (torch.complex128, 1e-11), (torch.float32, 1e-3)):
+    for mm, nn in ((300, 100), (600, 200)):
+        t = rnd(mm, mm, dt) / 16; t.diagonal().add_(2.0)
+        b = rnd(mm, nn, dt)
+        for uplo, tri in ((0xC0, torch.tril), (0x60, torch.triu)):
+            b1 = b.clone(memory_format=torch.preserve_format)
+            {torch.float64: api.bli_dtrsm, torch.complex128: api.bli_ztrsm, torch.float32: api.bli_strsm}[dt](
+                0, uplo, 0, 0, mm, nn, 2.0, t, 1, mm, b1, 1, mm)
+            torch.cuda.synchronize()
+            want = torch.linalg.solve_triangular(tri(t), 2.0 * b, upper=(uplo == 0x60))
+            check(f"trsm {dt} {mm}x{nn} uplo={uplo:#x}", b1, want, tol)
+b = rnd(300, 100, torch.float64); t = rnd(300, 300, torch.float64); b1 = b.clone(memory_format=torch.preserve_format)
+api.bli_dtrmm(0, 0xC0, 0, 0, 300, 100, 2.0, t, 1, 300, b1, 1, 300); torch.cuda.synchronize()
+check("trmm lower", b1, 2.0 * (torch.tril(t) @ b), 1e-12)
+print("sanitize_driver: all cases ok; kernels:", sorted(api.kernel_stats()))
