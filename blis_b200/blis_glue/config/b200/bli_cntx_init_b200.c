@@ -13,16 +13,24 @@
        bli_family_b200.h raises BLIS_STACK_BUF_MAX_SIZE for the MR x NR tile.
        bli_info / bli_cntx queries therefore describe the GPU tiling truthfully.
      * the whole-operation gemm handler + thresholds (bli_b200_install).
-   The gemm/gemmtrsm microkernel slots keep the reference kernels, which serve
-   only operations outside this engine's scope (level-1/2, 1m): with the
-   handler installed no homogeneous gemm reaches them, and mixed-datatype gemm,
-   trsm and the other level-3 operations are taken by the bli_*_ex_b200
-   overrides of the glue before any control tree is built.
+     * the BLIS_GEMM_UKR slots: engine-backed microkernels (bli_gemm_b200_ukr.c), so that bli_info, direct
+       microkernel calls (bli_gemm_ukernel, the testsuite's gemm_ukr / gemmtrsm_ukr modules) and the reference
+       gemmtrsm kernel's gemm part all end in the engine.  The trsm/gemmtrsm/packm slots keep the reference kernels in
+       their run-time-blocksize form (bli_kernel_defs_b200.h sets BLIS_MR_x/BLIS_NR_x to -1), which is consistent with
+       whatever MR/NR the context holds.
+   No level-3 operation of a b200 build reaches a control tree: the bli_<op>_ex entry points of the library are the
+   glue's (frame/3/bli_l3_oapi_ex.c steps aside under BLIS_CONFIG_B200).
 */
 #include "blis.h"
 #include "blis_b200.h"
 
 void bli_b200_install( cntx_t* cntx );
+
+// engine-backed gemm microkernels (bli_gemm_b200_ukr.c); signature of gemm_ukr_ft (frame/3/bli_l3_ukr_ft.h:46-57)
+#define BLI_B200_UKR_PROT( ch ) \
+void bli_##ch##gemm_b200_ukr( dim_t m, dim_t n, dim_t k, const void* alpha, const void* a, const void* b, const void* beta, \
+                              void* c, inc_t rs_c, inc_t cs_c, const auxinfo_t* data, const cntx_t* cntx );
+BLI_B200_UKR_PROT( s ) BLI_B200_UKR_PROT( d ) BLI_B200_UKR_PROT( c ) BLI_B200_UKR_PROT( z )
 
 void bli_cntx_init_b200( cntx_t* cntx )
 {
@@ -53,6 +61,29 @@ void bli_cntx_init_b200( cntx_t* cntx )
 	  BLIS_NR, &blkszs[ BLIS_NR ], BLIS_NR,
 	  BLIS_MR, &blkszs[ BLIS_MR ], BLIS_MR,
 
+	  BLIS_VA_END
+	);
+
+	// -------------------------------------------------------------------------
+
+	// Engine-backed gemm microkernels.  They accept any storage of C; "column preference" mirrors the engine's
+	// own choice (D = C^T for column-stored C costs nothing).
+	bli_cntx_set_ukrs
+	(
+	  cntx,
+	  BLIS_GEMM_UKR, BLIS_FLOAT,    bli_sgemm_b200_ukr,
+	  BLIS_GEMM_UKR, BLIS_DOUBLE,   bli_dgemm_b200_ukr,
+	  BLIS_GEMM_UKR, BLIS_SCOMPLEX, bli_cgemm_b200_ukr,
+	  BLIS_GEMM_UKR, BLIS_DCOMPLEX, bli_zgemm_b200_ukr,
+	  BLIS_VA_END
+	);
+	bli_cntx_set_ukr_prefs
+	(
+	  cntx,
+	  BLIS_GEMM_UKR_ROW_PREF, BLIS_FLOAT,    FALSE,
+	  BLIS_GEMM_UKR_ROW_PREF, BLIS_DOUBLE,   FALSE,
+	  BLIS_GEMM_UKR_ROW_PREF, BLIS_SCOMPLEX, FALSE,
+	  BLIS_GEMM_UKR_ROW_PREF, BLIS_DCOMPLEX, FALSE,
 	  BLIS_VA_END
 	);
 

@@ -50,13 +50,29 @@ static int trsm_panel( const TrsmPlan<double>& p, int64_t i0, int mb, double alp
 	a.A = p.A + i0 * ( p.rs_a + p.cs_a ); a.rs_a = p.rs_a; a.cs_a = p.cs_a;
 	a.B = p.B + i0 * p.rs_b;              a.rs_b = p.rs_b; a.cs_b = p.cs_b;
 	a.n = p.n; a.pb = mb; a.upper = p.upper; a.unit = p.unit; a.alpha = alpha;
-	static bool attr = false;
-	if ( !attr ) { if ( set_smem( trsm_panel_kernel, TrsmPanelCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+	const bool ai = ( p.rs_a <= p.cs_a ), bk = ( p.rs_b <= p.cs_b );
+	a.a_vec = ( ( ai ? p.rs_a : p.cs_a ) == 1 && ( ( ai ? p.cs_a : p.rs_a ) % 2 ) == 0 && ( (uintptr_t)a.A % 16 ) == 0 ) ? 1 : 0;
 	const int64_t grid = ( p.n + TrsmPanelCfg::CN - 1 ) / TrsmPanelCfg::CN;
-	trsm_panel_kernel<<<(unsigned)grid, TrsmPanelCfg::NT, TrsmPanelCfg::SMEM_BYTES, p.st>>>( a );
-	B200_CUDA( cudaGetLastError() );
-	note_launch( "trsm_panel_kernel<double,256x64>" );
-	return kSuccess;
+	auto go = [&]( auto Uc, auto Ac, auto Bc ) -> int
+	{
+		constexpr bool U = decltype( Uc )::value, AI = decltype( Ac )::value, BK = decltype( Bc )::value;
+		auto kern = trsm_panel_kernel<U, AI, BK>;
+		static const std::string kname = kfmt( "trsm_panel_kernel<double,256x64,UPPER=%d,AI=%d,BK=%d>", U, AI, BK );
+		static bool attr = false;
+		if ( !attr ) { if ( set_smem( kern, TrsmPanelCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<(unsigned)grid, TrsmPanelCfg::NT, TrsmPanelCfg::SMEM_BYTES, p.st>>>( a );
+		B200_CUDA( cudaGetLastError() );
+		note_launch( kname.c_str() );
+		return kSuccess;
+	};
+	using Tt = std::true_type; using Ff = std::false_type;
+	switch ( ( p.upper ? 4 : 0 ) | ( ai ? 2 : 0 ) | ( bk ? 1 : 0 ) )
+	{
+		case 0: return go( Ff{}, Ff{}, Ff{} );  case 1: return go( Ff{}, Ff{}, Tt{} );
+		case 2: return go( Ff{}, Tt{}, Ff{} );  case 3: return go( Ff{}, Tt{}, Tt{} );
+		case 4: return go( Tt{}, Ff{}, Ff{} );  case 5: return go( Tt{}, Ff{}, Tt{} );
+		case 6: return go( Tt{}, Tt{}, Ff{} );  default: return go( Tt{}, Tt{}, Tt{} );
+	}
 }
 template <typename T> static int trsm_leaf_rows() { return TrsmBlk<T>::NB; }
 template <> int trsm_leaf_rows<double>() { return ctx().trsm_fused ? TrsmPanelCfg::PB : TrsmBlk<double>::NB; }

@@ -46,6 +46,7 @@ GLUE_SRC = ROOT / "blis_b200" / "blis_glue" / "plugin" / "bli_b200_glue.c"
 L3_EX_OPS = ("gemm", "gemmt", "her2k", "syr2k", "hemm", "symm", "trmm3", "herk", "syrk", "trmm", "trsm")
 
 sys.path.insert(0, str(ROOT / "oracle"))
+sys.path.insert(0, str(ROOT))
 
 
 def _sub_once(text: str, old: str, new: str, what: str) -> str:
@@ -58,6 +59,10 @@ def make_overlay() -> Path:
     """Patched copies of the five reference files (see module docstring) under BUILD/overlay."""
     ov = BUILD / "overlay"
     ov.mkdir(parents=True, exist_ok=True)
+    # A quoted #include is resolved in the including file's own directory first, so the patched headers only win if the
+    # whole of frame/include is mirrored here (scratch copies; frame/include itself is then left out of the -I list).
+    for h in (REF / "frame" / "include").glob("*.h"):
+        shutil.copyfile(h, ov / h.name)
     t = (REF / "frame/include/bli_type_defs.h").read_text()
     t = _sub_once(t, "\t// Generic architecture/configuration\n\tBLIS_ARCH_GENERIC,",
                   "\t// NVIDIA B200 (whole-operation level-3 engine, config/b200)\n\tBLIS_ARCH_B200,\n\n"
@@ -140,7 +145,7 @@ def _inc_dirs(ov: Path):
         for d in [r] + sorted(x for x in r.rglob("*") if x.is_dir()):
             if build_ref.IGNORE_DIRS & set(d.relative_to(REF).parts):
                 continue
-            if any(d.glob("*.h")):
+            if any(d.glob("*.h")) and d != REF / "frame" / "include":
                 dirs.append(d)
     return dirs
 
