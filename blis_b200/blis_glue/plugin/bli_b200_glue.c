@@ -514,9 +514,9 @@ static void bli_b200_report( void )
 }
 __attribute__((constructor)) static void bli_b200_ctor( void )
 {
+	const char* v = getenv( "BLIS_B200_VERBOSE" );
+	if ( v != NULL && v[0] == '1' ) atexit( bli_b200_report );     /* also in a config/b200 build, where nothing is registered at run time */
 	const char* e = getenv( "BLIS_B200_PLUGIN" );
 	if ( e == NULL || e[0] != '1' ) return;
 	bli_plugin_register_b200();
-	const char* v = getenv( "BLIS_B200_VERBOSE" );
-	if ( v != NULL && v[0] == '1' ) atexit( bli_b200_report );
 }

@@ -236,6 +236,23 @@ def _build_blastest(incs, libdir: Path, libname: str, outdir: Path, extra_link=(
         shutil.copyfile(REF / "blastest" / "input" / f"{ch}blat3.in", outdir / f"{ch}blat3.in")
 
 
+def _derive_ukr_ops():
+    """input.operations.ukr: only the level-3 MICROKERNEL modules gemm, trsm, gemmtrsm (switch 2 = "only these") --
+    with the b200 context their gemm part runs in the engine-backed BLIS_GEMM_UKR slot (bli_gemm_b200_ukr.c)."""
+    lines = (REF / "testsuite" / "input.operations.fast").read_text().splitlines()
+    out, in_ukr = [], False
+    for ln in lines:
+        if ln.startswith("# --- Level-3 micro-kernels"):
+            in_ukr = True
+        elif ln.startswith("# --- Level-3 ---"):
+            in_ukr = False
+        m = re.match(r"^(\d)(\s+#\s+)(\w+)\s*$", ln)
+        if in_ukr and m and m.group(3) in ("gemm", "trsm", "gemmtrsm"):
+            ln = "2" + ln[1:]
+        out.append(ln)
+    (BINDIR / "input.operations.ukr").write_text("\n".join(out) + "\n")
+
+
 def build(force: bool = False) -> Path:
     if not REF.exists():
         if LIB.exists():
@@ -259,6 +276,7 @@ def build(force: bool = False) -> Path:
     subprocess.run(["gcc", "-shared", "-o", str(LIB), f"@{rsp}", f"-L{ROOT / 'blis_b200'}", "-lblis_b200", "-lm", "-lpthread",
                     "-Wl,-rpath,$ORIGIN/../../blis_b200"], check=True)
     _build_testsuite(incs)
+    _derive_ukr_ops()
     _build_blastest(incs, OUTDIR, "blis_b200cfg", BINDIR, extra_link=(f"-L{ROOT / 'blis_b200'}", "-lblis_b200"))
     # the same testers against the UNMODIFIED reference (run on the GPU box with the plugin preloaded, and as the CPU control)
     ref_incs = [f"-I{d}" for d in build_ref._inc_dirs()]

@@ -16,22 +16,31 @@ CFG_SRC = ROOT / "blis_b200" / "blis_glue" / "config" / "b200" / "bli_cntx_init_
 GLUE_SO = ROOT / "oracle" / "_ref" / "libblis_b200_glue.so"
 
 
+# Second flavour of the glue: NOTHING interposed.  The only binding is the one BLIS itself offers a plugin -- the
+# whole-operation gemm handler installed in the gemmsup_oft slot of the active context (frame/3/bli_l3_sup_oft.h:46-59,
+# bli_gemm_ex -> bli_gemmsup, frame/3/bli_l3_oapi_ex.c:76-77) -- so every dgemm_/cblas_dgemm/bli_?gemm call of an
+# unmodified libblis reaches the engine through bli_gemmsup_b200, and every other operation stays on the CPU.
+GLUE_SUP_SO = ROOT / "oracle" / "_ref" / "libblis_b200_glue_sup.so"
+
+
 def build(force: bool = False) -> Path:
     if not Path("/root/reference").exists():
         if GLUE_SO.exists():
             return GLUE_SO
         raise FileNotFoundError("no /root/reference and no prebuilt glue library")
-    if GLUE_SO.exists() and not force and GLUE_SO.stat().st_mtime >= GLUE_SRC.stat().st_mtime:
+    if GLUE_SO.exists() and GLUE_SUP_SO.exists() and not force and min(GLUE_SO.stat().st_mtime, GLUE_SUP_SO.stat().st_mtime) >= GLUE_SRC.stat().st_mtime:
         return GLUE_SO
     sys.path.insert(0, str(ROOT / "oracle"))
     import build_ref
     build_ref.build()
     incs = [f"-I{d}" for d in build_ref._inc_dirs()] + [f"-I{ROOT / 'include'}"]
-    cmd = ["gcc", "-std=c99", "-O2", "-fPIC", "-shared", "-D_POSIX_C_SOURCE=200809L", "-Wall", "-Wno-unused-function",
-           "-DBLIS_B200_OVERRIDE_TRSM_EX", "-DBLIS_B200_OVERRIDE_GEMMT_EX", "-DBLIS_B200_OVERRIDE_GEMM_EX", "-DBLIS_B200_OVERRIDE_GEMM_BATCH", *incs, str(GLUE_SRC), "-o", str(GLUE_SO),
-           f"-L{ROOT / 'blis_b200'}", "-lblis_b200", f"-L{GLUE_SO.parent}", "-lblis_ref",
-           "-Wl,-rpath,$ORIGIN/../../blis_b200", "-Wl,-rpath,$ORIGIN"]
-    subprocess.run(cmd, check=True)
+    for so, defs in ((GLUE_SO, ["-DBLIS_B200_OVERRIDE_TRSM_EX", "-DBLIS_B200_OVERRIDE_GEMMT_EX", "-DBLIS_B200_OVERRIDE_GEMM_EX", "-DBLIS_B200_OVERRIDE_GEMM_BATCH"]),
+                     (GLUE_SUP_SO, [])):
+        cmd = ["gcc", "-std=c99", "-O2", "-fPIC", "-shared", "-D_POSIX_C_SOURCE=200809L", "-Wall", "-Wno-unused-function",
+               *defs, *incs, str(GLUE_SRC), "-o", str(so),
+               f"-L{ROOT / 'blis_b200'}", "-lblis_b200", f"-L{so.parent}", "-lblis_ref",
+               "-Wl,-rpath,$ORIGIN/../../blis_b200", "-Wl,-rpath,$ORIGIN"]
+        subprocess.run(cmd, check=True)
     return GLUE_SO
 
 

@@ -100,3 +100,122 @@ def test_reference_testsuite_mixed_datatype_gemm_on_the_engine():
     assert not bad, "\n".join(bad[:10])
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "testsuite_mixed.b200.txt").write_text("\n".join(lines[::97]) + f"\n{len(lines)} experiments, all PASS\n" + m.group(0))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The boundary without symbol interposition ("make the boundary real")
+GLUE_SUP = REFDIR / "libblis_b200_glue_sup.so"
+CFG = REFDIR / "b200cfg"
+BLAT_REF = REFDIR / "blastest_ref"
+L3_LINE = re.compile(r"^blis_[sdcz](gemm|trsm|gemmt|syrk|herk|syr2k|her2k|hemm|symm|trmm|trmm3)_")
+KERNELS = re.compile(r"libblis \(b200\): (\d+) CUDA kernels")
+
+
+def _save(name, text):
+    (ROOT / "gpurun_out").mkdir(exist_ok=True)
+    (ROOT / "gpurun_out" / name).write_text(text)
+
+
+def test_gemm_served_by_the_gemmsup_handler_slot_only():
+    """The plugin route proper (SURVEY 8b "whole-op gemm hook"): the glue flavour built WITHOUT any -DBLIS_B200_OVERRIDE_*
+    defines no bli_<op>_ex symbol, so the unmodified libblis keeps its own bli_gemm_ex and reaches the engine only through
+    the gemmsup_oft slot of its context (frame/3/bli_l3_oapi_ex.c:76-77 -> frame/3/bli_l3_sup.c:37-135 -> bli_gemmsup_b200).
+    The reference testsuite's gemm rows (s/d/c/z, every transa/transb, row/column/general storage) must PASS and must
+    have launched engine kernels."""
+    _need(GLUE_SUP, TS / "test_libblis.x", TS / "input.general.n100", TS / "input.operations.gemm")
+    nm = subprocess.run(["nm", "-D", "--defined-only", str(GLUE_SUP)], capture_output=True, text=True).stdout
+    assert " bli_gemmsup_b200" in nm and not re.search(r" T bli_(gemm|trsm)_ex$", nm, re.M), "the sup flavour must not interpose bli_*_ex"
+    env = dict(os.environ, LD_PRELOAD=str(GLUE_SUP), BLIS_B200_PLUGIN="1", BLIS_B200_VERBOSE="1")
+    r = subprocess.run([str(TS / "test_libblis.x"), "-g", str(TS / "input.general.n100"), "-o", str(TS / "input.operations.gemm")],
+                       capture_output=True, text=True, timeout=1200, env=env, cwd=str(TS))
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if re.match(r"^blis_[sdcz]gemm_", ln)]
+    m = KERNELS.search(r.stderr)
+    assert lines and m and int(m.group(1)) >= len(lines), "the handler slot was not used: " + r.stderr[-500:]
+    bad = [ln for ln in lines if not ln.rstrip().endswith("PASS")]
+    assert not bad, "\n".join(bad[:10])
+    _save("testsuite_gemm_via_gemmsup_slot.b200.txt", "\n".join(lines) + "\n" + m.group(0) + "\n")
+
+
+def _run_cfg_testsuite(general, operations):
+    env = dict(os.environ, BLIS_B200_VERBOSE="1")
+    env.pop("LD_PRELOAD", None)
+    return subprocess.run([str(CFG / "test_libblis.x"), "-g", str(TS / general), "-o", str(operations)],
+                          capture_output=True, text=True, timeout=1500, env=env, cwd=str(CFG))
+
+
+def test_config_b200_library_passes_the_reference_testsuite():
+    """Route 2 of INTEGRATION.md: libblis compiled WITH the b200 sub-configuration (tests/b200cfg_build.py), the
+    reference's testsuite linked against it, no LD_PRELOAD and no run-time registration.  bli_arch_string() must say
+    b200, all level-3 experiments must PASS, and they must have run on the engine."""
+    _need(CFG / "test_libblis.x", REFDIR / "libblis_b200cfg.so", TS / "input.general.n100", TS / "input.operations.l3")
+    ldd = subprocess.run(["ldd", str(CFG / "test_libblis.x")], capture_output=True, text=True).stdout
+    assert "libblis_b200cfg.so" in ldd and "libblis_ref.so" not in ldd, ldd
+    r = _run_cfg_testsuite("input.general.n100", TS / "input.operations.l3")
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert re.search(r"^% active sub-configuration\s+b200\s*$", r.stdout, re.M), r.stdout[:1500]
+    lines = [ln for ln in r.stdout.splitlines() if L3_LINE.match(ln)]
+    m = KERNELS.search(r.stderr)
+    assert len(lines) >= 3000 and m and int(m.group(1)) > len(lines), (len(lines), r.stderr[-500:])
+    bad = [ln for ln in lines if not ln.rstrip().endswith("PASS")]
+    assert not bad, "\n".join(bad[:10])
+    _save("testsuite_config_b200_n100.txt", "\n".join(lines[::16]) + f"\n{len(lines)} experiments, all PASS\n{m.group(0)}\n"
+          + "\n".join(ln for ln in r.stdout.splitlines() if ln.startswith("% active sub-conf") or ln.startswith("% version")) + "\n")
+
+
+def test_config_b200_microkernel_slots_run_on_the_engine():
+    """The kernel slots of the b200 context stay truthful (hard part 1): the reference testsuite's level-3
+    MICROKERNEL modules (gemm_ukr, trsm_ukr, gemmtrsm_ukr: testsuite/src/test_gemm_ukr.c etc.) call whatever is registered
+    under BLIS_GEMM_UKR / BLIS_GEMMTRSM_?_UKR / BLIS_TRSM_?_UKR with packed micropanels of the context's MR x NR; with the
+    b200 context the gemm slot is bli_?gemm_b200_ukr (config/b200/bli_gemm_b200_ukr.c -> b200_gemm)."""
+    _need(CFG / "test_libblis.x", CFG / "input.operations.ukr", TS / "input.general.n100")
+    r = _run_cfg_testsuite("input.general.n100", CFG / "input.operations.ukr")
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if re.match(r"^blis_[sdcz](gemm|trsm|gemmtrsm)_ukr", ln)]
+    m = KERNELS.search(r.stderr)
+    assert lines and m and int(m.group(1)) >= len([ln for ln in lines if "gemm" in ln]), (len(lines), r.stderr[-500:])
+    bad = [ln for ln in lines if not ln.rstrip().endswith("PASS")]
+    assert not bad, "\n".join(bad[:10])
+    _save("testsuite_config_b200_ukr.txt", "\n".join(lines) + "\n" + m.group(0) + "\n")
+
+
+def _run_blat3(exe_dir, ch, env):
+    out = exe_dir / f"out.{ch}blat3"
+    if out.exists():
+        out.unlink()
+    with open(exe_dir / f"{ch}blat3.in") as fin:
+        r = subprocess.run([str(exe_dir / f"{ch}blat3.x")], stdin=fin, capture_output=True, text=True, timeout=1500, env=env, cwd=str(exe_dir))
+    text = out.read_text() if out.exists() else ""
+    return r, text
+
+
+def _check_blat3(ch, r, text, tag):
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    nops = {"s": 6, "d": 6, "c": 9, "z": 9}[ch]          # gemm symm trmm trsm syrk syr2k (+ hemm herk her2k)
+    assert len(re.findall(r"PASSED THE TESTS OF ERROR-EXITS", text)) == nops, text[-2500:]
+    assert len(re.findall(r"PASSED THE COMPUTATIONAL TESTS", text)) == nops, text[-2500:]
+    assert not re.search(r"FAIL|SUSPECT|ILLEGAL|\*\*\*\*\*\*", text), text[-2500:]
+    m = KERNELS.search(r.stderr)
+    calls = sum(int(x) for x in re.findall(r"\(\s*(\d+) CALLS\)", text))
+    assert m and int(m.group(1)) > calls // 4, ("the engine was not used", r.stderr[-400:], calls)
+    _save(f"blastest_{ch}blat3_{tag}.txt", text + m.group(0) + "\n")
+
+
+@pytest.mark.parametrize("ch", ["d", "s", "z", "c"])
+def test_netlib_blat3_on_config_b200(ch):
+    """blastest/src/?blat3.c (the netlib level-3 testers: error exits through xerbla + exact computational checks at the
+    ?gemm_/?trsm_/... boundary, Makefile:863-940) linked against libblis_b200cfg.so -- no LD_PRELOAD."""
+    _need(CFG / f"{ch}blat3.x", CFG / f"{ch}blat3.in", REFDIR / "libblis_b200cfg.so")
+    env = dict(os.environ, BLIS_B200_VERBOSE="1")
+    env.pop("LD_PRELOAD", None)
+    r, text = _run_blat3(CFG, ch, env)
+    _check_blat3(ch, r, text, "config_b200")
+
+
+@pytest.mark.parametrize("ch", ["d", "z"])
+def test_netlib_blat3_on_the_plugin(ch):
+    """The same testers linked against the UNMODIFIED reference, with the plugin preloaded (route 1)."""
+    _need(BLAT_REF / f"{ch}blat3.x", GLUE)
+    env = dict(os.environ, LD_PRELOAD=str(GLUE), BLIS_B200_PLUGIN="1", BLIS_B200_VERBOSE="1")
+    r, text = _run_blat3(BLAT_REF, ch, env)
+    _check_blat3(ch, r, text, "plugin")

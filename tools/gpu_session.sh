@@ -3,6 +3,7 @@
 #   tools/gpu_session.sh [stage ...]       stages run in the order given; outputs land in gpurun_out/
 # Stages:
 #   newtests   the parity tests added this round (TMA paths, skinny shapes, tile counters, fused trsm)
+#   dropin     tests/test_blis_dropin_gpu.py (reference testsuite + netlib ?blat3 on the plugin, the gemmsup slot, config/b200)
 #   pytest     the whole -m gpu suite
 #   smoke      __graft_entry__.smoke()
 #   sanitize   compute-sanitizer memcheck + racecheck over tools/sanitize_driver.py
@@ -20,6 +21,9 @@ case "$stage" in
 newtests)
 	( time timeout 1500 python -m pytest tests -x -q -m gpu -k "fused or tma_paths or large_ragged or skinny_k64 or tile_counters" ) > gpurun_out/pytest_new.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_new.log
 	tail -12 gpurun_out/pytest_new.log ;;
+dropin)
+	( time timeout 2400 python -m pytest tests/test_blis_dropin_gpu.py -q -m gpu ) > gpurun_out/pytest_dropin.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_dropin.log
+	tail -25 gpurun_out/pytest_dropin.log ;;
 pytest)
 	( time timeout 2400 python -m pytest tests -x -q -m gpu ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 	tail -8 gpurun_out/pytest_gpu.log ;;
