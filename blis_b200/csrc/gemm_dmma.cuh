@@ -47,6 +47,9 @@ struct GemmArgs
 	int      nseg;
 	const T* Xseg[7];
 	const T* Yseg[7];
+	// TMA kernels, nseg > 1: the panels of an operand sit at base + slot*stride (one 3-D tensor map per operand, third
+	// coordinate = slot); segx[s] / segy[s] is the slot of k panel s (launch_dmma_tma fills them in).
+	int      segx[8], segy[8];
 	// Triangular D (the gemmt family: frame/3/gemmt/bli_gemmt_{l,u}_ker_var2.c computes only the stored
 	// triangle of C).  tri == 0: full;  tri == 1: only q - p <= tri_off;  tri == 2: only q - p >= tri_off.
 	// Tiles wholly outside are skipped, rows of tiles crossing the diagonal are clipped in the epilogue.

@@ -41,6 +41,12 @@ __device__ __forceinline__ void tma_load_2d( uint32_t dst, const CUtensorMap* ma
 	              :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory" );
 }
 
+__device__ __forceinline__ void tma_load_3d( uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar )
+{
+	asm volatile( "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+	              :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory" );
+}
+
 // Producer side: ask L2 for the BP x BQ tile of D at (p0, q0) now (one bulk prefetch per row); the consumers' epilogue
 // reads it after the k loop.  Needs 16-byte aligned rows (d_vec_ok); nothing is requested when beta == 0.
 template <typename T>
@@ -112,7 +118,10 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 	}
 	__syncthreads();
 
-	const int64_t KT = ( g.K + BK - 1 ) / BK;
+	// k-panel accumulation (b200_gemm_kpanels: the pc loop of bli_gemm_blk_var3 inside one launch): nseg panels of K each,
+	// described by 3-D tensor maps whose third coordinate selects the panel; the consumers see one long k loop.
+	const int64_t KT_SEG = ( g.K + BK - 1 ) / BK;
+	const int64_t KT = KT_SEG * g.nseg;
 	const int num_tiles = g.tiles_p * g.tiles_q;
 
 	if ( tid >= Cfg::NCONS )
@@ -143,19 +152,40 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 				mbar_wait( empty_bar( stage ), phase ^ 1u );
 				const uint32_t xs = sbase + (uint32_t)stage * Cfg::STAGE_BYTES, ys = xs + Cfg::OPER_BYTES;
 				const uint32_t fb = full_bar( stage );
-				const int k0 = (int)( kt * BK );
 				mbar_arrive_expect_tx( fb, 2u * Cfg::OPER_BYTES );
-				if constexpr ( XK ) tma_load_2d( xs, &tmx, k0, p0, fb );
-				else
+				if ( g.nseg == 1 )
 				{
-					#pragma unroll
-					for ( int b = 0; b < BP / 16; ++b ) tma_load_2d( xs + b * 2048, &tmx, p0 + b * 16, k0, fb );
+					const int k0 = (int)( kt * BK );
+					if constexpr ( XK ) tma_load_2d( xs, &tmx, k0, p0, fb );
+					else
+					{
+						#pragma unroll
+						for ( int b = 0; b < BP / 16; ++b ) tma_load_2d( xs + b * 2048, &tmx, p0 + b * 16, k0, fb );
+					}
+					if constexpr ( YK ) tma_load_2d( ys, &tmy, k0, q0, fb );
+					else
+					{
+						#pragma unroll
+						for ( int b = 0; b < BQ / 16; ++b ) tma_load_2d( ys + b * 2048, &tmy, q0 + b * 16, k0, fb );
+					}
 				}
-				if constexpr ( YK ) tma_load_2d( ys, &tmy, k0, q0, fb );
 				else
 				{
-					#pragma unroll
-					for ( int b = 0; b < BQ / 16; ++b ) tma_load_2d( ys + b * 2048, &tmy, q0 + b * 16, k0, fb );
+					const int seg = (int)( kt / KT_SEG );
+					const int k0 = (int)( ( kt - seg * KT_SEG ) * BK );
+					const int sx = g.segx[seg], sy = g.segy[seg];
+					if constexpr ( XK ) tma_load_3d( xs, &tmx, k0, p0, sx, fb );
+					else
+					{
+						#pragma unroll
+						for ( int b = 0; b < BP / 16; ++b ) tma_load_3d( xs + b * 2048, &tmx, p0 + b * 16, k0, sx, fb );
+					}
+					if constexpr ( YK ) tma_load_3d( ys, &tmy, k0, q0, sy, fb );
+					else
+					{
+						#pragma unroll
+						for ( int b = 0; b < BQ / 16; ++b ) tma_load_3d( ys + b * 2048, &tmy, q0 + b * 16, k0, sy, fb );
+					}
 				}
 				if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
 			}

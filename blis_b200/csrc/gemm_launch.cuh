@@ -136,19 +136,77 @@ static int make_tmap( CUtensorMap* tm, const void* base, size_t es, bool kmajor,
 	if ( r != CUDA_SUCCESS ) return fail( "cuTensorMapEncodeTiled failed (%d)", (int)r );
 	return kSuccess;
 }
+// k panels of one operand as slots of ONE 3-D tensor map: all panel pointers must sit at base + slot*stride with a
+// 16-byte aligned stride (true for the gather buffers of the multi-GPU path and for panels cut out of one matrix).
+template <typename T>
+static bool seg_slots( const T* p0, const T* const* more, int nseg, const T** base, int64_t* stride_bytes, int* slots )
+{
+	const T* lo = p0; int64_t S = 0;
+	for ( int s = 1; s < nseg; ++s ) lo = std::min( lo, more[s - 1] );
+	for ( int s = 0; s < nseg; ++s )
+	{
+		const int64_t d = (const char*)( s ? more[s - 1] : p0 ) - (const char*)lo;
+		if ( d > 0 && ( S == 0 || d < S ) ) S = d;
+	}
+	if ( S == 0 ) S = 16;                                        // all panels identical
+	if ( S % 16 != 0 || S >= ( 1ll << 40 ) ) return false;
+	for ( int s = 0; s < nseg; ++s )
+	{
+		const int64_t d = (const char*)( s ? more[s - 1] : p0 ) - (const char*)lo;
+		if ( d % S != 0 || d / S >= ( 1 << 20 ) ) return false;
+		slots[s] = (int)( d / S );
+	}
+	*base = lo; *stride_bytes = S;
+	return true;
+}
+// 3-D variant of make_tmap: dims {.., .., nslots}, box {.., .., 1}; the shared-memory image of a box equals the 2-D one.
+static int make_tmap3( CUtensorMap* tm, const void* base, bool kmajor, int64_t rows, int64_t K, int64_t ld, int64_t slot_bytes, int nslots )
+{
+	EncodeTiledFn enc = encode_tiled_fn();
+	if ( !enc ) return fail( "cuTensorMapEncodeTiled not available" );
+	cuuint64_t dims[3]    = { (cuuint64_t)( kmajor ? K : rows ), (cuuint64_t)( kmajor ? rows : K ), (cuuint64_t)nslots };
+	cuuint64_t strides[2] = { (cuuint64_t)ld * 8, (cuuint64_t)slot_bytes };
+	cuuint32_t box[3]     = { 16, (cuuint32_t)( kmajor ? 128 : 16 ), 1 };
+	cuuint32_t estr[3]    = { 1, 1, 1 };
+	const CUresult r = enc( tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, estr,
+	                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, (CUtensorMapL2promotion)ctx().tma_l2_promotion,
+	                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+	if ( r != CUDA_SUCCESS ) return fail( "cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r );
+	return kSuccess;
+}
 template <typename T>
 static bool tma_eligible( const GemmArgs<T>& g, bool xk, bool yk, bool al )
 {
 	// TMA needs 16-byte aligned bases and strides (== al), a leading dimension that covers the row, 32-bit box coordinates
-	return al && g.nseg == 1 && g.P < ( 1ll << 31 ) && g.Q < ( 1ll << 31 ) && g.K < ( 1ll << 31 ) &&
+	if ( g.nseg > 1 )
+	{
+		if ( !std::is_same<T, double>::value || g.tri || g.ktri ) return false;
+		const T* b; int64_t S; int sl[8];
+		if ( !seg_slots( g.X, g.Xseg, g.nseg, &b, &S, sl ) || !seg_slots( g.Y, g.Yseg, g.nseg, &b, &S, sl ) ) return false;
+	}
+	return al && g.P < ( 1ll << 31 ) && g.Q < ( 1ll << 31 ) && g.K < ( 1ll << 31 ) &&
 	       g.ldx >= ( xk ? g.K : g.P ) && g.ldy >= ( yk ? g.K : g.Q ) && g.ldx * 8 < ( 1ll << 40 ) && g.ldy * 8 < ( 1ll << 40 );
 }
 template <bool TRI = false, bool CST = false>
-static int launch_dmma_tma( const GemmArgs<double>& g, bool xk, bool yk, int grid, cudaStream_t st )
+static int launch_dmma_tma( const GemmArgs<double>& g_in, bool xk, bool yk, int grid, cudaStream_t st )
 {
+	GemmArgs<double> g = g_in;
 	CUtensorMap tmx, tmy, tmd;
-	if ( make_tmap( &tmx, g.X, 8, xk, g.P, g.K, g.ldx ) != kSuccess ) return kFailure;
-	if ( make_tmap( &tmy, g.Y, 8, yk, g.Q, g.K, g.ldy ) != kSuccess ) return kFailure;
+	if ( g.nseg > 1 )
+	{
+		const double *bx, *by; int64_t sx, sy;
+		if ( !seg_slots( g.X, g.Xseg, g.nseg, &bx, &sx, g.segx ) || !seg_slots( g.Y, g.Yseg, g.nseg, &by, &sy, g.segy ) )
+			return fail( "k panels are not slots of one strided buffer" );
+		int nx = 0, ny = 0;
+		for ( int s = 0; s < g.nseg; ++s ) { nx = std::max( nx, g.segx[s] + 1 ); ny = std::max( ny, g.segy[s] + 1 ); }
+		if ( make_tmap3( &tmx, bx, xk, g.P, g.K, g.ldx, sx, nx ) != kSuccess ) return kFailure;
+		if ( make_tmap3( &tmy, by, yk, g.Q, g.K, g.ldy, sy, ny ) != kSuccess ) return kFailure;
+	}
+	else
+	{
+		if ( make_tmap( &tmx, g.X, 8, xk, g.P, g.K, g.ldx ) != kSuccess ) return kFailure;
+		if ( make_tmap( &tmy, g.Y, 8, yk, g.Q, g.K, g.ldy ) != kSuccess ) return kFailure;
+	}
 	// D as {16 columns, 32 rows} boxes (CST: the epilogue reads D from shared memory); a copy of tmx when unused
 	if ( CST ) { if ( make_tmap( &tmd, g.D, 8, true, g.P, g.Q, g.ldd, 32 ) != kSuccess ) return kFailure; }
 	else tmd = tmx;
