@@ -282,6 +282,15 @@ def trsm_inputs(torch, m, n_cols, device, seed, b_seed=None):
     return at, bt0
 
 
+def measured_hbm_peak():
+    """(GB/s, source): the driver-written copy bandwidth of this pool's B200s, else the profiling recipe's fallback."""
+    try:
+        v = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+        return v, "MEASURED_PEAKS.json hbm_gbs (driver-written: torch copy of 1 Gi bf16 elements, read+write bytes)"
+    except (OSError, ValueError, KeyError):
+        return 6650.0, "fallback of /opt/skills/guides/B200_PROFILING.md (no MEASURED_PEAKS.json)"
+
+
 def gemm_kernel_of(stats: dict) -> str:
     """The gemm tile kernel with the most launches in a kernel histogram."""
     g = {k: v for k, v in stats.items() if k.startswith("gemm_")}
@@ -336,6 +345,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-peak", action="store_true", help="skip the FP64 peak microbenchmark (profiling runs)")
     ap.add_argument("--no-check", action="store_true", help="N > 1: skip the post-timing parity check of the distributed result")
+    ap.add_argument("--no-skinny", action="store_true", help="skip the skinny k=64 leg (BASELINE configs[2] shape, HBM roofline)")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling leg (one 16384^3 over all GPUs)")
     ap.add_argument("--workload", default="headline", choices=["headline", "g3"],
                     help="g3 = BASELINE configs[4]: dgemm m=n=k=65536 2D-sharded over all ranks")
@@ -536,6 +546,34 @@ def main():
                 del a, b, c
             torch.cuda.empty_cache()
 
+        # ============================================================== skinny dgemm (BASELINE configs[2]: the sup shapes, k = 64)
+        skinny_line = None
+        if args.op == "both" and args.workload == "headline" and not args.no_skinny:
+            from blis_b200 import dist as bdist
+            ks = 64
+            sj = bdist.DistSkinnyGemm(n, n * world, ks, world, rank, dev, alpha=ALPHA, beta=BETA, root=0)
+            ssteps = max(args.steps, 20)
+            sms, sper, sl, sstats, _ = timed(sj.step, ssteps, args.warmup)
+            sck = None if args.no_check else sj.verify()
+            if sck is not None:
+                t = torch.tensor([1.0 if sck["bit_equal"] else 0.0, -sck["resid"]], dtype=torch.float64, device=dev)
+                if dist is not None:
+                    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                sck = {"bit_equal_to_single_gpu_engine": bool(t[0].item() == 1.0), "testsuite_resid_max_over_ranks": float(-t[1].item())}
+            if rank == 0:
+                hbm = measured_hbm_peak()
+                gbs = sj.bytes_rank / (sum(sper) / len(sper) * 1e-3) / 1e9
+                skinny_line = {"value": sj.total_flops / (sms * 1e-3) / 1e9, "unit": "GFLOPS", "ms_per_step": sms, "steps": ssteps,
+                               "scaling": "weak", "workload": f"dgemm m={n} n={n}*N k={ks} column-major fp64, alpha=2.0 beta=1.2 (BASELINE configs[2] skinny shape per GPU)",
+                               "parallelism": sj.describe() if world > 1 else "single GPU", "gpu_launches": sl, "check": sck,
+                               "l2": "C block (2 GiB per GPU) far exceeds the 126 MB L2; A and B (8 MB each) are L2 resident by design",
+                               "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm[0], "unit": "GB/s", "frac": gbs / hbm[0], "traffic": None,
+                                            "peak_source": hbm[1], "kernel": gemm_kernel_of(sstats), "kernels": sstats,
+                                            "algorithmic_bytes_per_step_per_gpu": sj.bytes_rank,
+                                            "dmma_frac": (sj.total_flops / world) / (sum(sper) / len(sper) * 1e-3) / 1e12 / dmma_peak()}}
+            del sj
+            torch.cuda.empty_cache()
+
         # ============================================================== dtrsm
         trsm_line = None
         if args.op in ("both", "dtrsm") and args.workload == "headline":
@@ -546,15 +584,22 @@ def main():
             else:
                 from blis_b200 import dist as bdist
                 j0, j1 = bdist.trsm_column_block(rank, world, n_t)
-                par_t = f"B split into {world} column blocks (bli_thread_range_sub, bf=128), A replicated; strong scaling, no data-path collective"
+                par_t = (f"B split into {world} column blocks (bli_thread_range_sub, bf=128), A replicated; strong scaling, no data-path collective; "
+                     "one b200_dist_trsm call per solve")
             at, bt0 = trsm_inputs(torch, m_t, j1 - j0, dev, 0xB200, b_seed=0xB201 + rank)
             bt = bt0.clone(memory_format=torch.preserve_format)
 
             def restore():
                 bt.copy_(bt0)
 
+            if world > 1:
+                bdist.native_init(dev)
+
             def tstep():
-                api.bli_dtrsm(0, 0xC0, 0, 0, m_t, j1 - j0, ALPHA, at, 1, m_t, bt, 1, m_t)
+                if world > 1:       # ONE C-ABI call: the engine cuts this rank's column block itself (b200_dist_trsm; A already replicated)
+                    api.dist_trsm(torch.float64, 0, 0xC0, 0, 0, -1, m_t, n_t, ALPHA, at, 1, m_t, bt, 1, m_t)
+                else:
+                    api.bli_dtrsm(0, 0xC0, 0, 0, m_t, j1 - j0, ALPHA, at, 1, m_t, bt, 1, m_t)
             restore()
             tsteps = max(2, min(args.steps, 5))
             tms, tper, tl, tstats, tclocks = timed(tstep, tsteps, args.warmup, around=restore)
@@ -625,7 +670,7 @@ def main():
                            "l2": "inputs (3 x 2 GiB per GPU) far exceed the 126 MB L2; no flush needed",
                            "timing": "CUDA events on the launching stream, max over ranks"},
                 "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": head["launches"], "roofline": head["roof"], "cpu_baseline": cpu,
-                "dtrsm": trsm_line,
+                "dtrsm": trsm_line, "skinny": skinny_line,
             }
             if world > 1:
                 line["check"] = head["check"]; line["strong"] = head["strong"]

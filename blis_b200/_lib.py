@@ -27,8 +27,17 @@ EXPORTS = [
     "b200_trsm", "b200_strsm", "b200_dtrsm", "b200_ctrsm", "b200_ztrsm",
     "b200_gemmt", "b200_syrk", "b200_herk", "b200_syr2k", "b200_her2k",
     "b200_hemm", "b200_symm", "b200_trmm3", "b200_trmm", "b200_gemm_md", "b200_gemm_batch",
+    "b200_partition_2x2", "b200_range_sub", "b200_dist_plan", "b200_dist_unique_id", "b200_dist_init", "b200_dist_finalize",
+    "b200_dist_gemm", "b200_dist_last_wait_ms", "b200_dist_gemm_1d", "b200_dist_trsm",
     "b200_blksz", "b200_measure_peak", "b200_launch_count", "b200_set_option", "b200_last_kernel", "b200_kernel_stats",
 ]
+
+class DistPlan(C.Structure):
+    """b200_dist_plan_t (include/blis_b200.h)."""
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("pr", C.c_int), ("pc", C.c_int), ("i", C.c_int), ("j", C.c_int),
+                ("m0", C.c_int64), ("m1", C.c_int64), ("n0", C.c_int64), ("n1", C.c_int64), ("kb", C.c_int64),
+                ("L", C.c_int), ("T", C.c_int), ("steps", C.c_int), ("na", C.c_int), ("nb", C.c_int)]
+
 
 _lib = None
 
@@ -80,6 +89,18 @@ def load() -> C.CDLL:
     lib.b200_gemm_md.argtypes = [ci, ci, ci, ci, ci, ci, i64, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
     lib.b200_gemm_md.restype = ci
     lib.b200_gemm_batch.argtypes = [ci, ci] + [vp] * 17; lib.b200_gemm_batch.restype = ci
+    pi64 = C.POINTER(i64)
+    lib.b200_partition_2x2.argtypes = [i64, i64, i64, pi64, pi64]; lib.b200_partition_2x2.restype = None
+    lib.b200_range_sub.argtypes = [i64, i64, i64, i64, ci, pi64, pi64]; lib.b200_range_sub.restype = None
+    lib.b200_dist_plan.argtypes = [ci, ci, i64, i64, i64, i64, C.POINTER(DistPlan)]; lib.b200_dist_plan.restype = ci
+    lib.b200_dist_unique_id.argtypes = [vp]; lib.b200_dist_unique_id.restype = ci
+    lib.b200_dist_init.argtypes = [ci, ci, vp]; lib.b200_dist_init.restype = ci
+    lib.b200_dist_finalize.argtypes = []; lib.b200_dist_finalize.restype = ci
+    lib.b200_dist_gemm.argtypes = [ci, i64, i64, i64, i64, vp, vp, vp, vp, vp, i64, i64, ci]; lib.b200_dist_gemm.restype = ci
+    lib.b200_dist_last_wait_ms.argtypes = []; lib.b200_dist_last_wait_ms.restype = C.c_double
+    lib.b200_dist_gemm_1d.argtypes = [ci, ci, ci, i64, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
+    lib.b200_dist_gemm_1d.restype = ci
+    lib.b200_dist_trsm.argtypes = [ci, ci, ci, ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64]; lib.b200_dist_trsm.restype = ci
     lib.b200_blksz.argtypes = [ci, ci]; lib.b200_blksz.restype = i64
     lib.b200_measure_peak.argtypes = [ci, ci]; lib.b200_measure_peak.restype = C.c_double
     lib.b200_launch_count.argtypes = []; lib.b200_launch_count.restype = C.c_ulonglong

@@ -86,6 +86,80 @@ def bli_gemm_kpanels(dtype, transa, transb, m, n, k, alpha, a_panels, rs_a, cs_a
     check(rc, "bli_gemm_kpanels")
 
 
+# ----------------------------------------------------------------------------- multi-GPU (one process per GPU)
+DIST_COLS, DIST_ROWS = 0, 1
+DIST_AB_STATIC, DIST_TRACE = 1, 2
+
+
+def partition_2x2(n_thread: int, work1: int, work2: int):
+    """bli_thread_partition_2x2 through the C ABI (host arithmetic only)."""
+    a, b = C.c_int64(), C.c_int64()
+    _lib.load().b200_partition_2x2(n_thread, work1, work2, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def range_sub(work_id: int, n_way: int, n: int, bf: int, handle_edge_low: bool = False):
+    """bli_thread_range_sub through the C ABI (host arithmetic only)."""
+    a, b = C.c_int64(), C.c_int64()
+    _lib.load().b200_range_sub(work_id, n_way, n, bf, int(handle_edge_low), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def dist_plan(world: int, rank: int, m: int, n: int, k: int, kb: int) -> "_lib.DistPlan":
+    p = _lib.DistPlan()
+    check(_lib.load().b200_dist_plan(world, rank, m, n, k, kb, C.byref(p)), "b200_dist_plan")
+    return p
+
+
+def dist_init(device=None) -> None:
+    """Bootstrap the engine's NCCL communicator from an initialised torch.distributed process group: rank 0 draws the
+    unique id (b200_dist_unique_id), torch.distributed carries the 128 bytes, every rank calls b200_dist_init."""
+    import torch.distributed as dist
+    lib = _lib.load()
+    if device is not None:
+        torch.cuda.set_device(device)
+    check(lib.b200_init(-1), "b200_init")
+    buf = (C.c_ubyte * 128)()
+    if dist.get_rank() == 0:
+        check(lib.b200_dist_unique_id(buf), "b200_dist_unique_id")
+    box = [bytes(buf)]
+    dist.broadcast_object_list(box, src=0)
+    ident = (C.c_ubyte * 128).from_buffer_copy(box[0])
+    check(lib.b200_dist_init(dist.get_world_size(), dist.get_rank(), ident), "b200_dist_init")
+
+
+def dist_finalize() -> None:
+    check(_lib.load().b200_dist_finalize(), "b200_dist_finalize")
+
+
+def dist_gemm(dtype, m, n, k, kb, alpha, a_loc, b_loc, beta, c_loc, rs_c, cs_c, flags=0) -> None:
+    lib = _lib.load()
+    _bind_stream(c_loc)
+    al, be = _scalar_buf(dtype, alpha), _scalar_buf(dtype, beta)
+    check(lib.b200_dist_gemm(_DT[dtype], m, n, k, kb, C.addressof(al), _ptr(a_loc), _ptr(b_loc), C.addressof(be),
+                             _ptr(c_loc), rs_c, cs_c, flags), "b200_dist_gemm")
+
+
+def dist_last_wait_ms() -> float:
+    return float(_lib.load().b200_dist_last_wait_ms())
+
+
+def dist_gemm_1d(dtype, split, root, m, n, k, alpha, a, rs_a, cs_a, b, rs_b, cs_b, beta, c_loc, rs_c, cs_c) -> None:
+    lib = _lib.load()
+    _bind_stream(c_loc)
+    al, be = _scalar_buf(dtype, alpha), _scalar_buf(dtype, beta)
+    check(lib.b200_dist_gemm_1d(_DT[dtype], split, root, m, n, k, C.addressof(al), _ptr(a), rs_a, cs_a, _ptr(b), rs_b, cs_b,
+                                C.addressof(be), _ptr(c_loc), rs_c, cs_c), "b200_dist_gemm_1d")
+
+
+def dist_trsm(dtype, side, uploa, transa, diaga, root, m, n, alpha, a, rs_a, cs_a, b_loc, rs_b, cs_b) -> None:
+    lib = _lib.load()
+    _bind_stream(b_loc)
+    al = _scalar_buf(dtype, alpha)
+    check(lib.b200_dist_trsm(_DT[dtype], int(side), int(uploa), int(transa), int(diaga), root, m, n, C.addressof(al),
+                             _ptr(a), rs_a, cs_a, _ptr(b_loc), rs_b, cs_b), "b200_dist_trsm")
+
+
 def _typed_trsm(dtype):
     def f(side, uploa, transa, diaga, m, n, alpha, a, rs_a, cs_a, b, rs_b, cs_b):
         lib = _lib.load()

@@ -9,6 +9,7 @@
 //   host_strucmm.cuh  bli_hemm_ex / symm / trmm3 / trmm (:349-689)
 //   host_md.cuh       mixed-datatype gemm (frame/3/gemm/bli_gemm_cntl.c:87-392)
 //   host_batch.cuh    ?gemm_batch_ (frame/compat/extra/bla_gemm_batch.c)
+//   host_dist.cuh     multi-GPU gemm / trsm (one process per GPU, NCCL): the reference's jc x ic partitioning across GPUs
 //   host_util.cuh     scalar traits, strided copy / scale / transpose kernels
 // The kernels themselves are launched from gemm_{d,z,s,c}.cu (gemm_launch.cuh).
 
@@ -19,6 +20,7 @@
 #include "host_strucmm.cuh"
 #include "host_md.cuh"
 #include "host_batch.cuh"
+#include "host_dist.cuh"
 
 
 // ---- C ABI --------------------------------------------------------------------------
@@ -232,6 +234,53 @@ extern "C" b200_err_t b200_gemm_kpanels( int dt, int transa, int transb, b200_di
 	return fail( "b200_gemm_kpanels: only d and z are supported" );
 }
 
+// ---- multi-GPU (host_dist.cuh) ------------------------------------------------------------------------------------
+extern "C" void b200_partition_2x2( b200_dim_t n_thread, b200_dim_t work1, b200_dim_t work2, b200_dim_t* nt1, b200_dim_t* nt2 )
+{ partition_2x2( n_thread, work1, work2, nt1, nt2 ); }
+extern "C" void b200_range_sub( b200_dim_t work_id, b200_dim_t n_way, b200_dim_t n, b200_dim_t bf, int handle_edge_low, b200_dim_t* start, b200_dim_t* end )
+{ range_sub( work_id, n_way, n, bf, handle_edge_low != 0, start, end ); }
+extern "C" b200_err_t b200_dist_plan( int world, int rank, b200_dim_t m, b200_dim_t n, b200_dim_t k, b200_dim_t kb, b200_dist_plan_t* plan )
+{ return dist_plan( world, rank, m, n, k, kb, plan ); }
+extern "C" b200_err_t b200_dist_unique_id( void* id ) { return dist_unique_id( id ); }
+extern "C" b200_err_t b200_dist_init( int world, int rank, const void* id ) { return dist_init( world, rank, id ); }
+extern "C" b200_err_t b200_dist_finalize( void ) { return dist_finalize(); }
+extern "C" double b200_dist_last_wait_ms( void ) { return dist_last_wait_ms(); }
+extern "C" b200_err_t b200_dist_gemm( int dt, b200_dim_t m, b200_dim_t n, b200_dim_t k, b200_dim_t kb, const void* alpha,
+	const void* a_loc, const void* b_loc, const void* beta, void* c_loc, b200_inc_t rs_c, b200_inc_t cs_c, int flags )
+{
+	if ( !alpha || !beta ) return fail( "b200_dist_gemm: alpha and beta must be non-NULL host pointers" );
+	if ( dt == B200_DOUBLE )
+		return dist_gemm<double>( m, n, k, kb, (const double*)alpha, (const double*)a_loc, (const double*)b_loc, (const double*)beta, (double*)c_loc, rs_c, cs_c, flags );
+	if ( dt == B200_DCOMPLEX )
+		return dist_gemm<double2>( m, n, k, kb, (const double2*)alpha, (const double2*)a_loc, (const double2*)b_loc, (const double2*)beta, (double2*)c_loc, rs_c, cs_c, flags );
+	return fail( "b200_dist_gemm: only d and z are supported (k-panel accumulation, b200_gemm_kpanels)" );
+}
+extern "C" b200_err_t b200_dist_gemm_1d( int dt, int split, int root, b200_dim_t m, b200_dim_t n, b200_dim_t k, const void* alpha,
+	void* a, b200_inc_t rs_a, b200_inc_t cs_a, void* b, b200_inc_t rs_b, b200_inc_t cs_b, const void* beta, void* c_loc, b200_inc_t rs_c, b200_inc_t cs_c )
+{
+	if ( !alpha || !beta ) return fail( "b200_dist_gemm_1d: alpha and beta must be non-NULL host pointers" );
+	switch ( dt )
+	{
+		case B200_FLOAT:    return dist_gemm_1d<float>  ( split, root, m, n, k, (const float*)alpha,   (float*)a,   rs_a, cs_a, (float*)b,   rs_b, cs_b, (const float*)beta,   (float*)c_loc,   rs_c, cs_c );
+		case B200_DOUBLE:   return dist_gemm_1d<double> ( split, root, m, n, k, (const double*)alpha,  (double*)a,  rs_a, cs_a, (double*)b,  rs_b, cs_b, (const double*)beta,  (double*)c_loc,  rs_c, cs_c );
+		case B200_SCOMPLEX: return dist_gemm_1d<float2> ( split, root, m, n, k, (const float2*)alpha,  (float2*)a,  rs_a, cs_a, (float2*)b,  rs_b, cs_b, (const float2*)beta,  (float2*)c_loc,  rs_c, cs_c );
+		case B200_DCOMPLEX: return dist_gemm_1d<double2>( split, root, m, n, k, (const double2*)alpha, (double2*)a, rs_a, cs_a, (double2*)b, rs_b, cs_b, (const double2*)beta, (double2*)c_loc, rs_c, cs_c );
+	}
+	return fail( "b200_dist_gemm_1d: unsupported datatype %d", dt );
+}
+extern "C" b200_err_t b200_dist_trsm( int dt, int side, int uploa, int transa, int diaga, int root, b200_dim_t m, b200_dim_t n, const void* alpha,
+	void* a, b200_inc_t rs_a, b200_inc_t cs_a, void* b_loc, b200_inc_t rs_b, b200_inc_t cs_b )
+{
+	switch ( dt )
+	{
+		case B200_FLOAT:    return dist_trsm<float>  ( side, uploa, transa, diaga, root, m, n, (const float*)alpha,   (float*)a,   rs_a, cs_a, (float*)b_loc,   rs_b, cs_b );
+		case B200_DOUBLE:   return dist_trsm<double> ( side, uploa, transa, diaga, root, m, n, (const double*)alpha,  (double*)a,  rs_a, cs_a, (double*)b_loc,  rs_b, cs_b );
+		case B200_SCOMPLEX: return dist_trsm<float2> ( side, uploa, transa, diaga, root, m, n, (const float2*)alpha,  (float2*)a,  rs_a, cs_a, (float2*)b_loc,  rs_b, cs_b );
+		case B200_DCOMPLEX: return dist_trsm<double2>( side, uploa, transa, diaga, root, m, n, (const double2*)alpha, (double2*)a, rs_a, cs_a, (double2*)b_loc, rs_b, cs_b );
+	}
+	return fail( "b200_dist_trsm: unsupported datatype %d", dt );
+}
+
 extern "C" b200_dim_t b200_blksz( int dt, int bs )
 {
 	auto pick = [&]( int mr, int nr, int mc, int kc, int nc ) -> b200_dim_t
@@ -267,6 +316,7 @@ extern "C" b200_err_t b200_set_option( const char* key, long long value )
 	else if ( !strcmp( key, "host_kpipe" ) ) c.host_kpipe = (int)value;
 	else if ( !strcmp( key, "dmma_cst" ) ) c.dmma_cst = (int)value;
 	else if ( !strcmp( key, "trsm_fused" ) ) c.trsm_fused = (int)value;
+	else if ( !strcmp( key, "dist_ab_static" ) ) dist().ab_static = (int)value;
 	else if ( !strcmp( key, "tma_l2_promotion" ) ) c.tma_l2_promotion = (int)std::min<long long>( 3, std::max<long long>( 0, value ) );
 	else if ( !strcmp( key, "raster_group" ) ) c.raster_group = (int)std::max<long long>( 1, value );
 	else if ( !strcmp( key, "reserve_sms" ) )

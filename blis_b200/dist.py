@@ -245,13 +245,43 @@ def summa_host(plan: SummaPlan, ex: PanelExchange, hosts, c_dense: torch.Tensor,
     cur.wait_stream(s_out)                      # whoever synchronises `cur` has C at home
 
 
+_native_up = False
+
+
+def native_init(device) -> None:
+    """Bring up the engine's own NCCL communicator (b200_dist_init) once per process, bootstrapped over the already
+    initialised torch.distributed group (api.dist_init)."""
+    global _native_up
+    if not _native_up:
+        from . import api
+        api.dist_init(device)
+        _native_up = True
+
+
+def native_finalize() -> None:
+    global _native_up
+    if _native_up:
+        from . import api
+        torch.cuda.synchronize()
+        api.dist_finalize()
+        _native_up = False
+
+
 class DistGemm:
     """C := beta*C + alpha*A*B on a Pr x Pc grid of GPUs; every rank holds its block of C and its
-    block-cyclic k-panels of A's row panel / B's column panel (synthetic data generated in place)."""
+    block-cyclic k-panels of A's row panel / B's column panel (synthetic data generated in place).
 
-    def __init__(self, M: int, N: int, K: int, world: int, rank: int, device, alpha=2.0, beta=1.2, kb: int = 2048):
+    `step()` is ONE call of the C ABI, b200_dist_gemm (blis_b200/csrc/host_dist.cuh): the whole pipeline -- gathers on the
+    engine's communication stream, double buffering, one k-panel launch per step -- runs in the engine.  The Python
+    pipeline below (`summa`, `PanelExchange`) is the same schedule written against torch.distributed; it serves the gloo
+    test of the index logic on CPU, the host-shard path (`step_host`) and, in `verify()`, as the independent replay."""
+
+    def __init__(self, M: int, N: int, K: int, world: int, rank: int, device, alpha=2.0, beta=1.2, kb: int = 2048, native: bool = True):
         from . import api
         self.api = api
+        self.native = bool(native) and torch.device(device).type == "cuda"
+        if self.native:
+            native_init(device)
         self.plan = SummaPlan(world, rank, M, N, K, kb)
         p = self.plan
         self.alpha, self.beta = alpha, beta
@@ -269,7 +299,8 @@ class DistGemm:
         p = self.plan
         return (f"2D block decomposition of C on a {p.pr}x{p.pc} grid (bli_thread_partition_2x2), C_ij {p.m_loc}x{p.n_loc} per GPU, "
                 f"global {p.M}x{p.N}x{p.K}; A/B k-panels (kb={p.kb}) all-gathered in row/column groups with NCCL, "
-                f"double buffered under the DMMA kernels; no reduction (k not split across GPUs)")
+                f"double buffered under the DMMA kernels; no reduction (k not split across GPUs); "
+                + ("one b200_dist_gemm call per product (pipeline inside the engine, C ABI)" if self.native else "pipeline driven from Python"))
 
     def _panel(self, first, a_t, b_t):
         p = self.plan
@@ -284,7 +315,16 @@ class DistGemm:
             self.api.bli_gemm_kpanels(torch.float64, 0, 0, p.m_loc, p.n_loc, p.kb, self.alpha, a_ts[lo:lo + 8], 1, p.m_loc,
                                       b_ts[lo:lo + 8], 1, p.kb, self.beta if (first and lo == 0) else 1.0, self.c, 1, p.m_loc)
 
-    def step(self):
+    def step(self, flags: int | None = None):
+        p = self.plan
+        if not self.native:
+            return summa(p, self.ex, self._panel, gemm_step=self._step_panels)
+        # A and B never change between the products of this job: their first gather may run under the previous product
+        self.api.dist_gemm(torch.float64, p.M, p.N, p.K, p.kb, self.alpha, self.a_loc, self.b_loc, self.beta, self.c, 1, p.m_loc,
+                           self.api.DIST_AB_STATIC if flags is None else flags)
+
+    def step_py(self):
+        """The same product with the pipeline driven from Python over torch.distributed (what step() was in round 1)."""
         summa(self.plan, self.ex, self._panel, gemm_step=self._step_panels)
 
     # ---- parity of the distributed result ----------------------------------------------------------------------------
@@ -306,10 +346,13 @@ class DistGemm:
         self.step()
         torch.cuda.synchronize()
         c_dist = cd.clone()
-        a_all = [torch.empty_like(self.a_loc) for _ in range(p.pc)]
-        b_all = [torch.empty_like(self.b_loc) for _ in range(p.pr)]
-        dist.all_gather(a_all, self.a_loc, group=ex.row_pg)
-        dist.all_gather(b_all, self.b_loc, group=ex.col_pg)
+        # whole shards into ONE tensor per operand: the replay's panels are then slots of one strided buffer, like the
+        # engine's receive buffers, so both runs are served by the same kernel (its name is compared below)
+        kern_dist = self.api.last_kernel()
+        a_all = torch.empty((p.pc,) + tuple(self.a_loc.shape), dtype=self.a_loc.dtype, device=self.a_loc.device)
+        b_all = torch.empty((p.pr,) + tuple(self.b_loc.shape), dtype=self.b_loc.dtype, device=self.b_loc.device)
+        dist.all_gather_into_tensor(a_all.view(-1), self.a_loc.reshape(-1), group=ex.row_pg)
+        dist.all_gather_into_tensor(b_all.view(-1), self.b_loc.reshape(-1), group=ex.col_pg)
         a_of = lambda t: a_all[t % p.pc][t // p.pc]           # noqa: E731  panel t of A: owner column t % Pc, local index t // Pc
         b_of = lambda t: b_all[t % p.pr][t // p.pr]           # noqa: E731
         cd.copy_(c0)
@@ -318,13 +361,14 @@ class DistGemm:
             self._step_panels(s == 0, [a_of(t) for t in ts], [b_of(t) for t in ts])
         torch.cuda.synchronize()
         bit_equal = bool(torch.equal(cd, c_dist))
+        kern_replay = self.api.last_kernel()
         g = torch.Generator(device=cd.device); g.manual_seed(7 + p.rank)
         tv = (torch.rand(p.n_loc, dtype=cd.dtype, device=cd.device, generator=g) * 2 - 1) / p.N
         z = self.beta * (c0.t() @ tv)
         for t in range(p.T):
             z += self.alpha * (a_of(t).t() @ (b_of(t).t() @ tv))
         resid = float(torch.linalg.vector_norm(c_dist.t() @ tv - z))
-        out = {"bit_equal": bit_equal, "resid": resid,
+        out = {"bit_equal": bit_equal, "resid": resid, "kernel": kern_dist, "kernel_replay": kern_replay,
                "how": "C_ij after step() vs the same b200_gemm_kpanels schedule replayed on whole-shard all_gather'ed panels (bit for bit), "
                       "and the testsuite residual ||C t - (beta C0 t + alpha A (B t))|| of the distributed block"}
         if hosts is not None:
@@ -402,9 +446,12 @@ class DistTrsm:
     """Left-side trsm on `world` GPUs: B (and X) split into column blocks by bli_thread_range_sub, the triangular A
     replicated, no data-path collective.  Every rank holds A and its block of B (synthetic data generated in place)."""
 
-    def __init__(self, m: int, n: int, world: int, rank: int, device, alpha=2.0, uplo=0xC0, trans=0, diag=0, seed=0xB200):
+    def __init__(self, m: int, n: int, world: int, rank: int, device, alpha=2.0, uplo=0xC0, trans=0, diag=0, seed=0xB200, native: bool = True):
         from . import api
-        self.api, self.m, self.alpha, self.uplo, self.trans, self.diag = api, m, alpha, uplo, trans, diag
+        self.api, self.m, self.n, self.alpha, self.uplo, self.trans, self.diag = api, m, n, alpha, uplo, trans, diag
+        self.native = bool(native) and world > 1 and torch.device(device).type == "cuda"
+        if self.native:
+            native_init(device)
         self.j0, self.j1 = trsm_column_block(rank, world, n)
         self.n_loc = self.j1 - self.j0
         g = torch.Generator(device=device); g.manual_seed(seed)
@@ -421,9 +468,15 @@ class DistTrsm:
         bv = self.b[j0:j1].t()                                # column-major m x w view
         self.api.bli_dtrsm(0, self.uplo, self.trans, self.diag, self.m, j1 - j0, self.alpha, self.a, 1, self.m, bv, 1, self.m)
 
-    def step(self):
+    def step(self, root: int = -1):
+        """One solve of this rank's column block.  Native: ONE b200_dist_trsm call (the engine cuts the same block with
+        bli_thread_range_sub; root >= 0 broadcasts A from that rank first, root < 0: A is already replicated)."""
         self.b.copy_(self.b0)
-        self._solve_cols(0, self.n_loc)
+        if self.native:
+            self.api.dist_trsm(torch.float64, 0, self.uplo, self.trans, self.diag, root, self.m, self.n, self.alpha,
+                               self.a, 1, self.m, self.b.t(), 1, self.m)
+        else:
+            self._solve_cols(0, self.n_loc)
 
     def host_block(self):
         h = torch.empty(self.b0.shape, dtype=self.b0.dtype).pin_memory()
@@ -444,6 +497,66 @@ class DistTrsm:
         cur = _CudaStream(torch.cuda.current_stream(self.b.device))
         trsm_host_blocks(self._solve_cols, self.b, b_host, col_blocks(self.n_loc, nblk), cur, _CudaStream(self._s_in),
                          _CudaStream(self._s_out))
+
+
+class DistSkinnyGemm:
+    """Skinny product C (m x n) := beta*C + alpha*A (m x k) * B (k x n) with k << m, n (the shapes the reference's sup path
+    serves, frame/3/bli_l3_sup.c:37-135) on `world` GPUs: 1-D split of C's COLUMNS in units of 128 (bli_thread_range_sub),
+    every rank holds its columns of B and C, and the small operand A is broadcast once from rank `root`.
+    ONE b200_dist_gemm_1d call per product."""
+
+    def __init__(self, m: int, n: int, k: int, world: int, rank: int, device, alpha=2.0, beta=1.2, root: int = 0, dtype=torch.float64, seed=0xB200):
+        from . import api
+        self.api, self.m, self.n, self.k, self.alpha, self.beta, self.root, self.dtype = api, m, n, k, alpha, beta, root, dtype
+        self.world, self.rank = world, rank
+        if world > 1 and torch.device(device).type == "cuda":
+            native_init(device)
+        self.j0, self.j1 = partition.thread_range_sub(rank, world, n, 128)
+        self.n_loc = self.j1 - self.j0
+        g = torch.Generator(device=device); g.manual_seed(seed)
+        rnd = lambda *shape: (torch.rand(*shape, dtype=torch.float64, device=device, generator=g) * 2 - 1).to(dtype)   # noqa: E731
+        a_root = rnd(k, m) / k                                  # dense image of the column-major m x k operand
+        # only `root` holds A before the product; the other ranks' buffers are poisoned so that the broadcast is needed
+        self.a = a_root if (rank == root or root < 0) else torch.full_like(a_root, float("nan"))
+        self.a_ref = a_root
+        g.manual_seed(seed + 1 + rank)
+        self.b = rnd(max(self.n_loc, 1), k)[: self.n_loc]       # dense image of column-major k x n_loc
+        self.c0 = rnd(max(self.n_loc, 1), m)[: self.n_loc]      # dense image of column-major m x n_loc
+        self.c = self.c0.clone()
+        self.total_flops = 2.0 * m * n * k
+        self.bytes_rank = self.c.element_size() * (m * k + k * self.n_loc + 2 * m * self.n_loc)
+
+    def describe(self) -> str:
+        return (f"1-D split of C's columns over {self.world} GPUs (bli_thread_range_sub, bf=128): C {self.m}x{self.n_loc} per GPU of {self.m}x{self.n}, "
+                f"k={self.k}; A ({self.m}x{self.k}) broadcast from rank {self.root} per product (ncclBroadcast), B and C local; no reduction")
+
+    def step(self):
+        self.api.dist_gemm_1d(self.dtype, self.api.DIST_COLS, self.root if self.world > 1 else -1, self.m, self.n, self.k, self.alpha,
+                              self.a.t(), 1, self.m, self.b.t(), 1, self.k, self.beta, self.c.t(), 1, self.m)
+
+    def verify(self) -> dict:
+        """The rank's block against the single-GPU engine on the same operands (bit for bit: same kernel, same k order)
+        and the testsuite residual (testsuite/src/test_gemm.c:393-401)."""
+        self.c.copy_(self.c0)
+        if self.world > 1 and self.rank != self.root and self.root >= 0:
+            self.a.fill_(float("nan"))
+        self.step()
+        torch.cuda.synchronize()
+        got = self.c.clone()
+        a_ok = bool(torch.equal(self.a, self.a_ref))
+        if self.n_loc == 0:
+            return {"bit_equal": a_ok, "resid": 0.0}
+        ref = self.c0.clone()
+        fn = {torch.float64: self.api.bli_dgemm, torch.float32: self.api.bli_sgemm,
+              torch.complex128: self.api.bli_zgemm, torch.complex64: self.api.bli_cgemm}[self.dtype]
+        fn(0, 0, self.m, self.n_loc, self.k, self.alpha, self.a_ref.t(), 1, self.m, self.b.t(), 1, self.k, self.beta, ref.t(), 1, self.m)
+        torch.cuda.synchronize()
+        g = torch.Generator(device=got.device); g.manual_seed(7 + self.rank)
+        tv = ((torch.rand(self.n_loc, dtype=torch.float64, device=got.device, generator=g) * 2 - 1) / self.n).to(self.dtype)
+        z = self.beta * (self.c0.t() @ tv) + self.alpha * (self.a_ref.t() @ (self.b.t() @ tv))
+        resid = float(torch.linalg.vector_norm(got.t() @ tv - z))
+        self.c.copy_(got)
+        return {"bit_equal": a_ok and bool(torch.equal(got, ref)), "resid": resid}
 
 
 def trsm_column_block(rank: int, world: int, n: int, nr: int = 128):

@@ -288,6 +288,74 @@ b200_err_t b200_gemm_batch( int dt, int group_count, const int* group_size,
                       const void* beta,
                       void* const*       c, const b200_inc_t* rs_c, const b200_inc_t* cs_c );
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink ------------------
+ * The reference has no distributed layer; these entry points apply ITS partitioning arithmetic across GPUs:
+ * bli_thread_partition_2x2 (frame/thread/bli_thread.c:194-320) picks the Pr x Pc grid the way bli_rntm_factorize
+ * (frame/base/bli_rntm.c:424-489) picks ic x jc, bli_thread_range_sub (frame/thread/bli_thread_range.c:38-184) cuts
+ * the contiguous ranges (ragged edge on the last rank), and k is never split across ranks
+ * (frame/3/gemm/bli_gemm_blk_var3.c:110-112), so there is no reduction.
+ *
+ * Bootstrap: rank 0 calls b200_dist_unique_id() and the caller's launcher (MPI_Bcast, torch.distributed, a file)
+ * hands the B200_DIST_ID_BYTES bytes to every rank; every rank then calls b200_dist_init( world, rank, id ) once.
+ * NCCL is bound at run time (dlopen of libnccl.so.2). */
+#define B200_DIST_ID_BYTES 128
+#define B200_DIST_COLS      0     /* 1-D split of C's columns */
+#define B200_DIST_ROWS      1     /* 1-D split of C's rows */
+#define B200_DIST_AB_STATIC 1     /* flag: the A/B shards are not written by work queued on the calling stream, so the
+                                     first gather of this product may start under the previous product's kernels */
+#define B200_DIST_TRACE     2     /* flag: record per-step wait events (b200_dist_last_wait_ms) */
+typedef struct
+{
+	int        world, rank;
+	int        pr, pc, i, j;        /* process grid (bli_thread_partition_2x2( world, m, n )) and my coordinates, rank = i*pc + j */
+	b200_dim_t m0, m1, n0, n1;      /* my block of C: rows [m0, m1), columns [n0, n1) (bli_thread_range_sub, bf = 1) */
+	b200_dim_t kb;                  /* k panel width */
+	int        L, T, steps;         /* panels per step lcm(pr, pc), panels k/kb, steps T/L */
+	int        na, nb;              /* k panels of A / of B this rank holds: panel t of A lives on grid column t % pc,
+	                                   panel t of B on grid row t % pr */
+} b200_dist_plan_t;
+
+/* The reference's partitioning arithmetic itself (host only, no GPU needed; bit-exact, tests/test_partition.py). */
+void       b200_partition_2x2( b200_dim_t n_thread, b200_dim_t work1, b200_dim_t work2, b200_dim_t* nt1, b200_dim_t* nt2 );
+void       b200_range_sub( b200_dim_t work_id, b200_dim_t n_way, b200_dim_t n, b200_dim_t bf, int handle_edge_low,
+                      b200_dim_t* start, b200_dim_t* end );
+b200_err_t b200_dist_plan( int world, int rank, b200_dim_t m, b200_dim_t n, b200_dim_t k, b200_dim_t kb, b200_dist_plan_t* plan );
+
+b200_err_t b200_dist_unique_id( void* id );
+b200_err_t b200_dist_init( int world, int rank, const void* id );
+b200_err_t b200_dist_finalize( void );
+
+/* C := beta*C + alpha*A*B, global m x n x k, on the Pr x Pc grid of b200_dist_plan (dt = d or z; column-major device
+ * shards): a_loc = this rank's plan.na k panels of A's row block, each (m1-m0) x kb with leading dimension m1-m0, one
+ * after the other; b_loc = its plan.nb k panels of B's column block, each kb x (n1-n0) with leading dimension kb;
+ * c_loc = its block of C with strides (rs_c, cs_c).  Each step all-gathers L k panels in the row/column groups on the
+ * engine's communication stream, double buffered under ONE k-panel launch per step (b200_gemm_kpanels' kernel).
+ * Asynchronous: returns with the work queued on the calling thread's stream. */
+b200_err_t b200_dist_gemm( int dt, b200_dim_t m, b200_dim_t n, b200_dim_t k, b200_dim_t kb,
+                      const void* alpha, const void* a_loc, const void* b_loc,
+                      const void* beta, void* c_loc, b200_inc_t rs_c, b200_inc_t cs_c, int flags );
+double     b200_dist_last_wait_ms( void );
+
+/* Skinny products (m, n >> k: the shapes bli_gemmsup serves, frame/3/bli_l3_sup.c:37-135): 1-D split of C over ALL
+ * ranks in units of 128 (b200_range_sub( rank, world, n or m, 128, 0 )).  split = B200_DIST_COLS: c_loc and b are this
+ * rank's columns of C and of B, a is the whole m x k operand; split = B200_DIST_ROWS: c_loc and a are its rows, b is the
+ * whole k x n operand.  The whole ("small") operand is broadcast from rank `root` into every rank's buffer first
+ * (column-major, device resident); root < 0: it is already replicated and no collective runs. */
+b200_err_t b200_dist_gemm_1d( int dt, int split, int root, b200_dim_t m, b200_dim_t n, b200_dim_t k,
+                      const void* alpha, void* a, b200_inc_t rs_a, b200_inc_t cs_a,
+                      void* b, b200_inc_t rs_b, b200_inc_t cs_b,
+                      const void* beta, void* c_loc, b200_inc_t rs_c, b200_inc_t cs_c );
+
+/* trsm with B split into column blocks (side = left; row blocks for side = right) in units of 128 over all ranks --
+ * the reference's only parallel trsm loops run over the columns of B (frame/3/trsm/bli_trsm_cntl.c:446-451,
+ * bli_trsm_ll_ker_var2.c:209-212) -- and the triangular A replicated.  b_loc is this rank's block; m, n are GLOBAL.
+ * root >= 0: A (column-major, device resident on every rank) is first broadcast from that rank; root < 0: already
+ * replicated, no collective at all. */
+b200_err_t b200_dist_trsm( int dt, int side, int uploa, int transa, int diaga, int root,
+                      b200_dim_t m, b200_dim_t n, const void* alpha,
+                      void* a, b200_inc_t rs_a, b200_inc_t cs_a,
+                      void* b_loc, b200_inc_t rs_b, b200_inc_t cs_b );
+
 /* ---- blocksizes ------------------------------------------------------------
  * What bli_cntx_init_b200 registers through bli_cntx_set_blkszs()
  * (config/zen3/bli_cntx_init_zen3.c:37-258 is the pattern): the CTA tile
