@@ -288,6 +288,57 @@ def test_gemm_kpanels_accumulates_like_blk_var3(engine, oracle, ch):
         assert rel_err(to_numpy(tc), want) <= TOL[ch], (ch, oa, ob, oc)
 
 
+@pytest.mark.parametrize("tr", [(0, 0), (TRANSPOSE, 0), (0, TRANSPOSE), (TRANSPOSE, TRANSPOSE)])
+def test_gemm_kpanels_tma_slots_of_one_buffer(engine, oracle, tr):
+    """k panels that are slots of ONE strided buffer (the receive buffers of b200_dist_gemm) are served by the TMA kernel
+    through 3-D tensor maps whose third coordinate is the slot (gemm_dmma_tma.cuh: tma_load_3d; gemm_launch.cuh:
+    seg_slots / make_tmap3): all four staging orientations, slots in a scrambled order with gaps (and different orders
+    for A and B), ragged m, n and per-panel k, beta != 0 with a short total k (CST: D staged through the ring) and
+    beta == 0 on NaN-poisoned C, against the oracle's pc loop (one rank-k update per panel, beta then one:
+    frame/3/gemm/bli_gemm_blk_var3.c:110-112).  The kernel name proves the path."""
+    from blis_b200 import api
+    ta, tb = tr
+    engine.set_option("dgemm_cfg", 9)
+    try:
+        for (m, n, k, npan, be) in ((260, 388, 68, 5, 1.2), (516, 260, 100, 8, 0.0), (130, 140, 200, 7, 1.2)):
+            am, ak = (k, m) if ta else (m, k)
+            bk, bn = (n, k) if tb else (k, n)
+            slots_a = [9, 2, 5, 0, 7, 3, 11, 6][:npan]
+            slots_b = [1, 4, 0, 8, 2, 6, 3, 10][:npan]
+            abuf = torch.full((12, ak, am), float("nan"), dtype=torch.float64, device="cuda")      # slot = dense image of a column-major am x ak panel
+            bbuf = torch.full((11, bn, bk), float("nan"), dtype=torch.float64, device="cuda")
+            a_p = [gen.matrix("d", am, ak, 700 + s, "frac", "c") for s in range(npan)]
+            b_p = [gen.matrix("d", bk, bn, 800 + s, "frac", "c") for s in range(npan)]
+            for s in range(npan):
+                abuf[slots_a[s]].t().copy_(to_torch(a_p[s])); bbuf[slots_b[s]].t().copy_(to_torch(b_p[s]))
+            c = gen.matrix("d", m, n, 900, "frac", "c")
+            want = c.copy(order="K")
+            for s in range(npan):
+                oracle.gemm(ta, tb, 2.0, a_p[s], b_p[s], be if s == 0 else 1.0, want)
+            if be == 0.0:
+                c[...] = np.nan
+            tc = to_torch(c)
+            api.bli_gemm_kpanels(torch.float64, ta, tb, m, n, k, 2.0, [abuf[q].t() for q in slots_a], 1, am, [bbuf[q].t() for q in slots_b], 1, bk,
+                                 be, tc, *estr(c))
+            torch.cuda.synchronize()
+            kn = engine.last_kernel()
+            assert kn.startswith("gemm_dmma_tma_kernel") and f"XK={int(not tb)},YK={int(bool(ta))}" in kn, kn
+            assert ("CST=1" in kn) == (be != 0.0 and k * npan <= 1024), (kn, k, npan)
+            assert rel_err(to_numpy(tc), want) <= TOL["d"], (tr, m, n, k, npan, be, kn, rel_err(to_numpy(tc), want))
+        # panels of unrelated allocations cannot be slots of one map: the cp.async kernel serves them (same result)
+        ta_l = [torch.rand(64, 200, dtype=torch.float64, device="cuda") for _ in range(3)]      # column-major 200 x 64
+        tb_l = [torch.rand(136, 64, dtype=torch.float64, device="cuda") for _ in range(3)]      # column-major 64 x 136
+        ta_l[1] = torch.rand(64 * 200 + 1, dtype=torch.float64, device="cuda")[1:].view(64, 200)     # 8-byte offset: no 16-byte slot stride
+        tcc = torch.zeros(136, 200, dtype=torch.float64, device="cuda")
+        api.bli_gemm_kpanels(torch.float64, 0, 0, 200, 136, 64, 1.0, [x.t() for x in ta_l], 1, 200, [x.t() for x in tb_l], 1, 64, 0.0, tcc.t(), 1, 200)
+        torch.cuda.synchronize()
+        assert engine.last_kernel().startswith("gemm_dmma_ws_kernel"), engine.last_kernel()
+        wantc = sum(b_ @ a_ for a_, b_ in zip(ta_l, tb_l))
+        assert float((tcc - wantc).abs().max()) < 1e-11
+    finally:
+        engine.set_option("dgemm_cfg", -1)
+
+
 # Which option forces, and which kernel name proves, the TMA tensor-map kernel of a datatype.  Without forcing, the
 # small-problem rules (gemm_d.cu: 4*t128 < 3*SMs, gemm_s.cu: 20*t128 < 11*SMs) send shapes of this size to the
 # cp.async small-tile kernels, so the orientation / ragged-edge / CST logic of the TMA kernels would go untested.
