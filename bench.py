@@ -478,6 +478,12 @@ def main():
                         "traffic": traffic, "peak_source": PEAK_SRC, "kernel": kern, "kernels": stats,
                         "algorithmic_flop_per_step_per_gpu": flops_rank,
                         "algorithmic_bytes_per_step_per_gpu": 8.0 * 4 * n * n if world == 1 else None}
+            if world > 1 and job.native:
+                # how long the compute stream sat waiting for gathers in one more product (events around every wait, in the engine)
+                job.step(flags=api.DIST_AB_STATIC | api.DIST_TRACE)
+                wait_ms = allmax(api.dist_last_wait_ms())
+                if roof is not None:
+                    roof["gather_wait_ms_per_product_max_over_ranks"] = wait_ms
             gemm_line = dict(value=value, ms=ms, launches=launches, roof=roof, clocks=clocks, parallelism=parallelism, total_flops=total_flops)
 
             # ---- e2e

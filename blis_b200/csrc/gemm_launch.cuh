@@ -12,6 +12,7 @@
 #include "gemm_ffma_ws.cuh"
 #include "../../include/blis_b200.h"
 #include <algorithm>
+#include <numeric>
 #include <string>
 #include <type_traits>
 #include <utility>
@@ -146,7 +147,7 @@ static bool seg_slots( const T* p0, const T* const* more, int nseg, const T** ba
 	for ( int s = 0; s < nseg; ++s )
 	{
 		const int64_t d = (const char*)( s ? more[s - 1] : p0 ) - (const char*)lo;
-		if ( d > 0 && ( S == 0 || d < S ) ) S = d;
+		S = std::gcd( S, d );                                      // gcd( 0, d ) = d
 	}
 	if ( S == 0 ) S = 16;                                        // all panels identical
 	if ( S % 16 != 0 || S >= ( 1ll << 40 ) ) return false;

@@ -302,7 +302,9 @@ static int dist_gemm( int64_t m, int64_t n, int64_t k, int64_t kb, const T* alph
 	const int qa = p.L / p.pc, qb = p.L / p.pr;                               // panels I contribute per step
 	const size_t a_panel = (size_t)kb * m_loc, b_panel = (size_t)kb * n_loc;   // elements
 	// every rank of my grid row has the same m_loc (same i), every rank of my grid column the same n_loc (same j)
-	if ( dist_grow( d, (size_t)p.L * a_panel * sizeof(T), (size_t)p.L * b_panel * sizeof(T) ) != kSuccess ) return kFailure;
+	// a group of ONE rank needs no gather at all: the kernels read that operand's panels straight from the caller's shard
+	const bool gather_a = ( p.pc > 1 ), gather_b = ( p.pr > 1 );
+	if ( dist_grow( d, gather_a ? (size_t)p.L * a_panel * sizeof(T) : 0, gather_b ? (size_t)p.L * b_panel * sizeof(T) : 0 ) != kSuccess ) return kFailure;
 
 	const bool ab_static = ( flags & B200_DIST_AB_STATIC ) || d.ab_static;
 	if ( !ab_static )
@@ -314,11 +316,12 @@ static int dist_gemm( int64_t m, int64_t n, int64_t k, int64_t kb, const T* alph
 	auto start = [&]( int s ) -> int
 	{
 		const int bf = s & 1;
+		if ( !gather_a && !gather_b ) return kSuccess;            // one rank: nothing to move
 		if ( d.buf_used[bf] ) B200_CUDA( cudaStreamWaitEvent( d.comm_stream, d.buf_free[bf], 0 ) );
 		// receive layout: [source rank in group][its q-th panel of this step] -> slot = src*q_per_rank + q
 		B200_NCCL( d.nccl.GroupStart() );
-		B200_NCCL( d.nccl.AllGather( a_loc + (size_t)s * qa * a_panel, d.abuf[bf], (size_t)qa * a_panel * sizeof(T), /*ncclUint8*/ 1, d.row, d.comm_stream ) );
-		B200_NCCL( d.nccl.AllGather( b_loc + (size_t)s * qb * b_panel, d.bbuf[bf], (size_t)qb * b_panel * sizeof(T), 1, d.col, d.comm_stream ) );
+		if ( gather_a ) B200_NCCL( d.nccl.AllGather( a_loc + (size_t)s * qa * a_panel, d.abuf[bf], (size_t)qa * a_panel * sizeof(T), /*ncclUint8*/ 1, d.row, d.comm_stream ) );
+		if ( gather_b ) B200_NCCL( d.nccl.AllGather( b_loc + (size_t)s * qb * b_panel, d.bbuf[bf], (size_t)qb * b_panel * sizeof(T), 1, d.col, d.comm_stream ) );
 		B200_NCCL( d.nccl.GroupEnd() );
 		B200_CUDA( cudaEventRecord( d.gathered[bf], d.comm_stream ) );
 		d.buf_used[bf] = true;
@@ -339,19 +342,19 @@ static int dist_gemm( int64_t m, int64_t n, int64_t k, int64_t kb, const T* alph
 	{
 		const int bf = s & 1;
 		if ( trace ) B200_CUDA( cudaEventRecord( d.ev_wait0[s], st ) );
-		B200_CUDA( cudaStreamWaitEvent( st, d.gathered[bf], 0 ) );
+		if ( gather_a || gather_b ) B200_CUDA( cudaStreamWaitEvent( st, d.gathered[bf], 0 ) );
 		if ( trace ) B200_CUDA( cudaEventRecord( d.ev_wait1[s], st ) );
 		// global panel t = s*L + l: A from grid column t % Pc (its (l / Pc)-th panel of the step), B from grid row t % Pr
 		const T* ap[8]; const T* bp[8];
 		for ( int l = 0; l < p.L; ++l )
 		{
 			const int t = s * p.L + l;
-			ap[l] = (const T*)d.abuf[bf] + ( (size_t)( t % p.pc ) * qa + (size_t)( l / p.pc ) ) * a_panel;
-			bp[l] = (const T*)d.bbuf[bf] + ( (size_t)( t % p.pr ) * qb + (size_t)( l / p.pr ) ) * b_panel;
+			ap[l] = gather_a ? (const T*)d.abuf[bf] + ( (size_t)( t % p.pc ) * qa + (size_t)( l / p.pc ) ) * a_panel : a_loc + (size_t)t * a_panel;
+			bp[l] = gather_b ? (const T*)d.bbuf[bf] + ( (size_t)( t % p.pr ) * qb + (size_t)( l / p.pr ) ) * b_panel : b_loc + (size_t)t * b_panel;
 		}
 		if ( gemm_dev<T>( false, false, m_loc, n_loc, kb, *alpha, ap[0], 1, m_loc, bp[0], 1, kb, s == 0 ? *beta : one,
 		                  c_loc, rs_c, cs_c, st, p.L, ap + 1, bp + 1 ) != kSuccess ) return kFailure;
-		B200_CUDA( cudaEventRecord( d.buf_free[bf], st ) );
+		if ( gather_a || gather_b ) B200_CUDA( cudaEventRecord( d.buf_free[bf], st ) );
 		if ( s + 2 < p.steps && start( s + 2 ) != kSuccess ) return kFailure;
 	}
 	return kSuccess;

@@ -24,6 +24,13 @@ newtests)
 dropin)
 	( time timeout 2400 python -m pytest tests/test_blis_dropin_gpu.py -q -m gpu ) > gpurun_out/pytest_dropin.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_dropin.log
 	tail -25 gpurun_out/pytest_dropin.log ;;
+distN)
+	# needs gpurun --gpus N: the native multi-GPU driver under torchrun, then the bench at N (reference arm skipped)
+	N=$(nvidia-smi -L | wc -l)
+	timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 tests/dist_native_driver.py > gpurun_out/dist_native_n$N.log 2>&1; echo "rc=$?" >> gpurun_out/dist_native_n$N.log
+	grep -c '_ok": true' gpurun_out/dist_native_n$N.log; grep -o '"[a-z_0-9]*_ok": false' gpurun_out/dist_native_n$N.log | sort | uniq -c; tail -3 gpurun_out/dist_native_n$N.log | cut -c1-600
+	timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "rc=$?"
+	cat gpurun_out/bench_n$N.json | cut -c1-6000; tail -5 gpurun_out/bench_n$N.err ;;
 pytest)
 	( time timeout 2400 python -m pytest tests -x -q -m gpu ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 	tail -8 gpurun_out/pytest_gpu.log ;;
