@@ -46,7 +46,10 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 		case 6: return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
 		case 9: if ( tma_eligible( g, xk, yk, al ) )
 		        {
-		        	// small k: the read-modify-write of D is staged through the TMA ring as well (gemm_dmma_tma.cuh, CST)
+		        	// small k: two consumer groups take turns on the tensor pipe, each epilogue under the other's k loop (gemm_dmma_pp.cuh)
+	        	if ( c.dmma_pp && g.nseg == 1 && g.K <= c.dmma_pp && g.d_vec_ok )
+	        		return launch_dmma_pp( g, xk, yk, tiles( 128, 128 ), st );
+	        	// small k: the read-modify-write of D is staged through the TMA ring as well (gemm_dmma_tma.cuh, CST)
 		        	if ( c.dmma_cst && !g.beta_is_zero && g.d_vec_ok && g.K * g.nseg <= c.dmma_cst && g.ldd >= g.Q && g.ldd * 8 < ( 1ll << 40 ) )
 		        		return launch_dmma_tma<false, true>( g, xk, yk, tiles( 128, 128 ), st );
 		        	return launch_dmma_tma( g, xk, yk, tiles( 128, 128 ), st );

@@ -5,6 +5,7 @@
 #include "gemm_dmma.cuh"
 #include "gemm_dmma_ws.cuh"
 #include "gemm_dmma_tma.cuh"
+#include "gemm_dmma_pp.cuh"
 #include "gemm_ffma_tma.cuh"
 #include "gemm_cfma_tma.cuh"
 #include "gemm_zmma_tma.cuh"
@@ -219,6 +220,29 @@ static int launch_dmma_tma( const GemmArgs<double>& g_in, bool xk, bool yk, int 
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, DmmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, DmmaTmaCfg::NT_ALL, DmmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy, tmd );
+		B200_CUDA( cudaGetLastError() );
+		note_launch( kname.c_str() );
+		return kSuccess;
+	};
+	using Tt = std::true_type; using Ff = std::false_type;
+	if ( xk ) return yk ? go( Tt{}, Tt{} ) : go( Tt{}, Ff{} );
+	return yk ? go( Ff{}, Tt{} ) : go( Ff{}, Ff{} );
+}
+
+// small k: two consumer groups taking turns on the tensor pipe (gemm_dmma_pp.cuh); nseg == 1, full D
+static int launch_dmma_pp( const GemmArgs<double>& g, bool xk, bool yk, int grid, cudaStream_t st )
+{
+	CUtensorMap tmx, tmy;
+	if ( make_tmap( &tmx, g.X, 8, xk, g.P, g.K, g.ldx ) != kSuccess ) return kFailure;
+	if ( make_tmap( &tmy, g.Y, 8, yk, g.Q, g.K, g.ldy, DmmaPpCfg::BQH ) != kSuccess ) return kFailure;
+	auto go = [&]( auto XKc, auto YKc ) -> int
+	{
+		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
+		auto kern = gemm_dmma_pp_kernel<XK, YK>;
+		static const std::string kname = kfmt( "gemm_dmma_pp_kernel<XK=%d,YK=%d>", XK, YK );
+		static bool attr = false;
+		if ( !attr ) { if ( set_smem( kern, DmmaPpCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<grid, DmmaPpCfg::NT_ALL, DmmaPpCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
 		B200_CUDA( cudaGetLastError() );
 		note_launch( kname.c_str() );
 		return kSuccess;

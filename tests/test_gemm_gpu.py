@@ -339,6 +339,43 @@ def test_gemm_kpanels_tma_slots_of_one_buffer(engine, oracle, tr):
         engine.set_option("dgemm_cfg", -1)
 
 
+def test_dgemm_ping_pong_small_k(engine, oracle):
+    """The ping-pong dgemm kernel for small k (gemm_dmma_pp.cuh: the two q-halves of a tile, each with its own TMA ring,
+    alternate on the tensor pipe, ordered by named barriers) against the oracle: all four staging orientations, ragged m/n/k (a CTA whose
+    last tile is ragged, a problem with fewer tiles than CTAs, more tiles than CTAs), beta == 0 on NaN-poisoned C and
+    beta != 0, row- and column-stored C; and bit-for-bit against the lockstep kernel (same k order per accumulator)."""
+    engine.set_option("dgemm_cfg", 9); engine.set_option("dmma_pp", 1 << 20)
+    seed = 7000
+    try:
+        for (m, n, k) in ((260, 132, 68), (128, 128, 16), (1540, 1412, 64), (2052, 3100, 132), (40, 24, 8)):
+            for ta in (NO_TRANSPOSE, TRANSPOSE):
+                for tb in (NO_TRANSPOSE, TRANSPOSE):
+                    for oc, be in (("c", 1.2), ("r", 0.0), ("c", 0.0)):
+                        seed += 1
+                        am, ak = (k, m) if ta & TRANSPOSE else (m, k)
+                        bk, bn = (n, k) if tb & TRANSPOSE else (k, n)
+                        a = gen.matrix("d", am, ak, seed, "frac", "c"); b = gen.matrix("d", bk, bn, seed + 5000, "frac", "c")
+                        c = gen.matrix("d", m, n, seed + 9000, "frac", oc)
+                        want = c.copy(order="K")
+                        oracle.gemm(ta, tb, 2.0, a, b, be, want)
+                        c0 = c.copy(order="K")
+                        if be == 0.0:
+                            c[...] = np.nan
+                        got = run_gemm(engine, "d", ta, tb, 2.0, a, b, be, c)
+                        kn = engine.last_kernel()
+                        assert kn.startswith("gemm_dmma_pp_kernel"), kn
+                        assert rel_err(got, want) <= TOL["d"], (m, n, k, ta, tb, oc, be, rel_err(got, want))
+                        engine.set_option("dmma_pp", 0); engine.set_option("dmma_cst", 0)
+                        try:
+                            lock = run_gemm(engine, "d", ta, tb, 2.0, a, b, be, c0 if be != 0.0 else c)
+                            assert engine.last_kernel().startswith("gemm_dmma_tma_kernel")
+                        finally:
+                            engine.set_option("dmma_pp", 1 << 20); engine.set_option("dmma_cst", 1024)
+                        assert np.array_equal(got, lock), (m, n, k, ta, tb, oc, be)
+    finally:
+        engine.set_option("dgemm_cfg", -1); engine.set_option("dmma_pp", 0); engine.set_option("dmma_cst", 1024)
+
+
 # Which option forces, and which kernel name proves, the TMA tensor-map kernel of a datatype.  Without forcing, the
 # small-problem rules (gemm_d.cu: 4*t128 < 3*SMs, gemm_s.cu: 20*t128 < 11*SMs) send shapes of this size to the
 # cp.async small-tile kernels, so the orientation / ragged-edge / CST logic of the TMA kernels would go untested.
