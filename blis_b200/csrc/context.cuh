@@ -63,7 +63,7 @@ struct Context
 	int          raster_group = 8;      // tile rows per raster group: the ~148 running tiles form a raster_group x 148/raster_group block
 	int          tma_l2_promotion = 2;  // CUtensorMapL2promotion: 0 none, 1 64 B, 2 128 B, 3 256 B
 	int          dmma_pp  = 0;          // dgemm TMA kernel: ping-pong the two q-halves of a tile for K <= this (0 = never)
-	int          dmma_cst = 1024;       // dgemm TMA kernel: stage D through the ring for K <= this (0 = never)
+	int          dmma_cst = 256;        // dgemm TMA kernel: stage D through the ring (TMA load + TMA store) for K <= this (0 = never); [B200] wins up to k = 256
 	int          host_kpipe = 1;        // host operands with long k: pipeline over k panels instead of column blocks
 	int          ktri_skip = 1;         // trmm/trmm3: tiles skip the k range in which the triangular operand is zero
 	int          transpose_y = 1;       // s/c: transpose a k-contiguous Y panel once instead of re-pairing registers in the k loop

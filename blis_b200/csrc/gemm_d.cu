@@ -50,7 +50,7 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 	        	if ( c.dmma_pp && g.nseg == 1 && g.K <= c.dmma_pp && g.d_vec_ok )
 	        		return launch_dmma_pp( g, xk, yk, tiles( 128, 128 ), st );
 	        	// small k: the read-modify-write of D is staged through the TMA ring as well (gemm_dmma_tma.cuh, CST)
-		        	if ( c.dmma_cst && !g.beta_is_zero && g.d_vec_ok && g.K * g.nseg <= c.dmma_cst && g.ldd >= g.Q && g.ldd * 8 < ( 1ll << 40 ) )
+		        	if ( c.dmma_cst && g.d_vec_ok && g.K * g.nseg <= c.dmma_cst && g.ldd >= g.Q && g.ldd * 8 < ( 1ll << 40 ) )
 		        		return launch_dmma_tma<false, true>( g, xk, yk, tiles( 128, 128 ), st );
 		        	return launch_dmma_tma( g, xk, yk, tiles( 128, 128 ), st );
 		        }

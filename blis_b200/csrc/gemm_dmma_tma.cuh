@@ -25,6 +25,7 @@
 // because the lines k(s,t) % 8 have pairwise distinct (k % 8) >> 1.
 #pragma once
 #include <cuda.h>
+#include <type_traits>
 #include "common.cuh"
 #include "gemm_dmma.cuh"
 #include "gemm_dmma_ws.cuh"
@@ -61,30 +62,52 @@ __device__ __forceinline__ void prefetch_d_tile_l2( const GemmArgs<T>& g, int p0
 		asm volatile( "cp.async.bulk.prefetch.L2.global [%0], %1;\n" :: "l"(dt + (int64_t)r * g.ldd), "r"(bytes) : "memory" );
 }
 
-struct DmmaTmaCfg
+template <int ST>
+struct DmmaTmaCfgT
 {
-	static constexpr int BP = 128, BQ = 128, BK = 16, WP = 4, WQ = 2, STAGES = 6;
+	static constexpr int BP = 128, BQ = 128, BK = 16, WP = 4, WQ = 2, STAGES = ST;
 	static constexpr int WTP = BP / WP, WTQ = BQ / WQ, MT = WTP / 8, NTL = WTQ / 8;
 	static constexpr int OPER_BYTES  = 128 * 128;                 // 16 KiB per operand per stage
 	static constexpr int STAGE_BYTES = 2 * OPER_BYTES;
 	static constexpr int NCONS = WP * WQ * 32, NPROD = 128, NT_ALL = NCONS + NPROD;
-	static constexpr int BAR_BYTES  = 2 * STAGES * 8 + 4 * 8 + 16;
+	static constexpr int BAR_BYTES  = 3 * STAGES * 8 + 4 * 8 + 16;               // full, empty, staged (CST) per stage + 4 scheduler barriers + tile slots
 	static constexpr int SMEM_BYTES = STAGE_BYTES * STAGES + BAR_BYTES + 1024;   // + slack for 1 KiB alignment
 };
+using DmmaTmaCfg    = DmmaTmaCfgT<6>;
+using DmmaTmaCfgCst = DmmaTmaCfgT<7>;      // CST holds the D stages until their TMA stores have drained: one more stage (224 KiB)
+
+__device__ __forceinline__ void tma_store_2d( const CUtensorMap* map, int c0, int c1, uint32_t src )
+{
+	asm volatile( "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n"
+	              :: "l"(map), "r"(src), "r"(c0), "r"(c1) : "memory" );
+}
+__device__ __forceinline__ void mbar_arrive_n( uint32_t bar, uint32_t n )
+{
+	asm volatile( "mbarrier.arrive.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"(n) : "memory" );
+}
 
 // CST ("C staged"): for small k the epilogue's read-modify-write of D dominates (k = 64: 8.4 us of DMMA per tile against
 // ~4 us of exposed global-load latency, ncu: 37 % of the stall samples behind the last DMMA).  With CST the producer also
 // TMA-loads the D tile, as FOUR extra ring stages of 32 rows x 128 columns (eight 128B-swizzled {16, 32} boxes = one
 // 32 KiB stage) issued right behind the tile's k stages, and the consumers take D from shared memory: warp row-group r
 // (rows 32r..32r+31) reads exactly extra stage r.  The loads travel through the same full/empty ring, so they are in
-// flight while the k loop runs and no register is spent on latency hiding.  Used when beta != 0, D rows are 16-byte
-// aligned and K <= 1024 (gemm_d.cu); the default instantiation is untouched.
+// flight while the k loop runs and no register is spent on latency hiding.
+// The WRITE half goes the same way back: a consumer overwrites the D values it read with beta*D + alpha*acc in place
+// (STS.128) and moves on to the next tile's k loop at once; a store thread (second producer warp) waits until the two
+// warps of a row group have staged their stage, hands it to the TMA unit (cp.async.bulk.tensor global <- shared, eight
+// {8, 32} boxes), and releases the ring slot when the unit has read it.  The tensor pipe therefore never waits for the
+// 128 KiB store burst of a tile to drain to HBM (ncu before: k = 64, beta = 0 -- no D read at all -- still only 81 % DMMA
+// busy).  The D stages are NOT swizzled: sixteen {8 columns, 32 rows} boxes with 64-byte rows, so that the eight lanes of
+// an LDS.128 / STS.128 quarter-warp (two rows x four chunks) cover 128 contiguous bytes (the 128B-swizzled {16, 32} boxes
+// of the first version cost 28 % bank conflicts, ncu r01).
+// beta == 0: the producer passes the four stages on empty (nothing is loaded).  Used when D rows are 16-byte aligned and
+// K <= 1024 (gemm_d.cu); seven ring stages; the default instantiation is untouched.
 template <bool XK, bool YK, bool TRI = false, bool CST = false>
 __global__ void __launch_bounds__( 384, 1 )
 gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
                       const __grid_constant__ CUtensorMap tmd )
 {
-	using Cfg = DmmaTmaCfg;
+	using Cfg = typename std::conditional<CST, DmmaTmaCfgCst, DmmaTmaCfg>::type;
 	constexpr int BP = Cfg::BP, BQ = Cfg::BQ, BK = Cfg::BK, WQ = Cfg::WQ, STAGES = Cfg::STAGES;
 	constexpr int MT = Cfg::MT, NTL = Cfg::NTL, KS = BK / 4;
 
@@ -95,9 +118,10 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 	const uint32_t bar_base = sbase + (uint32_t)Cfg::STAGE_BYTES * STAGES;
 	auto full_bar    = [&]( int s ) { return bar_base + (uint32_t)s * 8u; };
 	auto empty_bar   = [&]( int s ) { return bar_base + (uint32_t)( STAGES + s ) * 8u; };
-	auto sched_full  = [&]( int s ) { return bar_base + (uint32_t)( 2 * STAGES + s ) * 8u; };
-	auto sched_empty = [&]( int s ) { return bar_base + (uint32_t)( 2 * STAGES + 2 + s ) * 8u; };
-	volatile int* const sched_tile = reinterpret_cast<volatile int*>( smem + (size_t)Cfg::STAGE_BYTES * STAGES + ( 2 * STAGES + 4 ) * 8 );
+	auto staged_bar  = [&]( int s ) { return bar_base + (uint32_t)( 2 * STAGES + s ) * 8u; };      // CST: a row group has written its results
+	auto sched_full  = [&]( int s ) { return bar_base + (uint32_t)( 3 * STAGES + s ) * 8u; };
+	auto sched_empty = [&]( int s ) { return bar_base + (uint32_t)( 3 * STAGES + 2 + s ) * 8u; };
+	volatile int* const sched_tile = reinterpret_cast<volatile int*>( smem + (size_t)Cfg::STAGE_BYTES * STAGES + ( 3 * STAGES + 4 ) * 8 );
 
 	const int tid = threadIdx.x;
 	if ( tid == 0 )
@@ -107,12 +131,13 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 		{
 			mbar_init( full_bar( s ),  1 );                    // the producer's expect_tx arrival; bytes complete it
 			mbar_init( empty_bar( s ), Cfg::NCONS / 32 );
+			mbar_init( staged_bar( s ), WQ );                  // the two warps of a row group
 		}
 		#pragma unroll
 		for ( int s = 0; s < 2; ++s )
 		{
 			mbar_init( sched_full( s ),  1 );
-			mbar_init( sched_empty( s ), Cfg::NCONS / 32 );
+			mbar_init( sched_empty( s ), Cfg::NCONS / 32 + ( CST ? 1 : 0 ) );    // CST: the store thread follows the tiles too
 		}
 		asm volatile( "fence.mbarrier_init.release.cluster;\n" ::: "memory" );   // visible to the async proxy
 	}
@@ -128,6 +153,63 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 	{
 		// ============ PRODUCER warpgroup: one thread drives the TMA unit ============
 		setmaxnreg_dec<40>();
+		if constexpr ( CST )
+		{
+			if ( tid == Cfg::NCONS + 32 )
+			{
+				// ============ STORE thread: D stages -> global through the TMA unit, then the ring slot is free ============
+				asm volatile( "prefetch.tensormap [%0];\n" :: "l"(&tmd) : "memory" );
+				int stage = 0; uint32_t phase = 0;
+				uint32_t staged_parity = 0;                    // bit s: parity the next completion of staged_bar( s ) will have (a stage is a D stage only now and then)
+				for ( int it = 0; ; ++it )
+				{
+					const int slot = it & 1;
+					mbar_wait( sched_full( slot ), ( it >> 1 ) & 1 );
+					const int tile = sched_tile[slot];
+					mbar_arrive( sched_empty( slot ) );
+					if ( tile >= num_tiles ) break;
+					int tp, tq;
+					tile_coords( tile, g.tiles_p, g.tiles_q, g.raster, tp, tq );
+					const int p0 = tp * BP, q0 = tq * BQ;
+					const bool fast = ( g.d_vec_ok && min( (int64_t)BQ, g.Q - q0 ) == BQ );
+					for ( int64_t kt = 0; kt < KT; ++kt ) { if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; } }   // the k stages are not mine
+					int st0 = stage;
+					#pragma unroll 1
+					for ( int qd = 0; qd < BP / 32; ++qd )
+					{
+						// The row group's two warps arrive here for EVERY tile, after the stage's load has landed (they waited for it) and,
+						// on the fast path, after they have written their results.  This thread never waits on a full barrier itself: it
+						// skips the k stages without looking at them, so it may be several ring wraps away from what a parity can tell apart.
+						mbar_wait( staged_bar( stage ), ( staged_parity >> stage ) & 1u );
+						staged_parity ^= 1u << stage;
+						if ( fast )
+						{
+							const uint32_t cs = sbase + (uint32_t)stage * Cfg::STAGE_BYTES;
+							#pragma unroll
+							for ( int b = 0; b < BQ / 8; ++b ) tma_store_2d( &tmd, q0 + b * 8, p0 + qd * 32, cs + b * 2048 );
+							asm volatile( "cp.async.bulk.commit_group;\n" ::: "memory" );
+						}
+						if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
+					}
+					// release the four slots in order, each as soon as the unit has READ it
+					#pragma unroll 1
+					for ( int qd = 0; qd < BP / 32; ++qd )
+					{
+						if ( fast )
+						{
+							if      ( qd == 0 ) asm volatile( "cp.async.bulk.wait_group.read 3;\n" ::: "memory" );
+							else if ( qd == 1 ) asm volatile( "cp.async.bulk.wait_group.read 2;\n" ::: "memory" );
+							else if ( qd == 2 ) asm volatile( "cp.async.bulk.wait_group.read 1;\n" ::: "memory" );
+							else                asm volatile( "cp.async.bulk.wait_group.read 0;\n" ::: "memory" );
+						}
+						mbar_arrive_n( empty_bar( st0 ), Cfg::NCONS / 32 );
+						if ( ++st0 == STAGES ) st0 = 0;
+					}
+				}
+				asm volatile( "cp.async.bulk.wait_group 0;\n" ::: "memory" );     // all stores complete before the CTA exits
+				return;
+			}
+		}
 		if ( tid != Cfg::NCONS ) return;
 		asm volatile( "prefetch.tensormap [%0];\n" :: "l"(&tmx) : "memory" );
 		asm volatile( "prefetch.tensormap [%0];\n" :: "l"(&tmy) : "memory" );
@@ -197,9 +279,13 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 					mbar_wait( empty_bar( stage ), phase ^ 1u );
 					const uint32_t cs = sbase + (uint32_t)stage * Cfg::STAGE_BYTES;
 					const uint32_t fb = full_bar( stage );
-					mbar_arrive_expect_tx( fb, (uint32_t)Cfg::STAGE_BYTES );
-					#pragma unroll
-					for ( int b = 0; b < BQ / 16; ++b ) tma_load_2d( cs + b * 4096, &tmd, q0 + b * 16, p0 + qd * 32, fb );
+					if ( g.beta_is_zero ) mbar_arrive( fb );                       // D is not read: the stage is handed over empty
+					else
+					{
+						mbar_arrive_expect_tx( fb, (uint32_t)Cfg::STAGE_BYTES );
+						#pragma unroll
+						for ( int b = 0; b < BQ / 8; ++b ) tma_load_2d( cs + b * 2048, &tmd, q0 + b * 8, p0 + qd * 32, fb );
+					}
 					if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
 				}
 			}
@@ -316,36 +402,40 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 		auto keep = [&]( int d ) { if constexpr ( TRI ) return in_band( d, dlo, dhi ); else return true; };
 		if constexpr ( CST )
 		{
-			// the four D stages of this tile: row-group r = warp / WQ takes its 32 rows from stage r; every warp walks the ring
-			const bool fast = ( g.d_vec_ok && q_lim == BQ && interior );
-			#pragma unroll 1
-			for ( int qd = 0; qd < BP / 32; ++qd )
+			// the four D stages of this tile: row-group r = warp / WQ owns stage r (rows 32r..32r+31); nobody else touches it.
+			// The store thread releases all four, so a consumer only steps over them.
+			const bool fast = ( g.d_vec_ok && q_lim == BQ );
+			int st = stage + warp / WQ; uint32_t ph = phase;
+			if ( st >= STAGES ) { st -= STAGES; ph ^= 1u; }
+			mbar_wait( full_bar( st ), ph );                        // also on edge tiles: the store thread releases the slot on my word
+			if ( fast )
 			{
-				mbar_wait( full_bar( stage ), phase );
-				if ( fast && qd == warp / WQ )
+				// stage layout: sixteen un-swizzled {8 columns, 32 rows} boxes of 2 KiB (one per 8x8 tile column): a row is 64 bytes,
+				// so the eight lanes of an LDS.128 / STS.128 quarter-warp (two rows x four 16-byte chunks) cover 128 contiguous bytes
+				unsigned char* cs = smem + (size_t)st * Cfg::STAGE_BYTES + ( wq0 >> 3 ) * 2048 + gq * 64 + t4 * 16;
+				#pragma unroll
+				for ( int i = 0; i < MT; ++i )
 				{
-					const unsigned char* cs = smem + (size_t)stage * Cfg::STAGE_BYTES + ( wq0 >> 4 ) * 4096 + gq * 128;
-					#pragma unroll
-					for ( int i = 0; i < MT; ++i )
+					double2 o[NTL];
+					if ( !g.beta_is_zero )
 					{
-						if ( wp0 + i * 8 + gq >= p_lim ) continue;
-						double2* __restrict__ dp = reinterpret_cast<double2*>( g.D + ( p0 + wp0 + i * 8 + gq ) * g.ldd + q0 + wq0 + 2 * t4 );
-						double2 o[NTL];
 						#pragma unroll
-						for ( int j = 0; j < NTL; ++j )
-							o[j] = *reinterpret_cast<const double2*>( cs + ( j >> 1 ) * 4096 + i * 1024 + ( ( ( ( ( j & 1 ) << 2 ) | t4 ) ^ gq ) << 4 ) );
-						#pragma unroll
-						for ( int j = 0; j < NTL; ++j )
-						{
-							const double r0 = fma( g.beta, o[j].x, g.alpha * acc[i][j][0] ), r1 = fma( g.beta, o[j].y, g.alpha * acc[i][j][1] );
-							__stcs( dp + j * 4, make_double2( r0, r1 ) );
-						}
+						for ( int j = 0; j < NTL; ++j ) o[j] = *reinterpret_cast<const double2*>( cs + j * 2048 + i * 512 );
+					}
+					#pragma unroll
+					for ( int j = 0; j < NTL; ++j )
+					{
+						double r0 = g.alpha * acc[i][j][0], r1 = g.alpha * acc[i][j][1];
+						if ( !g.beta_is_zero ) { r0 = fma( g.beta, o[j].x, r0 ); r1 = fma( g.beta, o[j].y, r1 ); }
+						*reinterpret_cast<double2*>( cs + j * 2048 + i * 512 ) = make_double2( r0, r1 );
 					}
 				}
-				__syncwarp();
-				if ( lane == 0 ) mbar_arrive( empty_bar( stage ) );
-				if ( ++stage == STAGES ) { stage = 0; phase ^= 1u; }
+				asm volatile( "fence.proxy.async.shared::cta;\n" ::: "memory" );    // my STS before the TMA unit's reads
 			}
+			__syncwarp();
+			if ( lane == 0 ) mbar_arrive( staged_bar( st ) );
+			stage += BP / 32;
+			if ( stage >= STAGES ) { stage -= STAGES; phase ^= 1u; }
 			if ( fast ) continue;
 		}
 		if ( g.d_vec_ok && q_lim == BQ && interior )

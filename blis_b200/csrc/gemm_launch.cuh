@@ -176,6 +176,21 @@ static int make_tmap3( CUtensorMap* tm, const void* base, bool kmajor, int64_t r
 	if ( r != CUDA_SUCCESS ) return fail( "cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r );
 	return kSuccess;
 }
+// D tile stages of the dgemm CST path: dims {Q, P}, box {8 columns, 32 rows}, no swizzle (64-byte rows in shared memory).
+static int make_tmap_d8( CUtensorMap* tm, const void* base, int64_t P, int64_t Q, int64_t ldd )
+{
+	EncodeTiledFn enc = encode_tiled_fn();
+	if ( !enc ) return fail( "cuTensorMapEncodeTiled not available" );
+	cuuint64_t dims[2]    = { (cuuint64_t)Q, (cuuint64_t)P };
+	cuuint64_t strides[1] = { (cuuint64_t)ldd * 8 };
+	cuuint32_t box[2]     = { 8, 32 };
+	cuuint32_t estr[2]    = { 1, 1 };
+	const CUresult r = enc( tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr,
+	                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)ctx().tma_l2_promotion,
+	                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+	if ( r != CUDA_SUCCESS ) return fail( "cuTensorMapEncodeTiled (D) failed (%d)", (int)r );
+	return kSuccess;
+}
 template <typename T>
 static bool tma_eligible( const GemmArgs<T>& g, bool xk, bool yk, bool al )
 {
@@ -209,17 +224,18 @@ static int launch_dmma_tma( const GemmArgs<double>& g_in, bool xk, bool yk, int 
 		if ( make_tmap( &tmx, g.X, 8, xk, g.P, g.K, g.ldx ) != kSuccess ) return kFailure;
 		if ( make_tmap( &tmy, g.Y, 8, yk, g.Q, g.K, g.ldy ) != kSuccess ) return kFailure;
 	}
-	// D as {16 columns, 32 rows} boxes (CST: the epilogue reads D from shared memory); a copy of tmx when unused
-	if ( CST ) { if ( make_tmap( &tmd, g.D, 8, true, g.P, g.Q, g.ldd, 32 ) != kSuccess ) return kFailure; }
+	// D as un-swizzled {8 columns, 32 rows} boxes (CST: the epilogue works on D in shared memory); a copy of tmx when unused
+	if ( CST ) { if ( make_tmap_d8( &tmd, g.D, g.P, g.Q, g.ldd ) != kSuccess ) return kFailure; }
 	else tmd = tmx;
 	auto go = [&]( auto XKc, auto YKc ) -> int
 	{
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
 		auto kern = gemm_dmma_tma_kernel<XK, YK, TRI, CST>;
+		using KCfg = typename std::conditional<CST, DmmaTmaCfgCst, DmmaTmaCfg>::type;
 		static const std::string kname = kfmt( "gemm_dmma_tma_kernel<XK=%d,YK=%d,TRI=%d,CST=%d>", XK, YK, TRI, CST );
 		static bool attr = false;
-		if ( !attr ) { if ( set_smem( kern, DmmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
-		kern<<<grid, DmmaTmaCfg::NT_ALL, DmmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy, tmd );
+		if ( !attr ) { if ( set_smem( kern, KCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
+		kern<<<grid, KCfg::NT_ALL, KCfg::SMEM_BYTES, st>>>( g, tmx, tmy, tmd );
 		B200_CUDA( cudaGetLastError() );
 		note_launch( kname.c_str() );
 		return kSuccess;

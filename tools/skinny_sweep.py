@@ -42,5 +42,5 @@ for k in ks:
                                          "kernel": api.last_kernel()}
     out[f"k{k}"] = row
     print(k, {kk: (v["tflops"], v["gbs"]) for kk, v in row.items()}, file=sys.stderr, flush=True)
-api.set_option("dmma_pp", 0); api.set_option("dmma_cst", 1024)
+api.set_option("dmma_pp", 0); api.set_option("dmma_cst", 256)
 print(json.dumps(out))
