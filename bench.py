@@ -345,6 +345,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-peak", action="store_true", help="skip the FP64 peak microbenchmark (profiling runs)")
     ap.add_argument("--no-check", action="store_true", help="N > 1: skip the post-timing parity check of the distributed result")
+    ap.add_argument("--no-g3", action="store_true", help="N = 8: skip the 65536^3 leg (BASELINE configs[4])")
     ap.add_argument("--no-skinny", action="store_true", help="skip the skinny k=64 leg (BASELINE configs[2] shape, HBM roofline)")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling leg (one 16384^3 over all GPUs)")
     ap.add_argument("--workload", default="headline", choices=["headline", "g3"],
@@ -548,6 +549,27 @@ def main():
                           "workload": wl_gemm, "parallelism": sjob.describe(), "kernel": gemm_kernel_of(sstats), "check": scheck}
                 del sjob
             gemm_line["strong"] = strong
+
+            # ---- BASELINE configs[4]: dgemm 65536^3 2D-sharded over 8 GPUs (only at N = 8; strong-scaled by definition)
+            g3 = None
+            if world == 8 and not args.no_g3 and args.workload == "headline":
+                from blis_b200 import dist as bdist
+                job = None
+                torch.cuda.empty_cache()
+                gjob = bdist.DistGemm(65536, 65536, 65536, world, rank, dev, alpha=ALPHA, beta=BETA, kb=kb)
+                gms, gper, _, gstats, _ = timed(gjob.step, 2, 3)
+                gcheck = None if args.no_check else gjob.verify()
+                if gcheck is not None:
+                    t = torch.tensor([1.0 if gcheck["bit_equal"] else 0.0, -gcheck["resid"]], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                    gcheck = {"bit_equal_to_single_gpu_replay": bool(t[0].item() == 1.0), "testsuite_resid_max_over_ranks": float(-t[1].item())}
+                g3 = {"value": gjob.total_flops / (gms * 1e-3) / 1e9, "unit": "GFLOPS", "ms_per_step": gms, "steps": 2, "warmup": 3, "scaling": "strong",
+                      "workload": "dgemm m=n=k=65536 column-major fp64, 2D-sharded over 8 GPUs, alpha=2.0 beta=1.2 (BASELINE configs[4])",
+                      "parallelism": gjob.describe(), "kernel": gemm_kernel_of(gstats), "check": gcheck,
+                      "frac_of_dmma_peak_per_gpu": gjob.total_flops / world / (gms * 1e-3) / 1e12 / dmma_peak()}
+                del gjob
+                torch.cuda.empty_cache()
+            gemm_line["g3"] = g3
             if world == 1:
                 del a, b, c
             torch.cuda.empty_cache()
@@ -679,7 +701,7 @@ def main():
                 "dtrsm": trsm_line, "skinny": skinny_line,
             }
             if world > 1:
-                line["check"] = head["check"]; line["strong"] = head["strong"]
+                line["check"] = head["check"]; line["strong"] = head["strong"]; line["g3"] = head.get("g3")
         else:
             t = trsm_line
             line = {
