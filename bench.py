@@ -463,6 +463,13 @@ def main():
                 parallelism = job.describe()
             ms, per, launches, stats, clocks = timed(step, args.steps, args.warmup)
             value = total_flops / (ms * 1e-3) / 1e9
+            wait_ms = transport = None
+            if world > 1 and job.native:
+                # how long the compute stream sat waiting for gathers in one more product (events around every wait, in the engine);
+                # taken right behind the timed region, while all ranks are still in step
+                job.step(flags=api.DIST_AB_STATIC | api.DIST_TRACE)
+                wait_ms = allmax(api.dist_last_wait_ms())
+                transport = api.dist_transport()
             roof = None
             if rank == 0:
                 kern_ms = sum(per) / len(per)
@@ -479,12 +486,9 @@ def main():
                         "traffic": traffic, "peak_source": PEAK_SRC, "kernel": kern, "kernels": stats,
                         "algorithmic_flop_per_step_per_gpu": flops_rank,
                         "algorithmic_bytes_per_step_per_gpu": 8.0 * 4 * n * n if world == 1 else None}
-            if world > 1 and job.native:
-                # how long the compute stream sat waiting for gathers in one more product (events around every wait, in the engine)
-                job.step(flags=api.DIST_AB_STATIC | api.DIST_TRACE)
-                wait_ms = allmax(api.dist_last_wait_ms())
-                if roof is not None:
-                    roof["gather_wait_ms_per_product_max_over_ranks"] = wait_ms
+            if roof is not None and wait_ms is not None:
+                roof["gather_wait_ms_per_product_max_over_ranks"] = wait_ms
+                roof["panel_transport"] = transport
             gemm_line = dict(value=value, ms=ms, launches=launches, roof=roof, clocks=clocks, parallelism=parallelism, total_flops=total_flops)
 
             # ---- e2e
@@ -536,6 +540,7 @@ def main():
             strong = None
             if world > 1 and not args.no_strong and args.workload == "headline":
                 from blis_b200 import dist as bdist
+                job.close()
                 del job
                 torch.cuda.empty_cache()
                 sjob = bdist.DistGemm(n, n, n, world, rank, dev, alpha=ALPHA, beta=BETA, kb=int(os.environ.get("B200_DIST_KB_STRONG", "1024")))
@@ -547,6 +552,7 @@ def main():
                     scheck = {"bit_equal_to_single_gpu_replay": bool(t[0].item() == 1.0), "testsuite_resid_max_over_ranks": float(-t[1].item())}
                 strong = {"value": sjob.total_flops / (sms * 1e-3) / 1e9, "unit": "GFLOPS", "ms_per_step": sms, "scaling": "strong",
                           "workload": wl_gemm, "parallelism": sjob.describe(), "kernel": gemm_kernel_of(sstats), "check": scheck}
+                sjob.close()
                 del sjob
             gemm_line["strong"] = strong
 
@@ -567,6 +573,7 @@ def main():
                       "workload": "dgemm m=n=k=65536 column-major fp64, 2D-sharded over 8 GPUs, alpha=2.0 beta=1.2 (BASELINE configs[4])",
                       "parallelism": gjob.describe(), "kernel": gemm_kernel_of(gstats), "check": gcheck,
                       "frac_of_dmma_peak_per_gpu": gjob.total_flops / world / (gms * 1e-3) / 1e12 / dmma_peak()}
+                gjob.close()
                 del gjob
                 torch.cuda.empty_cache()
             gemm_line["g3"] = g3

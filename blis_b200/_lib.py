@@ -28,7 +28,7 @@ EXPORTS = [
     "b200_gemmt", "b200_syrk", "b200_herk", "b200_syr2k", "b200_her2k",
     "b200_hemm", "b200_symm", "b200_trmm3", "b200_trmm", "b200_gemm_md", "b200_gemm_batch",
     "b200_partition_2x2", "b200_range_sub", "b200_dist_plan", "b200_dist_unique_id", "b200_dist_init", "b200_dist_finalize",
-    "b200_dist_gemm", "b200_dist_last_wait_ms", "b200_dist_gemm_1d", "b200_dist_trsm",
+    "b200_dist_gemm", "b200_dist_last_wait_ms", "b200_dist_register", "b200_dist_unregister", "b200_dist_transport", "b200_dist_gemm_1d", "b200_dist_trsm",
     "b200_blksz", "b200_measure_peak", "b200_launch_count", "b200_set_option", "b200_last_kernel", "b200_kernel_stats",
 ]
 
@@ -98,6 +98,9 @@ def load() -> C.CDLL:
     lib.b200_dist_finalize.argtypes = []; lib.b200_dist_finalize.restype = ci
     lib.b200_dist_gemm.argtypes = [ci, i64, i64, i64, i64, vp, vp, vp, vp, vp, i64, i64, ci]; lib.b200_dist_gemm.restype = ci
     lib.b200_dist_last_wait_ms.argtypes = []; lib.b200_dist_last_wait_ms.restype = C.c_double
+    lib.b200_dist_register.argtypes = [vp, vp]; lib.b200_dist_register.restype = ci
+    lib.b200_dist_unregister.argtypes = [vp, vp]; lib.b200_dist_unregister.restype = ci
+    lib.b200_dist_transport.argtypes = []; lib.b200_dist_transport.restype = ci
     lib.b200_dist_gemm_1d.argtypes = [ci, ci, ci, i64, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, vp, i64, i64]
     lib.b200_dist_gemm_1d.restype = ci
     lib.b200_dist_trsm.argtypes = [ci, ci, ci, ci, ci, ci, i64, i64, vp, vp, i64, i64, vp, i64, i64]; lib.b200_dist_trsm.restype = ci

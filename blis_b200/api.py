@@ -140,6 +140,19 @@ def dist_gemm(dtype, m, n, k, kb, alpha, a_loc, b_loc, beta, c_loc, rs_c, cs_c, 
                              _ptr(c_loc), rs_c, cs_c, flags), "b200_dist_gemm")
 
 
+def dist_register(a_loc, b_loc) -> bool:
+    """Collective.  True: later dist_gemm calls on these shards with DIST_AB_STATIC pull the panels with the copy engines."""
+    return _lib.load().b200_dist_register(_ptr(a_loc), _ptr(b_loc)) == _lib.BLIS_SUCCESS
+
+
+def dist_unregister(a_loc, b_loc) -> None:
+    _lib.load().b200_dist_unregister(_ptr(a_loc), _ptr(b_loc))
+
+
+def dist_transport() -> str:
+    return {0: "none", 1: "NCCL all-gather", 2: "copy-engine gets"}[_lib.load().b200_dist_transport()]
+
+
 def dist_last_wait_ms() -> float:
     return float(_lib.load().b200_dist_last_wait_ms())
 

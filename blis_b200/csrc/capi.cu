@@ -245,6 +245,9 @@ extern "C" b200_err_t b200_dist_unique_id( void* id ) { return dist_unique_id( i
 extern "C" b200_err_t b200_dist_init( int world, int rank, const void* id ) { return dist_init( world, rank, id ); }
 extern "C" b200_err_t b200_dist_finalize( void ) { return dist_finalize(); }
 extern "C" double b200_dist_last_wait_ms( void ) { return dist_last_wait_ms(); }
+extern "C" b200_err_t b200_dist_register( const void* a_loc, const void* b_loc ) { return dist_register( a_loc, b_loc ); }
+extern "C" b200_err_t b200_dist_unregister( const void* a_loc, const void* b_loc ) { return dist_unregister( a_loc, b_loc ); }
+extern "C" int b200_dist_transport( void ) { return dist().last_transport; }
 extern "C" b200_err_t b200_dist_gemm( int dt, b200_dim_t m, b200_dim_t n, b200_dim_t k, b200_dim_t kb, const void* alpha,
 	const void* a_loc, const void* b_loc, const void* beta, void* c_loc, b200_inc_t rs_c, b200_inc_t cs_c, int flags )
 {

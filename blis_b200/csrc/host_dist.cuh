@@ -143,6 +143,15 @@ struct DistState
 	cudaEvent_t inputs = nullptr, done = nullptr;
 	bool       buf_used[2] = { false, false };
 	int        ab_static = 0;                                  // b200_set_option("dist_ab_static", 1)
+	// one-sided transport: shards registered with b200_dist_register are mapped into every rank (CUDA IPC) and the k
+	// panels are PULLED by the copy engines over NVLink (cudaMemcpyAsync peer copies): no SM is taken from the DMMA kernel
+	cudaStream_t comm_stream2 = nullptr;                       // B panels (A panels travel on comm_stream)
+	cudaEvent_t  pulled2 = nullptr;
+	struct Reg { const void *a, *b; std::vector<const char*> peer_a, peer_b; };
+	std::vector<Reg> regs;
+	struct Opened { int rank; cudaIpcMemHandle_t h; char* base; };
+	std::vector<Opened> opened;                                // every peer allocation mapped so far (an allocation is opened once)
+	int        last_transport = 0;                             // 0 none, 1 NCCL all-gather, 2 copy-engine gets
 	// timing of the last b200_dist_gemm (events on the compute stream; b200_dist_last_wait_ms)
 	std::vector<cudaEvent_t> ev_wait0, ev_wait1;
 	int        last_steps = 0;
@@ -215,6 +224,10 @@ static int dist_finalize()
 	for ( auto e : d.ev_wait0 ) cudaEventDestroy( e );
 	for ( auto e : d.ev_wait1 ) cudaEventDestroy( e );
 	d.ev_wait0.clear(); d.ev_wait1.clear();
+	for ( auto& o : d.opened ) cudaIpcCloseMemHandle( o.base );
+	d.opened.clear(); d.regs.clear();
+	if ( d.comm_stream2 ) { cudaStreamDestroy( d.comm_stream2 ); d.comm_stream2 = nullptr; }
+	if ( d.pulled2 ) { cudaEventDestroy( d.pulled2 ); d.pulled2 = nullptr; }
 	cudaStreamDestroy( d.comm_stream ); d.comm_stream = nullptr;
 	d.up = false; d.world = 1; d.rank = 0;
 	return kSuccess;
@@ -235,6 +248,8 @@ static int dist_init( int world, int rank, const void* id128 )
 	B200_CUDA( cudaDeviceGetStreamPriorityRange( &lo, &hi ) );
 	// the gathers are short and on the critical path of the NEXT step only: give them priority over the persistent gemm CTAs
 	B200_CUDA( cudaStreamCreateWithPriority( &d.comm_stream, cudaStreamNonBlocking, hi ) );
+	B200_CUDA( cudaStreamCreateWithPriority( &d.comm_stream2, cudaStreamNonBlocking, hi ) );
+	B200_CUDA( cudaEventCreateWithFlags( &d.pulled2, cudaEventDisableTiming ) );
 	for ( int b = 0; b < 2; ++b )
 	{
 		B200_CUDA( cudaEventCreateWithFlags( &d.gathered[b], cudaEventDisableTiming ) );
@@ -271,6 +286,91 @@ static int dist_grow( DistState& d, size_t abytes, size_t bbytes )
 		B200_CUDA( cudaMalloc( &d.bbuf[b], nb ) );
 	}
 	d.abytes = na; d.bbytes = nb;
+	return kSuccess;
+}
+
+// ---- registration of static shards for one-sided gets (collective over all ranks) ------------------------------------
+// Every rank passes its A and B shards (device memory from cudaMalloc, e.g. a torch tensor); the CUDA IPC handles of the
+// allocations behind them travel through the communicator, every rank maps every other rank's shards, and from then on
+// b200_dist_gemm( ..., B200_DIST_AB_STATIC ) on exactly these pointers moves the k panels with peer copies issued by the
+// RECEIVER (the copy engines pull over NVLink; nothing runs on an SM and nothing is asked of the owner).  The contract of
+// B200_DIST_AB_STATIC is what makes a one-sided get legal: the shards are complete before the call and are not written
+// while products that use them are in flight.  Fails (on every rank alike) when the memory cannot be shared between the
+// processes; the caller then simply keeps the NCCL transport.
+typedef CUresult ( *MemGetAddressRangeFn )( CUdeviceptr*, size_t*, CUdeviceptr );
+static int dist_register( const void* a_loc, const void* b_loc )
+{
+	if ( ensure_init() != kSuccess ) return kFailure;
+	DistState& d = dist();
+	if ( !d.up ) return fail( "b200_dist_register: call b200_dist_init first" );
+	std::lock_guard<std::mutex> lk( d.mu );
+	for ( auto& r : d.regs ) if ( r.a == a_loc && r.b == b_loc ) return kSuccess;
+	struct Rec { cudaIpcMemHandle_t h[2]; unsigned long long off[2]; int ok; int pad; };
+	static_assert( sizeof( Rec ) % 8 == 0, "record size" );
+	Rec mine; memset( &mine, 0, sizeof( mine ) ); mine.ok = 1;
+	static MemGetAddressRangeFn range_fn = nullptr;
+	if ( !range_fn )
+	{
+		void* fp = nullptr; cudaDriverEntryPointQueryResult q;
+		if ( cudaGetDriverEntryPoint( "cuMemGetAddressRange", &fp, cudaEnableDefault, &q ) == cudaSuccess && q == cudaDriverEntryPointSuccess )
+			range_fn = (MemGetAddressRangeFn)fp;
+	}
+	const void* ptrs[2] = { a_loc, b_loc };
+	for ( int x = 0; x < 2 && mine.ok; ++x )
+	{
+		CUdeviceptr base = 0; size_t size = 0;
+		if ( !range_fn || classify( ptrs[x] ) != MemKind::Device || range_fn( &base, &size, (CUdeviceptr)ptrs[x] ) != CUDA_SUCCESS ) { mine.ok = 0; break; }
+		if ( cudaIpcGetMemHandle( &mine.h[x], (void*)base ) != cudaSuccess ) { cudaGetLastError(); mine.ok = 0; break; }
+		mine.off[x] = (unsigned long long)( (CUdeviceptr)ptrs[x] - base );
+	}
+	// all records to all ranks (through the communicator; this is a set-up call, so it may synchronise)
+	Rec* dev = nullptr;
+	std::vector<Rec> all( d.world );
+	B200_CUDA( cudaMalloc( &dev, sizeof( Rec ) * ( d.world + 1 ) ) );
+	B200_CUDA( cudaMemcpyAsync( dev + d.world, &mine, sizeof( Rec ), cudaMemcpyHostToDevice, d.comm_stream ) );
+	B200_NCCL( d.nccl.AllGather( dev + d.world, dev, sizeof( Rec ), 1, d.comm, d.comm_stream ) );
+	B200_CUDA( cudaMemcpyAsync( all.data(), dev, sizeof( Rec ) * d.world, cudaMemcpyDeviceToHost, d.comm_stream ) );
+	B200_CUDA( cudaStreamSynchronize( d.comm_stream ) );
+	int ok = 1;
+	for ( auto& r : all ) ok &= r.ok;
+	DistState::Reg reg; reg.a = a_loc; reg.b = b_loc;
+	reg.peer_a.assign( d.world, nullptr ); reg.peer_b.assign( d.world, nullptr );
+	for ( int r = 0; r < d.world && ok; ++r )
+	{
+		if ( r == d.rank ) { reg.peer_a[r] = (const char*)a_loc; reg.peer_b[r] = (const char*)b_loc; continue; }
+		for ( int x = 0; x < 2 && ok; ++x )
+		{
+			char* base = nullptr;
+			for ( auto& o : d.opened ) if ( o.rank == r && !memcmp( &o.h, &all[r].h[x], sizeof( cudaIpcMemHandle_t ) ) ) base = o.base;
+			if ( !base )
+			{
+				void* vp = nullptr;
+				if ( cudaIpcOpenMemHandle( &vp, all[r].h[x], cudaIpcMemLazyEnablePeerAccess ) != cudaSuccess ) { cudaGetLastError(); ok = 0; break; }
+				base = (char*)vp;
+				d.opened.push_back( { r, all[r].h[x], base } );
+			}
+			( x == 0 ? reg.peer_a : reg.peer_b )[r] = base + all[r].off[x];
+		}
+	}
+	// agree on the outcome: one rank that could not map a peer makes everybody stay on NCCL
+	mine.ok = ok;
+	B200_CUDA( cudaMemcpyAsync( dev + d.world, &mine, sizeof( Rec ), cudaMemcpyHostToDevice, d.comm_stream ) );
+	B200_NCCL( d.nccl.AllGather( dev + d.world, dev, sizeof( Rec ), 1, d.comm, d.comm_stream ) );
+	B200_CUDA( cudaMemcpyAsync( all.data(), dev, sizeof( Rec ) * d.world, cudaMemcpyDeviceToHost, d.comm_stream ) );
+	B200_CUDA( cudaStreamSynchronize( d.comm_stream ) );
+	cudaFree( dev );
+	for ( auto& r : all ) ok &= r.ok;
+	if ( !ok ) return fail( "b200_dist_register: the shards cannot be shared between the ranks (CUDA IPC); NCCL transport stays in use" );
+	d.regs.push_back( std::move( reg ) );
+	return kSuccess;
+}
+static int dist_unregister( const void* a_loc, const void* b_loc )
+{
+	DistState& d = dist();
+	std::lock_guard<std::mutex> lk( d.mu );
+	if ( d.up ) cudaDeviceSynchronize();
+	for ( size_t x = 0; x < d.regs.size(); ++x )
+		if ( d.regs[x].a == a_loc && d.regs[x].b == b_loc ) { d.regs.erase( d.regs.begin() + x ); return kSuccess; }
 	return kSuccess;
 }
 
@@ -313,11 +413,37 @@ static int dist_gemm( int64_t m, int64_t n, int64_t k, int64_t kb, const T* alph
 		B200_CUDA( cudaEventRecord( d.inputs, st ) );
 		B200_CUDA( cudaStreamWaitEvent( d.comm_stream, d.inputs, 0 ) );
 	}
+	const DistState::Reg* reg = nullptr;
+	if ( ab_static ) for ( auto& r : d.regs ) if ( r.a == a_loc && r.b == b_loc ) reg = &r;
+	d.last_transport = ( gather_a || gather_b ) ? ( reg ? 2 : 1 ) : 0;
 	auto start = [&]( int s ) -> int
 	{
 		const int bf = s & 1;
 		if ( !gather_a && !gather_b ) return kSuccess;            // one rank: nothing to move
 		if ( d.buf_used[bf] ) B200_CUDA( cudaStreamWaitEvent( d.comm_stream, d.buf_free[bf], 0 ) );
+		if ( reg )
+		{
+			// one-sided: I pull every group member's panels of this step into my receive buffer (same slot layout as the
+			// all-gather); A panels on comm_stream, B panels on comm_stream2, so two copy engines work at once
+			if ( gather_b )
+			{
+				if ( d.buf_used[bf] ) B200_CUDA( cudaStreamWaitEvent( d.comm_stream2, d.buf_free[bf], 0 ) );
+				for ( int ii = 0; ii < p.pr; ++ii )
+					B200_CUDA( cudaMemcpyAsync( (char*)d.bbuf[bf] + (size_t)ii * qb * b_panel * sizeof(T),
+					                            reg->peer_b[ii * p.pc + p.j] + (size_t)s * qb * b_panel * sizeof(T),
+					                            (size_t)qb * b_panel * sizeof(T), cudaMemcpyDeviceToDevice, d.comm_stream2 ) );
+				B200_CUDA( cudaEventRecord( d.pulled2, d.comm_stream2 ) );
+			}
+			if ( gather_a )
+				for ( int jj = 0; jj < p.pc; ++jj )
+					B200_CUDA( cudaMemcpyAsync( (char*)d.abuf[bf] + (size_t)jj * qa * a_panel * sizeof(T),
+					                            reg->peer_a[p.i * p.pc + jj] + (size_t)s * qa * a_panel * sizeof(T),
+					                            (size_t)qa * a_panel * sizeof(T), cudaMemcpyDeviceToDevice, d.comm_stream ) );
+			if ( gather_b ) B200_CUDA( cudaStreamWaitEvent( d.comm_stream, d.pulled2, 0 ) );
+			B200_CUDA( cudaEventRecord( d.gathered[bf], d.comm_stream ) );
+			d.buf_used[bf] = true;
+			return kSuccess;
+		}
 		// receive layout: [source rank in group][its q-th panel of this step] -> slot = src*q_per_rank + q
 		B200_NCCL( d.nccl.GroupStart() );
 		if ( gather_a ) B200_NCCL( d.nccl.AllGather( a_loc + (size_t)s * qa * a_panel, d.abuf[bf], (size_t)qa * a_panel * sizeof(T), /*ncclUint8*/ 1, d.row, d.comm_stream ) );

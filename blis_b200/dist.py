@@ -294,12 +294,22 @@ class DistGemm:
         self.ex = PanelExchange(p, self.a_loc, self.b_loc)
         self.total_flops = 2.0 * p.M * p.N * p.K
         self.launches_per_step = p.steps
+        # static shards: share them between the ranks once, so that the k panels are pulled by the copy engines
+        self.one_sided = False
+        if self.native and world > 1 and os.environ.get("B200_DIST_TRANSPORT", "ce") != "nccl":
+            self.one_sided = self.api.dist_register(self.a_loc, self.b_loc)
+
+    def close(self):
+        if getattr(self, "one_sided", False):
+            self.api.dist_unregister(self.a_loc, self.b_loc)
+            self.one_sided = False
 
     def describe(self) -> str:
         p = self.plan
         return (f"2D block decomposition of C on a {p.pr}x{p.pc} grid (bli_thread_partition_2x2), C_ij {p.m_loc}x{p.n_loc} per GPU, "
-                f"global {p.M}x{p.N}x{p.K}; A/B k-panels (kb={p.kb}) all-gathered in row/column groups with NCCL, "
-                f"double buffered under the DMMA kernels; no reduction (k not split across GPUs); "
+                f"global {p.M}x{p.N}x{p.K}; A/B k-panels (kb={p.kb}) gathered in row/column groups "
+                + ("by one-sided peer copies (copy engines over NVLink, registered static shards), " if self.one_sided else "with NCCL all-gather, ")
+                + f"double buffered under the DMMA kernels; no reduction (k not split across GPUs); "
                 + ("one b200_dist_gemm call per product (pipeline inside the engine, C ABI)" if self.native else "pipeline driven from Python"))
 
     def _panel(self, first, a_t, b_t):

@@ -335,6 +335,16 @@ b200_err_t b200_dist_gemm( int dt, b200_dim_t m, b200_dim_t n, b200_dim_t k, b20
                       const void* alpha, const void* a_loc, const void* b_loc,
                       const void* beta, void* c_loc, b200_inc_t rs_c, b200_inc_t cs_c, int flags );
 double     b200_dist_last_wait_ms( void );
+/* One-sided transport for STATIC shards (collective over all ranks): the allocations behind a_loc and b_loc are shared
+ * between the ranks (CUDA IPC handles carried by the communicator) and later b200_dist_gemm calls on exactly these
+ * pointers with B200_DIST_AB_STATIC move the k panels with peer copies issued by the receiving rank -- the copy engines
+ * pull over NVLink, no SM is taken from the DMMA kernel, nothing is asked of the owner.  Returns B200_FAILURE on every
+ * rank alike when the memory cannot be shared (the NCCL all-gather transport then stays in use).
+ * b200_dist_transport(): what the last b200_dist_gemm of this rank used: 0 nothing to move, 1 NCCL all-gather,
+ * 2 copy-engine gets. */
+b200_err_t b200_dist_register( const void* a_loc, const void* b_loc );
+b200_err_t b200_dist_unregister( const void* a_loc, const void* b_loc );
+int        b200_dist_transport( void );
 
 /* Skinny products (m, n >> k: the shapes bli_gemmsup serves, frame/3/bli_l3_sup.c:37-135): 1-D split of C over ALL
  * ranks in units of 128 (b200_range_sub( rank, world, n or m, 128, 0 )).  split = B200_DIST_COLS: c_loc and b are this

@@ -69,6 +69,18 @@ try:
         job = bdist.DistGemm(M, N, K, world, rank, dev, alpha=2.0, beta=1.2, kb=kb)
         assert job.native
         ck = job.verify()
+        out[f"gemm_{tag}_transport"] = api.dist_transport()
+        if world > 1:
+            # the one-sided transport (registered shards pulled by the copy engines) served it -- or, where the box cannot share
+            # memory between processes, registration failed on every rank alike and NCCL did
+            out[f"gemm_{tag}_transport_ok"] = (api.dist_transport() == ("copy-engine gets" if job.one_sided else "NCCL all-gather"))
+            if tag == "4steps" and job.one_sided:
+                # the same product over NCCL (registration dropped): same bits
+                ce = job.c.clone(memory_format=torch.preserve_format)
+                job.close()
+                ck2 = job.verify()
+                out["gemm_nccl_transport_bit_ok"] = ck2["bit_equal"] and api.dist_transport() == "NCCL all-gather" and bool(torch.equal(ce, job.c))
+                job.one_sided = api.dist_register(job.a_loc, job.b_loc)
         out[f"gemm_{tag}_bit_ok"] = ck["bit_equal"]
         out[f"gemm_{tag}_resid_ok"] = ck["resid"] < 1e-14
         out[f"gemm_{tag}_same_kernel_ok"] = ck["kernel"] == ck["kernel_replay"]
@@ -101,6 +113,7 @@ try:
             job.c.copy_(c0); job.step(); torch.cuda.synchronize()
             out["gemm_inputs_written_on_stream_ok"] = bool(torch.equal(one, job.c)) and not bool(torch.isnan(one).any())
             del big
+        job.close()
         del job
     # z through the same entry
     p = api.dist_plan(world, rank, pr * 512, pc * 384, 2 * 128 * L, 128)
