@@ -68,6 +68,7 @@ try:
                                "ragged": (pr * 1536 + 37, pc * 1280 + 5, 2 * 384 * L, 384)}.items():
         job = bdist.DistGemm(M, N, K, world, rank, dev, alpha=2.0, beta=1.2, kb=kb)
         assert job.native
+        c_init = job.c.clone(memory_format=torch.preserve_format)
         ck = job.verify()
         out[f"gemm_{tag}_transport"] = api.dist_transport()
         if world > 1:
@@ -78,6 +79,7 @@ try:
                 # the same product over NCCL (registration dropped): same bits
                 ce = job.c.clone(memory_format=torch.preserve_format)
                 job.close()
+                job.c.copy_(c_init)
                 ck2 = job.verify()
                 out["gemm_nccl_transport_bit_ok"] = ck2["bit_equal"] and api.dist_transport() == "NCCL all-gather" and bool(torch.equal(ce, job.c))
                 job.one_sided = api.dist_register(job.a_loc, job.b_loc)
