@@ -541,7 +541,11 @@ class DistSkinnyGemm:
                 f"k={self.k}; A ({self.m}x{self.k}) broadcast from rank {self.root} per product (ncclBroadcast), B and C local; no reduction")
 
     def step(self):
-        self.api.dist_gemm_1d(self.dtype, self.api.DIST_COLS, self.root if self.world > 1 else -1, self.m, self.n, self.k, self.alpha,
+        if self.world == 1:       # one GPU: the plain C-ABI gemm (no communicator exists)
+            fn = {torch.float64: self.api.bli_dgemm, torch.float32: self.api.bli_sgemm,
+                  torch.complex128: self.api.bli_zgemm, torch.complex64: self.api.bli_cgemm}[self.dtype]
+            return fn(0, 0, self.m, self.n, self.k, self.alpha, self.a.t(), 1, self.m, self.b.t(), 1, self.k, self.beta, self.c.t(), 1, self.m)
+        self.api.dist_gemm_1d(self.dtype, self.api.DIST_COLS, self.root, self.m, self.n, self.k, self.alpha,
                               self.a.t(), 1, self.m, self.b.t(), 1, self.k, self.beta, self.c.t(), 1, self.m)
 
     def verify(self) -> dict:

@@ -50,13 +50,18 @@ launches)
 	timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-peak > gpurun_out/bench_under_ncu.log 2>&1 ;;
 ncu_dgemm)
 	ncu --set full --clock-control none --import-source on -k regex:gemm_dmma -s 3 -c 1 -o gpurun_out/dgemm_full -f python bench.py --op dgemm --steps 2 --warmup 3 --no-cpu --no-e2e --no-peak > gpurun_out/ncu_full.log 2>&1
-	python tools/ncu_key.py gpurun_out/dgemm_full.ncu-rep > gpurun_out/ncu_dgemm_16384.txt 2>&1; head -12 gpurun_out/ncu_dgemm_16384.txt ;;
+	python tools/ncu_key.py gpurun_out/dgemm_full.ncu-rep > gpurun_out/ncu_dgemm_16384.txt 2>&1; head -12 gpurun_out/ncu_dgemm_16384.txt; rm -f gpurun_out/dgemm_full.ncu-rep ;;
 ncu_trsm)
 	ncu --set full --clock-control none --import-source on -k regex:trsm_ -s 40 -c 1 -o gpurun_out/trsm_full -f python bench.py --op dtrsm --steps 1 --warmup 3 --no-cpu --no-e2e --no-peak > gpurun_out/ncu_trsm.log 2>&1
-	python tools/ncu_key.py gpurun_out/trsm_full.ncu-rep > gpurun_out/ncu_trsm_panel.txt 2>&1; head -12 gpurun_out/ncu_trsm_panel.txt ;;
+	python tools/ncu_key.py gpurun_out/trsm_full.ncu-rep > gpurun_out/ncu_trsm_panel.txt 2>&1; head -12 gpurun_out/ncu_trsm_panel.txt; rm -f gpurun_out/trsm_full.ncu-rep ;;
 ncu_skinny)
 	ncu --set full --clock-control none --import-source on -k regex:gemm_ -s 1 -c 1 -o gpurun_out/skinny_full -f python -m tools.one_gemm d 16384 64 -1 2 > /dev/null 2>&1
-	python tools/ncu_key.py gpurun_out/skinny_full.ncu-rep > gpurun_out/ncu_dgemm_k64.txt 2>&1; head -12 gpurun_out/ncu_dgemm_k64.txt ;;
+	python tools/ncu_key.py gpurun_out/skinny_full.ncu-rep > gpurun_out/ncu_dgemm_k64.txt 2>&1; head -12 gpurun_out/ncu_dgemm_k64.txt
+	python tools/ncu_src.py gpurun_out/skinny_full.ncu-rep 25 > gpurun_out/ncu_dgemm_k64_src.txt 2>&1; rm -f gpurun_out/skinny_full.ncu-rep ;;
+ncu_sgemm)
+	ncu --set full --clock-control none --import-source on -k regex:gemm_ffma_tma -s 1 -c 1 -o gpurun_out/sgemm_full -f python -m tools.one_gemm s 8192 8192 -1 2 > /dev/null 2>&1
+	python tools/ncu_key.py gpurun_out/sgemm_full.ncu-rep > gpurun_out/ncu_sgemm_8192.txt 2>&1; head -30 gpurun_out/ncu_sgemm_8192.txt
+	python tools/ncu_src.py gpurun_out/sgemm_full.ncu-rep 60 > gpurun_out/ncu_sgemm_8192_src.txt 2>&1; rm -f gpurun_out/sgemm_full.ncu-rep ;;
 sweep)
 	for ch in d s c z; do timeout 400 python -m tools.gpu_probe2 $ch -1 512,1024,2048,4096,8192,16384,512x64,4096x64,16384x64 > gpurun_out/sweep_$ch.log 2>&1; tail -1 gpurun_out/sweep_$ch.log; done ;;
 *)
