@@ -1,5 +1,6 @@
 // context.cu -- engine runtime: init, streams, errors, pinned staging.
 #include "context.cuh"
+#include <stdlib.h>
 #include "../../include/blis_b200.h"
 #include <algorithm>
 #include <map>
@@ -61,6 +62,27 @@ int* sched_slot( cudaStream_t st )
 	return c.sched_counters + 2 * it->second;
 }
 
+// Environment convention of the reference (frame/base/bli_env.c:68: BLIS_NUM_THREADS, BLIS_JC_NT, ... read once at
+// initialisation): every tuning knob of b200_set_option can be preset as BLIS_B200_<KEY> (upper case), e.g.
+// BLIS_B200_DGEMM_CFG=6, BLIS_B200_TRSM_FUSED=0, BLIS_B200_DMMA_CST=0; BLIS_B200_DEVICE picks the GPU when the caller did
+// not (b200_init( -1 ) with no device made current).  Unparsable values are ignored, as bli_env_get_var does.
+extern "C" int b200_set_option( const char* key, long long value );
+static void apply_env_options()
+{
+	static const char* keys[] = { "dgemm_cfg", "zgemm_cfg", "sgemm_cfg", "cgemm_cfg", "grid_mult", "dynamic_tiles", "transpose_y", "ktri_skip",
+	                              "host_kpipe", "dmma_cst", "dmma_pp", "trsm_fused", "dist_ab_static", "tma_l2_promotion", "raster_group", "reserve_sms" };
+	for ( const char* k : keys )
+	{
+		char name[64] = "BLIS_B200_"; size_t n = strlen( name );
+		for ( const char* p = k; *p && n + 1 < sizeof( name ); ++p ) name[n++] = (char)( *p >= 'a' && *p <= 'z' ? *p - 32 : *p );
+		name[n] = 0;
+		const char* v = getenv( name );
+		if ( !v || !*v ) continue;
+		char* end = nullptr; const long long val = strtoll( v, &end, 10 );
+		if ( end && *end == 0 ) b200_set_option( k, val );
+	}
+}
+
 static int do_init( int device )
 {
 	Context& c = ctx();
@@ -69,7 +91,12 @@ static int do_init( int device )
 	int ndev = 0;
 	if ( cudaGetDeviceCount( &ndev ) != cudaSuccess || ndev == 0 )
 		return fail( "b200_init: no CUDA device visible; this engine has no CPU fallback" );
-	if ( device < 0 ) B200_CUDA( cudaGetDevice( &device ) );
+	if ( device < 0 )
+	{
+		const char* ev = getenv( "BLIS_B200_DEVICE" );
+		if ( ev && *ev >= '0' && *ev <= '9' && atoi( ev ) < ndev ) device = atoi( ev );
+		else B200_CUDA( cudaGetDevice( &device ) );
+	}
 	B200_CUDA( cudaSetDevice( device ) );
 	cudaDeviceProp prop;
 	B200_CUDA( cudaGetDeviceProperties( &prop, device ) );
@@ -97,6 +124,7 @@ static int do_init( int device )
 	B200_CUDA( cudaMemset( c.sched_counters, 0, 2 * Context::kSchedSlots * sizeof(int) ) );
 	{ std::lock_guard<std::mutex> lk2( g_sched_mu ); g_sched_of_stream.clear(); }
 	c.ready = true;
+	apply_env_options();
 	return kSuccess;
 }
 

@@ -14,7 +14,7 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 		return (int)std::min<int64_t>( (int64_t)g.tiles_p * g.tiles_q, (int64_t)c.num_sms * c.grid_mult * per_sm );
 	};
 	int cfg = c.dgemm_cfg;
-	if ( g.nseg > 1 && ( cfg < 4 ) ) cfg = -1;          // k-panel accumulation needs a warp-specialised kernel
+	if ( cfg >= 0 && cfg < 4 ) cfg = -1;                // 0-3 were the retired single-role kernel
 	if ( g.tri || g.ktri )
 	{
 		// triangular D (gemmt family): the TRI instantiations of the default kernels
@@ -37,24 +37,21 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 	switch ( cfg )
 	{
 		default:
-		case 0: return launch_dmma<double, 128, 128, 16, 2, 4, 4>( g, xk, yk, al, tiles( 128, 128 ), st );
-		case 1: return launch_dmma<double, 128, 128, 16, 4, 2, 4>( g, xk, yk, al, tiles( 128, 128 ), st );
-		case 2: return launch_dmma<double, 128, 128, 8,  2, 4, 6>( g, xk, yk, al, tiles( 128, 128 ), st );
-		case 3: return launch_dmma<double, 128, 128, 32, 2, 4, 3>( g, xk, yk, al, tiles( 128, 128 ), st );
 		case 4: return launch_dmma_ws<double, 128, 128, 16, 2, 4, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
 		case 5: return launch_dmma_ws<double, 128, 128, 32, 2, 4, 3>( g, xk, yk, al, tiles( 128, 128 ), st );
 		case 6: return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
-		case 9: if ( tma_eligible( g, xk, yk, al ) )
-		        {
-		        	// small k: two consumer groups take turns on the tensor pipe, each epilogue under the other's k loop (gemm_dmma_pp.cuh)
-	        	if ( c.dmma_pp && g.nseg == 1 && g.K <= c.dmma_pp && g.d_vec_ok )
-	        		return launch_dmma_pp( g, xk, yk, tiles( 128, 128 ), st );
-	        	// small k: the read-modify-write of D is staged through the TMA ring as well (gemm_dmma_tma.cuh, CST)
-		        	if ( c.dmma_cst && g.d_vec_ok && g.K * g.nseg <= c.dmma_cst && g.ldd >= g.Q && g.ldd * 8 < ( 1ll << 40 ) )
-		        		return launch_dmma_tma<false, true>( g, xk, yk, tiles( 128, 128 ), st );
-		        	return launch_dmma_tma( g, xk, yk, tiles( 128, 128 ), st );
-		        }
-		        return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
+		case 9:
+			if ( tma_eligible( g, xk, yk, al ) )
+			{
+				// small k, opt-in: two consumer groups take turns on the tensor pipe (gemm_dmma_pp.cuh; measured slower)
+				if ( c.dmma_pp && g.nseg == 1 && g.K <= c.dmma_pp && g.d_vec_ok )
+					return launch_dmma_pp( g, xk, yk, tiles( 128, 128 ), st );
+				// small k: D travels through the TMA ring in both directions (gemm_dmma_tma.cuh, CST)
+				if ( c.dmma_cst && g.d_vec_ok && g.K * g.nseg <= c.dmma_cst && g.ldd >= g.Q && g.ldd * 8 < ( 1ll << 40 ) )
+					return launch_dmma_tma<false, true>( g, xk, yk, tiles( 128, 128 ), st );
+				return launch_dmma_tma( g, xk, yk, tiles( 128, 128 ), st );
+			}
+			return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );
 		case 7:  return launch_dmma_ws<double, 128, 64, 16, 4, 1, 3>( g, xk, yk, al, tiles( 128, 64, 2 ), st );
 		case 10: return launch_dmma_ws<double, 64, 64, 16, 2, 2, 4>( g, xk, yk, al, tiles( 64, 64, 2 ), st );
 		case 8:  return launch_dmma_ws<double, 64, 128, 16, 1, 4, 3>( g, xk, yk, al, tiles( 64, 128, 2 ), st );

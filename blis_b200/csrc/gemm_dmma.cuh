@@ -1,4 +1,6 @@
-// gemm_dmma.cuh -- FP64 tensor-core (DMMA) gemm for d and z.
+// gemm_dmma.cuh -- FP64 tensor-core (DMMA) gemm for d and z: the kernel contract (GemmArgs), the tile raster, the triangular
+// schedules and the cp.async tile loader shared by the kernels in gemm_dmma_ws.cuh / gemm_dmma_tma.cuh / gemm_dmma_pp.cuh /
+// gemm_zmma_tma.cuh (the single-role kernel that first lived here was retired in round 2: 31.3 against 36.4 TFLOP/s).
 //
 // Replaces, for datatypes d/z, the reference's five-loop gemm:
 //   jc/pc/ic loops            frame/3/gemm/bli_gemm_blk_var{2,3,1}.c
@@ -170,198 +172,5 @@ struct DmmaCfg
 	static constexpr int  SMEM_BYTES  = STAGE_BYTES * STAGES;
 	static_assert( BK % 8 == 0 && BP % ( 8 * WP ) == 0 && BQ % ( 8 * WQ ) == 0, "tile shape" );
 };
-
-template <typename T, int BP, int BQ, int BK, int WP, int WQ, int STAGES, bool XK, bool YK, bool AL>
-__global__ void __launch_bounds__( WP * WQ * 32, 1 )
-gemm_dmma_kernel( const GemmArgs<T> g )
-{
-	using Cfg = DmmaCfg<T, BP, BQ, BK, WP, WQ, STAGES, XK, YK, AL>;
-	constexpr bool CPLX = Cfg::CPLX;
-	constexpr int  NT = Cfg::NT, MT = Cfg::MT, NTL = Cfg::NTL;
-	constexpr int  SXK = BK + Cfg::PADK, SXP = BP + Cfg::PADC, SYQ = BQ + Cfg::PADC;
-
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	T* const smem = reinterpret_cast<T*>( smem_raw );
-
-	const int tid  = threadIdx.x;
-	const int lane = tid & 31, warp = tid >> 5;
-	const int gq   = lane >> 2;      // "g": row of the A fragment / column of B
-	const int t4   = lane & 3;       // "t": k index inside a k4 step
-	const int wp0  = ( warp / WQ ) * Cfg::WTP;
-	const int wq0  = ( warp % WQ ) * Cfg::WTQ;
-
-	const int64_t KT = ( g.K + BK - 1 ) / BK;
-	const int num_tiles = g.tiles_p * g.tiles_q;
-	const bool cjx = CPLX && g.conjx, cjy = CPLX && g.conjy;
-
-	for ( int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x )
-	{
-		int tp, tq;
-		tile_coords( tile, g.tiles_p, g.tiles_q, g.raster, tp, tq );
-		const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
-		const int p_lim = (int)min( (int64_t)BP, g.P - p0 );
-		const int q_lim = (int)min( (int64_t)BQ, g.Q - q0 );
-		if ( tri_skip_tile( g, p0, q0, p_lim, q_lim ) ) continue;
-
-		const T* gx = XK ? g.X + p0 * g.ldx : g.X + p0;
-		const T* gy = YK ? g.Y + q0 * g.ldy : g.Y + q0;
-
-		auto issue = [&]( int64_t kt, int stage )
-		{
-			const int k_lim = (int)min( (int64_t)BK, g.K - kt * BK );
-			T* xs = smem + (size_t)stage * ( Cfg::XS_ELEMS + Cfg::YS_ELEMS );
-			T* ys = xs + Cfg::XS_ELEMS;
-			if constexpr ( XK ) load_tile<T, BP, BK, Cfg::PADK, NT, AL>( smem_u32( xs ), gx + kt * BK, g.ldx, p_lim, k_lim, tid );
-			else                load_tile<T, BK, BP, Cfg::PADC, NT, AL>( smem_u32( xs ), gx + kt * BK * g.ldx, g.ldx, k_lim, p_lim, tid );
-			if constexpr ( YK ) load_tile<T, BQ, BK, Cfg::PADK, NT, AL>( smem_u32( ys ), gy + kt * BK, g.ldy, q_lim, k_lim, tid );
-			else                load_tile<T, BK, BQ, Cfg::PADC, NT, AL>( smem_u32( ys ), gy + kt * BK * g.ldy, g.ldy, k_lim, q_lim, tid );
-		};
-
-		// accumulators: real -> acc[MT][NTL][2]; complex -> re and im planes
-		double acc[CPLX ? 2 : 1][MT][NTL][2];
-		#pragma unroll
-		for ( int c = 0; c < ( CPLX ? 2 : 1 ); ++c )
-			#pragma unroll
-			for ( int i = 0; i < MT; ++i )
-				#pragma unroll
-				for ( int j = 0; j < NTL; ++j ) { acc[c][i][j][0] = 0.0; acc[c][i][j][1] = 0.0; }
-
-		// ---- pipeline prologue
-		#pragma unroll
-		for ( int s = 0; s < STAGES - 1; ++s )
-		{
-			if ( s < KT ) issue( s, s );
-			cp_async_commit();
-		}
-
-		// ---- main loop over k tiles
-		for ( int64_t kt = 0; kt < KT; ++kt )
-		{
-			cp_async_wait<STAGES - 2>();
-			__syncthreads();
-			{
-				const int64_t kn = kt + STAGES - 1;
-				if ( kn < KT ) issue( kn, (int)( kn % STAGES ) );
-				cp_async_commit();
-			}
-			const T* xs = smem + (size_t)( kt % STAGES ) * ( Cfg::XS_ELEMS + Cfg::YS_ELEMS );
-			const T* ys = xs + Cfg::XS_ELEMS;
-
-			#pragma unroll
-			for ( int kk = 0; kk < BK / 4; ++kk )
-			{
-				T xf[MT], yf[NTL];
-				#pragma unroll
-				for ( int i = 0; i < MT; ++i )
-				{
-					const int p = wp0 + i * 8 + gq, k = kk * 4 + t4;
-					xf[i] = XK ? xs[p * SXK + k] : xs[k * SXP + p];
-				}
-				#pragma unroll
-				for ( int j = 0; j < NTL; ++j )
-				{
-					const int q = wq0 + j * 8 + gq, k = kk * 4 + t4;
-					yf[j] = YK ? ys[q * SXK + k] : ys[k * SYQ + q];
-				}
-				if constexpr ( !CPLX )
-				{
-					#pragma unroll
-					for ( int i = 0; i < MT; ++i )
-						#pragma unroll
-						for ( int j = 0; j < NTL; ++j )
-							dmma884( acc[0][i][j][0], acc[0][i][j][1], xf[i], yf[j] );
-				}
-				else
-				{
-					// (xr + i xi)(yr + i yi): re += xr*yr - xi*yi ; im += xr*yi + xi*yr
-					double xr[MT], xi[MT], nxi[MT];
-					#pragma unroll
-					for ( int i = 0; i < MT; ++i )
-					{
-						xr[i]  = xf[i].x;
-						xi[i]  = flip_sign( xf[i].y, cjx );
-						nxi[i] = -xi[i];
-					}
-					#pragma unroll
-					for ( int j = 0; j < NTL; ++j )
-					{
-						const double yr = yf[j].x, yi = flip_sign( yf[j].y, cjy );
-						#pragma unroll
-						for ( int i = 0; i < MT; ++i )
-						{
-							dmma884( acc[0][i][j][0], acc[0][i][j][1], xr[i],  yr );
-							dmma884( acc[1][i][j][0], acc[1][i][j][1], xr[i],  yi );
-							dmma884( acc[0][i][j][0], acc[0][i][j][1], nxi[i], yi );
-							dmma884( acc[1][i][j][0], acc[1][i][j][1], xi[i],  yr );
-						}
-					}
-				}
-			}
-		}
-		cp_async_wait<0>();
-
-		// ---- epilogue: D = alpha*acc + beta*D   (beta == 0: D is not read)
-		int dlo, dhi;
-		tri_band( g, p0, q0, dlo, dhi );
-		#pragma unroll
-		for ( int i = 0; i < MT; ++i )
-		{
-			const int pl = wp0 + i * 8 + gq;
-			if ( pl >= p_lim ) continue;
-			T* drow = g.D + ( p0 + pl ) * g.ldd + q0;
-			#pragma unroll
-			for ( int j = 0; j < NTL; ++j )
-			{
-				const int ql = wq0 + j * 8 + 2 * t4;
-				const bool one = ( ql < q_lim && in_band( ql - pl, dlo, dhi ) );
-				const bool two = ( ql + 1 < q_lim && in_band( ql + 1 - pl, dlo, dhi ) );
-				if ( !one && !two ) continue;
-				if constexpr ( !CPLX )
-				{
-					double r0 = g.alpha * acc[0][i][j][0];
-					double r1 = g.alpha * acc[0][i][j][1];
-					if ( one && two && g.d_vec_ok )
-					{
-						double2* dp = reinterpret_cast<double2*>( drow + ql );
-						if ( !g.beta_is_zero ) { const double2 o = *dp; r0 = fma( g.beta, o.x, r0 ); r1 = fma( g.beta, o.y, r1 ); }
-						*dp = make_double2( r0, r1 );
-					}
-					else
-					{
-						if ( one )
-						{
-							if ( !g.beta_is_zero ) r0 = fma( g.beta, drow[ql], r0 );
-							drow[ql] = r0;
-						}
-						if ( two )
-						{
-							if ( !g.beta_is_zero ) r1 = fma( g.beta, drow[ql + 1], r1 );
-							drow[ql + 1] = r1;
-						}
-					}
-				}
-				else
-				{
-					#pragma unroll
-					for ( int e = 0; e < 2; ++e )
-					{
-						if ( e == 0 ? !one : !two ) continue;
-						const double ar = acc[0][i][j][e], ai = acc[1][i][j][e];
-						// ab *= alpha (bli_tscals), then c := ab + beta*c (bli_txpbys)
-						double rr, ri;
-						cscal( g.alpha.x, g.alpha.y, ar, ai, rr, ri );
-						if ( !g.beta_is_zero )
-						{
-							const double2 o = drow[ql + e];
-							cxpby( g.beta.x, g.beta.y, o.x, o.y, rr, ri );
-						}
-						drow[ql + e] = make_double2( rr, ri );
-					}
-				}
-			}
-		}
-		__syncthreads();   // all fragment reads done before the next tile's prologue overwrites smem
-	}
-}
 
 } // namespace b200

@@ -51,33 +51,6 @@ static int set_smem( KernT kern, int bytes )
 
 // ---- kernel launchers -------------------------------------------------------------
 
-template <typename T, int BP, int BQ, int BK, int WP, int WQ, int ST>
-static int launch_dmma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
-{
-	auto go = [&]( auto XKc, auto YKc, auto ALc ) -> int
-	{
-		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value, AL = decltype( ALc )::value;
-		using Cfg = DmmaCfg<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
-		auto kern = gemm_dmma_kernel<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
-		static const std::string kname = kfmt( "gemm_dmma_kernel<%s,%dx%dx%d,%dst,XK=%d,YK=%d,AL=%d>", tname<T>(), BP, BQ, BK, ST, XK, YK, AL );
-		static bool attr = false;
-		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
-		kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>( g );
-		B200_CUDA( cudaGetLastError() );
-		note_launch( kname.c_str() );
-		return kSuccess;
-	};
-	using Tt = std::true_type; using Ff = std::false_type;
-	const int sel = ( xk ? 4 : 0 ) | ( yk ? 2 : 0 ) | ( al ? 1 : 0 );
-	switch ( sel )
-	{
-		case 0: return go( Ff{}, Ff{}, Ff{} );  case 1: return go( Ff{}, Ff{}, Tt{} );
-		case 2: return go( Ff{}, Tt{}, Ff{} );  case 3: return go( Ff{}, Tt{}, Tt{} );
-		case 4: return go( Tt{}, Ff{}, Ff{} );  case 5: return go( Tt{}, Ff{}, Tt{} );
-		case 6: return go( Tt{}, Tt{}, Ff{} );  default: return go( Tt{}, Tt{}, Tt{} );
-	}
-}
-
 template <typename T, int BP, int BQ, int BK, int WP, int WQ, int ST, bool TRI = false>
 static int launch_dmma_ws( const GemmArgs<T>& g, bool xk, bool yk, bool al, int grid, cudaStream_t st )
 {

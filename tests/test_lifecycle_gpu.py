@@ -21,3 +21,20 @@ def test_finalize_then_reinit():
         assert out[f"same_bits_{cycle}"], out
         assert out[f"host_{cycle}"] < 1e-12 and out[f"batch_{cycle}"] < 1e-12, out
     assert out["launches"] >= 4 * 2 + 3 * 3
+
+
+def test_environment_presets_follow_the_blis_env_convention():
+    """BLIS_B200_<KEY> presets a b200_set_option knob at initialisation (the reference reads BLIS_* variables once at init,
+    frame/base/bli_env.c:68): BLIS_B200_DGEMM_CFG=6 must route an aligned dgemm to the cp.async kernel instead of the TMA one."""
+    import os
+    import subprocess
+    import sys
+    code = ("import torch; from blis_b200 import api; "
+            "a=torch.rand(512,512,dtype=torch.float64,device='cuda'); c=torch.zeros_like(a); "
+            "api.bli_dgemm(0,0,512,512,512,1.0,a,1,512,a,1,512,0.0,c,1,512); torch.cuda.synchronize(); print(api.last_kernel())")
+    root = str(__import__("pathlib").Path(__file__).resolve().parent.parent)
+    for env_extra, want in (({"BLIS_B200_DGEMM_CFG": "6"}, "gemm_dmma_ws_kernel<double,128x128x16"), ({"BLIS_B200_DGEMM_CFG": "9"}, "gemm_dmma_tma_kernel"),
+                            ({"BLIS_B200_DGEMM_CFG": "nonsense"}, "gemm_dmma_")):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root, env=dict(os.environ, **env_extra))
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert r.stdout.strip().splitlines()[-1].startswith(want), (env_extra, r.stdout)
