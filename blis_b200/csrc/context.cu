@@ -61,6 +61,13 @@ int* sched_slot( cudaStream_t st )
 	}
 	return c.sched_counters + 2 * it->second;
 }
+int* sk_flags_of( int* sched_pair )
+{
+	Context& c = ctx();
+	if ( !sched_pair || !c.sched_counters ) return nullptr;
+	const int64_t slot = ( sched_pair - c.sched_counters ) / 2;
+	return c.sched_counters + 2 * Context::kSchedSlots + slot * 8 * Context::kSkTail;
+}
 
 // Environment convention of the reference (frame/base/bli_env.c:68: BLIS_NUM_THREADS, BLIS_JC_NT, ... read once at
 // initialisation): every tuning knob of b200_set_option can be preset as BLIS_B200_<KEY> (upper case), e.g.
@@ -70,7 +77,7 @@ extern "C" int b200_set_option( const char* key, long long value );
 static void apply_env_options()
 {
 	static const char* keys[] = { "dgemm_cfg", "zgemm_cfg", "sgemm_cfg", "cgemm_cfg", "grid_mult", "dynamic_tiles", "transpose_y", "ktri_skip",
-	                              "host_kpipe", "dmma_cst", "dmma_pp", "trsm_fused", "dist_ab_static", "tma_l2_promotion", "raster_group", "reserve_sms" };
+	                              "host_kpipe", "dmma_cst", "dmma_pp", "dgemm_splitk", "trsm_fused", "dist_ab_static", "tma_l2_promotion", "raster_group", "reserve_sms" };
 	for ( const char* k : keys )
 	{
 		char name[64] = "BLIS_B200_"; size_t n = strlen( name );
@@ -120,8 +127,9 @@ static int do_init( int device )
 		uint64_t thresh = UINT64_MAX;
 		cudaMemPoolSetAttribute( pool, cudaMemPoolAttrReleaseThreshold, &thresh );
 	}
-	B200_CUDA( cudaMalloc( (void**)&c.sched_counters, 2 * Context::kSchedSlots * sizeof(int) ) );
-	B200_CUDA( cudaMemset( c.sched_counters, 0, 2 * Context::kSchedSlots * sizeof(int) ) );
+	const size_t sched_bytes = (size_t)( 2 + 8 * Context::kSkTail ) * Context::kSchedSlots * sizeof(int);
+	B200_CUDA( cudaMalloc( (void**)&c.sched_counters, sched_bytes ) );
+	B200_CUDA( cudaMemset( c.sched_counters, 0, sched_bytes ) );
 	{ std::lock_guard<std::mutex> lk2( g_sched_mu ); g_sched_of_stream.clear(); }
 	c.ready = true;
 	apply_env_options();

@@ -58,12 +58,14 @@ struct Context
 	// dynamic tile scheduling: self re-arming {tile, done} pairs, ONE PAIR PER STREAM (kernels of one stream run one
 	// after the other, so a stream's pair is never shared by two running kernels; see sched_slot)
 	static constexpr int kSchedSlots = 2048;
-	int*         sched_counters = nullptr;
+	static constexpr int kSkTail = 160;  // split-k tail (gemm_dmma_tma.cuh SK): at most this many tail tiles, one self re-arming counter per consumer warp (8) each, per stream
+	int*         sched_counters = nullptr;   // kSchedSlots pairs, then kSchedSlots x 8*kSkTail split-k counters
 	int          dynamic_tiles = 1;
 	int          raster_group = 8;      // tile rows per raster group: the ~148 running tiles form a raster_group x 148/raster_group block
 	int          tma_l2_promotion = 2;  // CUtensorMapL2promotion: 0 none, 1 64 B, 2 128 B, 3 256 B
 	int          dmma_pp  = 0;          // dgemm TMA kernel: ping-pong the two q-halves of a tile for K <= this (0 = never)
 	int          dmma_cst = 256;        // dgemm TMA kernel: stage D through the ring (TMA load + TMA store) for K <= this (0 = never); [B200] wins up to k = 256
+	int          dgemm_splitk = 1;      // dgemm TMA kernel: cut the tiles of a partial last wave into k chunks (mid-size problems; 0 = never split k)
 	int          host_kpipe = 1;        // host operands with long k: pipeline over k panels instead of column blocks
 	int          ktri_skip = 1;         // trmm/trmm3: tiles skip the k range in which the triangular operand is zero
 	int          transpose_y = 1;       // s/c: transpose a k-contiguous Y panel once instead of re-pairing registers in the k loop
@@ -77,6 +79,8 @@ int ensure_init();                         // lazy init + cudaSetDevice(engine d
 void note_launch( const char* name );
 // The {tile, done} counter pair dynamic tile scheduling uses on stream `st` (nullptr: none left -> static schedule).
 int* sched_slot( cudaStream_t st );
+// The split-k counters that belong to a stream's pair (8*Context::kSkTail ints, all zero between launches).
+int* sk_flags_of( int* sched_pair );
 cudaStream_t cur_stream();                 // thread's selected stream or the engine's
 
 // ---- pointer classification ------------------------------------------------------

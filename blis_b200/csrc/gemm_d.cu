@@ -4,6 +4,43 @@
 
 namespace b200 {
 
+// Split-k tail schedule (GemmArgs::sk_*): `tiles` 128x128 tiles on `grid` persistent CTAs.  The r = tiles % grid tiles of the
+// last wave are cut into S chunks each; with S chosen so that r*S units fill whole rounds of the grid, the tail costs
+// ceil(r*S/grid)/S of a tile time instead of 1.  Returns S (0: leave the schedule alone).
+static int splitk_plan( int64_t tiles, int grid, int64_t kt, int* full )
+{
+	if ( grid <= 0 || tiles <= 0 ) return 0;
+	const int64_t waves = ( tiles + grid - 1 ) / grid;
+	const int64_t r = tiles % grid;
+	if ( r == 0 || waves > 8 ) return 0;                          // nothing idle / the tail is under ~1.5 % of the run
+	double best = 0.97; int S = 0;                               // a chunk's fix-up (park + add, ~3 % of a tile at k = 2048) must be paid for
+	for ( int s : { 2, 3, 4, 5, 6, 8 } )
+	{
+		if ( kt / s < 16 ) break;                                   // >= 256 k per chunk
+		const double t = (double)( ( r * s + grid - 1 ) / grid ) / s + 0.01 * s;
+		if ( t < best - 1e-9 ) { best = t; S = s; }
+	}
+	if ( S == 0 || ( 1.0 - best ) / (double)waves < 0.03 ) return 0;   // under 3 % of the whole launch
+	*full = (int)( tiles - r );
+	return S;
+}
+// the launch itself: the accumulator slots (r*S x 128 KiB) come from the stream-ordered pool, the counters are the stream's
+// own (self re-arming, context.cu)
+static int launch_dmma_tma_splitk( GemmArgs<double>& g, bool xk, bool yk, int grid, int S, int full, cudaStream_t st )
+{
+	const int64_t r = (int64_t)g.tiles_p * g.tiles_q - full;
+	int* flags = sk_flags_of( g.tile_counter );
+	if ( !flags || r > Context::kSkTail ) return launch_dmma_tma( g, xk, yk, grid, st );
+	void* ws = nullptr;
+	if ( dev_alloc( &ws, (size_t)r * S * 128 * 128 * 8, st ) != kSuccess ) return kFailure;
+	g.sk_full = full; g.sk_split = S; g.sk_ws = (double*)ws; g.sk_flags = flags;
+	const int64_t units = full + r * S;
+	const int rc = launch_dmma_tma<false, false, true>( g, xk, yk, (int)std::min<int64_t>( units, grid ), st );
+	dev_free( ws, st );
+	g.sk_full = 0; g.sk_split = 0; g.sk_ws = nullptr; g.sk_flags = nullptr;
+	return rc;
+}
+
 template <>
 int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, cudaStream_t st )
 {
@@ -49,6 +86,14 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 				// small k: D travels through the TMA ring in both directions (gemm_dmma_tma.cuh, CST)
 				if ( c.dmma_cst && g.d_vec_ok && g.K * g.nseg <= c.dmma_cst && g.ldd >= g.Q && g.ldd * 8 < ( 1ll << 40 ) )
 					return launch_dmma_tma<false, true>( g, xk, yk, tiles( 128, 128 ), st );
+				// mid-size: a last wave that would leave SMs idle is cut into k chunks (split-k tail, gemm_dmma_tma.cuh SK)
+				if ( c.dgemm_splitk && g.nseg == 1 )
+				{
+					const int grid = tiles( 128, 128 );
+					int full = 0;
+					const int S = splitk_plan( (int64_t)g.tiles_p * g.tiles_q, c.num_sms * c.grid_mult, ( g.K + 15 ) / 16, &full );
+					if ( S ) return launch_dmma_tma_splitk( g, xk, yk, grid, S, full, st );
+				}
 				return launch_dmma_tma( g, xk, yk, tiles( 128, 128 ), st );
 			}
 			return launch_dmma_ws<double, 128, 128, 16, 4, 2, 5>( g, xk, yk, al, tiles( 128, 128 ), st );

@@ -64,7 +64,28 @@ struct GemmArgs
 	//   ktri == 3: Y(k,q) == 0 for k > q   -> k < q0 + q_lim      ktri == 4: Y(k,q) == 0 for k < q -> k >= q0
 	int      ktri;
 	int      raster;            // tile rows per raster group (tile_coords); 8 unless tuned
+	// Split-k tail (gemm_dmma_tma_kernel<..., SK>; mid-size problems whose last wave would leave SMs idle): work units
+	// 0 .. sk_full-1 are whole tiles; every later tile is cut into sk_split equal k chunks, one unit each.  A chunk parks
+	// its accumulators in sk_ws (slot tail*sk_split + chunk, 128x128 doubles in lane order); per consumer warp (a warp owns
+	// the same part of the tile in every chunk) the LAST arrival at sk_flags[8*tail + warp] adds the sk_split slots IN
+	// CHUNK ORDER (so the result does not depend on who was last), re-arms the counter and runs the ordinary epilogue.
+	// sk_split == 0: off.
+	int      sk_full, sk_split;
+	T*       sk_ws;
+	int*     sk_flags;
 };
+
+// Work unit -> (tile, k chunk or -1, k-tile range) under the split-k tail schedule above.
+template <typename T>
+__device__ __forceinline__ void sk_unit( const GemmArgs<T>& g, int unit, int64_t KT, int& tile, int& chunk, int64_t& kt0, int64_t& kt1 )
+{
+	if ( unit < g.sk_full ) { tile = unit; chunk = -1; kt0 = 0; kt1 = KT; return; }
+	const int v = unit - g.sk_full;
+	tile  = g.sk_full + v / g.sk_split;
+	chunk = v - ( tile - g.sk_full ) * g.sk_split;
+	kt0 = KT * chunk / g.sk_split;
+	kt1 = KT * ( chunk + 1 ) / g.sk_split;
+}
 
 // k-tile range [kt0, kt1) a tile has to visit (all of [0, KT) unless an operand is triangular).
 template <typename T>

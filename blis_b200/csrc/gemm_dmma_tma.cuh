@@ -102,7 +102,12 @@ __device__ __forceinline__ void mbar_arrive_n( uint32_t bar, uint32_t n )
 // of the first version cost 28 % bank conflicts, ncu r01).
 // beta == 0: the producer passes the four stages on empty (nothing is loaded).  Used when D rows are 16-byte aligned and
 // K <= 1024 (gemm_d.cu); seven ring stages; the default instantiation is untouched.
-template <bool XK, bool YK, bool TRI = false, bool CST = false>
+// SK ("split k"): the tail schedule of GemmArgs::sk_* -- tiles of the last, partial wave are cut into k chunks so that
+// every SM has work until the end (2048^3: 256 tiles on 148 SMs = 2 rounds for 1.73 rounds of work).  The reference never
+// splits k inside one gemm (bli_gemm_blk_var3.c:110-112 runs the pc loop sequentially); here the chunks of a tile are added
+// in chunk order by whichever CTA finishes last, so the result is reproducible, but it is rounded differently from the
+// unsplit product (within the same error bound).  Plain products only (no TRI, no CST, one k panel).
+template <bool XK, bool YK, bool TRI = false, bool CST = false, bool SK = false>
 __global__ void __launch_bounds__( 384, 1 )
 gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
                       const __grid_constant__ CUtensorMap tmd )
@@ -110,6 +115,7 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 	using Cfg = typename std::conditional<CST, DmmaTmaCfgCst, DmmaTmaCfg>::type;
 	constexpr int BP = Cfg::BP, BQ = Cfg::BQ, BK = Cfg::BK, WQ = Cfg::WQ, STAGES = Cfg::STAGES;
 	constexpr int MT = Cfg::MT, NTL = Cfg::NTL, KS = BK / 4;
+	static_assert( !( SK && ( TRI || CST ) ), "split k: plain products only" );
 
 	extern __shared__ unsigned char smem_unaligned[];
 	const uint32_t raw = smem_u32( smem_unaligned );
@@ -147,12 +153,12 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 	// described by 3-D tensor maps whose third coordinate selects the panel; the consumers see one long k loop.
 	const int64_t KT_SEG = ( g.K + BK - 1 ) / BK;
 	const int64_t KT = KT_SEG * g.nseg;
-	const int num_tiles = g.tiles_p * g.tiles_q;
+	const int num_tiles = SK ? g.sk_full + ( g.tiles_p * g.tiles_q - g.sk_full ) * g.sk_split : g.tiles_p * g.tiles_q;   // work units
 
 	if ( tid >= Cfg::NCONS )
 	{
 		// ============ PRODUCER warpgroup: one thread drives the TMA unit ============
-		setmaxnreg_dec<40>();
+		setmaxnreg_dec<SK ? 56 : 40>();               // 256 x 224 + 128 x 56 = 64512 registers
 		if constexpr ( CST )
 		{
 			if ( tid == Cfg::NCONS + 32 )
@@ -218,15 +224,16 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 		{
 			const int slot = it & 1;
 			mbar_wait( sched_empty( slot ), ( ( it >> 1 ) & 1 ) ^ 1u );
-			const int tile = g.tile_counter ? atomicAdd( g.tile_counter, 1 ) : (int)( blockIdx.x + (unsigned)it * gridDim.x );
+			int tile = g.tile_counter ? atomicAdd( g.tile_counter, 1 ) : (int)( blockIdx.x + (unsigned)it * gridDim.x );
 			sched_tile[slot] = tile;
 			mbar_arrive( sched_full( slot ) );
 			if ( tile >= num_tiles ) break;
+			int64_t kt0 = 0, kt1 = KT;
+			if constexpr ( SK ) { int chunk; sk_unit( g, tile, KT, tile, chunk, kt0, kt1 ); }
 			int tp, tq;
 			tile_coords( tile, g.tiles_p, g.tiles_q, g.raster, tp, tq );
 			const int p0 = tp * BP, q0 = tq * BQ;
 			if ( TRI && tri_skip_tile( g, p0, q0, (int)min( (int64_t)BP, g.P - p0 ), (int)min( (int64_t)BQ, g.Q - q0 ) ) ) continue;
-			int64_t kt0 = 0, kt1 = KT;
 			if constexpr ( TRI ) tile_k_range( g, p0, (int)min( (int64_t)BP, g.P - p0 ), q0, (int)min( (int64_t)BQ, g.Q - q0 ), BK, KT, kt0, kt1 );
 			if constexpr ( !CST ) prefetch_d_tile_l2( g, p0, q0, BP, BQ );
 			for ( int64_t kt = kt0; kt < kt1; ++kt )
@@ -334,10 +341,13 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 	{
 		const int slot = it & 1;
 		mbar_wait( sched_full( slot ), ( it >> 1 ) & 1 );
-		const int tile = sched_tile[slot];
+		int tile = sched_tile[slot];
 		__syncwarp();
 		if ( lane == 0 ) mbar_arrive( sched_empty( slot ) );
 		if ( tile >= num_tiles ) break;
+		int64_t kt0 = 0, kt1 = KT;
+		int chunk = -1;
+		if constexpr ( SK ) sk_unit( g, tile, KT, tile, chunk, kt0, kt1 );
 		int tp, tq;
 		tile_coords( tile, g.tiles_p, g.tiles_q, g.raster, tp, tq );
 		const int64_t p0 = (int64_t)tp * BP, q0 = (int64_t)tq * BQ;
@@ -364,7 +374,6 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 					dmma884( acc[i][j][0], acc[i][j][1], xf[i], yf[j] );
 		};
 
-		int64_t kt0 = 0, kt1 = KT;
 		if constexpr ( TRI ) tile_k_range( g, p0, p_lim, q0, q_lim, BK, KT, kt0, kt1 );
 		for ( int64_t kt = kt0; kt < kt1; ++kt )
 		{
@@ -391,6 +400,48 @@ gemm_dmma_tma_kernel( const GemmArgs<double> g, const __grid_constant__ CUtensor
 					__syncwarp();
 					if ( lane == 0 ) mbar_arrive( empty_bar( stage ) );
 					stage = ns; phase = nph;
+				}
+			}
+		}
+
+		if constexpr ( SK )
+		{
+			if ( chunk >= 0 )
+			{
+				// A k chunk of a tail tile.  Every warp owns the same 32 x 64 part of the tile in every chunk, so the fix-up is
+				// a per-WARP affair (no CTA barrier): park the accumulators (coalesced 16-byte stores, L2), count in at the
+				// warp's own counter, and go on to the next unit -- unless this warp is the last of the tile's sk_split chunks
+				// to arrive: then it adds all slots IN CHUNK ORDER (so the rounding never depends on who was last), re-arms
+				// the counter and runs the ordinary epilogue.  Nobody ever waits for another CTA.
+				const int tail = tile - g.sk_full;
+				constexpr int SLOT = MT * NTL * Cfg::NCONS;                      // double2 per accumulator slot (128 KiB)
+				double2* const slot0 = reinterpret_cast<double2*>( g.sk_ws ) + (int64_t)tail * g.sk_split * SLOT + tid;
+				double2* const mine  = slot0 + (int64_t)chunk * SLOT;
+				int* const flag = g.sk_flags + tail * ( Cfg::NCONS / 32 ) + warp;
+				#pragma unroll
+				for ( int i = 0; i < MT; ++i )
+					#pragma unroll
+					for ( int j = 0; j < NTL; ++j ) __stcg( mine + ( i * NTL + j ) * Cfg::NCONS, make_double2( acc[i][j][0], acc[i][j][1] ) );
+				__syncwarp();
+				int seen = 0;
+				if ( lane == 0 ) { __threadfence(); seen = atomicAdd( flag, 1 ); }
+				seen = __shfl_sync( 0xffffffffu, seen, 0 );
+				if ( seen != g.sk_split - 1 ) continue;
+				if ( lane == 0 ) { __threadfence(); *flag = 0; }
+				__syncwarp();
+				#pragma unroll 1
+				for ( int c = 0; c < g.sk_split; ++c )
+				{
+					const double2* part = slot0 + (int64_t)c * SLOT;
+					#pragma unroll
+					for ( int i = 0; i < MT; ++i )
+						#pragma unroll
+						for ( int j = 0; j < NTL; ++j )
+						{
+							const double2 w = __ldcg( part + ( i * NTL + j ) * Cfg::NCONS );
+							if ( c == 0 ) { acc[i][j][0] = w.x; acc[i][j][1] = w.y; }
+							else          { acc[i][j][0] += w.x; acc[i][j][1] += w.y; }
+						}
 				}
 			}
 		}

@@ -177,7 +177,7 @@ static bool tma_eligible( const GemmArgs<T>& g, bool xk, bool yk, bool al )
 	return al && g.P < ( 1ll << 31 ) && g.Q < ( 1ll << 31 ) && g.K < ( 1ll << 31 ) &&
 	       g.ldx >= ( xk ? g.K : g.P ) && g.ldy >= ( yk ? g.K : g.Q ) && g.ldx * 8 < ( 1ll << 40 ) && g.ldy * 8 < ( 1ll << 40 );
 }
-template <bool TRI = false, bool CST = false>
+template <bool TRI = false, bool CST = false, bool SK = false>
 static int launch_dmma_tma( const GemmArgs<double>& g_in, bool xk, bool yk, int grid, cudaStream_t st )
 {
 	GemmArgs<double> g = g_in;
@@ -203,9 +203,10 @@ static int launch_dmma_tma( const GemmArgs<double>& g_in, bool xk, bool yk, int 
 	auto go = [&]( auto XKc, auto YKc ) -> int
 	{
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
-		auto kern = gemm_dmma_tma_kernel<XK, YK, TRI, CST>;
+		auto kern = gemm_dmma_tma_kernel<XK, YK, TRI, CST, SK>;
 		using KCfg = typename std::conditional<CST, DmmaTmaCfgCst, DmmaTmaCfg>::type;
-		static const std::string kname = kfmt( "gemm_dmma_tma_kernel<XK=%d,YK=%d,TRI=%d,CST=%d>", XK, YK, TRI, CST );
+		static const std::string kname = SK ? kfmt( "gemm_dmma_tma_kernel<XK=%d,YK=%d,TRI=%d,CST=%d,SK=1>", XK, YK, TRI, CST )
+		                                    : kfmt( "gemm_dmma_tma_kernel<XK=%d,YK=%d,TRI=%d,CST=%d>", XK, YK, TRI, CST );
 		static bool attr = false;
 		if ( !attr ) { if ( set_smem( kern, KCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, KCfg::NT_ALL, KCfg::SMEM_BYTES, st>>>( g, tmx, tmy, tmd );

@@ -76,6 +76,7 @@ static int gemm_dev( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T 
 		else        g.ktri = swapped ? ( lower ? 2 : 1 ) : ( lower ? 4 : 3 );
 	}
 	g.tile_counter = sched_slot( st );
+	g.sk_full = 0; g.sk_split = 0; g.sk_ws = nullptr; g.sk_flags = nullptr;
 	for ( int sgm = 1; sgm < nseg; ++sgm )
 	{
 		g.Xseg[sgm - 1] = swapped ? b_more[sgm - 1] : a_more[sgm - 1];

@@ -462,6 +462,49 @@ def test_gemm_tma_kernels_large_ragged_vs_reference(engine, ref, ch):
         assert any("CST=1" in kn for kn in seen) and any("CST=0" in kn for kn in seen), seen
 
 
+def test_dgemm_split_k_tail_mid_size(engine, ref):
+    """Mid-size dgemm whose last wave of 128x128 tiles would leave SMs idle takes the split-k tail schedule of the TMA
+    kernel (gemm_dmma_tma_kernel<...,SK=1>: tail tiles cut into k chunks, partial accumulators added in chunk order by the
+    last unit).  Checked against the real reference library (elementwise), for bit-for-bit equality with the UNSPLIT kernel
+    on power-of-two inputs (every summation order is exact there), for run-to-run reproducibility on ordinary inputs, and
+    with ragged m, n, k, every staging orientation, both C storages, beta == 0 on a NaN-poisoned C."""
+    seed, seen = 12000, set()
+    cases = [(2048, 2048, 2048, NO_TRANSPOSE, NO_TRANSPOSE, "c", 1.2),       # 256 tiles on 148 SMs: 148 whole + 108 x 4 chunks
+             (2040, 2000, 2100, TRANSPOSE, NO_TRANSPOSE, "r", 0.0),          # ragged in m, n and k
+             (1412, 1540, 1028, NO_TRANSPOSE, TRANSPOSE, "c", 1.2),          # 156 tiles: 148 whole + 8 x 2
+             (1664, 2304, 772, TRANSPOSE, TRANSPOSE, "c", 1.2)]              # 234 tiles: 148 whole + 86 x 3
+    for (m, n, k, ta, tb, oc, be) in cases:
+        seed += 1
+        am, ak = (k, m) if ta & TRANSPOSE else (m, k)
+        bk, bn = (n, k) if tb & TRANSPOSE else (k, n)
+        a = gen.matrix("d", am, ak, seed, "frac", "c"); b = gen.matrix("d", bk, bn, seed + 5000, "frac", "c")
+        c = gen.matrix("d", m, n, seed + 9000, "frac", oc)
+        want = c.copy(order="K")
+        ref.gemm(ta, tb, 2.0, a, b, be, want)
+        if be == 0.0:
+            c[...] = np.nan
+        got = run_gemm(engine, "d", ta, tb, 2.0, a, b, be, c)
+        kn = engine.last_kernel()
+        assert kn.startswith("gemm_dmma_tma_kernel") and "SK=1" in kn, (kn, m, n, k)
+        seen.add(kn)
+        assert rel_err(got, want) <= TOL["d"] * 4, (m, n, k, kn, rel_err(got, want))
+        again = run_gemm(engine, "d", ta, tb, 2.0, a, b, be, c)
+        assert np.array_equal(got, again), ("split-k result is not reproducible", m, n, k)
+        # exact inputs: split and unsplit must agree bit for bit
+        a2 = gen.matrix("d", am, ak, seed + 1, "pow2", "c"); b2 = gen.matrix("d", bk, bn, seed + 5001, "pow2", "c")
+        c2 = gen.matrix("d", m, n, seed + 9001, "pow2", oc)
+        split = run_gemm(engine, "d", ta, tb, 2.0, a2, b2, 1.0, c2)
+        engine.set_option("dgemm_splitk", 0)
+        try:
+            whole = run_gemm(engine, "d", ta, tb, 2.0, a2, b2, 1.0, c2)
+            kn0 = engine.last_kernel()
+        finally:
+            engine.set_option("dgemm_splitk", 1)
+        assert "SK=1" not in kn0, kn0
+        assert np.array_equal(split, whole), ("split-k differs from the unsplit kernel on exact inputs", m, n, k)
+    assert len(seen) == 4, seen                                              # all four staging orientations
+
+
 @pytest.mark.parametrize("ch", list("sdcz"))
 @pytest.mark.parametrize("n", [4096, 16384])
 def test_gemm_skinny_k64_baseline_shapes_testsuite_residual(engine, ch, n):
