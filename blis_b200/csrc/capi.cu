@@ -320,6 +320,8 @@ extern "C" b200_err_t b200_set_option( const char* key, long long value )
 	else if ( !strcmp( key, "dmma_cst" ) ) c.dmma_cst = (int)value;
 	else if ( !strcmp( key, "dmma_pp" ) ) c.dmma_pp = (int)value;
 	else if ( !strcmp( key, "dgemm_splitk" ) ) c.dgemm_splitk = (int)value;
+	else if ( !strcmp( key, "batch_grouped" ) ) c.batch_grouped = (int)value;
+	else if ( !strcmp( key, "batch_grouped_max" ) ) c.batch_grouped_max = std::max<long long>( 0, value );
 	else if ( !strcmp( key, "trsm_fused" ) ) c.trsm_fused = (int)value;
 	else if ( !strcmp( key, "dist_ab_static" ) ) dist().ab_static = (int)value;
 	else if ( !strcmp( key, "tma_l2_promotion" ) ) c.tma_l2_promotion = (int)std::min<long long>( 3, std::max<long long>( 0, value ) );

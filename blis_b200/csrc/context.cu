@@ -77,7 +77,7 @@ extern "C" int b200_set_option( const char* key, long long value );
 static void apply_env_options()
 {
 	static const char* keys[] = { "dgemm_cfg", "zgemm_cfg", "sgemm_cfg", "cgemm_cfg", "grid_mult", "dynamic_tiles", "transpose_y", "ktri_skip",
-	                              "host_kpipe", "dmma_cst", "dmma_pp", "dgemm_splitk", "trsm_fused", "dist_ab_static", "tma_l2_promotion", "raster_group", "reserve_sms" };
+	                              "host_kpipe", "dmma_cst", "dmma_pp", "dgemm_splitk", "batch_grouped", "batch_grouped_max", "trsm_fused", "dist_ab_static", "tma_l2_promotion", "raster_group", "reserve_sms" };
 	for ( const char* k : keys )
 	{
 		char name[64] = "BLIS_B200_"; size_t n = strlen( name );
@@ -343,6 +343,8 @@ extern "C" void b200_finalize( void )
 		if ( c.batch_join[i] )    { cudaEventDestroy( c.batch_join[i] );     c.batch_join[i] = nullptr; }
 	}
 	if ( c.batch_fork ) { cudaEventDestroy( c.batch_fork ); c.batch_fork = nullptr; }
+	if ( c.batch_desc_done ) { cudaEventDestroy( c.batch_desc_done ); c.batch_desc_done = nullptr; }
+	if ( c.batch_desc ) { cudaFreeHost( c.batch_desc ); c.batch_desc = nullptr; c.batch_desc_bytes = 0; }
 	if ( c.sched_counters ) { cudaFree( c.sched_counters ); c.sched_counters = nullptr; }
 	c.ready = false;
 }

@@ -41,6 +41,9 @@ struct Context
 	cudaStream_t batch_streams[kBatchStreams] = {};   // b200_gemm_batch: independent small problems run concurrently
 	cudaEvent_t  batch_fork = nullptr, batch_join[kBatchStreams] = {};
 	std::mutex   batch_mu;
+	void*        batch_desc = nullptr;    // pinned upload buffer of the grouped kernel's problem records (guarded by batch_mu)
+	size_t       batch_desc_bytes = 0;
+	cudaEvent_t  batch_desc_done = nullptr;
 	// pinned staging ring for pageable host operands
 	static constexpr int    kStageBufs  = 2;
 	static constexpr size_t kStageBytes = (size_t)64 << 20;
@@ -66,6 +69,8 @@ struct Context
 	int          dmma_pp  = 0;          // dgemm TMA kernel: ping-pong the two q-halves of a tile for K <= this (0 = never)
 	int          dmma_cst = 256;        // dgemm TMA kernel: stage D through the ring (TMA load + TMA store) for K <= this (0 = never); [B200] wins up to k = 256
 	int          dgemm_splitk = 1;      // dgemm TMA kernel: cut the tiles of a partial last wave into k chunks (mid-size problems; 0 = never split k)
+	int          batch_grouped = 1;     // b200_gemm_batch: small device-resident problems share ONE launch (gemm_grouped.cuh); 0 = a launch each on the stream pool
+	long long    batch_grouped_max = 128ll * 128 * 128;   // ... "small" = m*n*k at most this
 	int          host_kpipe = 1;        // host operands with long k: pipeline over k panels instead of column blocks
 	int          ktri_skip = 1;         // trmm/trmm3: tiles skip the k range in which the triangular operand is zero
 	int          transpose_y = 1;       // s/c: transpose a k-contiguous Y panel once instead of re-pairing registers in the k loop

@@ -262,20 +262,25 @@ gemm_ffma_tma_kernel( const GemmArgs<float> g, const __grid_constant__ CUtensorM
 				}
 			}
 		};
+		// Issue order: j outer, i inner, so that the PAIR operand (y2, 64 bits) is the one consecutive FFMA2 share and sits
+		// in the operand reuse latch.  tools/ffma2_probe.cu (no memory traffic, this register tile): 2.24 clocks per FFMA2
+		// per scheduler with the pair reused, 2.43 with the scalar reused (i outer), against 2.02 for a few accumulators
+		// with both operands fixed -- the FP32 pipe is bound by register-file operand delivery as ptxas allocates and
+		// orders it, not by issue slots or occupancy (a 192 x 128 variant with three warps per scheduler measured 58.5
+		// against 58.9 TFLOP/s).  ptxas keeps this order for about half of the k loop (SASS: 462 of 1024 FFMA2 with
+		// .reuse on the pair); [B200] 16384^3: 58.9 -> 59.5 TFLOP/s.
 		auto fma_group = [&]( const float ( &xv )[8][4], const float ( &yv )[8][4] )
 		{
 			#pragma unroll
 			for ( int kk = 0; kk < 4; ++kk )
 			{
-				unsigned long long y2[4];
 				#pragma unroll
-				for ( int j = 0; j < 4; ++j ) y2[j] = pack2( yv[2 * j][kk], yv[2 * j + 1][kk] );
-				#pragma unroll
-				for ( int i = 0; i < 8; ++i )
+				for ( int j = 0; j < 4; ++j )
 				{
-					const unsigned long long x2 = pack2( xv[i][kk], xv[i][kk] );     // scalar-broadcast operand of FFMA2
+					const unsigned long long y2 = pack2( yv[2 * j][kk], yv[2 * j + 1][kk] );
 					#pragma unroll
-					for ( int j = 0; j < 4; ++j ) acc2[i][j] = ffma2( x2, y2[j], acc2[i][j] );
+					for ( int i = 0; i < 8; ++i )
+						acc2[i][j] = ffma2( pack2( xv[i][kk], xv[i][kk] ), y2, acc2[i][j] );     // scalar-broadcast operand of FFMA2
 				}
 			}
 		};

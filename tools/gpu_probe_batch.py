@@ -6,7 +6,7 @@ from blis_b200 import api
 from tools.gpu_probe2 import timeit
 
 count = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-sizes = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "64,128,256,512").split(",")]
+sizes = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else "16,32,64,128,256").split(",")]
 dev = "cuda"
 out = {}
 for ch, dt, fn in (("d", torch.float64, api.bli_dgemm), ("s", torch.float32, api.bli_sgemm)):
@@ -18,9 +18,14 @@ for ch, dt, fn in (("d", torch.float64, api.bli_dgemm), ("s", torch.float32, api
             for x, y, z in zip(a, b, c):
                 fn(0, 0, n, n, n, 2.0, x, 1, n, y, 1, n, 1.2, z, 1, n)
         g = [dict(transa=0, transb=0, m=n, n=n, k=n, alpha=2.0, beta=1.2, a=a, b=b, c=c)]
-        t_loop = timeit(loop); t_batch = timeit(lambda: api.gemm_batch(dt, g))
+        t_loop = timeit(loop)
+        api.set_option("batch_grouped", 0)
+        t_pool = timeit(lambda: api.gemm_batch(dt, g))               # one launch per problem on the stream pool
+        api.set_option("batch_grouped", 1)
+        t_batch = timeit(lambda: api.gemm_batch(dt, g))              # small problems: ONE launch of the grouped kernel
         flop = 2.0 * n ** 3 * count
-        out[f"{ch}{n}"] = {"loop_TF": round(flop / t_loop / 1e12, 3), "batch_TF": round(flop / t_batch / 1e12, 3), "speedup": round(t_loop / t_batch, 2)}
+        out[f"{ch}{n}"] = {"loop_TF": round(flop / t_loop / 1e12, 3), "pool_TF": round(flop / t_pool / 1e12, 3), "batch_TF": round(flop / t_batch / 1e12, 3),
+                           "speedup": round(t_loop / t_batch, 2), "kernel": api.last_kernel()}
         print(ch, n, count, json.dumps(out[f"{ch}{n}"]), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/probe_batch.json", "w"), indent=1)
