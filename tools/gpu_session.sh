@@ -12,6 +12,9 @@
 #   launches   ncu launch list of the default bench command
 #   ncu_dgemm / ncu_trsm / ncu_skinny   one `ncu --set full` capture of that kernel + tools/ncu_key.py summary
 #   sweep      configs[2] sweep (s/d/c/z squares + k=64)
+#   midsize / ncu_splitk   dgemm split-k tail: mid-size sweep with and without it, one ncu capture at 2048^3
+#   batchprobe   batched small gemm: loop vs stream pool vs grouped kernel
+#   probes     tools/lds_probe.cu and tools/ffma2_probe.cu microbenchmarks
 mkdir -p gpurun_out
 nvidia-smi > gpurun_out/nvidia-smi.txt 2>&1
 lscpu | head -25 > gpurun_out/lscpu.txt
@@ -62,6 +65,16 @@ ncu_sgemm)
 	ncu --set full --clock-control none --import-source on -k regex:gemm_ffma_tma -s 1 -c 1 -o gpurun_out/sgemm_full -f python -m tools.one_gemm s 8192 8192 -1 2 > /dev/null 2>&1
 	python tools/ncu_key.py gpurun_out/sgemm_full.ncu-rep > gpurun_out/ncu_sgemm_8192.txt 2>&1; head -30 gpurun_out/ncu_sgemm_8192.txt
 	python tools/ncu_src.py gpurun_out/sgemm_full.ncu-rep 60 > gpurun_out/ncu_sgemm_8192_src.txt 2>&1; rm -f gpurun_out/sgemm_full.ncu-rep ;;
+ncu_splitk)
+	ncu --set full --clock-control none --import-source on -k regex:gemm_dmma_tma -s 1 -c 1 -o gpurun_out/splitk_full -f python -m tools.one_gemm d 2048 2048 -1 2 > /dev/null 2>&1
+	python tools/ncu_key.py gpurun_out/splitk_full.ncu-rep > gpurun_out/ncu_dgemm_2048_splitk.txt 2>&1; head -30 gpurun_out/ncu_dgemm_2048_splitk.txt; rm -f gpurun_out/splitk_full.ncu-rep ;;
+midsize)
+	timeout 300 python -m tools.midsize_sweep 1536,1792,2048,2304,2560,2816,3072,3328,3584,4096 > gpurun_out/midsize_sweep.json 2> gpurun_out/midsize_sweep.err; cat gpurun_out/midsize_sweep.err ;;
+batchprobe)
+	timeout 400 python -m tools.gpu_probe_batch 512 16,32,64,128,256 2>&1 | tail -12 ;;
+probes)
+	nvcc -gencode arch=compute_100a,code=sm_100a -O3 tools/lds_probe.cu -o /tmp/lds_probe && /tmp/lds_probe > gpurun_out/lds_probe.txt 2>&1
+	nvcc -gencode arch=compute_100a,code=sm_100a -O3 tools/ffma2_probe.cu -o /tmp/ffma2_probe && /tmp/ffma2_probe > gpurun_out/ffma2_probe.txt 2>&1; cat gpurun_out/ffma2_probe.txt ;;
 sweep)
 	for ch in d s c z; do timeout 400 python -m tools.gpu_probe2 $ch -1 512,1024,2048,4096,8192,16384,512x64,4096x64,16384x64 > gpurun_out/sweep_$ch.log 2>&1; tail -1 gpurun_out/sweep_$ch.log; done ;;
 *)
