@@ -320,6 +320,7 @@ extern "C" b200_err_t b200_set_option( const char* key, long long value )
 	else if ( !strcmp( key, "dmma_cst" ) ) c.dmma_cst = (int)value;
 	else if ( !strcmp( key, "dmma_pp" ) ) c.dmma_pp = (int)value;
 	else if ( !strcmp( key, "dgemm_splitk" ) ) c.dgemm_splitk = (int)value;
+	else if ( !strcmp( key, "trsm_host_pipe" ) ) c.trsm_host_pipe = (int)value;
 	else if ( !strcmp( key, "batch_grouped" ) ) c.batch_grouped = (int)value;
 	else if ( !strcmp( key, "batch_grouped_max" ) ) c.batch_grouped_max = std::max<long long>( 0, value );
 	else if ( !strcmp( key, "trsm_fused" ) ) c.trsm_fused = (int)value;

@@ -77,7 +77,7 @@ extern "C" int b200_set_option( const char* key, long long value );
 static void apply_env_options()
 {
 	static const char* keys[] = { "dgemm_cfg", "zgemm_cfg", "sgemm_cfg", "cgemm_cfg", "grid_mult", "dynamic_tiles", "transpose_y", "ktri_skip",
-	                              "host_kpipe", "dmma_cst", "dmma_pp", "dgemm_splitk", "batch_grouped", "batch_grouped_max", "trsm_fused", "dist_ab_static", "tma_l2_promotion", "raster_group", "reserve_sms" };
+	                              "host_kpipe", "dmma_cst", "dmma_pp", "dgemm_splitk", "trsm_host_pipe", "batch_grouped", "batch_grouped_max", "trsm_fused", "dist_ab_static", "tma_l2_promotion", "raster_group", "reserve_sms" };
 	for ( const char* k : keys )
 	{
 		char name[64] = "BLIS_B200_"; size_t n = strlen( name );
@@ -292,6 +292,15 @@ int stage_to_device( void* dst, const void* src, int64_t m, int64_t n, int64_t r
 int stage_to_host( void* dst, int64_t rs, int64_t cs, const void* src, int64_t m, int64_t n, size_t es, cudaStream_t st )
 {
 	return stage_xfer( const_cast<void*>( src ), dst, m, n, rs, cs, es, st, true );
+}
+
+int stage_block_to_device( void* dst, int64_t ldd, const void* src, int64_t m, int64_t n, int64_t rs, int64_t cs, size_t es, cudaStream_t st )
+{
+	return stage_xfer( dst, const_cast<void*>( src ), m, n, rs, cs, es, st, false, ldd );
+}
+int stage_block_to_host( void* dst, int64_t rs, int64_t cs, const void* src, int64_t ldd, int64_t m, int64_t n, size_t es, cudaStream_t st )
+{
+	return stage_xfer( const_cast<void*>( src ), dst, m, n, rs, cs, es, st, true, ldd );
 }
 
 // Only the stored triangle of a host-resident triangular matrix travels (the reference's packm never reads the other one

@@ -71,6 +71,7 @@ struct Context
 	int          dgemm_splitk = 1;      // dgemm TMA kernel: cut the tiles of a partial last wave into k chunks (mid-size problems; 0 = never split k)
 	int          batch_grouped = 1;     // b200_gemm_batch: small device-resident problems share ONE launch (gemm_grouped.cuh); 0 = a launch each on the stream pool
 	long long    batch_grouped_max = 128ll * 128 * 128;   // ... "small" = m*n*k at most this
+	int          trsm_host_pipe = 3;    // trsm with pinned host operands: A streams in the solve's own order, B in at most this many column blocks, X leaves block by block (0 = sequential transfers)
 	int          host_kpipe = 1;        // host operands with long k: pipeline over k panels instead of column blocks
 	int          ktri_skip = 1;         // trmm/trmm3: tiles skip the k range in which the triangular operand is zero
 	int          transpose_y = 1;       // s/c: transpose a k-contiguous Y panel once instead of re-pairing registers in the k loop
@@ -102,6 +103,9 @@ int stage_to_device( void* dst, const void* src, int64_t m, int64_t n, int64_t r
                      size_t es, cudaStream_t st );
 int stage_to_host( void* dst, int64_t rs, int64_t cs, const void* src, int64_t m, int64_t n,
                    size_t es, cudaStream_t st );
+// One rectangular piece of a larger column-major device image (leading dimension ldd elements) <- host (rs, cs).
+int stage_block_to_device( void* dst, int64_t ldd, const void* src, int64_t m, int64_t n, int64_t rs, int64_t cs, size_t es, cudaStream_t st );
+int stage_block_to_host( void* dst, int64_t rs, int64_t cs, const void* src, int64_t ldd, int64_t m, int64_t n, size_t es, cudaStream_t st );
 // m x m triangular host matrix -> dense column-major device image (ld = m); only the stored triangle is transferred.
 int stage_tri_to_device( void* dst, const void* src, int64_t m, int64_t rs, int64_t cs, bool upper,
                          size_t es, cudaStream_t st );

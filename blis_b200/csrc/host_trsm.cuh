@@ -4,6 +4,7 @@
 #include "host_gemm.cuh"
 #include "trsm.cuh"
 #include "trsm_panel.cuh"
+#include <functional>
 namespace b200 {
 
 // ---- trsm -----------------------------------------------------------------------------
@@ -21,7 +22,20 @@ struct TrsmPlan
 	int64_t  n;
 	bool     upper, unit, conj;
 	cudaStream_t st;
+	// A arriving from the host while the solve runs (trsm_host_pipe): one event per launch of the recursion, in the
+	// recursion's own order (trsm_upload_rec builds the list); nullptr: A is resident
+	const std::vector<cudaEvent_t>* a_ready = nullptr;
+	size_t*  a_next = nullptr;
+	// rows [i0, i0+mb) of X are final when their sub-solve returns: told once per subtree of at most notify_rows rows
+	// (trsm_host_pipeline sends them home while the rest of the solve runs); empty: nobody listens
+	std::function<void( int64_t, int64_t )> on_final;
+	int64_t  notify_rows = 0;
 };
+template <typename T>
+static void trsm_wait_a( const TrsmPlan<T>& p )
+{
+	if ( p.a_ready && *p.a_next < p.a_ready->size() ) cudaStreamWaitEvent( p.st, ( *p.a_ready )[( *p.a_next )++], 0 );
+}
 
 template <typename T>
 static int trsm_base( const TrsmPlan<T>& p, int64_t i0, int mb, T alpha )
@@ -89,8 +103,15 @@ template <> int trsm_leaf<double>( const TrsmPlan<double>& p, int64_t i0, int mb
 template <typename T>
 static int trsm_rec( const TrsmPlan<T>& p, int64_t i0, int64_t mb, T alpha )
 {
+	if ( p.on_final && mb <= p.notify_rows )
+	{
+		TrsmPlan<T> q = p; q.on_final = nullptr;
+		const int rc = trsm_rec( q, i0, mb, alpha );
+		if ( rc == kSuccess ) p.on_final( i0, mb );
+		return rc;
+	}
 	const int NB = trsm_leaf_rows<T>();
-	if ( mb <= NB ) return trsm_leaf<T>( p, i0, (int)mb, alpha );
+	if ( mb <= NB ) { trsm_wait_a( p ); return trsm_leaf<T>( p, i0, (int)mb, alpha ); }
 	const int64_t nblk = ( mb + NB - 1 ) / NB;
 	const int64_t m1 = ( ( nblk + 1 ) / 2 ) * NB, m2 = mb - m1;
 	const T one = Scalar<T>::make( 1.0, 0.0 ), mone = Scalar<T>::make( -1.0, 0.0 );
@@ -98,6 +119,7 @@ static int trsm_rec( const TrsmPlan<T>& p, int64_t i0, int64_t mb, T alpha )
 	{
 		if ( trsm_rec( p, i0, m1, alpha ) != kSuccess ) return kFailure;
 		// B2 := alpha*B2 - A21 * X1
+		trsm_wait_a( p );
 		if ( gemm_dev<T>( p.conj, false, m2, p.n, m1, mone,
 		                  p.A + ( i0 + m1 ) * p.rs_a + i0 * p.cs_a, p.rs_a, p.cs_a,
 		                  p.B + i0 * p.rs_b, p.rs_b, p.cs_b,
@@ -109,12 +131,146 @@ static int trsm_rec( const TrsmPlan<T>& p, int64_t i0, int64_t mb, T alpha )
 		// upper: the trailing block is solved first; split so the LAST block is the ragged one's partner
 		if ( trsm_rec( p, i0 + m2, m1, alpha ) != kSuccess ) return kFailure;
 		// B1 := alpha*B1 - A12 * X2
+		trsm_wait_a( p );
 		if ( gemm_dev<T>( p.conj, false, m2, p.n, m1, mone,
 		                  p.A + i0 * p.rs_a + ( i0 + m2 ) * p.cs_a, p.rs_a, p.cs_a,
 		                  p.B + ( i0 + m2 ) * p.rs_b, p.rs_b, p.cs_b,
 		                  alpha, p.B + i0 * p.rs_b, p.rs_b, p.cs_b, p.st ) != kSuccess ) return kFailure;
 		return trsm_rec( p, i0, m2, one );
 	}
+}
+
+// ---- host operands: pipeline ------------------------------------------------------------------------------------
+// A triangular solve with everything in host memory moves 8(m^2/2 + 2mn) bytes over PCIe; done in sequence (upload B,
+// upload A, solve, download X) none of it overlaps the kernels: T1 through the reference's dtrsm_ took 417 ms for 253 ms
+// of kernels.  Two things make the transfers disappear behind the solve:
+//   * A travels IN THE ORDER THE RECURSION READS IT.  trsm_rec touches A11 (recursively), then the block A21 (lower) /
+//     A12 (upper) of the update, then A22 -- and spends its time in the same proportion (a quarter, a half, a quarter of
+//     the flops for a quarter, a half, a quarter of the triangle's bytes).  trsm_upload_rec walks the same tree, uploads
+//     each diagonal block (<= 1024 rows, as a square) and each update block as one 2-D copy on the copy stream and records
+//     one event PER LAUNCH of the solve's recursion, in its order; trsm_rec waits for the next event before every launch.
+//     Only the stored triangle (plus the unstored half of the small diagonal squares, ~1.5 %) travels.
+//   * B travels in column blocks (the reference's own parallel dimension, bli_trsm_cntl.c:446-451: columns are
+//     independent): block 0 goes up first and is solved while A streams in; block j+1 goes up and block j-1 comes down
+//     (d2h stream) under the solve of block j.  Every block repeats the latency-bound diagonal panels (5.8 ms at T1), so
+//     there are only a few blocks (trsm_host_pipe = their maximal number; one for tall systems).
+//   * X goes home in ROW chunks: the rows of a finished sub-solve are final (trsm_rec tells, quarters of m), so only the
+//     last quarter's download is exposed.
+// [B200] T1 through dtrsm_: 417 ms (sequential) -> 301 ms = 29.2 TFLOP/s end to end (kernels alone: 251 ms).
+template <typename T>
+static int trsm_upload_rec( T* da, int64_t m, const T* a, int64_t rs_a, int64_t cs_a, bool upper, int64_t i0, int64_t mb,
+                            cudaStream_t s_in, std::vector<cudaEvent_t>& ev )
+{
+	constexpr size_t ES = sizeof(T);
+	const int NB = trsm_leaf_rows<T>();
+	// rows [r0, r1) x columns [c0, c1) of the effective view -> the device image, which keeps the host's orientation
+	auto piece = [&]( int64_t r0, int64_t r1, int64_t c0, int64_t c1, int launches ) -> int
+	{
+		int rc;
+		if ( rs_a == 1 ) rc = stage_block_to_device( da + r0 + c0 * m, m, a + r0 + c0 * cs_a, r1 - r0, c1 - c0, 1, cs_a, ES, s_in );
+		else             rc = stage_block_to_device( da + c0 + r0 * m, m, a + c0 + r0 * rs_a, c1 - c0, r1 - r0, 1, rs_a, ES, s_in );
+		if ( rc != kSuccess ) return rc;
+		cudaEvent_t e;
+		if ( cudaEventCreateWithFlags( &e, cudaEventDisableTiming ) != cudaSuccess ) return fail( "trsm: event creation failed" );
+		cudaEventRecord( e, s_in );
+		for ( int l = 0; l < launches; ++l ) ev.push_back( e );      // the same event serves every launch inside this piece
+		return kSuccess;
+	};
+	const int64_t nblk = ( mb + NB - 1 ) / NB;
+	if ( mb <= std::max<int64_t>( NB, 1024 ) ) return piece( i0, i0 + mb, i0, i0 + mb, (int)( 2 * nblk - 1 ) );
+	const int64_t m1 = ( ( nblk + 1 ) / 2 ) * NB, m2 = mb - m1;      // the split of trsm_rec
+	if ( !upper )
+	{
+		if ( trsm_upload_rec( da, m, a, rs_a, cs_a, upper, i0, m1, s_in, ev ) != kSuccess ) return kFailure;
+		if ( piece( i0 + m1, i0 + mb, i0, i0 + m1, 1 ) != kSuccess ) return kFailure;
+		return trsm_upload_rec( da, m, a, rs_a, cs_a, upper, i0 + m1, m2, s_in, ev );
+	}
+	if ( trsm_upload_rec( da, m, a, rs_a, cs_a, upper, i0 + m2, m1, s_in, ev ) != kSuccess ) return kFailure;
+	if ( piece( i0, i0 + m2, i0 + m2, i0 + mb, 1 ) != kSuccess ) return kFailure;
+	return trsm_upload_rec( da, m, a, rs_a, cs_a, upper, i0, m2, s_in, ev );
+}
+
+// a: effective m x m view (host or device), b: m x n host, pinned, column-stored (rs_b == 1)
+template <typename T>
+static int trsm_host_pipeline( int64_t m, int64_t n, T al, const T* a, int64_t rs_a, int64_t cs_a, bool a_host, bool upper, bool unit, bool conj,
+                               T* b, int64_t cs_b, cudaStream_t st )
+{
+	constexpr size_t ES = sizeof(T);
+	Context& cx = ctx();
+	cudaStream_t s_in = cx.copy_stream, s_out = cx.d2h_stream;
+	// column blocks: the first one is only as wide as A's journey lasts (its solve is gated by A anyway), the others share the rest
+	// Every block repeats the width-independent part of the solve (diagonal panels and the small updates: ~9 % of T1), which
+	// grows with m, while what a block saves is B's journey, which does not.  [B200] T1 (m = 32768): 1 / 2 / 3 blocks ->
+	// 301 / 317 / 325 ms, so tall systems keep one block (A streaming and X leaving in row chunks do the overlapping there).
+	int nblk = (int)std::min<int64_t>( std::max( 1, cx.trsm_host_pipe ), std::max<int64_t>( 1, n / 1024 ) );
+	nblk = std::min( nblk, m >= 24576 ? 1 : ( m >= 12288 ? 2 : 3 ) );
+	std::vector<int64_t> col{ 0 };
+	if ( nblk > 1 )
+	{
+		const int64_t first = std::max<int64_t>( 512, ( (int64_t)( 0.7 * (double)n / nblk ) + 127 ) / 128 * 128 );
+		col.push_back( std::min( n, first ) );
+		const int64_t rest = ( ( n - col.back() + nblk - 2 ) / ( nblk - 1 ) + 127 ) / 128 * 128;
+		while ( col.back() < n ) col.push_back( std::min( n, col.back() + rest ) );
+	}
+	else col.push_back( n );
+	nblk = (int)col.size() - 1;
+	void *da = nullptr, *db = nullptr;
+	if ( dev_alloc( &db, (size_t)m * n * ES, st ) != kSuccess ) return kFailure;
+	if ( a_host && dev_alloc( &da, (size_t)m * m * ES, st ) != kSuccess ) { dev_free( db, st ); return kFailure; }
+	std::vector<cudaEvent_t> ev_b( nblk ), ev_done, ev_a;
+	cudaEvent_t ev_alloc = nullptr, ev_out = nullptr;
+	for ( auto& e : ev_b ) cudaEventCreateWithFlags( &e, cudaEventDisableTiming );
+	cudaEventCreateWithFlags( &ev_alloc, cudaEventDisableTiming ); cudaEventCreateWithFlags( &ev_out, cudaEventDisableTiming );
+	cudaEventRecord( ev_alloc, st );
+	cudaStreamWaitEvent( s_in, ev_alloc, 0 ); cudaStreamWaitEvent( s_out, ev_alloc, 0 );
+	int rc = kSuccess;
+	auto send_b = [&]( int j ) -> int
+	{
+		const int64_t j0 = col[j], w = col[j + 1] - j0;
+		const int r = stage_block_to_device( (T*)db + j0 * m, m, b + j0 * cs_b, m, w, 1, cs_b, ES, s_in );
+		cudaEventRecord( ev_b[j], s_in );
+		return r;
+	};
+	rc = send_b( 0 );
+	T* adev = const_cast<T*>( a ); int64_t rs_ad = rs_a, cs_ad = cs_a;
+	if ( rc == kSuccess && a_host )
+	{
+		rc = trsm_upload_rec<T>( (T*)da, m, a, rs_a, cs_a, upper, 0, m, s_in, ev_a );
+		adev = (T*)da; rs_ad = ( rs_a == 1 ? 1 : m ); cs_ad = ( rs_a == 1 ? m : 1 );
+	}
+	for ( int j = 1; j < nblk && rc == kSuccess; ++j ) rc = send_b( j );
+	for ( int j = 0; j < nblk && rc == kSuccess; ++j )
+	{
+		const int64_t j0 = col[j], w = col[j + 1] - j0;
+		cudaStreamWaitEvent( st, ev_b[j], 0 );
+		size_t next = 0;
+		TrsmPlan<T> p{ adev, rs_ad, cs_ad, (T*)db + j0 * m, 1, m, w, upper, unit, conj, st };
+		if ( a_host && j == 0 ) { p.a_ready = &ev_a; p.a_next = &next; }     // later blocks run after block 0: all of A is there
+		// rows of X go home as soon as their sub-solve is done (quarters of the block), under the rest of the solve
+		p.notify_rows = std::max<int64_t>( 1024, ( m / 4 + 255 ) / 256 * 256 );
+		p.on_final = [&]( int64_t i0, int64_t mb )
+		{
+			if ( rc != kSuccess ) return;
+			cudaEvent_t e;
+			if ( cudaEventCreateWithFlags( &e, cudaEventDisableTiming ) != cudaSuccess ) { rc = fail( "trsm: event creation failed" ); return; }
+			ev_done.push_back( e );
+			cudaEventRecord( e, st );
+			cudaStreamWaitEvent( s_out, e, 0 );
+			rc = stage_block_to_host( b + j0 * cs_b + i0, 1, cs_b, (T*)db + j0 * m + i0, m, mb, w, ES, s_out );
+		};
+		const int rs = trsm_rec( p, 0, m, al );
+		if ( rc == kSuccess ) rc = rs;
+	}
+	cudaEventRecord( ev_out, s_out );
+	cudaStreamWaitEvent( st, ev_out, 0 );
+	if ( cudaStreamSynchronize( st ) != cudaSuccess && rc == kSuccess ) rc = fail( "b200_trsm: stream sync failed" );
+	if ( cudaStreamSynchronize( s_in ) != cudaSuccess && rc == kSuccess ) rc = fail( "b200_trsm: copy stream sync failed" );
+	for ( auto e : ev_b ) cudaEventDestroy( e );
+	for ( auto e : ev_done ) cudaEventDestroy( e );
+	{ cudaEvent_t last = nullptr; for ( auto e : ev_a ) { if ( e != last ) cudaEventDestroy( e ); last = e; } }
+	cudaEventDestroy( ev_alloc ); cudaEventDestroy( ev_out );
+	dev_free( da, st ); dev_free( db, st );
+	return rc;
 }
 
 template <typename T>
@@ -144,8 +300,17 @@ static int trsm_front( int side, int uplo, int transa, int diag, int64_t m, int6
 
 	void *da = nullptr, *db = nullptr;
 	int rc = kSuccess;
-	const bool b_host = ( classify( b ) != MemKind::Device );
+	const MemKind kind_b = classify( b );
+	const bool b_host = ( kind_b != MemKind::Device );
 	const bool zero_alpha = Scalar<T>::is_zero( al );
+	if ( ctx().trsm_host_pipe && !zero_alpha && kind_b == MemKind::HostPinned && rs_b == 1 && cs_b >= m && m >= 4096 && n >= 1024 )
+	{
+		// pinned host B (and possibly A), large: transfers run under the solve (trsm_host_pipeline)
+		const MemKind kind_a = classify( a );
+		const bool a_lines = ( rs_a == 1 && cs_a >= m ) || ( cs_a == 1 && rs_a >= m );
+		if ( kind_a == MemKind::Device || ( kind_a == MemKind::HostPinned && a_lines ) )
+			return trsm_host_pipeline<T>( m, n, al, a, rs_a, cs_a, kind_a != MemKind::Device, upper, diag == B200_UNIT_DIAG, conj, b, cs_b, st );
+	}
 	T* bdev = b; int64_t rs_bd = rs_b, cs_bd = cs_b;
 	if ( b_host )
 	{

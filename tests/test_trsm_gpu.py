@@ -150,6 +150,51 @@ def test_trsm_host_a_only_stored_triangle_travels(engine, oracle, pin):
     assert rel_err(to_numpy(tb_), want) <= 20 * TOL["z"]
 
 
+def test_trsm_pinned_host_operands_pipelined(engine, ref):
+    """Large solves with pinned host operands take the pipelined path (host_trsm.cuh: trsm_host_pipeline): A travels in the
+    order the recursion reads it (one event per launch), B in column blocks, X comes back block by block.  Against the
+    real reference library; the unstored triangle of A is NaN; column- and row-stored A, every uplo/trans, uneven
+    splits of the recursion (m = 4608 = 18 panels), two column blocks with a ragged second one, A already on the device,
+    the right-sided form on a row-stored B; and the result must equal the sequential path's (trsm_host_pipe = 0) to
+    rounding (the gemm updates see different shapes, so their tile schedules -- not their arithmetic -- may differ)."""
+    m, n, seed = 4608, 2200, 140
+    b0 = gen.matrix("d", m, n, 17, "frac", "c")
+    n0 = engine.launch_count()
+    for oa in ("c", "r"):
+        for uplo in (LOWER, UPPER):
+            for tr in (NO_TRANSPOSE, TRANSPOSE):
+                seed += 1
+                a = gen.triangular("d", m, seed, "frac", oa)
+                gen.poison_unstored(a, uplo == LOWER)
+                want = b0.copy(order="K")
+                ref.trsm(LEFT, uplo, tr, NONUNIT_DIAG, 2.0, a, want)
+                ta_, tb_ = to_torch(a, "cpu", pin=True), to_torch(b0, "cpu", pin=True)
+                engine.bli_dtrsm(LEFT, uplo, tr, NONUNIT_DIAG, m, n, 2.0, ta_, *estr(a), tb_, *estr(b0))
+                got = to_numpy(tb_)
+                err = rel_err(got, want)
+                assert err <= 20 * TOL["d"], (oa, uplo, tr, err)
+                if oa == "c" and tr == NO_TRANSPOSE:
+                    # the sequential path on the same operands, and A resident on the device with B on the host
+                    engine.set_option("trsm_host_pipe", 0)
+                    try:
+                        tb2 = to_torch(b0, "cpu", pin=True)
+                        engine.bli_dtrsm(LEFT, uplo, tr, NONUNIT_DIAG, m, n, 2.0, ta_, *estr(a), tb2, *estr(b0))
+                    finally:
+                        engine.set_option("trsm_host_pipe", 3)
+                    assert rel_err(to_numpy(tb2), got) <= 20 * TOL["d"], (uplo, rel_err(to_numpy(tb2), got))
+                    tb3 = to_torch(b0, "cpu", pin=True)
+                    engine.bli_dtrsm(LEFT, uplo, tr, NONUNIT_DIAG, m, n, 2.0, ta_.cuda(), *estr(a), tb3, *estr(b0))
+                    assert rel_err(to_numpy(tb3), want) <= 20 * TOL["d"], (uplo, "device A")
+    assert engine.launch_count() > n0
+    # right side, row-stored B (the transposed problem is column-stored): X * A^T = alpha * B, unit diagonal
+    a = gen.triangular("d", m, 991, "frac", "c"); gen.poison_unstored(a, True)
+    b = gen.matrix("d", 1100, m, 992, "frac", "r")
+    want = b.copy(order="K"); ref.trsm(RIGHT, LOWER, TRANSPOSE, UNIT_DIAG, 2.0, a, want)
+    ta_, tb_ = to_torch(a, "cpu", pin=True), to_torch(b, "cpu", pin=True)
+    engine.bli_dtrsm(RIGHT, LOWER, TRANSPOSE, UNIT_DIAG, 1100, m, 2.0, ta_, *estr(a), tb_, *estr(b))
+    assert rel_err(to_numpy(tb_), want) <= 20 * TOL["d"]
+
+
 def test_trsm_full_size_testsuite_residual(engine):
     """BASELINE config #4: dtrsm left/lower/notrans/nonunit m=32768 n=8192.
     resid = || B t - alpha inv(A) (B0 t) ||  ==  || A (X t) - alpha B0 t || scaled, via a triangular
