@@ -669,9 +669,10 @@ def main():
                         t0 = time.perf_counter(); fe.dtrsm_(m_t, n_t, ALPHA, ah.data_ptr(), m_t, bh.data_ptr(), m_t); tt += time.perf_counter() - t0
                     dt = tt / 2
                     te2e = {"value": tflops / dt / 1e9, "unit": "GFLOPS", "ms_per_step": dt * 1e3,
-                            "h2d_bytes_per_step": int(8 * (m_t * (m_t + 2048) // 2 + m_t * n_t)), "d2h_bytes_per_step": 8 * m_t * n_t,
+                            "h2d_bytes_per_step": int(8 * (m_t * (m_t + 1024) // 2 + m_t * n_t)), "d2h_bytes_per_step": 8 * m_t * n_t,
                             "how": "the reference's dtrsm_ (frame/compat/bla_trsm.c:126-217) with the B200 plugin registered, pinned host A and B: H2D of "
-                                   "the stored triangle of A (column panels cut at the diagonal) and of B, kernels, D2H of X; host wall clock"}
+                                   "B and of the stored triangle of A (diagonal squares of <= 1024 rows + the update blocks, in the order the solve "
+                                   "reads them, under the solve), kernels, D2H of X in row chunks as sub-solves finish; host wall clock"}
                     del ah, bh, bh0
                 except (OSError, RuntimeError, FileNotFoundError) as exc:
                     print(f"dtrsm e2e skipped: {exc!r}", file=sys.stderr)

@@ -391,7 +391,18 @@ double b200_measure_peak( int kind, int millis );
  * reports the difference over its timed region as "gpu_launches". */
 unsigned long long b200_launch_count( void );
 
-/* Tuning knob for sweeps, e.g. ("dgemm_cfg", 1); not part of the reference surface. */
+/* Tuning knobs, e.g. ("dgemm_cfg", 9); not part of the reference surface.  Every key can be preset in the environment
+ * as BLIS_B200_<KEY> (the reference's bli_env convention, frame/base/bli_env.c:68).  Keys that change WHICH schedule
+ * serves a call (results stay within the same error bound; exact inputs give identical bits):
+ *   dgemm_splitk      1 (default): mid-size dgemm cuts the tiles of a partial last wave into k chunks; 0: never split k
+ *   dmma_cst          k up to which dgemm moves D through the TMA unit both ways (default 256; 0: never)
+ *   trsm_fused        1 (default): fused 256-row diagonal-panel kernel for dtrsm; 0: 64-row block solves
+ *   trsm_host_pipe    max. column blocks of the pipelined trsm with pinned host operands (default 3; 0: sequential transfers)
+ *   host_kpipe        1 (default): gemm with host operands and long k is pipelined over k panels
+ *   batch_grouped     1 (default): small device-resident problems of b200_gemm_batch share ONE launch;
+ *   batch_grouped_max   "small" means m*n*k at most this (default 128^3)
+ * Kernel selection / sweeps: dgemm_cfg, zgemm_cfg, sgemm_cfg, cgemm_cfg, grid_mult, dynamic_tiles, raster_group,
+ * tma_l2_promotion, transpose_y, ktri_skip, dmma_pp, dist_ab_static, reserve_sms. */
 b200_err_t b200_set_option( const char* key, long long value );
 
 #ifdef __cplusplus
