@@ -234,6 +234,17 @@ extern "C" b200_err_t b200_gemm_kpanels( int dt, int transa, int transb, b200_di
 	return fail( "b200_gemm_kpanels: only d and z are supported" );
 }
 
+extern "C" int b200_trsm_upload_plan( b200_dim_t m, int leaf_rows, int upper, b200_dim_t* out, int cap )
+{
+	std::vector<TrsmPiece> plan;
+	if ( m > 0 && leaf_rows > 0 ) trsm_upload_plan( leaf_rows, upper != 0, 0, m, plan );
+	for ( size_t i = 0; i < plan.size() && (int)i < cap && out; ++i )
+	{
+		out[5 * i] = plan[i].r0; out[5 * i + 1] = plan[i].r1; out[5 * i + 2] = plan[i].c0; out[5 * i + 3] = plan[i].c1; out[5 * i + 4] = plan[i].launches;
+	}
+	return (int)plan.size();
+}
+
 // ---- multi-GPU (host_dist.cuh) ------------------------------------------------------------------------------------
 extern "C" void b200_partition_2x2( b200_dim_t n_thread, b200_dim_t work1, b200_dim_t work2, b200_dim_t* nt1, b200_dim_t* nt2 )
 { partition_2x2( n_thread, work1, work2, nt1, nt2 ); }

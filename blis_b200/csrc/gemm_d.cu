@@ -104,3 +104,11 @@ int launch_gemm_kernel<double>( GemmArgs<double>& g, bool xk, bool yk, bool al, 
 }
 
 } // namespace b200
+
+extern "C" int b200_splitk_plan( int64_t tiles, int grid, int64_t kt, int* full )
+{
+	int f = 0;
+	const int S = b200::splitk_plan( tiles, grid, kt, &f );
+	if ( full ) *full = S ? f : (int)tiles;
+	return S;
+}

@@ -23,7 +23,7 @@ struct TrsmPlan
 	bool     upper, unit, conj;
 	cudaStream_t st;
 	// A arriving from the host while the solve runs (trsm_host_pipe): one event per launch of the recursion, in the
-	// recursion's own order (trsm_upload_rec builds the list); nullptr: A is resident
+	// recursion's own order (trsm_upload builds the list); nullptr: A is resident
 	const std::vector<cudaEvent_t>* a_ready = nullptr;
 	size_t*  a_next = nullptr;
 	// rows [i0, i0+mb) of X are final when their sub-solve returns: told once per subtree of at most notify_rows rows
@@ -146,7 +146,7 @@ static int trsm_rec( const TrsmPlan<T>& p, int64_t i0, int64_t mb, T alpha )
 // of kernels.  Two things make the transfers disappear behind the solve:
 //   * A travels IN THE ORDER THE RECURSION READS IT.  trsm_rec touches A11 (recursively), then the block A21 (lower) /
 //     A12 (upper) of the update, then A22 -- and spends its time in the same proportion (a quarter, a half, a quarter of
-//     the flops for a quarter, a half, a quarter of the triangle's bytes).  trsm_upload_rec walks the same tree, uploads
+//     the flops for a quarter, a half, a quarter of the triangle's bytes).  trsm_upload_plan walks the same tree, uploads
 //     each diagonal block (<= 1024 rows, as a square) and each update block as one 2-D copy on the copy stream and records
 //     one event PER LAUNCH of the solve's recursion, in its order; trsm_rec waits for the next event before every launch.
 //     Only the stored triangle (plus the unstored half of the small diagonal squares, ~1.5 %) travels.
@@ -157,37 +157,47 @@ static int trsm_rec( const TrsmPlan<T>& p, int64_t i0, int64_t mb, T alpha )
 //   * X goes home in ROW chunks: the rows of a finished sub-solve are final (trsm_rec tells, quarters of m), so only the
 //     last quarter's download is exposed.
 // [B200] T1 through dtrsm_: 417 ms (sequential) -> 301 ms = 29.2 TFLOP/s end to end (kernels alone: 251 ms).
+struct TrsmPiece { int64_t r0, r1, c0, c1; int launches; };      // rows x columns of the effective view; launches of the solve that read it
+// The pieces in the order trsm_rec reads them (pure index arithmetic; b200_trsm_upload_plan exposes it to the CPU tests):
+// the split is trsm_rec's own; a diagonal block of at most max(leaf_rows, 1024) rows travels as one square and serves all
+// 2*ceil(mb/leaf_rows) - 1 launches of its subtree.
+static void trsm_upload_plan( int leaf_rows, bool upper, int64_t i0, int64_t mb, std::vector<TrsmPiece>& out )
+{
+	const int64_t NB = leaf_rows, nblk = ( mb + NB - 1 ) / NB;
+	if ( mb <= std::max<int64_t>( NB, 1024 ) ) { out.push_back( { i0, i0 + mb, i0, i0 + mb, (int)( 2 * nblk - 1 ) } ); return; }
+	const int64_t m1 = ( ( nblk + 1 ) / 2 ) * NB, m2 = mb - m1;      // the split of trsm_rec
+	if ( !upper )
+	{
+		trsm_upload_plan( leaf_rows, upper, i0, m1, out );
+		out.push_back( { i0 + m1, i0 + mb, i0, i0 + m1, 1 } );       // A21 of the update
+		trsm_upload_plan( leaf_rows, upper, i0 + m1, m2, out );
+	}
+	else
+	{
+		trsm_upload_plan( leaf_rows, upper, i0 + m2, m1, out );
+		out.push_back( { i0, i0 + m2, i0 + m2, i0 + mb, 1 } );       // A12 of the update
+		trsm_upload_plan( leaf_rows, upper, i0, m2, out );
+	}
+}
 template <typename T>
-static int trsm_upload_rec( T* da, int64_t m, const T* a, int64_t rs_a, int64_t cs_a, bool upper, int64_t i0, int64_t mb,
-                            cudaStream_t s_in, std::vector<cudaEvent_t>& ev )
+static int trsm_upload( T* da, int64_t m, const T* a, int64_t rs_a, int64_t cs_a, bool upper, cudaStream_t s_in, std::vector<cudaEvent_t>& ev )
 {
 	constexpr size_t ES = sizeof(T);
-	const int NB = trsm_leaf_rows<T>();
-	// rows [r0, r1) x columns [c0, c1) of the effective view -> the device image, which keeps the host's orientation
-	auto piece = [&]( int64_t r0, int64_t r1, int64_t c0, int64_t c1, int launches ) -> int
+	std::vector<TrsmPiece> plan;
+	trsm_upload_plan( trsm_leaf_rows<T>(), upper, 0, m, plan );
+	for ( const TrsmPiece& q : plan )
 	{
+		// the device image keeps the host's orientation (column- or row-stored)
 		int rc;
-		if ( rs_a == 1 ) rc = stage_block_to_device( da + r0 + c0 * m, m, a + r0 + c0 * cs_a, r1 - r0, c1 - c0, 1, cs_a, ES, s_in );
-		else             rc = stage_block_to_device( da + c0 + r0 * m, m, a + c0 + r0 * rs_a, c1 - c0, r1 - r0, 1, rs_a, ES, s_in );
+		if ( rs_a == 1 ) rc = stage_block_to_device( da + q.r0 + q.c0 * m, m, a + q.r0 + q.c0 * cs_a, q.r1 - q.r0, q.c1 - q.c0, 1, cs_a, ES, s_in );
+		else             rc = stage_block_to_device( da + q.c0 + q.r0 * m, m, a + q.c0 + q.r0 * rs_a, q.c1 - q.c0, q.r1 - q.r0, 1, rs_a, ES, s_in );
 		if ( rc != kSuccess ) return rc;
 		cudaEvent_t e;
 		if ( cudaEventCreateWithFlags( &e, cudaEventDisableTiming ) != cudaSuccess ) return fail( "trsm: event creation failed" );
 		cudaEventRecord( e, s_in );
-		for ( int l = 0; l < launches; ++l ) ev.push_back( e );      // the same event serves every launch inside this piece
-		return kSuccess;
-	};
-	const int64_t nblk = ( mb + NB - 1 ) / NB;
-	if ( mb <= std::max<int64_t>( NB, 1024 ) ) return piece( i0, i0 + mb, i0, i0 + mb, (int)( 2 * nblk - 1 ) );
-	const int64_t m1 = ( ( nblk + 1 ) / 2 ) * NB, m2 = mb - m1;      // the split of trsm_rec
-	if ( !upper )
-	{
-		if ( trsm_upload_rec( da, m, a, rs_a, cs_a, upper, i0, m1, s_in, ev ) != kSuccess ) return kFailure;
-		if ( piece( i0 + m1, i0 + mb, i0, i0 + m1, 1 ) != kSuccess ) return kFailure;
-		return trsm_upload_rec( da, m, a, rs_a, cs_a, upper, i0 + m1, m2, s_in, ev );
+		for ( int l = 0; l < q.launches; ++l ) ev.push_back( e );    // the same event serves every launch inside this piece
 	}
-	if ( trsm_upload_rec( da, m, a, rs_a, cs_a, upper, i0 + m2, m1, s_in, ev ) != kSuccess ) return kFailure;
-	if ( piece( i0, i0 + m2, i0 + m2, i0 + mb, 1 ) != kSuccess ) return kFailure;
-	return trsm_upload_rec( da, m, a, rs_a, cs_a, upper, i0, m2, s_in, ev );
+	return kSuccess;
 }
 
 // a: effective m x m view (host or device), b: m x n host, pinned, column-stored (rs_b == 1)
@@ -235,7 +245,7 @@ static int trsm_host_pipeline( int64_t m, int64_t n, T al, const T* a, int64_t r
 	T* adev = const_cast<T*>( a ); int64_t rs_ad = rs_a, cs_ad = cs_a;
 	if ( rc == kSuccess && a_host )
 	{
-		rc = trsm_upload_rec<T>( (T*)da, m, a, rs_a, cs_a, upper, 0, m, s_in, ev_a );
+		rc = trsm_upload<T>( (T*)da, m, a, rs_a, cs_a, upper, s_in, ev_a );
 		adev = (T*)da; rs_ad = ( rs_a == 1 ? 1 : m ); cs_ad = ( rs_a == 1 ? m : 1 );
 	}
 	for ( int j = 1; j < nblk && rc == kSuccess; ++j ) rc = send_b( j );
@@ -260,6 +270,7 @@ static int trsm_host_pipeline( int64_t m, int64_t n, T al, const T* a, int64_t r
 		};
 		const int rs = trsm_rec( p, 0, m, al );
 		if ( rc == kSuccess ) rc = rs;
+		if ( rc == kSuccess && p.a_ready && next != ev_a.size() ) rc = fail( "b200_trsm: upload plan (%zu events) and solve recursion (%zu launches) disagree", ev_a.size(), next );
 	}
 	cudaEventRecord( ev_out, s_out );
 	cudaStreamWaitEvent( st, ev_out, 0 );

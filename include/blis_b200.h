@@ -391,6 +391,19 @@ double b200_measure_peak( int kind, int millis );
  * reports the difference over its timed region as "gpu_launches". */
 unsigned long long b200_launch_count( void );
 
+/* ---- schedule arithmetic of the engine itself (host only, no GPU needed; tests/test_host_plans.py) ------------
+ * b200_splitk_plan: the split-k tail of mid-size dgemm (csrc/gemm_d.cu).  `tiles` 128x128 output tiles on `grid`
+ * persistent CTAs, `kt` 16-wide k steps per tile.  Returns S, the number of k chunks every tile of the partial last
+ * wave is cut into (0: whole tiles only), and in *full the number of tiles that stay whole.  The reference has no
+ * counterpart: it never splits k inside one gemm (frame/3/gemm/bli_gemm_blk_var3.c:110-112; bli_rntm_factorize,
+ * frame/base/bli_rntm.c:424-489, factors threads over ic x jc only); this is the rule that decides when the engine does.
+ * b200_trsm_upload_plan: the order in which a host-resident triangular A travels while trsm runs (csrc/host_trsm.cuh):
+ * pieces (r0, r1, c0, c1, launches) of the effective m x m view, in the order the recursive solve
+ * (bli_trsm_blk_var1's role, frame/3/trsm/bli_trsm_blk_var1.c:40-188) reads them; `launches` = launches of the solve
+ * that wait for the piece.  Writes at most `cap` pieces of five numbers each to `out`, returns the number of pieces. */
+int        b200_splitk_plan( b200_dim_t tiles, int grid, b200_dim_t kt, int* full );
+int        b200_trsm_upload_plan( b200_dim_t m, int leaf_rows, int upper, b200_dim_t* out, int cap );
+
 /* Tuning knobs, e.g. ("dgemm_cfg", 9); not part of the reference surface.  Every key can be preset in the environment
  * as BLIS_B200_<KEY> (the reference's bli_env convention, frame/base/bli_env.c:68).  Keys that change WHICH schedule
  * serves a call (results stay within the same error bound; exact inputs give identical bits):
