@@ -1,5 +1,5 @@
 """dgemm n^3 for mid-size n: the split-k tail schedule (dgemm_splitk 1) against whole tiles only (0).
-Dev tool.  usage: python -m tools.midsize_sweep [n,n,...]      prints one JSON line"""
+Dev tool.  usage: python -m tools.midsize_sweep [n,n,...] [dgemm_cfg]      prints one JSON line"""
 import json
 import sys
 
@@ -8,6 +8,8 @@ import torch
 from blis_b200 import api
 
 ns = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1536, 1792, 2048, 2304, 2560, 3072, 3584, 4096]
+if len(sys.argv) > 2:
+    api.set_option("dgemm_cfg", int(sys.argv[2]))          # e.g. 9: force the 128x128 TMA kernel below its usual size range
 dev = torch.device("cuda:0")
 
 
