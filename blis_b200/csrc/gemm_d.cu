@@ -9,15 +9,19 @@ namespace b200 {
 // ceil(r*S/grid)/S of a tile time instead of 1.  Returns S (0: leave the schedule alone).
 static int splitk_plan( int64_t tiles, int grid, int64_t kt, int* full )
 {
-	if ( grid <= 0 || tiles <= 0 ) return 0;
+	if ( grid <= 0 || tiles <= grid || kt <= 0 ) return 0;        // less than one wave: measured slower with chunks only (1280^3 forced: 22.9 -> 18.0)
 	const int64_t waves = ( tiles + grid - 1 ) / grid;
 	const int64_t r = tiles % grid;
 	if ( r == 0 || waves > 8 ) return 0;                          // nothing idle / the tail is under ~1.5 % of the run
-	double best = 0.97; int S = 0;                               // a chunk's fix-up (park + add, ~3 % of a tile at k = 2048) must be paid for
+	// Cost of the tail in tile times: ceil(r*S/grid) rounds of 1/S each, plus the fix-up of a round -- ~11 us on a B200
+	// (148 CTAs park 128 KiB each and the last arrivals read the slots back: [B200] ncu, 2048^3), i.e. 5/kt of a tile time
+	// (a 16-wide k step of a 128x128 tile takes 2.1 us).
+	double best = 1.0; int S = 0;
 	for ( int s : { 2, 3, 4, 5, 6, 8 } )
 	{
 		if ( kt / s < 16 ) break;                                   // >= 256 k per chunk
-		const double t = (double)( ( r * s + grid - 1 ) / grid ) / s + 0.01 * s;
+		const double rounds = (double)( ( r * s + grid - 1 ) / grid );
+		const double t = rounds * ( 1.0 / s + 5.0 / (double)kt );
 		if ( t < best - 1e-9 ) { best = t; S = s; }
 	}
 	if ( S == 0 || ( 1.0 - best ) / (double)waves < 0.03 ) return 0;   // under 3 % of the whole launch

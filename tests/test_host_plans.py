@@ -38,6 +38,7 @@ def test_splitk_plan_known_cases(lib):
     # whole waves, fewer tiles than one wave that already fill it, tiny k
     assert splitk(lib, 296, G, 128)[0] == 0
     assert splitk(lib, 144, G, 96)[0] == 0
+    assert splitk(lib, 100, G, 80)[0] == 0                   # less than one wave: chunks only were measured slower
     assert splitk(lib, 256, G, 16)[0] == 0                   # 256 k: chunks would be shorter than 256 k
 
 
@@ -55,7 +56,7 @@ def test_splitk_plan_properties(lib):
                 assert full % grid == 0 and 0 < r < grid and waves <= 8
                 assert kt // s >= 16                             # at least 256 k per chunk
                 # the tail must get cheaper by at least 3 % of the launch, in the plan's own cost model
-                tail = -(-r * s // grid) / s + 0.01 * s
+                tail = -(-r * s // grid) * (1.0 / s + 5.0 / kt)
                 assert (1.0 - tail) / waves >= 0.03 - 1e-12
                 # every chunk range is non-empty and they partition [0, kt)
                 cuts = [kt * c // s for c in range(s + 1)]
