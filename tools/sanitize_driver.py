@@ -84,4 +84,47 @@ for dt, tol in ((torch.float64, 1e-11), (torch.complex128, 1e-11), (torch.float3
 b = rnd(300, 100, torch.float64); t = rnd(300, 300, torch.float64); b1 = b.clone(memory_format=torch.preserve_format)
 api.bli_dtrmm(0, 0xC0, 0, 0, 300, 100, 2.0, t, 1, 300, b1, 1, 300); torch.cuda.synchronize()
 check("trmm lower", b1, 2.0 * (torch.tril(t) @ b), 1e-12)
+
+# ---- round 2 additions: split-k tail, fused trsm panel, grouped batch kernel, pipelined host trsm ---------------------
+import os  # noqa: E402
+
+# split-k tail of the TMA dgemm (156 tiles on 148 SMs -> 148 whole + 8 x 4 chunks); ragged m, n, k
+m, n, k = 1412, 1540, 1028
+a, b, c = rnd(m, k, torch.float64), rnd(k, n, torch.float64), rnd(m, n, torch.float64)
+c1 = c.clone(memory_format=torch.preserve_format)
+api.bli_dgemm(0, 0, m, n, k, 2.0, a, 1, m, b, 1, k, 1.2, c1, 1, m); torch.cuda.synchronize()
+check("gemm split-k tail", c1, 1.2 * c + 2.0 * (a @ b), 1e-12)
+assert "SK=1" in api.last_kernel(), api.last_kernel()
+
+# fused diagonal-panel trsm kernel (m > 256 rows: panels of 256 + a ragged last one), lower and upper
+for uplo, tri in ((0xC0, torch.tril), (0x60, torch.triu)):
+    t = rnd(700, 700, torch.float64) / 16; t.diagonal().add_(2.0)
+    b = rnd(700, 200, torch.float64); b1 = b.clone(memory_format=torch.preserve_format)
+    api.bli_dtrsm(0, uplo, 0, 0, 700, 200, 2.0, t, 1, 700, b1, 1, 700); torch.cuda.synchronize()
+    check(f"trsm fused panel uplo={uplo:#x}", b1, torch.linalg.solve_triangular(tri(t), 2.0 * b, upper=(uplo == 0x60)), 1e-11)
+assert "trsm_panel_kernel" in " ".join(api.kernel_stats()), sorted(api.kernel_stats())
+
+# grouped kernel: 60 small problems of three shapes in ONE launch (d and c)
+for dt, tol in ((torch.float64, 1e-12), (torch.complex64, 5e-5)):
+    groups, wants = [], []
+    for (mm, nn, kk, ta) in ((33, 31, 17, 0), (64, 64, 64, 8), (5, 100, 40, 0)):
+        aa = [rnd(*((kk, mm) if ta else (mm, kk)), dt) for _ in range(20)]; bb = [rnd(kk, nn, dt) for _ in range(20)]; cc = [rnd(mm, nn, dt) for _ in range(20)]
+        wants += [1.2 * z + 2.0 * ((x.t() if ta else x) @ y) for x, y, z in zip(aa, bb, cc)]
+        groups.append(dict(transa=ta, transb=0, m=mm, n=nn, k=kk, alpha=2.0, beta=1.2, a=aa, b=bb, c=cc))
+    api.gemm_batch(dt, groups); torch.cuda.synchronize()
+    got = [t for gr in groups for t in gr["c"]]
+    err = max(float((x - y).abs().max()) for x, y in zip(got, wants))
+    print(f"{'grouped batch ' + str(dt):28s} {api.last_kernel():70s} err={err:.2e}", flush=True)
+    assert err <= tol * 10 and api.last_kernel().startswith("gemm_grouped_kernel")
+
+# pinned host operands: A streams in the recursion's order, B in two column blocks, X comes back in row chunks
+if not os.environ.get("SANITIZE_SKIP_HOST"):
+    mm, nn = 4352, 2200
+    t = rnd(mm, mm, torch.float64) / 64; t.diagonal().add_(2.0)
+    b = rnd(mm, nn, torch.float64)
+    th = torch.empty(mm, mm, dtype=torch.float64).pin_memory().t(); th.copy_(t)
+    bh = torch.empty(nn, mm, dtype=torch.float64).pin_memory().t(); bh.copy_(b)
+    api.bli_dtrsm(0, 0xC0, 0, 0, mm, nn, 2.0, th, 1, mm, bh, 1, mm)
+    want = torch.linalg.solve_triangular(torch.tril(t), 2.0 * b, upper=False)
+    check("trsm pinned host pipeline", bh.cuda(), want, 1e-10)
 print("sanitize_driver: all cases ok; kernels:", sorted(api.kernel_stats()))
