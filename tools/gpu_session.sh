@@ -67,7 +67,8 @@ ncu_sgemm)
 	python tools/ncu_src.py gpurun_out/sgemm_full.ncu-rep 60 > gpurun_out/ncu_sgemm_8192_src.txt 2>&1; rm -f gpurun_out/sgemm_full.ncu-rep ;;
 ncu_splitk)
 	ncu --set full --clock-control none --import-source on -k regex:gemm_dmma_tma -s 1 -c 1 -o gpurun_out/splitk_full -f python -m tools.one_gemm d 2048 2048 -1 2 > /dev/null 2>&1
-	python tools/ncu_key.py gpurun_out/splitk_full.ncu-rep > gpurun_out/ncu_dgemm_2048_splitk.txt 2>&1; head -30 gpurun_out/ncu_dgemm_2048_splitk.txt; rm -f gpurun_out/splitk_full.ncu-rep ;;
+	python tools/ncu_key.py gpurun_out/splitk_full.ncu-rep > gpurun_out/ncu_dgemm_2048_splitk.txt 2>&1; head -30 gpurun_out/ncu_dgemm_2048_splitk.txt
+	python tools/ncu_src.py gpurun_out/splitk_full.ncu-rep 70 > gpurun_out/ncu_dgemm_2048_splitk_src.txt 2>&1; rm -f gpurun_out/splitk_full.ncu-rep ;;
 midsize)
 	timeout 300 python -m tools.midsize_sweep 1536,1792,2048,2304,2560,2816,3072,3328,3584,4096 > gpurun_out/midsize_sweep.json 2> gpurun_out/midsize_sweep.err; cat gpurun_out/midsize_sweep.err ;;
 batchprobe)
