@@ -328,6 +328,7 @@ extern "C" b200_err_t b200_set_option( const char* key, long long value )
 	else if ( !strcmp( key, "transpose_y" ) ) c.transpose_y = (int)value;
 	else if ( !strcmp( key, "ktri_skip" ) ) c.ktri_skip = (int)value;
 	else if ( !strcmp( key, "host_kpipe" ) ) c.host_kpipe = (int)value;
+	else if ( !strcmp( key, "host_trace" ) ) c.host_trace = (int)value;
 	else if ( !strcmp( key, "dmma_cst" ) ) c.dmma_cst = (int)value;
 	else if ( !strcmp( key, "dmma_pp" ) ) c.dmma_pp = (int)value;
 	else if ( !strcmp( key, "dgemm_splitk" ) ) c.dgemm_splitk = (int)value;

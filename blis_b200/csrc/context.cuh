@@ -72,6 +72,7 @@ struct Context
 	int          batch_grouped = 1;     // b200_gemm_batch: small device-resident problems share ONE launch (gemm_grouped.cuh); 0 = a launch each on the stream pool
 	long long    batch_grouped_max = 128ll * 128 * 128;   // ... "small" = m*n*k at most this
 	int          trsm_host_pipe = 3;    // trsm with pinned host operands: A streams in the solve's own order, B in at most this many column blocks, X leaves block by block (0 = sequential transfers)
+	int          host_trace = 0;        // print the event timeline of pipelined host-operand calls to stderr (diagnostic)
 	int          host_kpipe = 1;        // host operands with long k: pipeline over k panels instead of column blocks
 	int          ktri_skip = 1;         // trmm/trmm3: tiles skip the k range in which the triangular operand is zero
 	int          transpose_y = 1;       // s/c: transpose a k-contiguous Y panel once instead of re-pairing registers in the k loop

@@ -154,8 +154,11 @@ __global__ void add_scaled_kernel( R* __restrict__ c, const R* __restrict__ s, i
 // block pipeline of gemm_front cannot start the second block before ALL of A has arrived.  Here the product is
 // accumulated panel by panel over k (the pc loop of bli_gemm_blk_var3): round p needs only A(:, panel p) and
 // B(panel p, :), 1/np of the traffic, and is one full-size launch; the host C is staged meanwhile into a separate buffer
-// and merged (beta) during the last round, which runs per column block so that each finished block of C leaves on the
-// D2H stream under the kernels of the next one.  Exposed transfer: the first pair of panels and the last block of C.
+// and merged (beta) during the final phase, which runs per column block over the LAST TWO panels (one k-panel-accumulation
+// launch per block) so that each finished block of C leaves on the D2H stream under the kernels of the next one and the
+// downloads keep up.  Exposed transfer: the first, short pair of panels (2.5 ms) and the last, short block of C (2.4 ms).
+// [B200] 16384^3 through dgemm_: 266.8 -> ~253 ms per call (kernels alone 241.6 ms); b200_set_option("host_trace", 1) prints
+// the timeline.
 template <typename T>
 static int gemm_host_kpipe( bool conja, bool conjb, int64_t m, int64_t n, int64_t k, T al, const T* a, int64_t rs_a, int64_t cs_a,
                             const T* b, int64_t rs_b, int64_t cs_b, T be, T* c, int64_t rs_c, int64_t cs_c, cudaStream_t st )
@@ -168,13 +171,16 @@ static int gemm_host_kpipe( bool conja, bool conjb, int64_t m, int64_t n, int64_
 	const bool a_host = classify( a ) != MemKind::Device, b_host = classify( b ) != MemKind::Device;
 	const bool load_c = !Scalar<T>::is_zero( be );
 	// panel / block boundaries: uniform eighths, except that the LAST column block is quartered so that the exposed tail
-	// (last block of C going home) is short.  (A short FIRST k panel was measured slower: a row panel of a column-major B
-	// is a 2-D copy whose chunks are kw*8 bytes, and 4 KiB chunks move at a fraction of the PCIe rate.)
+	// (last block of C going home) is short, and the FIRST k panel is cut once more so that the first kernel starts early.
 	const int64_t kb = std::max<int64_t>( 512, ( ( k + 7 ) / 8 + 127 ) / 128 * 128 );
 	const int64_t nb = std::max<int64_t>( 512, ( ( n + 7 ) / 8 + 127 ) / 128 * 128 );
 	std::vector<int64_t> pk{ 0 }, pn{ 0 };
 	{
-		while ( pk.back() < k ) pk.push_back( std::min( k, pk.back() + kb ) );
+		// the first eighth is cut once more at a quarter (host_kpipe = divisor, 1 = 4): the first kernel starts after
+		// 2.5 ms instead of 9.7 ms ([B200] 16384^3, host_trace timeline; 4 KiB lines of B still move at 54 GB/s)
+		const int64_t first = kb / ( cx.host_kpipe >= 2 ? cx.host_kpipe : 4 ) / 128 * 128;
+		if ( kb >= 1024 && first >= 256 ) pk.push_back( first );
+		while ( pk.back() < k ) pk.push_back( std::min( k, pk.back() + kb - ( pk.size() == 2 && pk.back() < kb ? pk.back() : 0 ) ) );
 		while ( pn.back() < n ) pn.push_back( std::min( n, pn.back() + nb ) );
 		const int64_t n0 = std::max<int64_t>( 512, ( nb / 4 + 127 ) / 128 * 128 );
 		if ( pn.size() > 2 && n - pn[pn.size() - 2] > n0 ) pn.insert( pn.end() - 1, n - n0 );
@@ -184,12 +190,21 @@ static int gemm_host_kpipe( bool conja, bool conjb, int64_t m, int64_t n, int64_
 	int rc = kSuccess;
 	if ( ( a_host && dev_alloc( &da, (size_t)m * k * ES, st ) != kSuccess ) || ( b_host && dev_alloc( &db, (size_t)k * n * ES, st ) != kSuccess ) ||
 	     dev_alloc( &dc, (size_t)m * n * ES, st ) != kSuccess || ( load_c && dev_alloc( &ds, (size_t)m * n * ES, st ) != kSuccess ) ) rc = kFailure;
+	const bool trace = cx.host_trace != 0;                       // host_trace: print the timeline of this call (ms since the first enqueue) to stderr
 	std::vector<cudaEvent_t> ev( np + 2 * nblk + 1 );
-	for ( auto& e : ev ) cudaEventCreateWithFlags( &e, cudaEventDisableTiming );
+	for ( auto& e : ev ) cudaEventCreateWithFlags( &e, trace ? cudaEventDefault : cudaEventDisableTiming );
+	std::vector<cudaEvent_t> ev_k( trace ? np + 1 : 0 ), ev_out( trace ? nblk : 0 );
+	for ( auto& e : ev_k ) cudaEventCreate( &e );
+	for ( auto& e : ev_out ) cudaEventCreate( &e );
 	cudaEvent_t* ev_p = ev.data(); cudaEvent_t* ev_c = ev.data() + np; cudaEvent_t* ev_done = ev.data() + np + nblk; cudaEvent_t ev_alloc = ev.back();
 	cudaEventRecord( ev_alloc, st );
 	cudaStreamWaitEvent( s_in, ev_alloc, 0 ); cudaStreamWaitEvent( s_out, ev_alloc, 0 );
 	const T one = Scalar<T>::make( 1.0, 0.0 ), zero = Scalar<T>::make( 0.0, 0.0 );
+	// the final phase folds the last two k panels into its per-block launches when they have the same width (d and z: the
+	// k-panel accumulation kernels)
+	constexpr bool kPanelsOk = std::is_same<T, double>::value || std::is_same<T, double2>::value;
+	const int tail_p = ( kPanelsOk && np >= 3 && pk[np] - pk[np - 1] == pk[np - 1] - pk[np - 2] ) ? 2 : 1;
+	const T *tail_a = nullptr, *tail_b = nullptr;
 	int c_sent = 0;                                  // column blocks of the host C already queued for staging
 	auto send_c = [&]( int upto ) -> int
 	{
@@ -215,15 +230,30 @@ static int gemm_host_kpipe( bool conja, bool conjb, int64_t m, int64_t n, int64_
 		const T* bp = b_host ? (const T*)db + p0 * n : b + p0 * rs_b;  const int64_t rs_bp = b_host ? 1 : rs_b, cs_bp = b_host ? kw : cs_b;
 		cudaStreamWaitEvent( st, ev_p[p], 0 );
 		if ( rc != kSuccess ) break;
-		if ( p + 1 < np )
+		if ( p < np - tail_p )
+		{
 			rc = gemm_dev<T>( conja, conjb, m, n, kw, al, ap, rs_ap, cs_ap, bp, rs_bp, cs_bp, p == 0 ? zero : one, (T*)dc, 1, m, st );
+			if ( trace ) cudaEventRecord( ev_k[p], st );
+		}
+		else if ( p + 1 < np ) { tail_a = ap; tail_b = bp; }          // first panel of the final phase: used together with the last one
 		else
 		{
+			// final phase, per column block: the last tail_p panels in ONE launch (k-panel accumulation), the merge of the
+			// host C, and the block leaves.  With two panels a block computes for longer than it travels ([B200] 16384^3:
+			// 8.1 ms against 4.7 ms), so the D2H stream keeps up and only the last, short block is exposed; with one panel
+			// the downloads fell 9 ms behind (timeline: host_trace).
 			rc = send_c( nblk );
 			for ( int j = 0; j < nblk && rc == kSuccess; ++j )
 			{
 				const int64_t j0 = pn[j], w = pn[j + 1] - j0;
-				rc = gemm_dev<T>( conja, conjb, m, w, kw, al, ap, rs_ap, cs_ap, bp + j0 * cs_bp, rs_bp, cs_bp, p == 0 ? zero : one, (T*)dc + j0 * m, 1, m, st );
+				const T beta_j = ( np == tail_p ) ? zero : one;
+				if ( tail_p == 2 )
+				{
+					const T* a_more[1] = { ap };  const T* b_more[1] = { bp + j0 * cs_bp };
+					rc = gemm_dev<T>( conja, conjb, m, w, kw, al, tail_a, rs_ap, cs_ap, tail_b + j0 * cs_bp, rs_bp, cs_bp, beta_j, (T*)dc + j0 * m, 1, m, st, 2, a_more, b_more );
+				}
+				else
+					rc = gemm_dev<T>( conja, conjb, m, w, kw, al, ap, rs_ap, cs_ap, bp + j0 * cs_bp, rs_bp, cs_bp, beta_j, (T*)dc + j0 * m, 1, m, st );
 				if ( rc == kSuccess && load_c )
 				{
 					cudaStreamWaitEvent( st, ev_c[j], 0 );
@@ -237,12 +267,30 @@ static int gemm_host_kpipe( bool conja, bool conjb, int64_t m, int64_t n, int64_
 				cudaEventRecord( ev_done[j], st );
 				cudaStreamWaitEvent( s_out, ev_done[j], 0 );
 				if ( rc == kSuccess ) rc = stage_to_host( c + j0 * cs_c, rs_c, cs_c, (T*)dc + j0 * m, m, w, ES, s_out );
+				if ( trace ) cudaEventRecord( ev_out[j], s_out );
 			}
 		}
 	}
 	if ( cudaStreamSynchronize( s_out ) != cudaSuccess || cudaStreamSynchronize( s_in ) != cudaSuccess || cudaStreamSynchronize( st ) != cudaSuccess )
 		rc = fail( "b200_gemm: stream sync failed: %s", cudaGetErrorString( cudaGetLastError() ) );
+	if ( trace && rc == kSuccess )
+	{
+		auto ms = [&]( cudaEvent_t e ) { float t = 0.f; cudaEventElapsedTime( &t, ev_alloc, e ); return t; };
+		fprintf( stderr, "gemm_host_kpipe %lld x %lld x %lld: panels in at", (long long)m, (long long)n, (long long)k );
+		for ( int p = 0; p < np; ++p ) fprintf( stderr, " %.1f", ms( ev_p[p] ) );
+		fprintf( stderr, " | C staged at" );
+		for ( int j = 0; j < nblk; ++j ) fprintf( stderr, " %.1f", ms( ev_c[j] ) );
+		fprintf( stderr, " | rounds done at" );
+		for ( int p = 0; p < np - tail_p; ++p ) fprintf( stderr, " %.1f", ms( ev_k[p] ) );
+		fprintf( stderr, " | last round blocks done at" );
+		for ( int j = 0; j < nblk; ++j ) fprintf( stderr, " %.1f", ms( ev_done[j] ) );
+		fprintf( stderr, " | blocks home at" );
+		for ( int j = 0; j < nblk; ++j ) fprintf( stderr, " %.1f", ms( ev_out[j] ) );
+		fprintf( stderr, " ms\n" );
+	}
 	for ( auto& e : ev ) cudaEventDestroy( e );
+	for ( auto& e : ev_k ) cudaEventDestroy( e );
+	for ( auto& e : ev_out ) cudaEventDestroy( e );
 	dev_free( da, st ); dev_free( db, st ); dev_free( dc, st ); dev_free( ds, st );
 	return rc;
 }

@@ -26,5 +26,9 @@ if dm:
     lo, hi2 = min(dm), max(dm)
     pre = sum(n for n, k, r in agg if k < lo); mid = sum(n for n, k, r in agg if lo <= k <= hi2); post = sum(n for n, k, r in agg if k > hi2)
     print(f"samples before first DMMA {100*pre/tot:.1f}%  within DMMA span {100*mid/tot:.1f}%  after last DMMA {100*post/tot:.1f}%")
+    print("--- top instructions AFTER the last DMMA (epilogue / fix-up)")
+    for n, k, r in sorted([a for a in agg if a[1] > hi2], reverse=True)[:30]:
+        print(f"{100*n/tot:6.2f}%  #{k:5d}  {r[ci['Source']].strip()[:110]}")
+    print("--- top instructions overall")
 for n, k, r in sorted(agg, reverse=True)[:top]:
     print(f"{100*n/tot:6.2f}%  #{k:5d}  {r[ci['Source']].strip()[:110]}")
