@@ -154,9 +154,10 @@ static int trsm_rec( const TrsmPlan<T>& p, int64_t i0, int64_t mb, T alpha )
 //     independent): block 0 goes up first and is solved while A streams in; block j+1 goes up and block j-1 comes down
 //     (d2h stream) under the solve of block j.  Every block repeats the latency-bound diagonal panels (5.8 ms at T1), so
 //     there are only a few blocks (trsm_host_pipe = their maximal number; one for tall systems).
-//   * X goes home in ROW chunks: the rows of a finished sub-solve are final (trsm_rec tells, quarters of m), so only the
-//     last quarter's download is exposed.
-// [B200] T1 through dtrsm_: 417 ms (sequential) -> 301 ms = 29.2 TFLOP/s end to end (kernels alone: 251 ms).
+//   * X goes home in ROW chunks: the rows of a finished sub-solve are final (trsm_rec tells, eighths of m), so only the
+//     last eighth's download is exposed.
+// [B200] T1 through dtrsm_: 417 ms (sequential) -> 298 ms = 29.5 TFLOP/s end to end (kernels alone: 251 ms).  What is left is
+// structural: the top-level update needs all of B and three quarters of A (99 ms of PCIe time) after a quarter of the flops.
 struct TrsmPiece { int64_t r0, r1, c0, c1; int launches; };      // rows x columns of the effective view; launches of the solve that read it
 // The pieces in the order trsm_rec reads them (pure index arithmetic; b200_trsm_upload_plan exposes it to the CPU tests):
 // the split is trsm_rec's own; a diagonal block of at most max(leaf_rows, 1024) rows travels as one square and serves all
@@ -256,8 +257,8 @@ static int trsm_host_pipeline( int64_t m, int64_t n, T al, const T* a, int64_t r
 		size_t next = 0;
 		TrsmPlan<T> p{ adev, rs_ad, cs_ad, (T*)db + j0 * m, 1, m, w, upper, unit, conj, st };
 		if ( a_host && j == 0 ) { p.a_ready = &ev_a; p.a_next = &next; }     // later blocks run after block 0: all of A is there
-		// rows of X go home as soon as their sub-solve is done (quarters of the block), under the rest of the solve
-		p.notify_rows = std::max<int64_t>( 1024, ( m / 4 + 255 ) / 256 * 256 );
+		// rows of X go home as soon as their sub-solve is done (eighths of the block), under the rest of the solve
+		p.notify_rows = std::max<int64_t>( 1024, ( m / 8 + 255 ) / 256 * 256 );
 		p.on_final = [&]( int64_t i0, int64_t mb )
 		{
 			if ( rc != kSuccess ) return;
