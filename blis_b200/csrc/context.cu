@@ -195,7 +195,7 @@ static void copy_lines( char* dst, size_t dpitch, const char* src, size_t spitch
 	const size_t total = len * lines;
 	unsigned nthr = 1;
 	if ( total >= ( (size_t)8 << 20 ) )
-		nthr = std::min<unsigned>( 8, std::max<unsigned>( 1, std::thread::hardware_concurrency() ) );
+		nthr = std::min<unsigned>( 12, std::max<unsigned>( 1, std::thread::hardware_concurrency() ) );
 	auto work = [=]( size_t l0, size_t l1 )
 	{
 		if ( dpitch == len && spitch == len ) { memcpy( dst + l0 * len, src + l0 * len, ( l1 - l0 ) * len ); return; }
@@ -258,30 +258,48 @@ static int stage_xfer( void* dev, void* host, int64_t m, int64_t n, int64_t rs, 
 		return fail( "stage: one column (%zu bytes) exceeds the staging buffer", colb );
 	const int64_t cols_per = std::max<int64_t>( 1, (int64_t)( Context::kStageBytes / colb ) );
 	int buf = 0;
-	for ( int64_t j0 = 0; j0 < n; j0 += cols_per, buf ^= 1 )
+	if ( !to_host )
 	{
-		const int64_t j1 = std::min( n, j0 + cols_per );
-		char* pin = (char*)c.stage[buf];
-		char* d   = (char*)dev + (size_t)j0 * (size_t)ldd * es;
-		const size_t dpitch = (size_t)ldd * es;        // == colb for a dense image
-		B200_CUDA( cudaEventSynchronize( c.stage_free[buf] ) );
-		if ( !to_host )
+		for ( int64_t j0 = 0; j0 < n; j0 += cols_per, buf ^= 1 )
 		{
+			const int64_t j1 = std::min( n, j0 + cols_per );
+			char* pin = (char*)c.stage[buf];
+			char* d   = (char*)dev + (size_t)j0 * (size_t)ldd * es;
+			const size_t dpitch = (size_t)ldd * es;        // == colb for a dense image
+			B200_CUDA( cudaEventSynchronize( c.stage_free[buf] ) );
 			if ( col_lines ) copy_lines( pin, colb, (const char*)host + (size_t)j0 * cs * es, (size_t)cs * es, colb, (size_t)( j1 - j0 ) );
 			else             gather_elems( pin, (const char*)host, m, j0, j1, rs, cs, es, false );
 			if ( dpitch == colb ) B200_CUDA( cudaMemcpyAsync( d, pin, colb * ( j1 - j0 ), cudaMemcpyHostToDevice, st ) );
 			else                  B200_CUDA( cudaMemcpy2DAsync( d, dpitch, pin, colb, colb, (size_t)( j1 - j0 ), cudaMemcpyHostToDevice, st ) );
 			B200_CUDA( cudaEventRecord( c.stage_free[buf], st ) );
 		}
-		else
-		{
-			if ( dpitch == colb ) B200_CUDA( cudaMemcpyAsync( pin, d, colb * ( j1 - j0 ), cudaMemcpyDeviceToHost, st ) );
-			else                  B200_CUDA( cudaMemcpy2DAsync( pin, colb, d, dpitch, colb, (size_t)( j1 - j0 ), cudaMemcpyDeviceToHost, st ) );
-			B200_CUDA( cudaStreamSynchronize( st ) );
-			if ( col_lines ) copy_lines( (char*)host + (size_t)j0 * cs * es, (size_t)cs * es, pin, colb, colb, (size_t)( j1 - j0 ) );
-			else             gather_elems( (char*)host, pin, m, j0, j1, rs, cs, es, true );
-		}
+		return kSuccess;
 	}
+	// device -> host, double buffered: the DMA of chunk i runs while the host threads unpack chunk i-1 (the first version
+	// waited for every chunk before unpacking it: DMA and unpacking took turns)
+	auto unpack = [&]( int b, int64_t j0, int64_t j1 ) -> int
+	{
+		B200_CUDA( cudaEventSynchronize( c.stage_free[b] ) );
+		const char* pin = (const char*)c.stage[b];
+		if ( col_lines ) copy_lines( (char*)host + (size_t)j0 * cs * es, (size_t)cs * es, pin, colb, colb, (size_t)( j1 - j0 ) );
+		else             gather_elems( (char*)host, pin, m, j0, j1, rs, cs, es, true );
+		return kSuccess;
+	};
+	int64_t prev0 = -1, prev1 = -1;
+	for ( int64_t j0 = 0; j0 < n; j0 += cols_per, buf ^= 1 )
+	{
+		const int64_t j1 = std::min( n, j0 + cols_per );
+		char* pin = (char*)c.stage[buf];
+		char* d   = (char*)dev + (size_t)j0 * (size_t)ldd * es;
+		const size_t dpitch = (size_t)ldd * es;
+		B200_CUDA( cudaEventSynchronize( c.stage_free[buf] ) );          // (an earlier upload from this buffer)
+		if ( dpitch == colb ) B200_CUDA( cudaMemcpyAsync( pin, d, colb * ( j1 - j0 ), cudaMemcpyDeviceToHost, st ) );
+		else                  B200_CUDA( cudaMemcpy2DAsync( pin, colb, d, dpitch, colb, (size_t)( j1 - j0 ), cudaMemcpyDeviceToHost, st ) );
+		B200_CUDA( cudaEventRecord( c.stage_free[buf], st ) );
+		if ( prev0 >= 0 && unpack( buf ^ 1, prev0, prev1 ) != kSuccess ) return kFailure;
+		prev0 = j0; prev1 = j1;
+	}
+	if ( prev0 >= 0 && unpack( buf ^ 1, prev0, prev1 ) != kSuccess ) return kFailure;
 	return kSuccess;
 }
 

@@ -265,8 +265,14 @@ static int gemm_host_kpipe( bool conja, bool conjb, int64_t m, int64_t n, int64_
 					note_launch( "add_scaled_kernel" );
 				}
 				cudaEventRecord( ev_done[j], st );
+			}
+			// the blocks go home in a second pass: for a pageable C stage_to_host blocks this thread (it unpacks the pinned
+			// ring), and every kernel of the final phase has to be queued before that starts
+			for ( int j = 0; j < nblk && rc == kSuccess; ++j )
+			{
+				const int64_t j0 = pn[j], w = pn[j + 1] - j0;
 				cudaStreamWaitEvent( s_out, ev_done[j], 0 );
-				if ( rc == kSuccess ) rc = stage_to_host( c + j0 * cs_c, rs_c, cs_c, (T*)dc + j0 * m, m, w, ES, s_out );
+				rc = stage_to_host( c + j0 * cs_c, rs_c, cs_c, (T*)dc + j0 * m, m, w, ES, s_out );
 				if ( trace ) cudaEventRecord( ev_out[j], s_out );
 			}
 		}

@@ -237,13 +237,14 @@ def test_gemm_host_operands_pipelined_blocks(engine, pin):
         assert rel_err(to_numpy(tc_), want) <= TOL["d"], (pin, beta, "k panels")
 
 
+@pytest.mark.parametrize("kdim", [8200 + 40, 8192])
 @pytest.mark.parametrize("pin", [False, True])
-def test_gemm_host_operands_k_panel_pipeline(engine, pin):
+def test_gemm_host_operands_k_panel_pipeline(engine, pin, kdim):
     """Long k with host operands: the engine accumulates over k panels (A and B move panel by panel, the host C is staged
     separately and merged in the last round, finished column blocks leave under the next block's kernels).  Ragged last
     panel and last column block, transposed A, beta != 0 and beta == 0, pageable and pinned memory; same result with the
     k-panel pipeline switched off (column-block pipeline)."""
-    m, n, k = 1800, 4100 + 28, 8200 + 40
+    m, n, k = 1800, 4100 + 28, kdim             # 8240: ragged last panel, the final phase takes one panel; 8192: the last two, as one k-panel launch
     rng = np.random.default_rng(5)
     a = np.asfortranarray(rng.uniform(-1, 1, (k, m))); b = np.asfortranarray(rng.uniform(-1, 1, (k, n)))
     ab = torch.from_numpy(a).t() @ torch.from_numpy(b)
@@ -265,7 +266,16 @@ def test_gemm_host_operands_k_panel_pipeline(engine, pin):
             outs.append(to_numpy(tc_))
             assert rel_err(outs[-1], want) <= 4 * TOL["d"], (pin, beta, kpipe)
             if kpipe:
-                assert launches == (7 + 7 + (7 if beta != 0.0 else 0)), ("k-panel pipeline: 7 full rounds + 7 column blocks (+ 7 merges of C)", launches)
+                # the schedule of gemm_host_kpipe (host_gemm.cuh): k in eighths rounded to 128, the first one cut at a quarter; the
+                # final phase covers the last two panels when they are equally wide; 7 column blocks of n
+                kb = max(512, -(-(-(-k // 8)) // 128) * 128)
+                pk = [0] + ([kb // 4 // 128 * 128] if kb >= 1024 and kb // 4 // 128 * 128 >= 256 else [])
+                while pk[-1] < k:
+                    pk.append(min(k, pk[-1] + kb - (pk[-1] if len(pk) == 2 and pk[-1] < kb else 0)))
+                npan = len(pk) - 1
+                tail = 2 if npan >= 3 and pk[-1] - pk[-2] == pk[-2] - pk[-3] else 1
+                assert (npan, tail) == ((9, 1) if k == 8240 else (9, 2))
+                assert launches == (npan - tail) + 7 + (7 if beta != 0.0 else 0), ("k-panel pipeline: full rounds + 7 column blocks (+ 7 merges of C)", launches)
 
 
 @pytest.mark.parametrize("ch", ["d", "z"])
