@@ -317,8 +317,18 @@ static int gemm_front( int transa, int transb, int64_t m, int64_t n, int64_t k,
 
 	if ( transa & B200_TRANSPOSE ) std::swap( rs_a, cs_a );
 	if ( transb & B200_TRANSPOSE ) std::swap( rs_b, cs_b );
-	const bool conja = Elem<T>::cplx && ( transa & B200_CONJ_NO_TRANSPOSE );
-	const bool conjb = Elem<T>::cplx && ( transb & B200_CONJ_NO_TRANSPOSE );
+	bool conja = Elem<T>::cplx && ( transa & B200_CONJ_NO_TRANSPOSE );
+	bool conjb = Elem<T>::cplx && ( transb & B200_CONJ_NO_TRANSPOSE );
+	// A ROW-stored host C (a row-major caller): everything below -- staging, column-block and k-panel pipelines -- moves
+	// columns, and a row-stored host matrix would crawl through the element-wise gather.  Solve the transposed problem
+	// instead, C^T = op(B)^T op(A)^T: its C is column-stored, and for a row-major caller so are its A and B.
+	if ( tri_operand == 0 && cs_c == 1 && rs_c != 1 && m > 1 && classify( c ) != MemKind::Device )
+	{
+		std::swap( m, n ); std::swap( a, b ); std::swap( conja, conjb );
+		const int64_t ra = rs_a, ca = cs_a;
+		rs_a = cs_b; cs_a = rs_b; rs_b = ca; cs_b = ra;
+		std::swap( rs_c, cs_c );
+	}
 	const T al = *alpha, be = *beta;
 	const bool need_ab = ( k > 0 && !Scalar<T>::is_zero( al ) );
 

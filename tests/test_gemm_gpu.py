@@ -235,6 +235,15 @@ def test_gemm_host_operands_pipelined_blocks(engine, pin):
             tc_.fill_(float("nan"))
         engine.bli_dgemm(TRANSPOSE, 0, m, n, k, 2.0, ta_, *estr(a), tb_, *estr(b), beta, tc_, *estr(c))
         assert rel_err(to_numpy(tc_), want) <= TOL["d"], (pin, beta, "k panels")
+    # a row-major caller (A, B, C row-stored): the engine solves the transposed problem, whose operands are column-stored,
+    # so the same pipelines serve it (m = 1300 becomes the pipelined dimension); complex with a conjugated operand too
+    m, n, k = 1300, 700, 2100
+    for ch, ta, al, be in (("d", NO_TRANSPOSE, 2.0, 1.2), ("z", CONJ_NO_TRANSPOSE, 2.0 + 0.2j, 1.2 + 0.5j)):
+        a = gen.matrix(ch, m, k, 77, "frac", "r", pad=1); b = gen.matrix(ch, k, n, 78, "frac", "r"); c = gen.matrix(ch, m, n, 79, "frac", "r", pad=2)
+        want = be * c + al * ((a.conj() if ta == CONJ_NO_TRANSPOSE else a) @ b)
+        ta_, tb_, tc_ = (to_torch(x, "cpu", pin=pin) for x in (a, b, c))
+        getattr(engine, GEMM[ch])(ta, 0, m, n, k, al, ta_, *estr(a), tb_, *estr(b), be, tc_, *estr(c))
+        assert rel_err(to_numpy(tc_), want) <= TOL[ch] * 4, (pin, ch, "row-major caller")
 
 
 @pytest.mark.parametrize("kdim", [8200 + 40, 8192])
