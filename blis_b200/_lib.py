@@ -22,7 +22,7 @@ BLIS_SUCCESS, BLIS_FAILURE = -1, -2
 # every symbol include/blis_b200.h declares
 EXPORTS = [
     "b200_init", "b200_finalize", "b200_last_error", "b200_device_count", "b200_info",
-    "b200_set_stream", "b200_get_stream", "b200_sync", "b200_malloc_pinned", "b200_free_pinned",
+    "b200_set_stream", "b200_get_stream", "b200_sync", "b200_malloc_pinned", "b200_free_pinned", "b200_pointer_kind",
     "b200_gemm", "b200_gemm_kpanels", "b200_sgemm", "b200_dgemm", "b200_cgemm", "b200_zgemm",
     "b200_trsm", "b200_strsm", "b200_dtrsm", "b200_ctrsm", "b200_ztrsm",
     "b200_gemmt", "b200_syrk", "b200_herk", "b200_syr2k", "b200_her2k",

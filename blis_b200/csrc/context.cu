@@ -401,6 +401,17 @@ extern "C" void* b200_malloc_pinned( size_t size )
 }
 extern "C" void b200_free_pinned( void* p ) { if ( p ) cudaFreeHost( p ); }
 
+extern "C" int b200_pointer_kind( const void* p )
+{
+	if ( ensure_init() != kSuccess ) return -1;
+	switch ( classify( p ) )
+	{
+		case MemKind::Device:     return 0;
+		case MemKind::HostPinned: return 1;
+		default:                  return 2;
+	}
+}
+
 extern "C" int b200_device_count( void )
 {
 	int n = 0;

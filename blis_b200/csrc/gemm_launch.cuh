@@ -60,7 +60,7 @@ static int launch_dmma_ws( const GemmArgs<T>& g, bool xk, bool yk, bool al, int 
 		using Cfg = DmmaWsCfg<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL>;
 		auto kern = gemm_dmma_ws_kernel<T, BP, BQ, BK, WP, WQ, ST, XK, YK, AL, TRI>;
 		static const std::string kname = kfmt( "gemm_dmma_ws_kernel<%s,%dx%dx%d,%dst,XK=%d,YK=%d,AL=%d,TRI=%d>", tname<T>(), BP, BQ, BK, ST, XK, YK, AL, TRI );
-		static bool attr = false;
+		static std::atomic<bool> attr{ false };
 		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, Cfg::NT_ALL, Cfg::SMEM_BYTES, st>>>( g );
 		B200_CUDA( cudaGetLastError() );
@@ -207,7 +207,7 @@ static int launch_dmma_tma( const GemmArgs<double>& g_in, bool xk, bool yk, int 
 		using KCfg = typename std::conditional<CST, DmmaTmaCfgCst, DmmaTmaCfg>::type;
 		static const std::string kname = SK ? kfmt( "gemm_dmma_tma_kernel<XK=%d,YK=%d,TRI=%d,CST=%d,SK=1>", XK, YK, TRI, CST )
 		                                    : kfmt( "gemm_dmma_tma_kernel<XK=%d,YK=%d,TRI=%d,CST=%d>", XK, YK, TRI, CST );
-		static bool attr = false;
+		static std::atomic<bool> attr{ false };
 		if ( !attr ) { if ( set_smem( kern, KCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, KCfg::NT_ALL, KCfg::SMEM_BYTES, st>>>( g, tmx, tmy, tmd );
 		B200_CUDA( cudaGetLastError() );
@@ -230,7 +230,7 @@ static int launch_dmma_pp( const GemmArgs<double>& g, bool xk, bool yk, int grid
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
 		auto kern = gemm_dmma_pp_kernel<XK, YK>;
 		static const std::string kname = kfmt( "gemm_dmma_pp_kernel<XK=%d,YK=%d>", XK, YK );
-		static bool attr = false;
+		static std::atomic<bool> attr{ false };
 		if ( !attr ) { if ( set_smem( kern, DmmaPpCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, DmmaPpCfg::NT_ALL, DmmaPpCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
 		B200_CUDA( cudaGetLastError() );
@@ -256,7 +256,7 @@ static int launch_ffma_tma( const GemmArgs<float>& g, bool xk, bool yk, int grid
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
 		auto kern = gemm_ffma_tma_kernel<XK, YK, TRI, CST>;
 		static const std::string kname = kfmt( "gemm_ffma_tma_kernel<XK=%d,YK=%d,TRI=%d,CST=%d>", XK, YK, TRI, CST );
-		static bool attr = false;
+		static std::atomic<bool> attr{ false };
 		if ( !attr ) { if ( set_smem( kern, FfmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, FfmaTmaCfg::NT_ALL, FfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy, tmd );
 		B200_CUDA( cudaGetLastError() );
@@ -281,7 +281,7 @@ static int launch_cfma_tma( const GemmArgs<float2>& g, bool xk, bool yk, int gri
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
 		auto kern = gemm_cfma_tma_kernel<XK, YK, TRI, CST>;
 		static const std::string kname = kfmt( "gemm_cfma_tma_kernel<XK=%d,YK=%d,TRI=%d,CST=%d>", XK, YK, TRI, CST );
-		static bool attr = false;
+		static std::atomic<bool> attr{ false };
 		if ( !attr ) { if ( set_smem( kern, CfmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		if ( !CST ) tmd = tmx;
 		kern<<<grid, CfmaTmaCfg::NT_ALL, CfmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy, tmd );
@@ -327,7 +327,7 @@ static int launch_zmma_tma( const GemmArgs<double2>& g, bool xk, bool yk, int gr
 		constexpr bool XK = decltype( XKc )::value, YK = decltype( YKc )::value;
 		auto kern = gemm_zmma_tma_kernel<XK, YK, TRI>;
 		static const std::string kname = kfmt( "gemm_zmma_tma_kernel<XK=%d,YK=%d,TRI=%d>", XK, YK, TRI );
-		static bool attr = false;
+		static std::atomic<bool> attr{ false };
 		if ( !attr ) { if ( set_smem( kern, ZmmaTmaCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, ZmmaTmaCfg::NT_ALL, ZmmaTmaCfg::SMEM_BYTES, st>>>( g, tmx, tmy );
 		B200_CUDA( cudaGetLastError() );
@@ -348,7 +348,7 @@ static int launch_ffma( const GemmArgs<T>& g, bool xk, bool yk, bool al, int gri
 		using Cfg = FfmaCfg<T, BP, BQ, BK, TP, TQ, ST>;
 		auto kern = gemm_ffma_kernel<T, BP, BQ, BK, TP, TQ, ST, XK, YK, AL>;
 		static const std::string kname = kfmt( "gemm_ffma_kernel<%s,%dx%dx%d,XK=%d,YK=%d,AL=%d>", tname<T>(), BP, BQ, BK, XK, YK, AL );
-		static bool attr = false;
+		static std::atomic<bool> attr{ false };
 		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>( g );
 		B200_CUDA( cudaGetLastError() );
@@ -375,7 +375,7 @@ static int launch_ffma_ws( const GemmArgs<T>& g, bool xk, bool yk, bool al, int 
 		using Cfg = FfmaWsCfg<T, BP, BQ, BK, TP, TQ, ST>;
 		auto kern = gemm_ffma_ws_kernel<T, BP, BQ, BK, TP, TQ, ST, XK, YK, AL>;
 		static const std::string kname = kfmt( "gemm_ffma_ws_kernel<%s,%dx%dx%d,XK=%d,YK=%d,AL=%d>", tname<T>(), BP, BQ, BK, XK, YK, AL );
-		static bool attr = false;
+		static std::atomic<bool> attr{ false };
 		if ( !attr ) { if ( set_smem( kern, Cfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<grid, Cfg::NT_ALL, Cfg::SMEM_BYTES, st>>>( g );
 		B200_CUDA( cudaGetLastError() );

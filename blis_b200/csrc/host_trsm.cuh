@@ -48,7 +48,7 @@ static int trsm_base( const TrsmPlan<T>& p, int64_t i0, int mb, T alpha )
 	constexpr int NT = 256;
 	auto kern = trsm_base_kernel<T, NB, CN, NT>;
 	constexpr int smem = trsm_base_smem<T, NB, CN>();
-	static bool attr = false;
+	static std::atomic<bool> attr{ false };
 	if ( !attr ) { if ( set_smem( kern, smem ) != kSuccess ) return kFailure; attr = true; }
 	const int64_t grid = ( p.n + CN - 1 ) / CN;
 	kern<<<(unsigned)grid, NT, smem, p.st>>>( a );
@@ -72,7 +72,7 @@ static int trsm_panel( const TrsmPlan<double>& p, int64_t i0, int mb, double alp
 		constexpr bool U = decltype( Uc )::value, AI = decltype( Ac )::value, BK = decltype( Bc )::value;
 		auto kern = trsm_panel_kernel<U, AI, BK>;
 		static const std::string kname = kfmt( "trsm_panel_kernel<double,256x64,UPPER=%d,AI=%d,BK=%d>", U, AI, BK );
-		static bool attr = false;
+		static std::atomic<bool> attr{ false };
 		if ( !attr ) { if ( set_smem( kern, TrsmPanelCfg::SMEM_BYTES ) != kSuccess ) return kFailure; attr = true; }
 		kern<<<(unsigned)grid, TrsmPanelCfg::NT, TrsmPanelCfg::SMEM_BYTES, p.st>>>( a );
 		B200_CUDA( cudaGetLastError() );

@@ -96,6 +96,13 @@ b200_err_t  b200_sync( void );
  * config/b200 (docs/ConfigurationHowTo.md:195-207), signature void* f(size_t). */
 void*       b200_malloc_pinned( size_t size );
 void        b200_free_pinned( void* p );
+/* Where the engine will find an operand: 0 device (or managed) memory, used in
+ * place; 1 page-locked host memory (b200_malloc_pinned, bli_obj_create under
+ * config/b200, cudaHostRegister), copied by the DMA engines directly; 2 pageable
+ * host memory, copied through the engine's pinned staging ring.  This is the
+ * per-call classification every entry point applies to its operand pointers;
+ * -1 if no device is usable. */
+int         b200_pointer_kind( const void* p );
 
 /* ---- gemm ------------------------------------------------------------------
  * C := beta*C + alpha*transa(A)*transb(B),  C is m x n, k is the inner dim.

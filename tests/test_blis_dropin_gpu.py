@@ -219,3 +219,46 @@ def test_netlib_blat3_on_the_plugin(ch):
     env = dict(os.environ, LD_PRELOAD=str(GLUE), BLIS_B200_PLUGIN="1", BLIS_B200_VERBOSE="1")
     r, text = _run_blat3(BLAT_REF, ch, env)
     _check_blat3(ch, r, text, "plugin")
+
+
+_OBJ_BUFFER_SCRIPT = r"""
+import ctypes as C, json, sys
+import numpy as np
+blis = C.CDLL(sys.argv[1], mode=C.RTLD_GLOBAL)          # pulls in libblis_b200.so through its RUNPATH
+blis.bli_init()
+blis.bli_arch_string.restype = C.c_char_p; blis.bli_arch_query_id.restype = C.c_int
+blis.bli_malloc_user.restype = C.c_void_p; blis.bli_malloc_user.argtypes = [C.c_size_t, C.POINTER(C.c_int)]
+blis.bli_free_user.argtypes = [C.c_void_p]
+blis.b200_pointer_kind.argtypes = [C.c_void_p]; blis.b200_launch_count.restype = C.c_uint64
+n = 512; err = C.c_int(0)
+ptrs = [blis.bli_malloc_user(8 * n * n, C.byref(err)) for _ in range(3)]
+kinds = [blis.b200_pointer_kind(p) for p in ptrs]
+a, b, c = (np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n * n,)).reshape(n, n, order="F") for p in ptrs)
+rng = np.random.default_rng(7)
+a[:] = rng.integers(-3, 4, (n, n)); b[:] = rng.integers(-3, 4, (n, n)); c[:] = rng.integers(-3, 4, (n, n))
+want = 2.0 * (a @ b) + 3.0 * c                           # small integers: exact in fp64 whatever the summation order
+l0 = blis.b200_launch_count()
+i = C.c_int(n); al = C.c_double(2.0); be = C.c_double(3.0)
+blis.dgemm_(b"N", b"N", C.byref(i), C.byref(i), C.byref(i), C.byref(al), C.c_void_p(ptrs[0]), C.byref(i), C.c_void_p(ptrs[1]), C.byref(i),
+            C.byref(be), C.c_void_p(ptrs[2]), C.byref(i))
+heap = np.zeros(16); pageable = blis.b200_pointer_kind(heap.ctypes.data)
+out = dict(arch=blis.bli_arch_string(blis.bli_arch_query_id()).decode(), kinds=kinds, pageable=pageable, exact=bool((c == want).all()),
+           launches=int(blis.b200_launch_count() - l0))
+for p in ptrs: blis.bli_free_user(p)
+print(json.dumps(out))
+"""
+
+
+def test_config_b200_obj_buffers_are_page_locked():
+    """SURVEY 8f rank 4 / 8b "memory-allocation hooks": under config/b200, BLIS_MALLOC_USER is b200_malloc_pinned
+    (config/b200/bli_family_b200.h), so what bli_obj_create hands out (bli_malloc_user, frame/base/bli_obj.c:190;
+    frame/base/bli_malloc.c) is page-locked and the engine's copies take the direct-DMA path: b200_pointer_kind says 1
+    for such a buffer (2 for ordinary heap memory), and dgemm_ on them is served by the engine, exactly."""
+    _need(REFDIR / "libblis_b200cfg.so")
+    env = dict(os.environ); env.pop("LD_PRELOAD", None)
+    r = subprocess.run([sys.executable, "-c", _OBJ_BUFFER_SCRIPT, str(REFDIR / "libblis_b200cfg.so")], capture_output=True, text=True,
+                       timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["arch"] == "b200" and out["kinds"] == [1, 1, 1] and out["pageable"] == 2, out
+    assert out["exact"] and out["launches"] >= 1, out
