@@ -30,7 +30,7 @@ EXPORTS = [
     "b200_partition_2x2", "b200_range_sub", "b200_dist_plan", "b200_dist_unique_id", "b200_dist_init", "b200_dist_finalize",
     "b200_dist_gemm", "b200_dist_last_wait_ms", "b200_dist_register", "b200_dist_unregister", "b200_dist_transport", "b200_dist_gemm_1d", "b200_dist_trsm",
     "b200_blksz", "b200_measure_peak", "b200_launch_count", "b200_set_option", "b200_last_kernel", "b200_kernel_stats",
-    "b200_splitk_plan", "b200_trsm_upload_plan",
+    "b200_splitk_plan", "b200_trsm_upload_plan", "b200_trsm_rowblock_plan",
 ]
 
 class DistPlan(C.Structure):

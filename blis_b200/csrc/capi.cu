@@ -234,6 +234,19 @@ extern "C" b200_err_t b200_gemm_kpanels( int dt, int transa, int transb, b200_di
 	return fail( "b200_gemm_kpanels: only d and z are supported" );
 }
 
+extern "C" int b200_trsm_rowblock_plan( b200_dim_t m, b200_dim_t n, int leaf_rows, int upper, b200_dim_t rb, b200_dim_t* out, int cap )
+{
+	std::vector<TrsmPiece> plan;
+	TrsmRowSched sched;
+	if ( m <= 0 || leaf_rows <= 0 || !trsm_row_sched( m, n, leaf_rows, rb, sched ) ) return 0;      // 0: the column-block pipeline serves this shape
+	trsm_rowblock_plan( leaf_rows, upper != 0, m, sched, plan );
+	for ( size_t i = 0; i < plan.size() && (int)i < cap && out; ++i )
+	{
+		out[5 * i] = plan[i].r0; out[5 * i + 1] = plan[i].r1; out[5 * i + 2] = plan[i].c0; out[5 * i + 3] = plan[i].c1; out[5 * i + 4] = plan[i].launches;
+	}
+	return (int)plan.size();
+}
+
 extern "C" int b200_trsm_upload_plan( b200_dim_t m, int leaf_rows, int upper, b200_dim_t* out, int cap )
 {
 	std::vector<TrsmPiece> plan;
@@ -333,6 +346,9 @@ extern "C" b200_err_t b200_set_option( const char* key, long long value )
 	else if ( !strcmp( key, "dmma_pp" ) ) c.dmma_pp = (int)value;
 	else if ( !strcmp( key, "dgemm_splitk" ) ) c.dgemm_splitk = (int)value;
 	else if ( !strcmp( key, "trsm_host_pipe" ) ) c.trsm_host_pipe = (int)value;
+	else if ( !strcmp( key, "trsm_host_rb" ) ) c.trsm_host_rb = value;
+	else if ( !strcmp( key, "trsm_host_rb_min_m" ) ) c.trsm_host_rb_min_m = std::max<long long>( 0, value );
+	else if ( !strcmp( key, "trsm_host_rb_div" ) ) c.trsm_host_rb_div = std::max<long long>( 2, value );
 	else if ( !strcmp( key, "batch_grouped" ) ) c.batch_grouped = (int)value;
 	else if ( !strcmp( key, "batch_grouped_max" ) ) c.batch_grouped_max = std::max<long long>( 0, value );
 	else if ( !strcmp( key, "trsm_fused" ) ) c.trsm_fused = (int)value;

@@ -77,7 +77,7 @@ extern "C" int b200_set_option( const char* key, long long value );
 static void apply_env_options()
 {
 	static const char* keys[] = { "dgemm_cfg", "zgemm_cfg", "sgemm_cfg", "cgemm_cfg", "grid_mult", "dynamic_tiles", "transpose_y", "ktri_skip",
-	                              "host_kpipe", "host_trace", "dmma_cst", "dmma_pp", "dgemm_splitk", "trsm_host_pipe", "batch_grouped", "batch_grouped_max", "trsm_fused", "dist_ab_static", "tma_l2_promotion", "raster_group", "reserve_sms" };
+	                              "host_kpipe", "host_trace", "dmma_cst", "dmma_pp", "dgemm_splitk", "trsm_host_pipe", "trsm_host_rb", "trsm_host_rb_min_m", "trsm_host_rb_div", "batch_grouped", "batch_grouped_max", "trsm_fused", "dist_ab_static", "tma_l2_promotion", "raster_group", "reserve_sms" };
 	for ( const char* k : keys )
 	{
 		char name[64] = "BLIS_B200_"; size_t n = strlen( name );

@@ -71,7 +71,10 @@ struct Context
 	int          dgemm_splitk = 1;      // dgemm TMA kernel: cut the tiles of a partial last wave into k chunks (mid-size problems; 0 = never split k)
 	int          batch_grouped = 1;     // b200_gemm_batch: small device-resident problems share ONE launch (gemm_grouped.cuh); 0 = a launch each on the stream pool
 	long long    batch_grouped_max = 128ll * 128 * 128;   // ... "small" = m*n*k at most this
-	int          trsm_host_pipe = 3;    // trsm with pinned host operands: A streams in the solve's own order, B in at most this many column blocks, X leaves block by block (0 = sequential transfers)
+	int          trsm_host_pipe = 1;    // trsm with pinned host operands: transfers run under the solve (row-block pipeline, host_trsm.cuh); 0 = sequential transfers
+	long long    trsm_host_rb = 0;      // its rows per block (0 = the engine's choice: m / trsm_host_rb_div in whole 256 rows for m >= trsm_host_rb_min_m; -1 = sequential transfers)
+	long long    trsm_host_rb_div = 32;
+	long long    trsm_host_rb_min_m = 4096;
 	int          host_trace = 0;        // print the event timeline of pipelined host-operand calls to stderr (diagnostic)
 	int          host_kpipe = 1;        // host operands with long k: pipeline over k panels instead of column blocks
 	int          ktri_skip = 1;         // trmm/trmm3: tiles skip the k range in which the triangular operand is zero

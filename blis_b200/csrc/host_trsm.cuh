@@ -22,12 +22,12 @@ struct TrsmPlan
 	int64_t  n;
 	bool     upper, unit, conj;
 	cudaStream_t st;
-	// A arriving from the host while the solve runs (trsm_host_pipe): one event per launch of the recursion, in the
-	// recursion's own order (trsm_upload builds the list); nullptr: A is resident
+	// A arriving from the host while the solve runs (trsm_host_rowpipe): one event per launch of the recursion, in the
+	// recursion's own order; nullptr: A is resident
 	const std::vector<cudaEvent_t>* a_ready = nullptr;
 	size_t*  a_next = nullptr;
 	// rows [i0, i0+mb) of X are final when their sub-solve returns: told once per subtree of at most notify_rows rows
-	// (trsm_host_pipeline sends them home while the rest of the solve runs); empty: nobody listens
+	// (trsm_host_rowpipe sends them home while the rest of the solve runs); empty: nobody listens
 	std::function<void( int64_t, int64_t )> on_final;
 	int64_t  notify_rows = 0;
 };
@@ -142,22 +142,13 @@ static int trsm_rec( const TrsmPlan<T>& p, int64_t i0, int64_t mb, T alpha )
 
 // ---- host operands: pipeline ------------------------------------------------------------------------------------
 // A triangular solve with everything in host memory moves 8(m^2/2 + 2mn) bytes over PCIe; done in sequence (upload B,
-// upload A, solve, download X) none of it overlaps the kernels: T1 through the reference's dtrsm_ took 417 ms for 253 ms
-// of kernels.  Two things make the transfers disappear behind the solve:
-//   * A travels IN THE ORDER THE RECURSION READS IT.  trsm_rec touches A11 (recursively), then the block A21 (lower) /
-//     A12 (upper) of the update, then A22 -- and spends its time in the same proportion (a quarter, a half, a quarter of
-//     the flops for a quarter, a half, a quarter of the triangle's bytes).  trsm_upload_plan walks the same tree, uploads
-//     each diagonal block (<= 1024 rows, as a square) and each update block as one 2-D copy on the copy stream and records
-//     one event PER LAUNCH of the solve's recursion, in its order; trsm_rec waits for the next event before every launch.
-//     Only the stored triangle (plus the unstored half of the small diagonal squares, ~1.5 %) travels.
-//   * B travels in column blocks (the reference's own parallel dimension, bli_trsm_cntl.c:446-451: columns are
-//     independent): block 0 goes up first and is solved while A streams in; block j+1 goes up and block j-1 comes down
-//     (d2h stream) under the solve of block j.  Every block repeats the latency-bound diagonal panels (5.8 ms at T1), so
-//     there are only a few blocks (trsm_host_pipe = their maximal number; one for tall systems).
-//   * X goes home in ROW chunks: the rows of a finished sub-solve are final (trsm_rec tells, eighths of m), so only the
-//     last eighth's download is exposed.
-// [B200] T1 through dtrsm_: 417 ms (sequential) -> 298 ms = 29.5 TFLOP/s end to end (kernels alone: 251 ms).  What is left is
-// structural: the top-level update needs all of B and three quarters of A (99 ms of PCIe time) after a quarter of the flops.
+// upload A, solve, download X) none of it overlaps the kernels: T1 through the reference's dtrsm_ took 417 ms for 251 ms
+// of kernels.  trsm_host_rowpipe (below) hides the transfers behind the solve; its building blocks:
+//   * A travels IN THE ORDER THE SOLVE READS IT: trsm_upload_plan walks trsm_rec's own tree over a diagonal block, uploads
+//     each diagonal square (<= 1024 rows) and each update block A21 (lower) / A12 (upper) as one 2-D copy on the copy
+//     stream and one event PER LAUNCH of the recursion is recorded, in its order; trsm_rec waits for the next event before
+//     every launch.  Only the stored triangle (plus the unstored half of the small diagonal squares, ~1.5 %) travels.
+//   * X goes home in ROW chunks: the rows of a finished sub-solve are final (trsm_rec tells through on_final).
 struct TrsmPiece { int64_t r0, r1, c0, c1; int launches; };      // rows x columns of the effective view; launches of the solve that read it
 // The pieces in the order trsm_rec reads them (pure index arithmetic; b200_trsm_upload_plan exposes it to the CPU tests):
 // the split is trsm_rec's own; a diagonal block of at most max(leaf_rows, 1024) rows travels as one square and serves all
@@ -180,85 +171,147 @@ static void trsm_upload_plan( int leaf_rows, bool upper, int64_t i0, int64_t mb,
 		trsm_upload_plan( leaf_rows, upper, i0, m2, out );
 	}
 }
-template <typename T>
-static int trsm_upload( T* da, int64_t m, const T* a, int64_t rs_a, int64_t cs_a, bool upper, cudaStream_t s_in, std::vector<cudaEvent_t>& ev )
+// ---- host operands: row blocks (left-looking top level) ---------------------------------------------------------------
+// Run as one recursion over all m rows, the first big update reads ALL of B and three quarters of A after a quarter of the
+// flops, so B's upload (and A's big block) stands exposed before it (round 2's first pipeline: 298 ms for 251 ms of
+// kernels, with B in one to three column blocks).  Cutting the TOP level into row blocks of rb rows and running it left-looking (the lazy order: block row j first
+// receives all its updates in ONE gemm, B_j := alpha*B_j - A[j, 0:j] * X[0:j], then is solved by the recursion) makes every
+// byte's deadline proportional to the flops before it:
+//   * B travels in row blocks and B_j is not touched before step j,
+//   * A travels in row panels: A[j, 0:j] for the update, then the diagonal block in the recursion's own order
+//     (trsm_upload_plan of that block), one event per launch as before,
+//   * the rows of X_j are final after step j and go home under steps j+1.. (in quarters of a block, so that of the last block
+//     only a quarter is exposed).
+// Same flops, same kernels (the updates above the block size merge into one gemm per block row; below it the recursion is
+// unchanged); only the first block's B_0 and diagonal squares (and the cheap first steps, which compute less than the next
+// block's bytes take) stay exposed.  Upper triangular: the mirror image, block rows from the bottom up.
+// Rows per block: `opt` > 0 explicit (rounded up to whole leaves), 0 the engine's choice for this shape, < 0 none.
+// Returns false when the call is not cut into block rows (one block is no pipeline).
+// [B200] (tools/trsm_e2e_sweep.py, profiles/r02b_trsm_e2e_sweep.md) T1 end to end, kernels alone 250.5 ms:
+//   rb = 8192 / 4096 / 2048 / 1024 / 512  ->  272.9 / 263.5 / 259.4 / 256.7 / 256.1 ms   (round 2's column blocks: 296.8)
+// m = 16384 (n = 8192): best at 512 (69.8 ms; 256: 75.7, 1024: 70.8, column blocks 87.9); m = 8192: 256 and 512 alike (22.3);
+// m = 4096: 256 (10.0 ms; 512: 10.9, column blocks 11.8) -- so the engine takes m/32 in whole 256 rows.  Graded schedules
+// (small first blocks, large later ones) measured like the uniform schedule of their LARGE size, and the same top level
+// with everything resident on the device measured like the plain recursion (250.1-251.2 vs 250.8 ms; worse for narrow B:
+// its block-row gemms have too few tiles), so the device-resident solve keeps the recursion.
+struct TrsmRowSched { int64_t rb; };
+static bool trsm_row_sched( int64_t m, int64_t n, int leaf_rows, long long opt, TrsmRowSched& s )
 {
-	constexpr size_t ES = sizeof(T);
-	std::vector<TrsmPiece> plan;
-	trsm_upload_plan( trsm_leaf_rows<T>(), upper, 0, m, plan );
-	for ( const TrsmPiece& q : plan )
+	if ( opt < 0 ) return false;
+	const Context& c = ctx();
+	int64_t rb = opt;
+	if ( rb == 0 )
 	{
-		// the device image keeps the host's orientation (column- or row-stored)
-		int rc;
-		if ( rs_a == 1 ) rc = stage_block_to_device( da + q.r0 + q.c0 * m, m, a + q.r0 + q.c0 * cs_a, q.r1 - q.r0, q.c1 - q.c0, 1, cs_a, ES, s_in );
-		else             rc = stage_block_to_device( da + q.c0 + q.r0 * m, m, a + q.c0 + q.r0 * rs_a, q.c1 - q.c0, q.r1 - q.r0, 1, rs_a, ES, s_in );
-		if ( rc != kSuccess ) return rc;
-		cudaEvent_t e;
-		if ( cudaEventCreateWithFlags( &e, cudaEventDisableTiming ) != cudaSuccess ) return fail( "trsm: event creation failed" );
-		cudaEventRecord( e, s_in );
-		for ( int l = 0; l < q.launches; ++l ) ev.push_back( e );    // the same event serves every launch inside this piece
+		if ( m < c.trsm_host_rb_min_m || n < 1024 ) return false;
+		rb = std::max<int64_t>( 256, ( m / std::max<long long>( 2, c.trsm_host_rb_div ) + 255 ) / 256 * 256 );
 	}
-	return kSuccess;
+	s.rb = ( rb + leaf_rows - 1 ) / leaf_rows * leaf_rows;
+	return s.rb < m;
+}
+static void trsm_row_blocks( int64_t m, int leaf_rows, const TrsmRowSched& s, bool upper, std::vector<std::pair<int64_t, int64_t>>& blk )
+{
+	// boundaries are multiples of the leaf size (counted from row 0 for both triangles, so that the blocks stay aligned)
+	const int64_t mr = ( m + leaf_rows - 1 ) / leaf_rows * leaf_rows;
+	for ( int64_t cum = 0; cum < mr; )                                // in processing order: top down (lower), bottom up (upper)
+	{
+		int64_t sz = std::min( s.rb, mr - cum );
+		if ( mr - cum - sz < s.rb / 2 ) sz = mr - cum;                // no sliver at the end
+		if ( !upper ) blk.push_back( { cum, std::min( m, cum + sz ) } );
+		else          blk.push_back( { mr - cum - sz, std::min( m, mr - cum ) } );
+		cum += sz;
+	}
+}
+// What travels up, in the order of its deadlines (b200_trsm_rowblock_plan exposes it to the CPU tests): per block row the
+// rows of B (a piece with c0 = c1 = -1 that no launch waits for: the stream's order covers it), the block A[j, 0:j]
+// (A[j, j+1:] for upper) its update gemm reads, then the diagonal block's pieces in the recursion's order.
+static void trsm_rowblock_plan( int leaf_rows, bool upper, int64_t m, const TrsmRowSched& s, std::vector<TrsmPiece>& out )
+{
+	std::vector<std::pair<int64_t, int64_t>> blk;
+	trsm_row_blocks( m, leaf_rows, s, upper, blk );
+	for ( const auto& [r0, r1] : blk )
+	{
+		out.push_back( { r0, r1, -1, -1, 0 } );                             // B_j
+		if ( !upper && r0 > 0 ) out.push_back( { r0, r1, 0, r0, 1 } );      // A[j, 0:j] of the block row's update
+		if ( upper && r1 < m )  out.push_back( { r0, r1, r1, m, 1 } );
+		trsm_upload_plan( leaf_rows, upper, r0, r1 - r0, out );
+	}
 }
 
 // a: effective m x m view (host or device), b: m x n host, pinned, column-stored (rs_b == 1)
 template <typename T>
-static int trsm_host_pipeline( int64_t m, int64_t n, T al, const T* a, int64_t rs_a, int64_t cs_a, bool a_host, bool upper, bool unit, bool conj,
-                               T* b, int64_t cs_b, cudaStream_t st )
+static int trsm_host_rowpipe( int64_t m, int64_t n, T al, const T* a, int64_t rs_a, int64_t cs_a, bool a_host, bool upper, bool unit, bool conj,
+                              T* b, int64_t cs_b, const TrsmRowSched& sched, cudaStream_t st )
 {
 	constexpr size_t ES = sizeof(T);
 	Context& cx = ctx();
 	cudaStream_t s_in = cx.copy_stream, s_out = cx.d2h_stream;
-	// column blocks: the first one is only as wide as A's journey lasts (its solve is gated by A anyway), the others share the rest
-	// Every block repeats the width-independent part of the solve (diagonal panels and the small updates: ~9 % of T1), which
-	// grows with m, while what a block saves is B's journey, which does not.  [B200] T1 (m = 32768): 1 / 2 / 3 blocks ->
-	// 301 / 317 / 325 ms, so tall systems keep one block (A streaming and X leaving in row chunks do the overlapping there).
-	int nblk = (int)std::min<int64_t>( std::max( 1, cx.trsm_host_pipe ), std::max<int64_t>( 1, n / 1024 ) );
-	nblk = std::min( nblk, m >= 24576 ? 1 : ( m >= 12288 ? 2 : 3 ) );
-	std::vector<int64_t> col{ 0 };
-	if ( nblk > 1 )
-	{
-		const int64_t first = std::max<int64_t>( 512, ( (int64_t)( 0.7 * (double)n / nblk ) + 127 ) / 128 * 128 );
-		col.push_back( std::min( n, first ) );
-		const int64_t rest = ( ( n - col.back() + nblk - 2 ) / ( nblk - 1 ) + 127 ) / 128 * 128;
-		while ( col.back() < n ) col.push_back( std::min( n, col.back() + rest ) );
-	}
-	else col.push_back( n );
-	nblk = (int)col.size() - 1;
+	const int leaf = trsm_leaf_rows<T>();
+	std::vector<std::pair<int64_t, int64_t>> blk;
+	trsm_row_blocks( m, leaf, sched, upper, blk );
+	const int nblk = (int)blk.size();
 	void *da = nullptr, *db = nullptr;
 	if ( dev_alloc( &db, (size_t)m * n * ES, st ) != kSuccess ) return kFailure;
 	if ( a_host && dev_alloc( &da, (size_t)m * m * ES, st ) != kSuccess ) { dev_free( db, st ); return kFailure; }
-	std::vector<cudaEvent_t> ev_b( nblk ), ev_done, ev_a;
+	std::vector<cudaEvent_t> ev_b( nblk, nullptr ), ev_done, ev_a, ev_own;
 	cudaEvent_t ev_alloc = nullptr, ev_out = nullptr;
-	for ( auto& e : ev_b ) cudaEventCreateWithFlags( &e, cudaEventDisableTiming );
 	cudaEventCreateWithFlags( &ev_alloc, cudaEventDisableTiming ); cudaEventCreateWithFlags( &ev_out, cudaEventDisableTiming );
 	cudaEventRecord( ev_alloc, st );
 	cudaStreamWaitEvent( s_in, ev_alloc, 0 ); cudaStreamWaitEvent( s_out, ev_alloc, 0 );
 	int rc = kSuccess;
-	auto send_b = [&]( int j ) -> int
-	{
-		const int64_t j0 = col[j], w = col[j + 1] - j0;
-		const int r = stage_block_to_device( (T*)db + j0 * m, m, b + j0 * cs_b, m, w, 1, cs_b, ES, s_in );
-		cudaEventRecord( ev_b[j], s_in );
-		return r;
-	};
-	rc = send_b( 0 );
 	T* adev = const_cast<T*>( a ); int64_t rs_ad = rs_a, cs_ad = cs_a;
-	if ( rc == kSuccess && a_host )
+	if ( a_host ) { adev = (T*)da; rs_ad = ( rs_a == 1 ? 1 : m ); cs_ad = ( rs_a == 1 ? m : 1 ); }
+	// everything that travels up, in the order of its deadlines (trsm_rowblock_plan): B_j, A[j, 0:j], the diagonal block's pieces
+	std::vector<TrsmPiece> plan;
+	trsm_rowblock_plan( leaf, upper, m, sched, plan );
+	int jb = 0;
+	for ( const TrsmPiece& q : plan )
 	{
-		rc = trsm_upload<T>( (T*)da, m, a, rs_a, cs_a, upper, s_in, ev_a );
-		adev = (T*)da; rs_ad = ( rs_a == 1 ? 1 : m ); cs_ad = ( rs_a == 1 ? m : 1 );
+		if ( rc != kSuccess ) break;
+		if ( q.c0 < 0 )
+		{
+			if ( jb >= nblk || q.r0 != blk[jb].first || q.r1 != blk[jb].second ) { rc = fail( "b200_trsm: row-block plan and block rows disagree" ); break; }
+			rc = stage_block_to_device( (T*)db + q.r0, m, b + q.r0, q.r1 - q.r0, n, 1, cs_b, ES, s_in );
+			if ( cudaEventCreateWithFlags( &ev_b[jb], cudaEventDisableTiming ) != cudaSuccess ) rc = fail( "trsm: event creation failed" );
+			else cudaEventRecord( ev_b[jb], s_in );
+			++jb;
+			continue;
+		}
+		if ( !a_host ) continue;
+		// the device image keeps the host's orientation (column- or row-stored)
+		if ( rs_a == 1 ) rc = stage_block_to_device( (T*)da + q.r0 + q.c0 * m, m, a + q.r0 + q.c0 * cs_a, q.r1 - q.r0, q.c1 - q.c0, 1, cs_a, ES, s_in );
+		else             rc = stage_block_to_device( (T*)da + q.c0 + q.r0 * m, m, a + q.c0 + q.r0 * rs_a, q.c1 - q.c0, q.r1 - q.r0, 1, rs_a, ES, s_in );
+		if ( rc != kSuccess ) break;
+		cudaEvent_t e;
+		if ( cudaEventCreateWithFlags( &e, cudaEventDisableTiming ) != cudaSuccess ) { rc = fail( "trsm: event creation failed" ); break; }
+		cudaEventRecord( e, s_in );
+		ev_own.push_back( e );
+		for ( int l = 0; l < q.launches; ++l ) ev_a.push_back( e );
 	}
-	for ( int j = 1; j < nblk && rc == kSuccess; ++j ) rc = send_b( j );
+	if ( rc == kSuccess && jb != nblk ) rc = fail( "b200_trsm: row-block plan and block rows disagree" );
+	size_t next = 0;
+	const T one = Scalar<T>::make( 1.0, 0.0 ), mone = Scalar<T>::make( -1.0, 0.0 );
 	for ( int j = 0; j < nblk && rc == kSuccess; ++j )
 	{
-		const int64_t j0 = col[j], w = col[j + 1] - j0;
+		const int64_t r0 = blk[j].first, r1 = blk[j].second, rows = r1 - r0;
 		cudaStreamWaitEvent( st, ev_b[j], 0 );
-		size_t next = 0;
-		TrsmPlan<T> p{ adev, rs_ad, cs_ad, (T*)db + j0 * m, 1, m, w, upper, unit, conj, st };
-		if ( a_host && j == 0 ) { p.a_ready = &ev_a; p.a_next = &next; }     // later blocks run after block 0: all of A is there
-		// rows of X go home as soon as their sub-solve is done (eighths of the block), under the rest of the solve
-		p.notify_rows = std::max<int64_t>( 1024, ( m / 8 + 255 ) / 256 * 256 );
+		TrsmPlan<T> p{ adev, rs_ad, cs_ad, (T*)db, 1, m, n, upper, unit, conj, st };
+		if ( a_host ) { p.a_ready = &ev_a; p.a_next = &next; }
+		T al_solve = al;
+		if ( !upper && r0 > 0 )
+		{
+			// B_j := alpha*B_j - A[j, 0:j] * X[0:j]
+			trsm_wait_a( p );
+			if ( gemm_dev<T>( conj, false, rows, n, r0, mone, adev + r0 * rs_ad, rs_ad, cs_ad, (T*)db, 1, m, al, (T*)db + r0, 1, m, st ) != kSuccess ) { rc = kFailure; break; }
+			al_solve = one;
+		}
+		if ( upper && r1 < m )
+		{
+			trsm_wait_a( p );
+			if ( gemm_dev<T>( conj, false, rows, n, m - r1, mone, adev + r0 * rs_ad + r1 * cs_ad, rs_ad, cs_ad, (T*)db + r1, 1, m, al, (T*)db + r0, 1, m, st ) != kSuccess ) { rc = kFailure; break; }
+			al_solve = one;
+		}
+		// the rows of X_j are final as their sub-solves finish: they go home in quarters of a block under the later steps
+		p.notify_rows = std::max<int64_t>( 1024, ( sched.rb / 4 + 255 ) / 256 * 256 );
 		p.on_final = [&]( int64_t i0, int64_t mb )
 		{
 			if ( rc != kSuccess ) return;
@@ -267,19 +320,19 @@ static int trsm_host_pipeline( int64_t m, int64_t n, T al, const T* a, int64_t r
 			ev_done.push_back( e );
 			cudaEventRecord( e, st );
 			cudaStreamWaitEvent( s_out, e, 0 );
-			rc = stage_block_to_host( b + j0 * cs_b + i0, 1, cs_b, (T*)db + j0 * m + i0, m, mb, w, ES, s_out );
+			rc = stage_block_to_host( b + i0, 1, cs_b, (T*)db + i0, m, mb, n, ES, s_out );
 		};
-		const int rs = trsm_rec( p, 0, m, al );
+		const int rs = trsm_rec( p, r0, rows, al_solve );
 		if ( rc == kSuccess ) rc = rs;
-		if ( rc == kSuccess && p.a_ready && next != ev_a.size() ) rc = fail( "b200_trsm: upload plan (%zu events) and solve recursion (%zu launches) disagree", ev_a.size(), next );
 	}
+	if ( rc == kSuccess && a_host && next != ev_a.size() ) rc = fail( "b200_trsm: row-block upload plan (%zu events) and solve (%zu launches) disagree", ev_a.size(), next );
 	cudaEventRecord( ev_out, s_out );
 	cudaStreamWaitEvent( st, ev_out, 0 );
 	if ( cudaStreamSynchronize( st ) != cudaSuccess && rc == kSuccess ) rc = fail( "b200_trsm: stream sync failed" );
 	if ( cudaStreamSynchronize( s_in ) != cudaSuccess && rc == kSuccess ) rc = fail( "b200_trsm: copy stream sync failed" );
-	for ( auto e : ev_b ) cudaEventDestroy( e );
+	for ( auto e : ev_b ) if ( e ) cudaEventDestroy( e );
 	for ( auto e : ev_done ) cudaEventDestroy( e );
-	{ cudaEvent_t last = nullptr; for ( auto e : ev_a ) { if ( e != last ) cudaEventDestroy( e ); last = e; } }
+	for ( auto e : ev_own ) cudaEventDestroy( e );
 	cudaEventDestroy( ev_alloc ); cudaEventDestroy( ev_out );
 	dev_free( da, st ); dev_free( db, st );
 	return rc;
@@ -317,11 +370,15 @@ static int trsm_front( int side, int uplo, int transa, int diag, int64_t m, int6
 	const bool zero_alpha = Scalar<T>::is_zero( al );
 	if ( ctx().trsm_host_pipe && !zero_alpha && kind_b == MemKind::HostPinned && rs_b == 1 && cs_b >= m && m >= 4096 && n >= 1024 )
 	{
-		// pinned host B (and possibly A), large: transfers run under the solve (trsm_host_pipeline)
+		// pinned host B (and possibly A), large: transfers run under the solve (trsm_host_rowpipe)
 		const MemKind kind_a = classify( a );
 		const bool a_lines = ( rs_a == 1 && cs_a >= m ) || ( cs_a == 1 && rs_a >= m );
 		if ( kind_a == MemKind::Device || ( kind_a == MemKind::HostPinned && a_lines ) )
-			return trsm_host_pipeline<T>( m, n, al, a, rs_a, cs_a, kind_a != MemKind::Device, upper, diag == B200_UNIT_DIAG, conj, b, cs_b, st );
+		{
+			TrsmRowSched sched;
+			if ( trsm_row_sched( m, n, trsm_leaf_rows<T>(), ctx().trsm_host_rb, sched ) )
+				return trsm_host_rowpipe<T>( m, n, al, a, rs_a, cs_a, kind_a != MemKind::Device, upper, diag == B200_UNIT_DIAG, conj, b, cs_b, sched, st );
+		}
 	}
 	T* bdev = b; int64_t rs_bd = rs_b, cs_bd = cs_b;
 	if ( b_host )

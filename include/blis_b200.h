@@ -410,6 +410,12 @@ unsigned long long b200_launch_count( void );
  * that wait for the piece.  Writes at most `cap` pieces of five numbers each to `out`, returns the number of pieces. */
 int        b200_splitk_plan( b200_dim_t tiles, int grid, b200_dim_t kt, int* full );
 int        b200_trsm_upload_plan( b200_dim_t m, int leaf_rows, int upper, b200_dim_t* out, int cap );
+/* b200_trsm_rowblock_plan: the same list for the row-block (left-looking) pipeline that serves tall systems with pinned
+ * host operands (csrc/host_trsm.cuh: trsm_host_rowpipe): per block row of `rb` rows, in processing order (top down for
+ * lower, bottom up for upper), the block of A its single update gemm reads, A[j, 0:j] (resp. A[j, j+1:]), followed by the
+ * pieces of the diagonal block in the recursion's order.  rb = 0 asks for the engine's own choice (option trsm_host_rb);
+ * returns 0 when the shape is served by the column-block pipeline instead. */
+int        b200_trsm_rowblock_plan( b200_dim_t m, b200_dim_t n, int leaf_rows, int upper, b200_dim_t rb, b200_dim_t* out, int cap );
 
 /* Tuning knobs, e.g. ("dgemm_cfg", 9); not part of the reference surface.  Every key can be preset in the environment
  * as BLIS_B200_<KEY> (the reference's bli_env convention, frame/base/bli_env.c:68).  Keys that change WHICH schedule
@@ -417,7 +423,8 @@ int        b200_trsm_upload_plan( b200_dim_t m, int leaf_rows, int upper, b200_d
  *   dgemm_splitk      1 (default): mid-size dgemm cuts the tiles of a partial last wave into k chunks; 0: never split k
  *   dmma_cst          k up to which dgemm moves D through the TMA unit both ways (default 256; 0: never)
  *   trsm_fused        1 (default): fused 256-row diagonal-panel kernel for dtrsm; 0: 64-row block solves
- *   trsm_host_pipe    max. column blocks of the pipelined trsm with pinned host operands (default 3; 0: sequential transfers)
+ *   trsm_host_pipe    1 (default): trsm with pinned host operands runs its transfers under the solve; 0: in sequence
+ *   trsm_host_rb      rows per block of that pipeline (0, default: m/32 in whole 256 rows; -1: same as trsm_host_pipe 0)
  *   host_kpipe        1 (default): gemm with host operands and long k is pipelined over k panels
  *   batch_grouped     1 (default): small device-resident problems of b200_gemm_batch share ONE launch;
  *   batch_grouped_max   "small" means m*n*k at most this (default 128^3)

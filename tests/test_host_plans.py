@@ -3,7 +3,9 @@
 * b200_splitk_plan  -- when mid-size dgemm cuts the tiles of its partial last wave into k chunks (csrc/gemm_d.cu);
 * b200_trsm_upload_plan -- the order in which a host-resident triangular A travels under the solve (csrc/host_trsm.cuh):
   its pieces must tile the stored triangle exactly (plus the unstored half of the small diagonal squares) and provide
-  exactly one event per launch of the recursive solve, in the recursion's order.
+  exactly one event per launch of the recursive solve, in the recursion's order;
+* b200_trsm_rowblock_plan -- the same for the row-block (left-looking) pipeline of tall systems: one update gemm per block
+  row reading A[j, 0:j], then the recursion inside the diagonal block.
 """
 import ctypes as C
 
@@ -20,6 +22,8 @@ def lib():
     l.b200_splitk_plan.argtypes = [C.c_int64, C.c_int, C.c_int64, C.POINTER(C.c_int)]
     l.b200_trsm_upload_plan.restype = C.c_int
     l.b200_trsm_upload_plan.argtypes = [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_int]
+    l.b200_trsm_rowblock_plan.restype = C.c_int
+    l.b200_trsm_rowblock_plan.argtypes = [C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_int64), C.c_int]
     return l
 
 
@@ -110,3 +114,83 @@ def test_trsm_upload_plan_matches_the_solve(lib, m, leaf, upper):
         # what travels beyond the triangle is the unstored half of diagonal squares of at most max(leaf, 1024) rows
         extra = int(cover.sum()) - int(tri.sum())
         assert extra <= m * max(leaf, 1024) // 2
+
+
+def rowblock_launches(m, leaf, upper, blocks):
+    """The launches of trsm_host_rowpipe (csrc/host_trsm.cuh) as regions of A in launch order: per block row the update
+    gemm over everything already solved, then trsm_rec on the diagonal block."""
+    out = []
+
+    def rec(i0, mb):
+        if mb <= leaf:
+            out.append((i0, i0 + mb, i0, i0 + mb)); return
+        nblk = -(-mb // leaf)
+        m1 = ((nblk + 1) // 2) * leaf; m2 = mb - m1
+        if not upper:
+            rec(i0, m1); out.append((i0 + m1, i0 + mb, i0, i0 + m1)); rec(i0 + m1, m2)
+        else:
+            rec(i0 + m2, m1); out.append((i0, i0 + m2, i0 + m2, i0 + mb)); rec(i0, m2)
+    for r0, r1 in blocks:
+        if not upper and r0 > 0:
+            out.append((r0, r1, 0, r0))
+        if upper and r1 < m:
+            out.append((r0, r1, r1, m))
+        rec(r0, r1 - r0)
+    return out
+
+
+@pytest.mark.parametrize("upper", [False, True])
+@pytest.mark.parametrize("m,leaf,rb", [(4608, 256, 1024), (32768, 256, 0), (16384, 256, 0), (5000, 256, 1280), (4100, 64, 1000), (8192, 32, 0),
+                                       (6144, 256, 4096), (9999, 256, 0)])
+def test_trsm_rowblock_plan_matches_the_solve(lib, m, leaf, upper, rb):
+    cap = 8 * (m // leaf + 2)
+    buf = (C.c_int64 * (5 * cap))()
+    n = lib.b200_trsm_rowblock_plan(m, 8192, leaf, int(upper), rb, buf, cap)
+    assert 0 < n <= cap
+    plan = np.ctypeslib.as_array(buf)[:5 * n].reshape(n, 5).copy()
+    # block rows, in processing order, are the B pieces (c0 = c1 = -1, no launch waits for them: the stream's order does)
+    blocks = [(int(r0), int(r1)) for r0, r1, c0, c1, nl in plan if c0 < 0]
+    assert all(nl == 0 for r0, r1, c0, c1, nl in plan if c0 < 0) and len(blocks) >= 2
+    order = blocks[::-1] if upper else blocks
+    assert order[0][0] == 0 and order[-1][1] == m and all(a[1] == b[0] for a, b in zip(order, order[1:]))     # they tile [0, m)
+    assert all(r0 % leaf == 0 for r0, _ in blocks)                                                            # on leaf boundaries
+    mr = -(-m // leaf) * leaf                                 # sizes are counted in whole leaves: the block that ends at row m is cut there
+    sizes = [(mr if r1 == m else r1) - r0 for r0, r1 in blocks]
+    if rb:
+        rows = -(-rb // leaf) * leaf                      # explicit: uniform (the last one takes a remainder below half a block)
+        assert all(s == rows for s in sizes[:-1]) and sizes[-1] < 1.5 * rows + leaf
+    else:
+        rows = -(-max(256, -(-(m // 32) // 256) * 256) // leaf) * leaf      # the engine's choice: m/32 in whole 256 rows
+        assert all(s == rows for s in sizes[:-1]) and sizes[-1] < 1.5 * rows + leaf
+    pieces = plan[plan[:, 2] >= 0]
+    launches = rowblock_launches(m, leaf, upper, blocks)
+    assert int(pieces[:, 4].sum()) == len(launches)
+    assert len(launches) == sum(2 * (-(-(r1 - r0) // leaf)) - 1 for r0, r1 in blocks) + len(blocks) - 1
+    owner = np.repeat(np.arange(len(pieces)), pieces[:, 4])
+    for (r0, r1, c0, c1), p in zip(launches, owner):
+        pr0, pr1, pc0, pc1, _ = pieces[p]
+        assert pr0 <= r0 and r1 <= pr1 and pc0 <= c0 and c1 <= pc1, (m, leaf, upper, (r0, r1, c0, c1), pieces[p])
+    # every piece of A travels after the rows of B it is used on, and reads X only where it was solved by then: its rows and
+    # its columns lie in block rows whose B has already gone up
+    seen = set()
+    for r0, r1, c0, c1, nl in plan:
+        if c0 < 0:
+            seen.update(range(int(r0) // leaf, -(-int(r1) // leaf)))
+        else:
+            assert all(x in seen for x in (int(r0) // leaf, (int(r1) - 1) // leaf, int(c0) // leaf, (int(c1) - 1) // leaf))
+    if m <= 10000:
+        cover = np.zeros((m, m), dtype=np.int8)
+        for r0, r1, c0, c1, _ in pieces:
+            cover[r0:r1, c0:c1] += 1
+        assert cover.max() == 1
+        tri = np.triu(np.ones((m, m), dtype=bool)) if upper else np.tril(np.ones((m, m), dtype=bool))
+        assert cover[tri].min() == 1
+        assert int(cover.sum()) - int(tri.sum()) <= m * max(leaf, 1024) // 2
+
+
+def test_trsm_rowblock_plan_declines_short_systems(lib):
+    buf = (C.c_int64 * 50)()
+    assert lib.b200_trsm_rowblock_plan(2048, 8192, 256, 0, 0, buf, 10) == 0       # below trsm_host_rb_min_m
+    assert lib.b200_trsm_rowblock_plan(32768, 512, 256, 0, 0, buf, 10) == 0       # too few right-hand sides
+    assert lib.b200_trsm_rowblock_plan(32768, 8192, 256, 0, -1, buf, 10) == 0     # switched off
+    assert lib.b200_trsm_rowblock_plan(2048, 8192, 256, 0, 4096, buf, 10) == 0    # one block is no pipeline

@@ -151,12 +151,11 @@ def test_trsm_host_a_only_stored_triangle_travels(engine, oracle, pin):
 
 
 def test_trsm_pinned_host_operands_pipelined(engine, ref):
-    """Large solves with pinned host operands take the pipelined path (host_trsm.cuh: trsm_host_pipeline): A travels in the
-    order the recursion reads it (one event per launch), B in column blocks, X comes back block by block.  Against the
-    real reference library; the unstored triangle of A is NaN; column- and row-stored A, every uplo/trans, uneven
-    splits of the recursion (m = 4608 = 18 panels), two column blocks with a ragged second one, A already on the device,
-    the right-sided form on a row-stored B; and the result must equal the sequential path's (trsm_host_pipe = 0) to
-    rounding (the gemm updates see different shapes, so their tile schedules -- not their arithmetic -- may differ)."""
+    """Large solves with pinned host operands take the pipelined path (host_trsm.cuh: trsm_host_rowpipe, the engine's own
+    block rows: 256 at this size): B travels in row blocks, A in the order the solve reads it (one event per launch), X
+    comes back block by block.  Against the real reference library; the unstored triangle of A is NaN; column- and
+    row-stored A, every uplo/trans, A already on the device, the right-sided form on a row-stored B; and the result must
+    equal the sequential path's (trsm_host_pipe = 0) to rounding (the updates are grouped differently)."""
     m, n, seed = 4608, 2200, 140
     b0 = gen.matrix("d", m, n, 17, "frac", "c")
     n0 = engine.launch_count()
@@ -180,7 +179,7 @@ def test_trsm_pinned_host_operands_pipelined(engine, ref):
                         tb2 = to_torch(b0, "cpu", pin=True)
                         engine.bli_dtrsm(LEFT, uplo, tr, NONUNIT_DIAG, m, n, 2.0, ta_, *estr(a), tb2, *estr(b0))
                     finally:
-                        engine.set_option("trsm_host_pipe", 3)
+                        engine.set_option("trsm_host_pipe", 1)
                     assert rel_err(to_numpy(tb2), got) <= 20 * TOL["d"], (uplo, rel_err(to_numpy(tb2), got))
                     tb3 = to_torch(b0, "cpu", pin=True)
                     engine.bli_dtrsm(LEFT, uplo, tr, NONUNIT_DIAG, m, n, 2.0, ta_.cuda(), *estr(a), tb3, *estr(b0))
@@ -193,6 +192,71 @@ def test_trsm_pinned_host_operands_pipelined(engine, ref):
     ta_, tb_ = to_torch(a, "cpu", pin=True), to_torch(b, "cpu", pin=True)
     engine.bli_dtrsm(RIGHT, LOWER, TRANSPOSE, UNIT_DIAG, 1100, m, 2.0, ta_, *estr(a), tb_, *estr(b))
     assert rel_err(to_numpy(tb_), want) <= 20 * TOL["d"]
+
+
+def test_trsm_pinned_host_operands_row_blocks(engine, ref):
+    """Tall solves with pinned host operands run the row-block (left-looking) pipeline (host_trsm.cuh: trsm_host_rowpipe):
+    B travels in row blocks, each block row receives all its updates in one gemm reading A[j, 0:j] and is then solved by
+    the recursion, X goes home block by block.  Forced at a size the reference solves in seconds (trsm_host_rb = 1024 on
+    m = 4608: four whole block rows and a ragged one; 1280 on m = 5000: nothing divides).  Against the real reference
+    library, the unstored triangle of A NaN; column- and row-stored A, every uplo/trans, unit diagonal, A resident on the
+    device, the right-sided form; an integer-valued system must come back bit for bit (the arithmetic per element is the
+    reference's sequence whatever the blocking)."""
+    n0 = engine.launch_count()
+    try:
+        for m, n, rb in ((4608, 2200, 1024), (5000, 1100, 1280)):
+            engine.set_option("trsm_host_rb", rb)
+            b0 = gen.matrix("d", m, n, 23, "frac", "c")
+            seed = 240 + m
+            for oa in ("c", "r"):
+                for uplo in (LOWER, UPPER):
+                    for tr in (NO_TRANSPOSE, TRANSPOSE):
+                        seed += 1
+                        diag = UNIT_DIAG if (seed % 3 == 0) else NONUNIT_DIAG
+                        a = gen.triangular("d", m, seed, "frac", oa)
+                        gen.poison_unstored(a, uplo == LOWER)
+                        want = b0.copy(order="K")
+                        ref.trsm(LEFT, uplo, tr, diag, 2.0, a, want)
+                        ta_, tb_ = to_torch(a, "cpu", pin=True), to_torch(b0, "cpu", pin=True)
+                        engine.bli_dtrsm(LEFT, uplo, tr, diag, m, n, 2.0, ta_, *estr(a), tb_, *estr(b0))
+                        err = rel_err(to_numpy(tb_), want)
+                        assert err <= 20 * TOL["d"], (m, oa, uplo, tr, err)
+                        if oa == "c" and tr == NO_TRANSPOSE:
+                            tb3 = to_torch(b0, "cpu", pin=True)
+                            engine.bli_dtrsm(LEFT, uplo, tr, diag, m, n, 2.0, ta_.cuda(), *estr(a), tb3, *estr(b0))
+                            assert rel_err(to_numpy(tb3), want) <= 20 * TOL["d"], (m, uplo, "device A")
+        # another datatype through the same pipeline (32-row leaves, conjugated A)
+        engine.set_option("trsm_host_rb", 1000)
+        m, n = 4100, 1030
+        a = gen.triangular("z", m, 995, "frac", "c"); gen.poison_unstored(a, False)
+        b = gen.matrix("z", m, n, 996, "frac", "c")
+        want = b.copy(order="K"); ref.trsm(LEFT, UPPER, CONJ_NO_TRANSPOSE, NONUNIT_DIAG, 2.0 - 1.0j, a, want)
+        ta_, tb_ = to_torch(a, "cpu", pin=True), to_torch(b, "cpu", pin=True)
+        engine.bli_ztrsm(LEFT, UPPER, CONJ_NO_TRANSPOSE, NONUNIT_DIAG, m, n, 2.0 - 1.0j, ta_, *estr(a), tb_, *estr(b))
+        assert rel_err(to_numpy(tb_), want) <= 20 * TOL["z"]
+        # right side, row-stored B (the transposed problem is column-stored): X * A^T = alpha * B
+        engine.set_option("trsm_host_rb", 1024)
+        m = 4608
+        a = gen.triangular("d", m, 993, "frac", "c"); gen.poison_unstored(a, True)
+        b = gen.matrix("d", 1100, m, 994, "frac", "r")
+        want = b.copy(order="K"); ref.trsm(RIGHT, LOWER, TRANSPOSE, NONUNIT_DIAG, 2.0, a, want)
+        ta_, tb_ = to_torch(a, "cpu", pin=True), to_torch(b, "cpu", pin=True)
+        engine.bli_dtrsm(RIGHT, LOWER, TRANSPOSE, NONUNIT_DIAG, 1100, m, 2.0, ta_, *estr(a), tb_, *estr(b))
+        assert rel_err(to_numpy(tb_), want) <= 20 * TOL["d"]
+        # exact system: unit lower triangle of small integers, integer right-hand sides, alpha = 1 -> every intermediate
+        # value is an integer far below 2^53 for this construction (strictly lower part sparse: one entry per row)
+        rng = np.random.default_rng(5)
+        a = np.asfortranarray(np.eye(m))
+        rows = np.arange(1, m); a[rows, rng.integers(0, rows)] = rng.integers(-1, 2, m - 1)
+        x = np.asfortranarray(rng.integers(-4, 5, (m, 1100)).astype(np.float64))
+        b = np.asfortranarray(a @ x)
+        assert np.abs(b).max() < 2.0 ** 40
+        ta_, tb_ = to_torch(a, "cpu", pin=True), to_torch(b, "cpu", pin=True)
+        engine.bli_dtrsm(LEFT, LOWER, NO_TRANSPOSE, UNIT_DIAG, m, 1100, 1.0, ta_, *estr(a), tb_, *estr(b))
+        assert np.array_equal(to_numpy(tb_), x)
+    finally:
+        engine.set_option("trsm_host_rb", 0)
+    assert engine.launch_count() > n0
 
 
 def test_trsm_full_size_testsuite_residual(engine):

@@ -117,7 +117,7 @@ for dt, tol in ((torch.float64, 1e-12), (torch.complex64, 5e-5)):
     print(f"{'grouped batch ' + str(dt):28s} {api.last_kernel():70s} err={err:.2e}", flush=True)
     assert err <= tol * 10 and api.last_kernel().startswith("gemm_grouped_kernel")
 
-# pinned host operands: A streams in the recursion's order, B in two column blocks, X comes back in row chunks
+# pinned host operands: B in row blocks, A in the order the solve reads it, X comes back block by block (trsm_host_rowpipe)
 if not os.environ.get("SANITIZE_SKIP_HOST"):
     mm, nn = 4352, 2200
     t = rnd(mm, mm, torch.float64) / 64; t.diagonal().add_(2.0)
