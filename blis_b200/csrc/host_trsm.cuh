@@ -195,7 +195,7 @@ static void trsm_upload_plan( int leaf_rows, bool upper, int64_t i0, int64_t mb,
 // with everything resident on the device measured like the plain recursion (250.1-251.2 vs 250.8 ms; worse for narrow B:
 // its block-row gemms have too few tiles), so the device-resident solve keeps the recursion.
 struct TrsmRowSched { int64_t rb; };
-static bool trsm_row_sched( int64_t m, int64_t n, int leaf_rows, long long opt, TrsmRowSched& s )
+static bool trsm_row_sched( int64_t m, int64_t n, int leaf_rows, long long opt, TrsmRowSched& s, bool pageable = false )
 {
 	if ( opt < 0 ) return false;
 	const Context& c = ctx();
@@ -204,6 +204,10 @@ static bool trsm_row_sched( int64_t m, int64_t n, int leaf_rows, long long opt, 
 	{
 		if ( m < c.trsm_host_rb_min_m || n < 1024 ) return false;
 		rb = std::max<int64_t>( 256, ( m / std::max<long long>( 2, c.trsm_host_rb_div ) + 255 ) / 256 * 256 );
+		// pageable operands are packed by host threads line by line (a block row of a column-stored matrix = lines of rb
+		// elements): at least 16 KiB lines.  [B200] T1 with pageable A and B: sequential 486 ms, rb = 1024 / 2048 / 8192 ->
+		// 510-550 / 437 / 431 ms; the packing rate (36 GB/s alone, ~25 GB/s beside the DMA engines) bounds it, not the GPU
+		if ( pageable ) rb = std::max<int64_t>( rb, 2048 );
 	}
 	s.rb = ( rb + leaf_rows - 1 ) / leaf_rows * leaf_rows;
 	return s.rb < m;
@@ -240,7 +244,7 @@ static void trsm_rowblock_plan( int leaf_rows, bool upper, int64_t m, const Trsm
 // a: effective m x m view (host or device), b: m x n host, pinned, column-stored (rs_b == 1)
 template <typename T>
 static int trsm_host_rowpipe( int64_t m, int64_t n, T al, const T* a, int64_t rs_a, int64_t cs_a, bool a_host, bool upper, bool unit, bool conj,
-                              T* b, int64_t cs_b, const TrsmRowSched& sched, cudaStream_t st )
+                              T* b, int64_t cs_b, bool b_pageable, const TrsmRowSched& sched, cudaStream_t st )
 {
 	constexpr size_t ES = sizeof(T);
 	Context& cx = ctx();
@@ -260,39 +264,54 @@ static int trsm_host_rowpipe( int64_t m, int64_t n, T al, const T* a, int64_t rs
 	int rc = kSuccess;
 	T* adev = const_cast<T*>( a ); int64_t rs_ad = rs_a, cs_ad = cs_a;
 	if ( a_host ) { adev = (T*)da; rs_ad = ( rs_a == 1 ? 1 : m ); cs_ad = ( rs_a == 1 ? m : 1 ); }
-	// everything that travels up, in the order of its deadlines (trsm_rowblock_plan): B_j, A[j, 0:j], the diagonal block's pieces
+	// everything that travels up, in the order of its deadlines (trsm_rowblock_plan): per block row B_j, A[j, 0:j], the
+	// diagonal block's pieces.  Uploads, kernels and downloads of a block row are queued together, block row by block row:
+	// from page-locked memory every copy is asynchronous, so the host runs ahead and the streams' events do the ordering;
+	// from PAGEABLE memory (what a legacy dtrsm_ caller passes) a copy occupies this thread while it packs into / unpacks
+	// from the pinned ring, so the kernels of block row j are queued before block row j+1 is packed, and the rows of X
+	// are unpacked one block row late (`pending`): waiting for X_j right after queueing step j would idle the GPU.
 	std::vector<TrsmPiece> plan;
 	trsm_rowblock_plan( leaf, upper, m, sched, plan );
-	int jb = 0;
-	for ( const TrsmPiece& q : plan )
+	struct Home { int64_t i0, mb; cudaEvent_t e; int j; };
+	std::vector<Home> pending;
+	auto send_home = [&]( int before_block )
 	{
-		if ( rc != kSuccess ) break;
-		if ( q.c0 < 0 )
+		size_t k = 0;
+		for ( ; k < pending.size() && pending[k].j < before_block && rc == kSuccess; ++k )
 		{
-			if ( jb >= nblk || q.r0 != blk[jb].first || q.r1 != blk[jb].second ) { rc = fail( "b200_trsm: row-block plan and block rows disagree" ); break; }
-			rc = stage_block_to_device( (T*)db + q.r0, m, b + q.r0, q.r1 - q.r0, n, 1, cs_b, ES, s_in );
-			if ( cudaEventCreateWithFlags( &ev_b[jb], cudaEventDisableTiming ) != cudaSuccess ) rc = fail( "trsm: event creation failed" );
-			else cudaEventRecord( ev_b[jb], s_in );
-			++jb;
-			continue;
+			cudaStreamWaitEvent( s_out, pending[k].e, 0 );
+			rc = stage_block_to_host( b + pending[k].i0, 1, cs_b, (T*)db + pending[k].i0, m, pending[k].mb, n, ES, s_out );
 		}
-		if ( !a_host ) continue;
-		// the device image keeps the host's orientation (column- or row-stored)
-		if ( rs_a == 1 ) rc = stage_block_to_device( (T*)da + q.r0 + q.c0 * m, m, a + q.r0 + q.c0 * cs_a, q.r1 - q.r0, q.c1 - q.c0, 1, cs_a, ES, s_in );
-		else             rc = stage_block_to_device( (T*)da + q.c0 + q.r0 * m, m, a + q.c0 + q.r0 * rs_a, q.c1 - q.c0, q.r1 - q.r0, 1, rs_a, ES, s_in );
-		if ( rc != kSuccess ) break;
-		cudaEvent_t e;
-		if ( cudaEventCreateWithFlags( &e, cudaEventDisableTiming ) != cudaSuccess ) { rc = fail( "trsm: event creation failed" ); break; }
-		cudaEventRecord( e, s_in );
-		ev_own.push_back( e );
-		for ( int l = 0; l < q.launches; ++l ) ev_a.push_back( e );
-	}
-	if ( rc == kSuccess && jb != nblk ) rc = fail( "b200_trsm: row-block plan and block rows disagree" );
-	size_t next = 0;
+		pending.erase( pending.begin(), pending.begin() + k );
+	};
+	size_t pi = 0, next = 0;
 	const T one = Scalar<T>::make( 1.0, 0.0 ), mone = Scalar<T>::make( -1.0, 0.0 );
 	for ( int j = 0; j < nblk && rc == kSuccess; ++j )
 	{
 		const int64_t r0 = blk[j].first, r1 = blk[j].second, rows = r1 - r0;
+		// -- up: B_j, then the pieces of A this block row reads
+		if ( pi >= plan.size() || plan[pi].c0 >= 0 || plan[pi].r0 != r0 || plan[pi].r1 != r1 ) { rc = fail( "b200_trsm: row-block plan and block rows disagree" ); break; }
+		++pi;
+		rc = stage_block_to_device( (T*)db + r0, m, b + r0, rows, n, 1, cs_b, ES, s_in );
+		if ( rc != kSuccess ) break;
+		if ( cudaEventCreateWithFlags( &ev_b[j], cudaEventDisableTiming ) != cudaSuccess ) { rc = fail( "trsm: event creation failed" ); break; }
+		cudaEventRecord( ev_b[j], s_in );
+		for ( ; pi < plan.size() && plan[pi].c0 >= 0 && rc == kSuccess; ++pi )
+		{
+			if ( !a_host ) continue;
+			const TrsmPiece& q = plan[pi];
+			// the device image keeps the host's orientation (column- or row-stored)
+			if ( rs_a == 1 ) rc = stage_block_to_device( (T*)da + q.r0 + q.c0 * m, m, a + q.r0 + q.c0 * cs_a, q.r1 - q.r0, q.c1 - q.c0, 1, cs_a, ES, s_in );
+			else             rc = stage_block_to_device( (T*)da + q.c0 + q.r0 * m, m, a + q.c0 + q.r0 * rs_a, q.c1 - q.c0, q.r1 - q.r0, 1, rs_a, ES, s_in );
+			if ( rc != kSuccess ) break;
+			cudaEvent_t e;
+			if ( cudaEventCreateWithFlags( &e, cudaEventDisableTiming ) != cudaSuccess ) { rc = fail( "trsm: event creation failed" ); break; }
+			cudaEventRecord( e, s_in );
+			ev_own.push_back( e );
+			for ( int l = 0; l < q.launches; ++l ) ev_a.push_back( e );
+		}
+		if ( rc != kSuccess ) break;
+		// -- the step: one update gemm over everything solved so far, then the recursion on the diagonal block
 		cudaStreamWaitEvent( st, ev_b[j], 0 );
 		TrsmPlan<T> p{ adev, rs_ad, cs_ad, (T*)db, 1, m, n, upper, unit, conj, st };
 		if ( a_host ) { p.a_ready = &ev_a; p.a_next = &next; }
@@ -310,7 +329,8 @@ static int trsm_host_rowpipe( int64_t m, int64_t n, T al, const T* a, int64_t rs
 			if ( gemm_dev<T>( conj, false, rows, n, m - r1, mone, adev + r0 * rs_ad + r1 * cs_ad, rs_ad, cs_ad, (T*)db + r1, 1, m, al, (T*)db + r0, 1, m, st ) != kSuccess ) { rc = kFailure; break; }
 			al_solve = one;
 		}
-		// the rows of X_j are final as their sub-solves finish: they go home in quarters of a block under the later steps
+		// -- home: the rows of X_j are final as their sub-solves finish (in quarters of a large block, so that of the last
+		// block row only a quarter is exposed)
 		p.notify_rows = std::max<int64_t>( 1024, ( sched.rb / 4 + 255 ) / 256 * 256 );
 		p.on_final = [&]( int64_t i0, int64_t mb )
 		{
@@ -319,12 +339,15 @@ static int trsm_host_rowpipe( int64_t m, int64_t n, T al, const T* a, int64_t rs
 			if ( cudaEventCreateWithFlags( &e, cudaEventDisableTiming ) != cudaSuccess ) { rc = fail( "trsm: event creation failed" ); return; }
 			ev_done.push_back( e );
 			cudaEventRecord( e, st );
-			cudaStreamWaitEvent( s_out, e, 0 );
-			rc = stage_block_to_host( b + i0, 1, cs_b, (T*)db + i0, m, mb, n, ES, s_out );
+			pending.push_back( { i0, mb, e, j } );
+			if ( !b_pageable ) send_home( j + 1 );
 		};
 		const int rs = trsm_rec( p, r0, rows, al_solve );
 		if ( rc == kSuccess ) rc = rs;
+		if ( rc == kSuccess ) send_home( j );                 // (pageable B: what block row j-1 left)
 	}
+	if ( rc == kSuccess ) send_home( nblk );
+	if ( rc == kSuccess && pi != plan.size() ) rc = fail( "b200_trsm: row-block plan and block rows disagree" );
 	if ( rc == kSuccess && a_host && next != ev_a.size() ) rc = fail( "b200_trsm: row-block upload plan (%zu events) and solve (%zu launches) disagree", ev_a.size(), next );
 	cudaEventRecord( ev_out, s_out );
 	cudaStreamWaitEvent( st, ev_out, 0 );
@@ -368,16 +391,19 @@ static int trsm_front( int side, int uplo, int transa, int diag, int64_t m, int6
 	const MemKind kind_b = classify( b );
 	const bool b_host = ( kind_b != MemKind::Device );
 	const bool zero_alpha = Scalar<T>::is_zero( al );
-	if ( ctx().trsm_host_pipe && !zero_alpha && kind_b == MemKind::HostPinned && rs_b == 1 && cs_b >= m && m >= 4096 && n >= 1024 )
+	if ( ctx().trsm_host_pipe && !zero_alpha && b_host && rs_b == 1 && cs_b >= m && m >= 4096 && n >= 1024 )
 	{
-		// pinned host B (and possibly A), large: transfers run under the solve (trsm_host_rowpipe)
+		// host B (and possibly A), column-stored, large: transfers run under the solve (trsm_host_rowpipe); page-locked
+		// operands are copied by the DMA engines directly, pageable ones through the pinned ring
 		const MemKind kind_a = classify( a );
 		const bool a_lines = ( rs_a == 1 && cs_a >= m ) || ( cs_a == 1 && rs_a >= m );
-		if ( kind_a == MemKind::Device || ( kind_a == MemKind::HostPinned && a_lines ) )
+		if ( kind_a == MemKind::Device || a_lines )
 		{
 			TrsmRowSched sched;
-			if ( trsm_row_sched( m, n, trsm_leaf_rows<T>(), ctx().trsm_host_rb, sched ) )
-				return trsm_host_rowpipe<T>( m, n, al, a, rs_a, cs_a, kind_a != MemKind::Device, upper, diag == B200_UNIT_DIAG, conj, b, cs_b, sched, st );
+			const bool pageable = ( kind_b == MemKind::HostPageable || kind_a == MemKind::HostPageable );
+			if ( trsm_row_sched( m, n, trsm_leaf_rows<T>(), ctx().trsm_host_rb, sched, pageable ) )
+				return trsm_host_rowpipe<T>( m, n, al, a, rs_a, cs_a, kind_a != MemKind::Device, upper, diag == B200_UNIT_DIAG, conj, b, cs_b,
+				                             kind_b == MemKind::HostPageable, sched, st );
 		}
 	}
 	T* bdev = b; int64_t rs_bd = rs_b, cs_bd = cs_b;

@@ -225,6 +225,22 @@ def test_trsm_pinned_host_operands_row_blocks(engine, ref):
                             tb3 = to_torch(b0, "cpu", pin=True)
                             engine.bli_dtrsm(LEFT, uplo, tr, diag, m, n, 2.0, ta_.cuda(), *estr(a), tb3, *estr(b0))
                             assert rel_err(to_numpy(tb3), want) <= 20 * TOL["d"], (m, uplo, "device A")
+        # PAGEABLE operands (what a legacy dtrsm_ caller passes) ride the same pipeline through the pinned ring, X unpacked one
+        # block row late: pageable A and B, pageable B with page-locked A, row-stored pageable A; the engine's own block rows
+        engine.set_option("trsm_host_rb", 0)
+        m, n = 4608, 2200
+        b0 = gen.matrix("d", m, n, 29, "frac", "c")
+        for oa, uplo, tr, pin_a in (("c", LOWER, NO_TRANSPOSE, False), ("c", UPPER, NO_TRANSPOSE, True), ("r", LOWER, TRANSPOSE, False),
+                                    ("r", UPPER, NO_TRANSPOSE, False)):
+            a = gen.triangular("d", m, 700 + uplo + tr + pin_a, "frac", oa)
+            gen.poison_unstored(a, uplo == LOWER)
+            want = b0.copy(order="K")
+            ref.trsm(LEFT, uplo, tr, NONUNIT_DIAG, 2.0, a, want)
+            ta_ = to_torch(a, "cpu", pin=True) if pin_a else torch.from_numpy(a.copy(order="K"))
+            bh = b0.copy(order="K"); tb_ = torch.from_numpy(bh)
+            assert not tb_.is_pinned() and tb_.stride() == (1, m)
+            engine.bli_dtrsm(LEFT, uplo, tr, NONUNIT_DIAG, m, n, 2.0, ta_, *estr(a), tb_, *estr(b0))
+            assert rel_err(bh, want) <= 20 * TOL["d"], ("pageable", oa, uplo, tr, rel_err(bh, want))
         # another datatype through the same pipeline (32-row leaves, conjugated A)
         engine.set_option("trsm_host_rb", 1000)
         m, n = 4100, 1030
