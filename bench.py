@@ -374,6 +374,16 @@ def main():
         return reference_arm(args, workload)
 
     # ------------------------------------------------------------------ b200 arm
+    # stdout carries ONE JSON line (driver contract).  Libraries write to fd 1 behind Python's back -- NCCL prints its
+    # version banner there when the engine creates its communicator (N > 1) --, so fd 1 points at stderr for the whole run
+    # and the line leaves through a saved duplicate of the real stdout.
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj: dict) -> None:
+        os.write(out_fd, (json.dumps(obj) + "\n").encode())
+
     import torch
     from blis_b200 import api
     torch.cuda.set_device(local_rank)
@@ -728,7 +738,7 @@ def main():
                 "clocks": t["clocks"], "e2e": t["e2e"], "gpu_launches": t["gpu_launches"], "roofline": t["roofline"], "cpu_baseline": cpu_t,
                 "testsuite_resid": t["testsuite_resid"],
             }
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
