@@ -194,3 +194,52 @@ def test_trsm_rowblock_plan_declines_short_systems(lib):
     assert lib.b200_trsm_rowblock_plan(32768, 512, 256, 0, 0, buf, 10) == 0       # too few right-hand sides
     assert lib.b200_trsm_rowblock_plan(32768, 8192, 256, 0, -1, buf, 10) == 0     # switched off
     assert lib.b200_trsm_rowblock_plan(2048, 8192, 256, 0, 4096, buf, 10) == 0    # one block is no pipeline
+
+
+@pytest.mark.parametrize("upper", [False, True])
+@pytest.mark.parametrize("m,leaf,rb", [(1576, 64, 512), (1000, 32, 300), (2048, 256, 512)])
+def test_trsm_rowblock_plan_is_sufficient_for_the_arithmetic(lib, m, leaf, upper, rb):
+    """The row-block pipeline replayed on the CPU exactly as csrc/host_trsm.cuh queues it: the device images of A and B
+    start as NaN, the plan's pieces are copied in the plan's order, and after each piece of A the launches that wait for
+    it run (update gemm of the block row, then the recursion's leaves and updates).  A launch that reads a byte that has
+    not travelled yet, or a row of X that is not final yet, poisons the result; the result must equal the solve of the
+    whole system.  alpha is applied exactly once per row, by the first operation that touches it."""
+    n, alpha = 24, 2.0
+    cap = 8 * (m // leaf + 2)
+    buf = (C.c_int64 * (5 * cap))()
+    # m < trsm_host_rb_min_m: an explicit block size still cuts the system (the engine's own choice would decline)
+    cnt = lib.b200_trsm_rowblock_plan(m, 8192, leaf, int(upper), rb, buf, cap)
+    assert 0 < cnt <= cap
+    plan = np.ctypeslib.as_array(buf)[:5 * cnt].reshape(cnt, 5).copy()
+    blocks = [(int(r0), int(r1)) for r0, r1, c0, c1, nl in plan if c0 < 0]
+    launches = iter(rowblock_launches(m, leaf, upper, blocks))
+    rng = np.random.default_rng(m + leaf + upper)
+    a = rng.uniform(-1, 1, (m, m)) / np.sqrt(m); a[np.arange(m), np.arange(m)] += 2.0
+    a = np.triu(a) if upper else np.tril(a)
+    b = rng.uniform(-1, 1, (m, n))
+    da, db = np.full((m, m), np.nan), np.full((m, n), np.nan)
+    scaled = np.zeros(m, dtype=bool)
+
+    def once(r0, r1):                       # alpha for rows that nobody has touched yet, 1 afterwards
+        assert scaled[r0:r1].all() or not scaled[r0:r1].any()
+        f = 1.0 if scaled[r0] else alpha
+        scaled[r0:r1] = True
+        return f
+
+    for r0, r1, c0, c1, nl in plan:
+        if c0 < 0:
+            db[r0:r1] = b[r0:r1]
+            continue
+        da[r0:r1, c0:c1] = np.where(np.isnan(a[r0:r1, c0:c1]), 0.0, a[r0:r1, c0:c1])
+        for _ in range(nl):
+            lr0, lr1, lc0, lc1 = next(launches)
+            if (lr0, lr1) == (lc0, lc1):    # leaf: triangular solve of a diagonal block, only its stored triangle is read
+                t = np.triu(da[lr0:lr1, lr0:lr1]) if upper else np.tril(da[lr0:lr1, lr0:lr1])
+                db[lr0:lr1] = np.linalg.solve(t, once(lr0, lr1) * db[lr0:lr1])
+            else:                           # update: B[rows] := alpha_once * B[rows] - A[rows, cols] X[cols]
+                assert scaled[lc0:lc1].all()
+                db[lr0:lr1] = once(lr0, lr1) * db[lr0:lr1] - da[lr0:lr1, lc0:lc1] @ db[lc0:lc1]
+    assert next(launches, None) is None
+    want = np.linalg.solve(a, alpha * b)
+    assert not np.isnan(db).any()
+    assert np.abs(db - want).max() <= 1e-11 * max(1.0, np.abs(want).max())
